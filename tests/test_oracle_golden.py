@@ -1,0 +1,61 @@
+"""CPU: the oracle restatement vs. the committed outputs of the unmodified reference.
+
+tests/golden/<case>.npz were produced by oracle/make_golden.py, which runs
+/root/reference's own build_model(cfg)/forward on the same seeded weights and clips.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tuber_oracle as O
+from oracle.cases import CASES, build_case
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 2e-5   # fp32 CPU vs fp32 CPU, different op grouping only
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_matches_reference_golden(name):
+    cfg, sd, clips, mask = build_case(name)
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    taps = {}
+    out = O.forward(cfg, sd, clips, mask, taps)
+    for key in ("pred_logits", "pred_boxes", "pred_logits_b"):
+        ref = torch.from_numpy(g[key])
+        assert tuple(out[key].shape) == tuple(ref.shape), key
+        emax, el2 = O.rel_err(out[key], ref)
+        assert emax <= TOL and el2 <= TOL, (name, key, emax, el2)
+    xt = taps["xt"]
+    assert tuple(xt.shape) == tuple(g["xt_shape"])
+    probe = xt.flatten()[torch.from_numpy(g["xt_probe_idx"])]
+    assert O.rel_err(probe, torch.from_numpy(g["xt_probe"]))[0] <= TOL
+    assert O.rel_err(taps["hs"][-1], torch.from_numpy(g["hs_last"]))[1] <= TOL
+    assert O.rel_err(taps["mem_c"][:, :16], torch.from_numpy(g["mem_c_first"]))[1] <= TOL
+
+
+def test_param_spec_counts():
+    """560 tensors for CSN50/decode (SURVEY.md section 8b probe of the live reference)."""
+    from oracle.cases import load_case_cfg
+    cfg = load_case_cfg("B_small")
+    assert len(O.param_spec(cfg)) == 560
+
+
+def test_reference_dict_shape():
+    cfg, sd, clips, mask = build_case("A_csn50")
+    out = O.as_reference_dict(O.forward(cfg, sd, clips, mask))
+    assert out["pred_logits"].shape == (1, 4, 80)
+    assert out["pred_boxes"].shape == (1, 4, 4)
+    assert out["pred_logits_b"].shape == (1, 4, 3)
+    assert len(out["aux_outputs"]) == 1
+
+
+def test_postprocess_ava_gate():
+    logits = torch.zeros(1, 2, 80)
+    boxes = torch.tensor([[[0.5, 0.5, 0.2, 0.4], [0.25, 0.25, 0.5, 0.5]]])
+    logits_b = torch.tensor([[[0.0, 5.0, 0.0], [0.0, 0.0, 0.0]]])
+    scores, xyxy, pb = O.postprocess_ava(logits, boxes, logits_b, torch.tensor([[100.0, 200.0]]))
+    assert scores[0, 1].abs().max() == 0            # p_actor = 1/3 < 0.8 -> gated to zero
+    assert torch.allclose(scores[0, 0], 0.5 * pb[0, 0])
+    assert torch.allclose(xyxy[0, 0], torch.tensor([80.0, 30.0, 120.0, 70.0]))
