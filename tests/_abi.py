@@ -1,0 +1,57 @@
+"""Test helper: thin torch-tensor wrappers over the single-operator entry points of the C-ABI."""
+import ctypes as C
+
+import torch
+
+import tuber_b200  # noqa: F401  (import shim)
+from tuber_b200 import _lib
+
+
+def P(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def to_split(x):
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), device="cuda", dtype=torch.float32)     # same bytes as fp32
+    _lib.check(_lib.load().tuber_op_to_split(P(x), P(out), rows, cols, stream()))
+    return out
+
+
+def from_split(s, rows, cols):
+    out = torch.empty((rows, cols), device="cuda", dtype=torch.float32)
+    _lib.check(_lib.load().tuber_op_from_split(P(s), P(out), rows, cols, stream()))
+    return out
+
+
+def pack_weight(w):
+    n, k = w.shape
+    out = torch.empty((n, k), device="cuda", dtype=torch.float32)
+    _lib.check(_lib.load().tuber_op_pack_weight(P(w), P(out), n, k, stream()))
+    return out
+
+
+def gemm_tc(a, w, scale=None, shift=None, res=None, res_split=False, res_mod=0, relu=False, c_split=False):
+    """a (M,K) fp32, w (N,K) fp32 -> (M,N) fp32 through the tcgen05 kernel (operands converted here)."""
+    m, k = a.shape
+    n = w.shape[0]
+    a_s, w_p = to_split(a.contiguous()), pack_weight(w.contiguous())
+    r = None
+    if res is not None:
+        r = to_split(res.contiguous()) if res_split else res.contiguous()
+    c = torch.empty((m, n), device="cuda", dtype=torch.float32)
+    _lib.check(_lib.load().tuber_op_gemm_tc(P(a_s), P(w_p), P(scale), P(shift), P(r), int(res_split), res_mod, P(c),
+                                            int(c_split), m, n, k, int(relu), stream()))
+    return from_split(c, m, n) if c_split else c
+
+
+def sgemm(a, w, bias=None, res=None, act=0):
+    m, k = a.shape
+    n = w.shape[0]
+    c = torch.empty((m, n), device="cuda", dtype=torch.float32)
+    _lib.check(_lib.load().tuber_op_sgemm(P(a.contiguous()), P(w.contiguous()), P(bias), P(res), P(c), m, n, k, act, stream()))
+    return c

@@ -1,0 +1,154 @@
+"""GPU: every single-operator entry point of the C-ABI against a torch fp64 restatement of the op."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double().cpu().flatten(), b.double().cpu().flatten()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from tests import _abi
+    return _abi
+
+
+def test_split_roundtrip(abi):
+    x = torch.randn(257, 192, device="cuda") * 3
+    y = abi.from_split(abi.to_split(x), 257, 192)
+    assert float(((y - x).abs() / x.abs().clamp_min(1e-6)).max()) < 2.0 ** -15
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 64, 64), (128, 128, 256), (1000, 256, 2048), (4096, 512, 128), (77, 192, 512),
+                                   (20000, 256, 64)])
+@pytest.mark.parametrize("variant", ["plain", "bn_relu_res", "split_out_split_res", "res_mod"])
+def test_gemm_tc(abi, m, n, k, variant):
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n + k)
+    a = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) / math.sqrt(k)
+    scale = shift = res = None
+    kw = {}
+    ref = a.double() @ w.double().t()
+    if variant != "plain":
+        scale = torch.rand(n, device="cuda", generator=g) + 0.5
+        shift = torch.randn(n, device="cuda", generator=g)
+        ref = ref * scale.double() + shift.double()
+    if variant in ("bn_relu_res", "split_out_split_res"):
+        res = torch.randn(m, n, device="cuda", generator=g)
+        ref = torch.relu(ref + res.double())
+        kw = dict(relu=True, res_split=variant == "split_out_split_res", c_split=variant == "split_out_split_res")
+    if variant == "res_mod":
+        mod = 13
+        res = torch.randn(mod, n, device="cuda", generator=g)
+        ref = ref + res.double()[torch.arange(m, device="cuda") % mod]
+        kw = dict(res_mod=mod)
+    out = abi.gemm_tc(a, w, scale, shift, res, **kw)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 3e-5, (m, n, k, variant)
+
+
+@pytest.mark.parametrize("m,n,k,act", [(90, 3, 256, 0), (90, 4, 256, 2), (720, 80, 256, 0), (8, 2, 2048, 0), (333, 256, 64, 1)])
+def test_sgemm(abi, m, n, k, act):
+    a = torch.randn(m, k, device="cuda")
+    w = torch.randn(n, k, device="cuda") / math.sqrt(k)
+    b = torch.randn(n, device="cuda")
+    ref = a.double() @ w.double().t() + b.double()
+    ref = torch.relu(ref) if act == 1 else (torch.sigmoid(ref) if act == 2 else ref)
+    assert _rel(abi.sgemm(a, w, b, None, act), ref) < 2e-6
+
+
+@pytest.mark.parametrize("c,st_t,st_s,dims", [(64, 1, 1, (2, 4, 9, 10)), (128, 2, 2, (1, 8, 16, 16)), (512, 2, 1, (2, 3, 5, 7)),
+                                              (256, 2, 2, (1, 5, 7, 9))])
+def test_dwconv(abi, c, st_t, st_s, dims):
+    from tuber_b200 import _lib
+    b, t, h, w = dims
+    x = torch.randn(b, c, t, h, w, device="cuda")
+    wt = torch.randn(c, 1, 3, 3, 3, device="cuda") * 0.3
+    scale, shift = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+    ref = F.conv3d(x.double(), wt.double(), stride=(st_t, st_s, st_s), padding=1, groups=c)
+    ref = torch.relu(ref * scale.double()[None, :, None, None, None] + shift.double()[None, :, None, None, None])
+    xin = x.permute(0, 2, 3, 4, 1).contiguous()
+    wpk = wt.reshape(c, 27).t().contiguous()
+    to, ho, wo = ref.shape[2:]
+    out = torch.empty((b * to * ho * wo, c), device="cuda")
+    _lib.check(_lib.load().tuber_op_dwconv(abi.P(xin), abi.P(wpk), abi.P(scale), abi.P(shift), abi.P(out), b, t, h, w, c, st_t, st_s,
+                                           abi.stream()))
+    got = abi.from_split(out, b * to * ho * wo, c).view(b, to, ho, wo, c).permute(0, 4, 1, 2, 3)
+    assert _rel(got, ref) < 3e-5
+
+
+@pytest.mark.parametrize("dims", [(1, 4, 32, 32), (2, 3, 45, 70)])
+def test_stem(abi, dims):
+    from tuber_b200 import _lib
+    b, t, h, w = dims
+    x = torch.randn(b, 3, t, h, w, device="cuda")
+    wt = torch.randn(64, 3, 3, 7, 7, device="cuda") * 0.05
+    scale, shift = torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda") * 0.1
+    ref = F.conv3d(x.double(), wt.double(), stride=(1, 2, 2), padding=(1, 3, 3))
+    ref = torch.relu(ref * scale.double()[None, :, None, None, None] + shift.double()[None, :, None, None, None])
+    refp = F.max_pool3d(ref, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    h1, w1, h2, w2 = ref.shape[3], ref.shape[4], refp.shape[3], refp.shape[4]
+    wpk = wt.reshape(64, 441).t().contiguous()
+    conv = torch.empty((b, t, h1, w1, 64), device="cuda")
+    pooled = torch.empty((b * t * h2 * w2, 64), device="cuda")
+    _lib.check(_lib.load().tuber_op_stem(abi.P(x), abi.P(wpk), abi.P(scale), abi.P(shift), abi.P(conv), abi.P(pooled), b, t, h, w,
+                                         abi.stream()))
+    assert _rel(conv.permute(0, 4, 1, 2, 3), ref) < 1e-5
+    got = abi.from_split(pooled, b * t * h2 * w2, 64).view(b, t, h2, w2, 64).permute(0, 4, 1, 2, 3)
+    assert _rel(got, refp) < 3e-5
+
+
+@pytest.mark.parametrize("c", [256, 2048])
+def test_layernorm(abi, c):
+    from tuber_b200 import _lib
+    x, r = torch.randn(77, c, device="cuda"), torch.randn(77, c, device="cuda")
+    g, b = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().tuber_op_layernorm(abi.P(x), abi.P(r), abi.P(g), abi.P(b), abi.P(out), 77, c, abi.stream()))
+    ref = F.layer_norm((x + r).double(), (c,), g.double(), b.double(), 1e-5)
+    assert _rel(out, ref) < 5e-6
+
+
+@pytest.mark.parametrize("nb,h,l,s,d,masked", [(2, 8, 256, 256, 32, True), (3, 8, 15, 15, 32, False), (2, 8, 15, 300, 32, True),
+                                               (5, 8, 1, 4, 256, False), (2, 8, 90, 1024, 32, False), (4, 8, 4, 4, 32, False)])
+def test_attention(abi, nb, h, l, s, d, masked):
+    from tuber_b200 import _lib
+    e = h * d
+    q, k, v = (torch.randn(nb, n, e, device="cuda") for n in (l, s, s))
+    kpm = None
+    if masked:
+        kpm = torch.zeros(nb, s, dtype=torch.uint8, device="cuda")
+        kpm[0, s // 2:] = 1
+        kpm[1, ::3] = 1
+    out = torch.empty(nb, l, e, device="cuda")
+    scale = d ** -0.5
+    _lib.check(_lib.load().tuber_op_attention(abi.P(q), abi.P(k), abi.P(v), abi.P(kpm), abi.P(out), nb, h, l, s, d, C.c_float(scale),
+                                              abi.stream()))
+    qh, kh, vh = (t.double().view(nb, -1, h, d).transpose(1, 2) for t in (q, k, v))
+    sc = qh @ kh.transpose(-1, -2) * scale
+    if kpm is not None:
+        sc = sc.masked_fill(kpm.bool()[:, None, None, :], float("-inf"))
+    ref = (sc.softmax(-1) @ vh).transpose(1, 2).reshape(nb, l, e)
+    assert _rel(out, ref) < 1e-5
+
+
+def test_posenc(abi):
+    from oracle import tuber_oracle as O
+    from tuber_b200 import _lib
+    b, t, h, w = 3, 2, 6, 8
+    mask = torch.zeros(b, t, h, w, dtype=torch.bool)
+    mask[1, :, :, 5:] = True
+    mask[2, :, 4:, :] = True
+    ref = O.position_sine_3d(mask, 256).flatten(2).transpose(1, 2)           # (B, THW, 256)
+    m8 = mask.to(torch.uint8).cuda()
+    out = torch.empty(b, t * h * w, 256, device="cuda")
+    _lib.check(_lib.load().tuber_op_posenc(abi.P(m8), abi.P(out), b, t, h, w, 256, abi.stream()))
+    torch.cuda.synchronize()
+    assert float((out.cpu() - ref).abs().max()) < 2e-5

@@ -1,0 +1,170 @@
+"""GPU: the CUDA forward (through build_model / the C-ABI) against the reference.
+
+* golden fixtures (tests/golden/*.npz, outputs of the unmodified reference, see oracle/make_golden.py)
+* the CPU oracle, stage by stage, on the small cases
+* size-independent properties at BASELINE.json's full clip size (32x256x256)
+Tolerance: BASELINE.json north_star -- 1e-3 relative, applied as in SURVEY.md section 8d to
+max|d|/max|ref| and to ||d||2/||ref||2 of each output tensor.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-3
+
+
+def _model(cfg, sd):
+    import tuber_b200
+    model, _, _ = tuber_b200.build_model(cfg)
+    model.load_state_dict(sd, strict=True)
+    return model.cuda().eval()
+
+
+def _rel(a, b):
+    from oracle import tuber_oracle as O
+    return O.rel_err(a.detach().float().cpu(), b.detach().float().cpu())
+
+
+def _layers_first(out, key):
+    t = out[key]
+    return t.permute(1, 0, 2, 3) if t.dim() == 4 else t      # (B,L,Q,*) -> (L,B,Q,*)
+
+
+from oracle.cases import CASES, build_case  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_matches_reference_golden(name):
+    cfg, sd, clips, mask = build_case(name)
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    model = _model(cfg, sd)
+    out = model.forward_raw(clips.cuda(), None if mask is None else mask.cuda())
+    torch.cuda.synchronize()
+    report = {}
+    for key in ("pred_logits", "pred_boxes", "pred_logits_b"):
+        ref = torch.from_numpy(g[key])
+        got = _layers_first(out, key)
+        if got.dim() == 2:                                   # JHMDB actor-ness head: one (B,2) for all layers
+            ref = ref[-1]
+        assert tuple(got.shape) == tuple(ref.shape), (key, got.shape, ref.shape)
+        report[key] = _rel(got, ref)
+    xt = model.debug_fetch("xt")
+    xs = tuple(int(v) for v in g["xt_shape"])               # (B,2048,T',H',W') in the reference
+    xt = xt.view(xs[0], xs[2], xs[3], xs[4], xs[1]).permute(0, 4, 1, 2, 3).contiguous().flatten()
+    report["xt_probe"] = _rel(xt[torch.from_numpy(g["xt_probe_idx"]).cuda()], torch.from_numpy(g["xt_probe"]))
+    hs = model.debug_fetch("hs").view(xs[0], cfg.CONFIG.MODEL.DEC_LAYERS, -1, 256)
+    report["hs_last"] = _rel(hs[:, -1], torch.from_numpy(g["hs_last"]))
+    print(name, {k: (f"{v[0]:.2e}", f"{v[1]:.2e}") for k, v in report.items()})
+    for key, (emax, el2) in report.items():
+        assert emax <= TOL and el2 <= TOL, (name, key, emax, el2)
+
+
+@pytest.mark.parametrize("name", ["A_csn50", "A_csn50_avg_bnrand"])
+def test_stages_match_oracle(name):
+    """Every named intermediate against the CPU oracle (localises a regression to a stage)."""
+    from oracle import tuber_oracle as O
+    from tuber_b200 import _lib
+    cfg, sd, clips, mask = build_case(name)
+    taps = {}
+    O.forward(cfg, sd, clips, mask, taps)
+    model = _model(cfg, sd)
+    _lib.check(_lib.load().tuber_set_debug_keep(model.plan(), 1))
+    model.forward_raw(clips.cuda(), None)
+    torch.cuda.synchronize()
+
+    def cl(t):      # reference (B,C,T,H,W) -> channels-last rows
+        return t.permute(0, 2, 3, 4, 1).contiguous().flatten()
+
+    checks = {"stem": cl(taps["stem"]), "layer1": cl(taps["layer1"]), "layer2": cl(taps["layer2"]), "layer3": cl(taps["layer3"]),
+              "layer4": cl(taps["layer4"]), "xt": cl(taps["xt"]), "xs": cl(taps["xs"]),
+              "pos": taps["pos"].flatten(2).transpose(1, 2)[:1].contiguous().flatten(),
+              "memory": taps["memory"].flatten(), "hs": taps["hs"].permute(1, 0, 2, 3).contiguous().flatten(),
+              "mem_c": taps["mem_c"].flatten()}
+    report = {k: _rel(model.debug_fetch(k), v) for k, v in checks.items()}
+    print(name, {k: f"{v[1]:.2e}" for k, v in report.items()})
+    for k, (emax, el2) in report.items():
+        assert el2 <= TOL, (name, k, emax, el2)
+
+
+def test_tensor_core_and_cuda_core_gemm_agree():
+    from tuber_b200 import _lib
+    cfg, sd, clips, _ = build_case("A_csn50_avg_bnrand")
+    model = _model(cfg, sd)
+    a = {k: v.clone() for k, v in model.forward_raw(clips.cuda()).items()}
+    _lib.check(_lib.load().tuber_set_force_simt(model.plan(), 1))
+    b = model.forward_raw(clips.cuda())
+    for k in a:
+        emax, el2 = _rel(a[k], b[k])
+        assert el2 < 1e-4, (k, emax, el2)
+
+
+def test_reference_call_signatures():
+    """forward(NestedTensor | list of clips) -> the reference's dict (tuber_ava.py:97-157)."""
+    import tuber_b200
+    cfg, sd, clips, _ = build_case("A_csn50")
+    model = _model(cfg, sd)
+    mask = torch.zeros((1, 128, 128), dtype=torch.bool)
+    out = model(tuber_b200.NestedTensor(clips, mask).to("cuda"))
+    assert out["pred_logits"].shape == (1, 4, 80) and out["pred_boxes"].shape == (1, 4, 4)
+    assert out["pred_logits_b"].shape == (1, 4, 3) and len(out["aux_outputs"]) == 1
+    out2 = model([clips[0].cuda()])
+    assert torch.equal(out["pred_logits"], out2["pred_logits"])
+    g = np.load(os.path.join(GOLD, "A_csn50.npz"))
+    assert _rel(out["pred_boxes"], torch.from_numpy(g["pred_boxes"][-1]))[0] <= TOL
+    scores, boxes, pb = tuber_b200.build_model(cfg)[2]["bbox"](out, torch.tensor([[240.0, 320.0]], device="cuda"))
+    assert scores.shape == (1, 4, 80) and boxes.shape == (1, 4, 4) and pb.shape == (1, 4, 1)
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    cfg, sd, clips, _ = build_case("A_csn50")
+    model = _model(cfg, sd)
+    x = clips.cuda()
+    eager = {k: v.clone() for k, v in model.forward_raw(x).items()}
+    model.use_cuda_graph(True)
+    out = {k: torch.empty_like(v) for k, v in eager.items()}
+    for _ in range(3):
+        for v in out.values():
+            v.zero_()
+        model.forward_raw(x, None, out)
+        torch.cuda.synchronize()
+        for k in eager:
+            assert torch.equal(out[k], eager[k]), k
+
+
+def test_no_fallback_off_device():
+    import tuber_b200
+    cfg, sd, clips, _ = build_case("A_csn50")
+    model, _, _ = tuber_b200.build_model(cfg)
+    with pytest.raises(RuntimeError):
+        model(clips)                                          # CPU model: must raise, never compute
+
+
+@pytest.mark.parametrize("yaml,batch", [("TubeR_CSN50_AVA21.yaml", 4), ("TubeR_CSN152_AVA21.yaml", 2)])
+def test_full_size_properties(yaml, batch):
+    """32x256x256 clips (BASELINE.json configs[1], [2]): clips are independent (any sub-batch gives the same
+    rows), an all-False mask equals no mask, boxes are in (0,1), outputs are finite."""
+    import tuber_b200
+    from oracle import tuber_oracle as O
+    cfg = tuber_b200.load_cfg(yaml)
+    sd = O.make_state_dict(cfg, seed=0, bn="random")
+    model = _model(cfg, sd)
+    clips = O.make_clips(batch, 32, 256, 256, seed=2).cuda()
+    full = {k: v.clone() for k, v in model.forward_raw(clips).items()}
+    for v in full.values():
+        assert torch.isfinite(v).all()
+    assert float(full["pred_boxes"].min()) > 0 and float(full["pred_boxes"].max()) < 1
+    part = model.forward_raw(clips[batch - 1:].contiguous())
+    for k in full:
+        emax, el2 = _rel(part[k], full[k][batch - 1:])
+        assert el2 < 1e-5, (k, emax, el2)
+    masked = model.forward_raw(clips, torch.zeros((batch, 256, 256), dtype=torch.bool, device="cuda"))
+    for k in full:
+        emax, el2 = _rel(masked[k], full[k])
+        assert el2 < 1e-5, (k, emax, el2)
+    info = model.shape_info(batch, 32, 256, 256)
+    assert (info.Tf, info.Hf, info.Wf, info.Tp) == (4, 16, 16, 1)

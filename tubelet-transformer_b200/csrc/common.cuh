@@ -1,0 +1,80 @@
+// Shared definitions for the tuber_b200 CUDA library (sm_100a only).
+//
+// Activation storage formats
+// --------------------------
+//   FMT_F32   : plain fp32, row-major [rows, ld].
+//   FMT_SPLIT : "split-bf16".  Every fp32 value v is stored as two bf16 numbers
+//               hi = bf16_rn(v), mid = bf16_rn(v - hi)  (16 mantissa bits in total).
+//               Row r of a [rows, ld] tensor occupies 2*ld bf16 = 4*ld bytes -- the same
+//               bytes as fp32 -- laid out as  hi[0..ld) | mid[0..ld).
+//               This is the operand format of the tcgen05 bf16x3 GEMM (gemm_tc.cu): TMA moves
+//               the hi and mid planes of a tile straight into the swizzled shared-memory
+//               layout the tensor core reads, and three MMAs (hi*hi + hi*mid + mid*hi) with
+//               fp32 accumulation in TMEM give ~2^-16 relative operand error, which the 1e-3
+//               parity bar needs (single-pass TF32, 2^-11, measurably fails it).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+enum TuberFmt { FMT_F32 = 0, FMT_SPLIT = 1 };
+enum TuberAct { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
+
+#define TB_DEVINL __device__ __forceinline__
+
+TB_DEVINL uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// v -> (hi, mid) with hi + mid == v to 16 mantissa bits
+TB_DEVINL void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& mid) {
+  hi = __float2bfloat16_rn(v);
+  mid = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+TB_DEVINL float bf16_lo_to_f32(uint32_t w) { return __uint_as_float(w << 16); }
+TB_DEVINL float bf16_hi_to_f32(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// 4 consecutive values -> one 8-byte store into each plane
+TB_DEVINL void store_split4(__nv_bfloat16* hi_ptr, __nv_bfloat16* mid_ptr, float4 v) {
+  __nv_bfloat16 h0, h1, h2, h3, m0, m1, m2, m3;
+  split_bf16(v.x, h0, m0);
+  split_bf16(v.y, h1, m1);
+  split_bf16(v.z, h2, m2);
+  split_bf16(v.w, h3, m3);
+  *reinterpret_cast<uint2*>(hi_ptr) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+  *reinterpret_cast<uint2*>(mid_ptr) = make_uint2(pack_bf16x2(m0, m1), pack_bf16x2(m2, m3));
+}
+
+TB_DEVINL float4 load_split4(const __nv_bfloat16* hi_ptr, const __nv_bfloat16* mid_ptr) {
+  uint2 h = __ldg(reinterpret_cast<const uint2*>(hi_ptr));
+  uint2 m = __ldg(reinterpret_cast<const uint2*>(mid_ptr));
+  float4 r;
+  r.x = bf16_lo_to_f32(h.x) + bf16_lo_to_f32(m.x);
+  r.y = bf16_hi_to_f32(h.x) + bf16_hi_to_f32(m.x);
+  r.z = bf16_lo_to_f32(h.y) + bf16_lo_to_f32(m.y);
+  r.w = bf16_hi_to_f32(h.y) + bf16_hi_to_f32(m.y);
+  return r;
+}
+
+// Row pointers of a split tensor (ld in elements)
+TB_DEVINL const __nv_bfloat16* split_hi(const void* base, long long row, int ld) {
+  return reinterpret_cast<const __nv_bfloat16*>(base) + row * 2 * ld;
+}
+TB_DEVINL __nv_bfloat16* split_hi(void* base, long long row, int ld) {
+  return reinterpret_cast<__nv_bfloat16*>(base) + row * 2 * ld;
+}
+
+TB_DEVINL float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+TB_DEVINL float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,101 @@
+// Host-side launch interface of the tuber_b200 kernels (internal; the public C-ABI is
+// include/tuber_b200.h).  Every launcher is asynchronous on the given stream and returns the
+// cudaError_t of the launch.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+// ---- stem (ir_CSN_152.py:109-122,176-179) ------------------------------------------------
+// x NCDHW fp32 (B,3,T,H,W); wpk [441][64] (k = ((c*3+kt)*7+kh)*7+kw, oc fastest);
+// y NDHWC fp32 [B,T,H1,W1,64] = relu(conv*scale+shift)
+cudaError_t launch_stem_conv(const float* x, const float* wpk, const float* scale, const float* shift,
+                             float* y, int B, int T, int H, int W, int H1, int W1, cudaStream_t st);
+// (1,3,3)/s(1,2,2)/p(0,1,1) max pool, fp32 [BT,H1,W1,C] -> split [BT,H2,W2,C]
+cudaError_t launch_maxpool_hw(const float* in, void* out_split, int BT, int H1, int W1, int H2, int W2,
+                              int C, cudaStream_t st);
+
+// ---- depthwise 3x3x3 (ir_CSN_152.py:48-51) + BN + ReLU -----------------------------------
+// in fp32 [B,Ti,Hi,Wi,C]; wpk [27][C] (tap = (kt*3+kh)*3+kw); out split [B,To,Ho,Wo,C]
+cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale, const float* shift,
+                          void* out_split, int B, int Ti, int Hi, int Wi, int C, int st_t, int st_s,
+                          int To, int Ho, int Wo, cudaStream_t st);
+
+// strided voxel gather (rows of row_bytes, multiple of 16): out[b,to,ho,wo] = in[b,to*st_t,ho*st_s,wo*st_s]
+cudaError_t launch_gather_rows(const void* in, void* out, int row_bytes, int B, int Ti, int Hi, int Wi,
+                               int st_t, int st_s, int To, int Ho, int Wo, cudaStream_t st);
+// generic frame slice: out[b, 0:Tn, hw] = in[b, t0:t0+Tn, hw]  (rows of row_bytes)
+cudaError_t launch_slice_frames(const void* in, void* out, int row_bytes, int B, int Tin, int HW, int t0,
+                                int Tn, cudaStream_t st);
+
+// temporal pooling of split features [B,Tin,HW,C] -> split [B,Tout,HW,C], window k, stride k
+cudaError_t launch_tpool(const void* in_split, void* out_split, int B, int Tin, int HW, int C, int k,
+                         int Tout, int is_max, cudaStream_t st);
+// mean over N rows of a split tensor [B,N,C] -> fp32 [B,C]
+cudaError_t launch_global_avgpool(const void* in_split, float* out, int B, int N, int C, cudaStream_t st);
+
+// ---- GEMM: C = act( scale[n] * ((A (+A2[row % a2_mod])) W^T)[m,n] + shift[n] + res[m % res_mod, n] ) ------
+// One argument block for both implementations:
+//   launch_gemm_tc   tcgen05 bf16x3 tensor-core kernel (gemm_tc.cu): A must be FMT_SPLIT, needs Wp,
+//                    N % 64 == 0, K % 64 == 0, no A2.
+//   launch_sgemm     fp32 CUDA-core kernel (kernels_simt.cu): any A format, needs Wf, K % 16 == 0; used for
+//                    the tiny-N heads (N = 2, 3, 4, 80) and as the debugging cross-check of the TC kernel.
+struct GemmArgs {
+  const void* A; int a_fmt; int lda;         // [M, lda] fp32 or split
+  const float* A2; int lda2; int a2_mod;     // optional fp32 addend on A rows (SIMT only; a2_mod <= 0: same row)
+  const float* Wf;                           // fp32 [N, K] row-major
+  const void* Wp;                            // packed split weights: bf16 [2][N][K]
+  const float* scale; const float* shift;    // [N] each, nullable (1 / 0)
+  const void* res; int res_fmt; int ldr; int res_mod;   // nullable residual, added before act
+  void* C; int c_fmt; int ldc;
+  void* C2; int ldc2;                        // optional second copy of C in the OTHER format
+  int M, N, K;
+  int act;                                   // ACT_NONE / ACT_RELU / ACT_SIGMOID (sigmoid: SIMT only)
+};
+cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st);
+
+// ---- LayerNorm over the last dim (C in {256, 2048}) of x (+ res) ---------------------------
+struct LnArgs {
+  const float* x; int ldx;
+  const void* res; int res_fmt; int ldr;     // optional: normalise x + res (fp32 or split; ldr 0 = broadcast row)
+  const float* gamma; const float* beta; float eps;
+  int rows, C;
+  float* out_f32; int ldo;                   // nullable; out row = (r / rpg) * group_stride + r % rpg + row_off
+  int rpg; long long group_stride; long long row_off;
+  void* out_split; int lds; int split_col_off;   // nullable; row r, columns split_col_off + [0,C)
+};
+cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t st);
+
+// ---- attention core: O = softmax(scale * Q K^T + mask) V, per (sequence n, head h) ---------
+struct SeqMap {        // first row of sequence n = (n / inner) * outer + (n % inner) * inner_stride; token i at + i * step
+  int inner; long long outer, inner_stride, step;
+};
+struct AttnArgs {
+  const float* q; int ldq; SeqMap qm;
+  const float* k; const float* v; int ldk, ldv; SeqMap km;
+  float* o_f32; void* o_split; int ldo; SeqMap om;
+  const uint8_t* kpm; int kpm_div;           // key padding mask [NB / kpm_div, S] (1 = ignore key) or null
+  int NB, H, L, S, D;                        // D = head dim (32, or any multiple of 32 for the warp kernel)
+  float scale;
+};
+cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st);
+
+// ---- masks and position code (backbone_builder.py:85-86, position_encoding.py:32-72) ------
+cudaError_t launch_mask_resize(const uint8_t* mask, uint8_t* fmask, int B, int H, int W, int T, int Hf,
+                               int Wf, cudaStream_t st);
+cudaError_t launch_posenc(const uint8_t* fmask, const float* dim_t, const float* dim_s, float* pos, int B,
+                          int T, int H, int W, int nt, int ns, cudaStream_t st);
+
+// ---- format conversion (tests, plumbing) --------------------------------------------------
+cudaError_t launch_to_split(const float* in, int ldi, void* out, int ldo, long long rows, int cols,
+                            cudaStream_t st);
+cudaError_t launch_from_split(const void* in, int ldi, float* out, int ldo, long long rows, int cols,
+                              cudaStream_t st);
+
+// ---- tcgen05 bf16x3 GEMM (gemm_tc.cu) -------------------------------------------------------
+cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st);
+const char* gemm_tc_last_error();
+// fp32 [N,K] -> packed split bf16 [2][N][K]
+cudaError_t launch_pack_weight(const float* w, void* out, int N, int K, cudaStream_t st);

@@ -1,0 +1,811 @@
+// CUDA-core kernels of the TubeR forward path (sm_100a): stem convolution, max pool,
+// depthwise 3x3x3 stencil, strided gathers, temporal pooling, fp32 GEMM for the token-sized
+// linear layers, LayerNorm, attention cores, padding-mask resize and the 3-D sine position code.
+// The tensor-core GEMM lives in gemm_tc.cu.  All activations are channels-last (NDHWC).
+#include <float.h>
+#include <math.h>
+
+#include "kernels.h"
+
+// =============================================================================================
+// Stem: Conv3d(3->64,(3,7,7),s(1,2,2),p(1,3,3)) + BN + ReLU     (ir_CSN_152.py:109-120,176-178)
+// One CTA = an 8x32 tile of conv outputs of one frame, all 64 channels.  The whole filter bank
+// (441x64 fp32 = 110 KB) and the 3-frame input patch live in shared memory; a thread keeps
+// 8 output columns x 4 channels in registers and slides the 7-tap window over a 21-wide row.
+// =============================================================================================
+namespace stem {
+constexpr int TH = 8, TW = 32, KVOL = 441, OC = 64;
+constexpr int PH = 2 * TH + 5, PW = 72;   // patch rows 21, cols 69 padded to 72
+constexpr int SMEM_BYTES = (KVOL * OC + 9 * PH * PW) * 4;
+}  // namespace stem
+
+__global__ void __launch_bounds__(512, 1)
+stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ wpk, const float* __restrict__ scale,
+                 const float* __restrict__ shift, float* __restrict__ y, int B, int T, int H, int W, int H1,
+                 int W1) {
+  using namespace stem;
+  extern __shared__ __align__(16) float smem[];
+  float* wsm = smem;                 // [441][64]
+  float* ism = smem + KVOL * OC;     // [9][PH][PW]
+  const int tid = threadIdx.x;
+  const int bt = blockIdx.z, b = bt / T, t = bt % T;
+  const int oh0 = blockIdx.y * TH, ow0 = blockIdx.x * TW;
+
+  for (int i = tid; i < KVOL * OC / 4; i += 512)
+    reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(wpk) + i);
+  const int ih0 = 2 * oh0 - 3, iw0 = 2 * ow0 - 3;
+  for (int i = tid; i < 9 * PH * PW; i += 512) {
+    int q = i % PW, r = (i / PW) % PH, ck = i / (PW * PH);
+    int c = ck / 3, kt = ck % 3;
+    int it = t + kt - 1, ih = ih0 + r, iw = iw0 + q;
+    float v = 0.f;
+    if (it >= 0 && it < T && ih >= 0 && ih < H && iw >= 0 && iw < W)
+      v = __ldg(x + ((((long long)b * 3 + c) * T + it) * H + ih) * W + iw);
+    ism[i] = v;
+  }
+  __syncthreads();
+
+  const int chg = tid & 15, seg = (tid >> 4) & 3, row = tid >> 6;
+  float acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+
+  for (int ck = 0; ck < 9; ++ck) {
+#pragma unroll 1
+    for (int kh = 0; kh < 7; ++kh) {
+      const float* irow = ism + (ck * PH + 2 * row + kh) * PW + 16 * seg;
+      float in[24];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        float4 v4 = reinterpret_cast<const float4*>(irow)[i];
+        in[4 * i] = v4.x; in[4 * i + 1] = v4.y; in[4 * i + 2] = v4.z; in[4 * i + 3] = v4.w;
+      }
+      const float* wrow = wsm + ((ck * 7 + kh) * 7) * OC + chg * 4;
+#pragma unroll
+      for (int kw = 0; kw < 7; ++kw) {
+        float4 w4 = *reinterpret_cast<const float4*>(wrow + kw * OC);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = in[2 * j + kw];
+          acc[j][0] = fmaf(a, w4.x, acc[j][0]);
+          acc[j][1] = fmaf(a, w4.y, acc[j][1]);
+          acc[j][2] = fmaf(a, w4.z, acc[j][2]);
+          acc[j][3] = fmaf(a, w4.w, acc[j][3]);
+        }
+      }
+    }
+  }
+  const int oh = oh0 + row;
+  if (oh >= H1) return;
+  float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + chg);
+  float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + chg);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int ow = ow0 + seg * 8 + j;
+    if (ow >= W1) continue;
+    float4 o;
+    o.x = fmaxf(fmaf(acc[j][0], sc.x, sh.x), 0.f);
+    o.y = fmaxf(fmaf(acc[j][1], sc.y, sh.y), 0.f);
+    o.z = fmaxf(fmaf(acc[j][2], sc.z, sh.z), 0.f);
+    o.w = fmaxf(fmaf(acc[j][3], sc.w, sh.w), 0.f);
+    reinterpret_cast<float4*>(y + (((long long)bt * H1 + oh) * W1 + ow) * OC)[chg] = o;
+  }
+}
+
+cudaError_t launch_stem_conv(const float* x, const float* wpk, const float* scale, const float* shift, float* y,
+                             int B, int T, int H, int W, int H1, int W1, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         stem::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(W1, stem::TW), ceil_div(H1, stem::TH), B * T);
+  stem_conv_kernel<<<grid, 512, stem::SMEM_BYTES, st>>>(x, wpk, scale, shift, y, B, T, H, W, H1, W1);
+  return cudaGetLastError();
+}
+
+// MaxPool3d((1,3,3),s(1,2,2),p(0,1,1))  (ir_CSN_152.py:122,179): fp32 -> split
+__global__ void maxpool_hw_kernel(const float* __restrict__ in, void* __restrict__ out, int BT, int H1, int W1,
+                                  int H2, int W2, int C) {
+  const int c4n = C >> 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)BT * H2 * W2 * c4n;
+  if (idx >= total) return;
+  int c4 = (int)(idx % c4n);
+  long long vox = idx / c4n;
+  int w2 = (int)(vox % W2), h2 = (int)((vox / W2) % H2);
+  long long bt = vox / ((long long)W2 * H2);
+  float4 m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+#pragma unroll
+  for (int dh = -1; dh <= 1; ++dh) {
+    int h = 2 * h2 + dh;
+    if (h < 0 || h >= H1) continue;
+#pragma unroll
+    for (int dw = -1; dw <= 1; ++dw) {
+      int w = 2 * w2 + dw;
+      if (w < 0 || w >= W1) continue;
+      float4 v = __ldg(reinterpret_cast<const float4*>(in + ((bt * H1 + h) * W1 + w) * C) + c4);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  }
+  __nv_bfloat16* hi = split_hi(out, vox, C) + c4 * 4;
+  store_split4(hi, hi + C, m);
+}
+
+cudaError_t launch_maxpool_hw(const float* in, void* out_split, int BT, int H1, int W1, int H2, int W2, int C,
+                              cudaStream_t st) {
+  long long total = (long long)BT * H2 * W2 * (C / 4);
+  maxpool_hw_kernel<<<ceil_div(total, 256), 256, 0, st>>>(in, out_split, BT, H1, W1, H2, W2, C);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// Depthwise 3x3x3 conv (groups = C), stride (st,ss,ss), pad 1, + BN + ReLU  (ir_CSN_152.py:48-56,77-79)
+// HBM-bound stencil: a thread owns 4 channels x 4 consecutive output columns, so the 9 input
+// rows it touches are read as float4 along the contiguous channel axis and each loaded value
+// feeds up to 3 outputs from registers.  fp32 in, split-bf16 out (operand of the next GEMM).
+// =============================================================================================
+template <int SS>
+__global__ void __launch_bounds__(256)
+dwconv_kernel(const float* __restrict__ in, const float* __restrict__ wpk, const float* __restrict__ scale,
+              const float* __restrict__ shift, void* __restrict__ out, int B, int Ti, int Hi, int Wi, int C,
+              int st_t, int To, int Ho, int Wo) {
+  constexpr int WS = 4, NIN = (WS - 1) * SS + 3;
+  const int c4n = C >> 2;
+  const int wstrips = (Wo + WS - 1) / WS;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * To * Ho * wstrips * c4n;
+  if (idx >= total) return;
+  int c4 = (int)(idx % c4n);
+  long long r = idx / c4n;
+  int wsi = (int)(r % wstrips); r /= wstrips;
+  int ho = (int)(r % Ho); r /= Ho;
+  int to = (int)(r % To);
+  int b = (int)(r / To);
+  const int wo0 = wsi * WS;
+  const int iw0 = wo0 * SS - 1;
+
+  float4 acc[WS];
+#pragma unroll
+  for (int j = 0; j < WS; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+#pragma unroll
+  for (int kt = 0; kt < 3; ++kt) {
+    int it = to * st_t - 1 + kt;
+    if (it < 0 || it >= Ti) continue;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      int ih = ho * SS - 1 + kh;
+      if (ih < 0 || ih >= Hi) continue;
+      const float* irow = in + (((long long)b * Ti + it) * Hi + ih) * (long long)Wi * C;
+      float4 x[NIN];
+#pragma unroll
+      for (int q = 0; q < NIN; ++q) {
+        int iw = iw0 + q;
+        x[q] = (iw >= 0 && iw < Wi) ? __ldg(reinterpret_cast<const float4*>(irow + (long long)iw * C) + c4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        float4 w = __ldg(reinterpret_cast<const float4*>(wpk + ((kt * 3 + kh) * 3 + kw) * C) + c4);
+#pragma unroll
+        for (int j = 0; j < WS; ++j) {
+          float4 v = x[j * SS + kw];
+          acc[j].x = fmaf(v.x, w.x, acc[j].x);
+          acc[j].y = fmaf(v.y, w.y, acc[j].y);
+          acc[j].z = fmaf(v.z, w.z, acc[j].z);
+          acc[j].w = fmaf(v.w, w.w, acc[j].w);
+        }
+      }
+    }
+  }
+  float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+  float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+  long long orow0 = (((long long)b * To + to) * Ho + ho) * Wo + wo0;
+#pragma unroll
+  for (int j = 0; j < WS; ++j) {
+    if (wo0 + j >= Wo) break;
+    float4 o;
+    o.x = fmaxf(fmaf(acc[j].x, sc.x, sh.x), 0.f);
+    o.y = fmaxf(fmaf(acc[j].y, sc.y, sh.y), 0.f);
+    o.z = fmaxf(fmaf(acc[j].z, sc.z, sh.z), 0.f);
+    o.w = fmaxf(fmaf(acc[j].w, sc.w, sh.w), 0.f);
+    __nv_bfloat16* hi = split_hi(out, orow0 + j, C) + c4 * 4;
+    store_split4(hi, hi + C, o);
+  }
+}
+
+cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale, const float* shift,
+                          void* out_split, int B, int Ti, int Hi, int Wi, int C, int st_t, int st_s, int To,
+                          int Ho, int Wo, cudaStream_t st) {
+  long long total = (long long)B * To * Ho * ((Wo + 3) / 4) * (C / 4);
+  int grid = ceil_div(total, 256);
+  if (st_s == 1)
+    dwconv_kernel<1><<<grid, 256, 0, st>>>(in, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, st_t, To, Ho, Wo);
+  else if (st_s == 2)
+    dwconv_kernel<2><<<grid, 256, 0, st>>>(in, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, st_t, To, Ho, Wo);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// Row gathers (raw 16-byte chunks; format-agnostic because a split row has fp32's byte count)
+// =============================================================================================
+__global__ void gather_rows_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int chunks, int B,
+                                   int Ti, int Hi, int Wi, int st_t, int st_s, int To, int Ho, int Wo) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * To * Ho * Wo * chunks;
+  if (idx >= total) return;
+  int ch = (int)(idx % chunks);
+  long long r = idx / chunks;
+  int wo = (int)(r % Wo); r /= Wo;
+  int ho = (int)(r % Ho); r /= Ho;
+  int to = (int)(r % To);
+  long long b = r / To;
+  long long src = ((b * Ti + (long long)to * st_t) * Hi + (long long)ho * st_s) * Wi + (long long)wo * st_s;
+  out[idx] = __ldg(in + src * chunks + ch);
+}
+
+cudaError_t launch_gather_rows(const void* in, void* out, int row_bytes, int B, int Ti, int Hi, int Wi, int st_t,
+                               int st_s, int To, int Ho, int Wo, cudaStream_t st) {
+  int chunks = row_bytes / 16;
+  long long total = (long long)B * To * Ho * Wo * chunks;
+  gather_rows_kernel<<<ceil_div(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(in),
+                                                          reinterpret_cast<uint4*>(out), chunks, B, Ti, Hi, Wi,
+                                                          st_t, st_s, To, Ho, Wo);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_slice_frames(const void* in, void* out, int row_bytes, int B, int Tin, int HW, int t0, int Tn,
+                                cudaStream_t st) {
+  // rows of frame range [t0, t0+Tn) are contiguous per clip: B strided 2-D copies
+  return cudaMemcpy2DAsync(out, (size_t)Tn * HW * row_bytes,
+                           reinterpret_cast<const char*>(in) + (size_t)t0 * HW * row_bytes,
+                           (size_t)Tin * HW * row_bytes, (size_t)Tn * HW * row_bytes, B,
+                           cudaMemcpyDeviceToDevice, st);
+}
+
+// Temporal avg / max pool with window = stride = k  (backbone_builder.py:43-46,73)
+__global__ void tpool_kernel(const void* __restrict__ in, void* __restrict__ out, int B, int Tin, int HW, int C,
+                             int k, int Tout, int is_max) {
+  const int c4n = C >> 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * Tout * HW * c4n;
+  if (idx >= total) return;
+  int c4 = (int)(idx % c4n);
+  long long r = idx / c4n;
+  int p = (int)(r % HW); r /= HW;
+  int to = (int)(r % Tout);
+  long long b = r / Tout;
+  float4 a = is_max ? make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < k; ++i) {
+    long long row = (b * Tin + (long long)to * k + i) * HW + p;
+    const __nv_bfloat16* hi = split_hi(in, row, C) + c4 * 4;
+    float4 v = load_split4(hi, hi + C);
+    if (is_max) {
+      a.x = fmaxf(a.x, v.x); a.y = fmaxf(a.y, v.y); a.z = fmaxf(a.z, v.z); a.w = fmaxf(a.w, v.w);
+    } else {
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  }
+  if (!is_max) {
+    float kk = (float)k;
+    a.x /= kk; a.y /= kk; a.z /= kk; a.w /= kk;
+  }
+  __nv_bfloat16* ho = split_hi(out, (b * Tout + to) * HW + p, C) + c4 * 4;
+  store_split4(ho, ho + C, a);
+}
+
+cudaError_t launch_tpool(const void* in_split, void* out_split, int B, int Tin, int HW, int C, int k, int Tout,
+                         int is_max, cudaStream_t st) {
+  long long total = (long long)B * Tout * HW * (C / 4);
+  tpool_kernel<<<ceil_div(total, 256), 256, 0, st>>>(in_split, out_split, B, Tin, HW, C, k, Tout, is_max);
+  return cudaGetLastError();
+}
+
+// AdaptiveAvgPool3d(1) over all positions (tuber_ava.py:48,124): split [B,N,C] -> fp32 [B,C]
+__global__ void global_avgpool_kernel(const void* __restrict__ in, float* __restrict__ out, int N, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int b = blockIdx.y;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int i = 0; i < N; ++i) {
+    const __nv_bfloat16* hi = split_hi(in, (long long)b * N + i, C);
+    acc += __bfloat162float(hi[c]) + __bfloat162float(hi[C + c]);
+  }
+  out[(long long)b * C + c] = acc / (float)N;
+}
+
+cudaError_t launch_global_avgpool(const void* in_split, float* out, int B, int N, int C, cudaStream_t st) {
+  dim3 grid(ceil_div(C, 128), B);
+  global_avgpool_kernel<<<grid, 128, 0, st>>>(in_split, out, N, C);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// fp32 CUDA-core GEMM: the tiny-N heads (tuber_ava.py:64-73, criterion.py:485-497) and the debugging
+// cross-check of the tensor-core kernel.  64x64 tile, BK=16, 256 threads, 4x4 micro-tile, register
+// prefetch of the next k-slab.  A / res / C may be fp32 or split-bf16.
+// =============================================================================================
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+sgemm_kernel(GemmArgs p) {
+  constexpr int BM = 64, BN = 64, BK = 16, LDS = BM + 4;
+  __shared__ __align__(16) float As[BK][LDS];
+  __shared__ __align__(16) float Ws[BK][LDS];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;   // loader: row within tile, k offset
+  const int ty = tid >> 4, tx = tid & 15;
+
+  const int am = m0 + lr, wn = n0 + lr;
+  const bool a_ok = am < p.M, w_ok = wn < p.N;
+  const float* a_ptr = nullptr;
+  const __nv_bfloat16* a_hi = nullptr;
+  if (p.a_fmt == FMT_F32)
+    a_ptr = reinterpret_cast<const float*>(p.A) + (long long)am * p.lda + lk;
+  else
+    a_hi = split_hi(p.A, am, p.lda) + lk;
+  const float* a2_ptr = nullptr;
+  if (p.A2) {
+    int r2 = p.a2_mod > 0 ? am % p.a2_mod : am;
+    a2_ptr = p.A2 + (long long)r2 * p.lda2 + lk;
+  }
+  const float* w_ptr = p.Wf + (long long)wn * p.K + lk;
+
+  auto load_a = [&](int k0) -> float4 {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a_ok) {
+      v = a_ptr ? __ldg(reinterpret_cast<const float4*>(a_ptr + k0)) : load_split4(a_hi + k0, a_hi + p.lda + k0);
+      if (a2_ptr) {
+        float4 u = __ldg(reinterpret_cast<const float4*>(a2_ptr + k0));
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      }
+    }
+    return v;
+  };
+  auto load_w = [&](int k0) -> float4 {
+    return w_ok ? __ldg(reinterpret_cast<const float4*>(w_ptr + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float4 ra = load_a(0), rw = load_w(0);
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    As[lk + 0][lr] = ra.x; As[lk + 1][lr] = ra.y; As[lk + 2][lr] = ra.z; As[lk + 3][lr] = ra.w;
+    Ws[lk + 0][lr] = rw.x; Ws[lk + 1][lr] = rw.y; Ws[lk + 2][lr] = rw.z; Ws[lk + 3][lr] = rw.w;
+    __syncthreads();
+    if (k0 + BK < p.K) {
+      ra = load_a(k0 + BK);
+      rw = load_w(k0 + BK);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 w = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+    const long long rr = p.res_mod > 0 ? m % p.res_mod : m;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.scale) v *= __ldg(p.scale + n);
+      if (p.shift) v += __ldg(p.shift + n);
+      if (p.res) {
+        if (p.res_fmt == FMT_F32) {
+          v += __ldg(reinterpret_cast<const float*>(p.res) + rr * p.ldr + n);
+        } else {
+          const __nv_bfloat16* h = split_hi(p.res, rr, p.ldr);
+          v += __bfloat162float(h[n]) + __bfloat162float(h[p.ldr + n]);
+        }
+      }
+      v = apply_act(v, p.act);
+      void* cf = p.c_fmt == FMT_F32 ? p.C : p.C2;
+      void* cs = p.c_fmt == FMT_F32 ? p.C2 : p.C;
+      const int ldf = p.c_fmt == FMT_F32 ? p.ldc : p.ldc2, lds = p.c_fmt == FMT_F32 ? p.ldc2 : p.ldc;
+      if (cf) reinterpret_cast<float*>(cf)[(long long)m * ldf + n] = v;
+      if (cs) {
+        __nv_bfloat16 hi, mid;
+        split_bf16(v, hi, mid);
+        __nv_bfloat16* h = split_hi(cs, m, lds);
+        h[n] = hi;
+        h[lds + n] = mid;
+      }
+    }
+  }
+}
+
+cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st) {
+  if (a.K % 16 != 0 || a.M <= 0 || a.N <= 0 || a.Wf == nullptr) return cudaErrorInvalidValue;
+  dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64));
+  sgemm_kernel<<<grid, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// LayerNorm (eps 1e-5) over C = 32*4*NV elements, one warp per row, optional fused residual add,
+// fp32 and/or split-bf16 outputs, optional output-row remap (stacks decoder layers, concat).
+// =============================================================================================
+template <int NV>   // float4 chunks per lane: C = 128 * NV
+__global__ void __launch_bounds__(256)
+layernorm_kernel(LnArgs p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= p.rows) return;
+  const long long r = warp;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int c = i * 128 + lane * 4;
+    v[i] = __ldg(reinterpret_cast<const float4*>(p.x + r * p.ldx + c));
+    if (p.res) {
+      float4 u;
+      if (p.res_fmt == FMT_F32) {
+        u = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + r * p.ldr + c));
+      } else {
+        const __nv_bfloat16* h = split_hi(p.res, r, p.ldr) + c;
+        u = load_split4(h, h + p.ldr);
+      }
+      v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+    }
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) / (float)p.C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = 1.f / sqrtf(warp_sum(q) / (float)p.C + p.eps);
+  long long orow = p.rpg > 0 ? (r / p.rpg) * p.group_stride + (r % p.rpg) + p.row_off : r + p.row_off;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int c = i * 128 + lane * 4;
+    float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+    float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + c));
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + c) = o;
+    if (p.out_split) {
+      __nv_bfloat16* hi = split_hi(p.out_split, orow, p.lds) + p.split_col_off + c;
+      store_split4(hi, hi + p.lds, o);
+    }
+  }
+}
+
+cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t st) {
+  int grid = ceil_div((long long)a.rows * 32, 256);
+  if (a.C == 256)
+    layernorm_kernel<2><<<grid, 256, 0, st>>>(a);
+  else if (a.C == 2048)
+    layernorm_kernel<16><<<grid, 256, 0, st>>>(a);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// Attention cores.  Q/K/V are fp32 slices of projection buffers; a sequence is addressed through
+// a SeqMap so the same kernels serve per-clip, per-frame and per-pixel (strided) sequences.
+// =============================================================================================
+__device__ __forceinline__ long long seq_row0(const SeqMap& m, int n) {
+  return (long long)(n / m.inner) * m.outer + (long long)(n % m.inner) * m.inner_stride;
+}
+
+// (a) head_dim 32, one thread per query, K/V tiles of 128 keys staged in shared memory,
+//     online softmax in chunks of 4 keys.  grid = (ceil(L/blockDim), H, NB).
+__global__ void __launch_bounds__(128)
+attn_smem_kernel(AttnArgs p) {
+  constexpr int D = 32, TS = 128;
+  __shared__ __align__(16) float Ks[TS][D];
+  __shared__ __align__(16) float Vs[TS][D];
+  __shared__ uint8_t Ms[TS];
+  const int n = blockIdx.z, h = blockIdx.y;
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = l < p.L;
+  const long long q0 = seq_row0(p.qm, n), k0 = seq_row0(p.km, n);
+
+  float q[D], acc[D];
+  float m = -INFINITY, lsum = 0.f;
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] = 0.f;
+  if (active) {
+    const float* qp = p.q + (q0 + (long long)l * p.qm.step) * p.ldq + h * D;
+#pragma unroll
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(qp) + d4);
+      q[4 * d4] = t.x * p.scale; q[4 * d4 + 1] = t.y * p.scale;
+      q[4 * d4 + 2] = t.z * p.scale; q[4 * d4 + 3] = t.w * p.scale;
+    }
+  }
+  const uint8_t* mrow = p.kpm ? p.kpm + (long long)(n / p.kpm_div) * p.S : nullptr;
+
+  for (int s0 = 0; s0 < p.S; s0 += TS) {
+    const int ts = min(TS, p.S - s0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ts * (D / 4); i += blockDim.x) {
+      int j = i / (D / 4), d4 = i % (D / 4);
+      long long krow = k0 + (long long)(s0 + j) * p.km.step;
+      reinterpret_cast<float4*>(&Ks[j][0])[d4] = __ldg(reinterpret_cast<const float4*>(p.k + krow * p.ldk + h * D) + d4);
+      reinterpret_cast<float4*>(&Vs[j][0])[d4] = __ldg(reinterpret_cast<const float4*>(p.v + krow * p.ldv + h * D) + d4);
+    }
+    for (int j = threadIdx.x; j < ts; j += blockDim.x) Ms[j] = mrow ? mrow[s0 + j] : 0;
+    __syncthreads();
+    if (!active) continue;
+    for (int j0 = 0; j0 < ts; j0 += 4) {
+      float s[4];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int j = j0 + i;
+        float dot = -INFINITY;
+        if (j < ts && !Ms[j]) {
+          dot = 0.f;
+#pragma unroll
+          for (int d4 = 0; d4 < D / 4; ++d4) {
+            float4 kk = reinterpret_cast<const float4*>(&Ks[j][0])[d4];
+            dot = fmaf(q[4 * d4], kk.x, dot);
+            dot = fmaf(q[4 * d4 + 1], kk.y, dot);
+            dot = fmaf(q[4 * d4 + 2], kk.z, dot);
+            dot = fmaf(q[4 * d4 + 3], kk.w, dot);
+          }
+        }
+        s[i] = dot;
+        cmax = fmaxf(cmax, dot);
+      }
+      if (cmax == -INFINITY) continue;
+      const float mnew = fmaxf(m, cmax);
+      const float corr = expf(m - mnew);      // m = -inf -> 0
+      float pr[4];
+      float psum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pr[i] = expf(s[i] - mnew);             // masked -> 0
+        psum += pr[i];
+      }
+      lsum = lsum * corr + psum;
+      m = mnew;
+#pragma unroll
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        float4 a = make_float4(acc[4 * d4] * corr, acc[4 * d4 + 1] * corr, acc[4 * d4 + 2] * corr,
+                               acc[4 * d4 + 3] * corr);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (j0 + i < ts) {
+            float4 vv = reinterpret_cast<const float4*>(&Vs[j0 + i][0])[d4];
+            a.x = fmaf(pr[i], vv.x, a.x); a.y = fmaf(pr[i], vv.y, a.y);
+            a.z = fmaf(pr[i], vv.z, a.z); a.w = fmaf(pr[i], vv.w, a.w);
+          }
+        }
+        acc[4 * d4] = a.x; acc[4 * d4 + 1] = a.y; acc[4 * d4 + 2] = a.z; acc[4 * d4 + 3] = a.w;
+      }
+    }
+  }
+  if (!active) return;
+  const float inv = 1.f / lsum;
+  const long long orow = seq_row0(p.om, n) + (long long)l * p.om.step;
+#pragma unroll
+  for (int d4 = 0; d4 < D / 4; ++d4) {
+    float4 o = make_float4(acc[4 * d4] * inv, acc[4 * d4 + 1] * inv, acc[4 * d4 + 2] * inv, acc[4 * d4 + 3] * inv);
+    if (p.o_f32) reinterpret_cast<float4*>(p.o_f32 + orow * p.ldo + h * D)[d4] = o;
+    if (p.o_split) {
+      __nv_bfloat16* hi = split_hi(p.o_split, orow, p.ldo) + h * D + d4 * 4;
+      store_split4(hi, hi + p.ldo, o);
+    }
+  }
+}
+
+// (b) any head_dim = 32*DPL, one warp per (sequence, head, query), keys streamed from global:
+//     for the tiny-S sites (S = T' = 4 temporal attention, 15-query decoder self-attention,
+//     the decode pool's 1x4 cross-attention with head_dim 256).
+template <int DPL>
+__global__ void __launch_bounds__(128)
+attn_warp_kernel(AttnArgs p) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)p.NB * p.H * p.L;
+  if (w >= total) return;
+  const int l = (int)(w % p.L);
+  const int h = (int)((w / p.L) % p.H);
+  const int n = (int)(w / ((long long)p.L * p.H));
+  const int D = 32 * DPL;
+  const float* qp = p.q + (seq_row0(p.qm, n) + (long long)l * p.qm.step) * p.ldq + h * D;
+  const long long k0 = seq_row0(p.km, n);
+  const uint8_t* mrow = p.kpm ? p.kpm + (long long)(n / p.kpm_div) * p.S : nullptr;
+  float q[DPL], acc[DPL];
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) {
+    q[i] = __ldg(qp + lane + 32 * i) * p.scale;
+    acc[i] = 0.f;
+  }
+  float m = -INFINITY, lsum = 0.f;
+  for (int j = 0; j < p.S; ++j) {
+    if (mrow && mrow[j]) continue;
+    const long long krow = k0 + (long long)j * p.km.step;
+    const float* kp = p.k + krow * p.ldk + h * D;
+    const float* vp = p.v + krow * p.ldv + h * D;
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) dot = fmaf(q[i], __ldg(kp + lane + 32 * i), dot);
+    dot = warp_sum(dot);
+    const float mnew = fmaxf(m, dot);
+    const float corr = expf(m - mnew);
+    const float pr = expf(dot - mnew);
+    lsum = lsum * corr + pr;
+    m = mnew;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) acc[i] = fmaf(pr, __ldg(vp + lane + 32 * i), acc[i] * corr);
+  }
+  const float inv = 1.f / lsum;
+  const long long orow = seq_row0(p.om, n) + (long long)l * p.om.step;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) {
+    float o = acc[i] * inv;
+    int c = h * D + lane + 32 * i;
+    if (p.o_f32) p.o_f32[orow * p.ldo + c] = o;
+    if (p.o_split) {
+      __nv_bfloat16 hi, mid;
+      split_bf16(o, hi, mid);
+      __nv_bfloat16* hp = split_hi(p.o_split, orow, p.ldo);
+      hp[c] = hi;
+      hp[p.ldo + c] = mid;
+    }
+  }
+}
+
+cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st) {
+  if (a.D % 32 != 0 || a.NB <= 0 || a.L <= 0 || a.S <= 0) return cudaErrorInvalidValue;
+  const bool small = a.S <= 16 || a.D != 32;
+  if (!small) {
+    int threads = a.L >= 128 ? 128 : ((a.L + 31) / 32) * 32;
+    dim3 grid(ceil_div(a.L, threads), a.H, a.NB);
+    attn_smem_kernel<<<grid, threads, 0, st>>>(a);
+  } else {
+    long long warps = (long long)a.NB * a.H * a.L;
+    int grid = ceil_div(warps * 32, 128);
+    if (a.D == 32)
+      attn_warp_kernel<1><<<grid, 128, 0, st>>>(a);
+    else if (a.D == 256)
+      attn_warp_kernel<8><<<grid, 128, 0, st>>>(a);
+    else
+      return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// Padding mask at feature resolution and the 3-D sine position code
+// =============================================================================================
+// nearest-neighbour resize (B,H,W) -> (B,T,Hf,Wf), repeated over T  (backbone_builder.py:85-86)
+__global__ void mask_resize_kernel(const uint8_t* __restrict__ mask, uint8_t* __restrict__ fmask, int B, int H,
+                                   int W, int T, int Hf, int Wf) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * T * Hf * Wf;
+  if (idx >= total) return;
+  int x = (int)(idx % Wf), y = (int)((idx / Wf) % Hf);
+  long long b = idx / ((long long)Wf * Hf * T);
+  const float sh = (float)H / (float)Hf, sw = (float)W / (float)Wf;
+  int sy = min((int)floorf((float)y * sh), H - 1);
+  int sx = min((int)floorf((float)x * sw), W - 1);
+  fmask[idx] = mask ? mask[(b * H + sy) * W + sx] : 0;
+}
+
+cudaError_t launch_mask_resize(const uint8_t* mask, uint8_t* fmask, int B, int H, int W, int T, int Hf, int Wf,
+                               cudaStream_t st) {
+  long long total = (long long)B * T * Hf * Wf;
+  mask_resize_kernel<<<ceil_div(total, 256), 256, 0, st>>>(mask, fmask, B, H, W, T, Hf, Wf);
+  return cudaGetLastError();
+}
+
+// PositionEmbeddingSine_3D(normalize=True)  (position_encoding.py:32-72), token-major output
+// pos[b, (t,y,x), c], c in [0,nt) from t, [nt,nt+ns) from y, [nt+ns,nt+2ns) from x.
+__global__ void posenc_kernel(const uint8_t* __restrict__ fmask, const float* __restrict__ dim_t,
+                              const float* __restrict__ dim_s, float* __restrict__ pos, int B, int T, int H, int W,
+                              int nt, int ns) {
+  const int d = nt + 2 * ns;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * T * H * W * d;
+  if (idx >= total) return;
+  int c = (int)(idx % d);
+  long long tok = idx / d;
+  int x = (int)(tok % W), y = (int)((tok / W) % H), t = (int)((tok / ((long long)W * H)) % T);
+  long long b = tok / ((long long)W * H * T);
+  const uint8_t* mb = fmask + b * T * H * W;
+  float e = 0.f, last = 0.f, div;
+  int ci;
+  if (c < nt) {
+    for (int i = 0; i < T; ++i) {
+      float nm = mb[((long long)i * H + y) * W + x] ? 0.f : 1.f;
+      last += nm;
+      if (i <= t) e += nm;
+    }
+    ci = c; div = dim_t[ci];
+  } else if (c < nt + ns) {
+    for (int i = 0; i < H; ++i) {
+      float nm = mb[((long long)t * H + i) * W + x] ? 0.f : 1.f;
+      last += nm;
+      if (i <= y) e += nm;
+    }
+    ci = c - nt; div = dim_s[ci];
+  } else {
+    for (int i = 0; i < W; ++i) {
+      float nm = mb[((long long)t * H + y) * W + i] ? 0.f : 1.f;
+      last += nm;
+      if (i <= x) e += nm;
+    }
+    ci = c - nt - ns; div = dim_s[ci];
+  }
+  const float two_pi = 6.283185307179586f;
+  float ph = (e / (last + 1e-6f) * two_pi) / div;
+  pos[idx] = (ci & 1) ? cosf(ph) : sinf(ph);
+}
+
+cudaError_t launch_posenc(const uint8_t* fmask, const float* dim_t, const float* dim_s, float* pos, int B, int T,
+                          int H, int W, int nt, int ns, cudaStream_t st) {
+  long long total = (long long)B * T * H * W * (nt + 2 * ns);
+  posenc_kernel<<<ceil_div(total, 256), 256, 0, st>>>(fmask, dim_t, dim_s, pos, B, T, H, W, nt, ns);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// fp32 <-> split-bf16
+// =============================================================================================
+__global__ void to_split_kernel(const float* __restrict__ in, int ldi, void* __restrict__ out, int ldo,
+                                long long rows, int cols) {
+  const int c4n = cols >> 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * c4n) return;
+  int c4 = (int)(idx % c4n);
+  long long r = idx / c4n;
+  float4 v = __ldg(reinterpret_cast<const float4*>(in + r * ldi) + c4);
+  __nv_bfloat16* hi = split_hi(out, r, ldo) + c4 * 4;
+  store_split4(hi, hi + ldo, v);
+}
+__global__ void from_split_kernel(const void* __restrict__ in, int ldi, float* __restrict__ out, int ldo,
+                                  long long rows, int cols) {
+  const int c4n = cols >> 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * c4n) return;
+  int c4 = (int)(idx % c4n);
+  long long r = idx / c4n;
+  const __nv_bfloat16* hi = split_hi(in, r, ldi) + c4 * 4;
+  reinterpret_cast<float4*>(out + r * ldo)[c4] = load_split4(hi, hi + ldi);
+}
+
+cudaError_t launch_to_split(const float* in, int ldi, void* out, int ldo, long long rows, int cols, cudaStream_t st) {
+  to_split_kernel<<<ceil_div(rows * (cols / 4), 256), 256, 0, st>>>(in, ldi, out, ldo, rows, cols);
+  return cudaGetLastError();
+}
+cudaError_t launch_from_split(const void* in, int ldi, float* out, int ldo, long long rows, int cols,
+                              cudaStream_t st) {
+  from_split_kernel<<<ceil_div(rows * (cols / 4), 256), 256, 0, st>>>(in, ldi, out, ldo, rows, cols);
+  return cudaGetLastError();
+}

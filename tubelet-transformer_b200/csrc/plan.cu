@@ -1,0 +1,1258 @@
+// C-ABI of the B200-native TubeR forward path (include/tuber_b200.h): weight ingest and packing,
+// workspace management and the launch sequence of one forward.
+//
+// The launch sequence follows DETR.forward (reference models/tuber_ava.py:97-148):
+//   backbone body      models/backbones/ir_CSN_152.py:172-186 (stem :176-179, bottlenecks :70-90)
+//   temporal pooling   models/backbone_builder.py:70-80 (decode pool: transformer_layers.py:380-448)
+//   mask + position    models/backbone_builder.py:85-89, models/transformer/position_encoding.py:32-72
+//   encoder / decoder  models/transformer/transformer.py:49-64,153-168,218-249
+//   class branch       models/transformer/transformer_layers.py:71-97, models/tuber_ava.py:129-141
+//   heads              models/tuber_ava.py:121-125,141-142, models/criterion.py:485-497
+// Activations are channels-last; "S" = split-bf16 (operand of the tcgen05 GEMM), "F" = fp32 (common.cuh).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/tuber_b200.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local char g_last_error[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof g_last_error, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(expr)                                                                                  \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(TUBER_ERR_CUDA, "%s:%d %s -> %s %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e), \
+                  gemm_tc_last_error());                                                          \
+  } while (0)
+#define TRY(expr)              \
+  do {                         \
+    int _s = (expr);           \
+    if (_s != TUBER_OK) return _s; \
+  } while (0)
+
+constexpr float BN_EPS = 1e-3f;   // ir_CSN_152.py:15
+constexpr float LN_EPS = 1e-5f;   // torch.nn.LayerNorm default
+constexpr int POOL_DIM = 2048;    // backbone_builder.py:49-52
+constexpr int CLS_FF = 2048;      // tuber_ava.py:60
+constexpr int CLS_HEADS = 8;      // tuber_ava.py:60,62
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+struct Lin {          // y = scale * (x W^T) + shift
+  float* wf = nullptr; void* wp = nullptr; float* scale = nullptr; float* shift = nullptr;
+  int N = 0, K = 0;
+};
+struct Dw { float* w = nullptr; float* scale = nullptr; float* shift = nullptr; int C = 0; };
+struct LnP { float* g = nullptr; float* b = nullptr; int C = 0; };
+
+struct Block {
+  Lin conv1, conv4, ds;
+  Dw dw;
+  bool has_ds = false;
+  int st_t = 1, st_s = 1, cin = 0, planes = 0, cout = 0;
+};
+struct EncLayer { Lin in, out, lin1, lin2; LnP n1, n2; };
+struct DecLayer {
+  Lin sa_in, sa_out, ca_q, ca_out, lin1, lin2;
+  LnP n1, n2, n3;
+  float* pq_sa = nullptr;   // [Q, 3d]: query_embed x [Wq;Wk;0]^T   (q = k = tgt + query_pos, transformer.py:225)
+  float* pq_ca = nullptr;   // [Q, d] : query_embed x Wq^T           (query = tgt + query_pos, :232)
+};
+
+struct KernelRec { const char* name; double bytes, flops; cudaEvent_t e0, e1; };
+struct Tap { const void* ptr; int fmt; long long rows; int cols; void* keep; };
+
+struct Ws {   // bump allocator over one device buffer; in dry mode only counts
+  char* base = nullptr; size_t cap = 0, off = 0, peak = 0; bool dry = false;
+  void* alloc(size_t bytes) {
+    size_t o = (off + 255) & ~(size_t)255;
+    off = o + bytes;
+    if (off > peak) peak = off;
+    if (dry) return reinterpret_cast<void*>((uintptr_t)0x1000 + o);
+    return base + o;
+  }
+};
+
+}  // namespace
+
+struct TuberPlan {
+  TuberConfig cfg;
+  int device = 0;
+  bool finalized = false;
+  std::unordered_map<std::string, HostTensor> host;
+  std::vector<void*> owned;          // device allocations of packed weights
+
+  // packed model
+  float* stem_w = nullptr; float* stem_scale = nullptr; float* stem_shift = nullptr;
+  std::vector<Block> blocks[4];
+  // decode pool (input-independent parts folded at finalize)
+  float* pool_tgt1 = nullptr;        // [2048] LN1(query_pool + self_attn(query_pool))
+  float* pool_q = nullptr;           // [2048] Wq tgt1 + bq of the cross attention
+  Lin pool_kv, pool_out, pool_lin1, pool_lin2;
+  LnP pool_n2, pool_n3, pool_nf;
+  Lin input_proj, class_proj;
+  std::vector<EncLayer> enc;
+  std::vector<DecLayer> dec;
+  LnP dec_norm;
+  Lin pos_proj;                      // N = Le*3d + Ld*2d: per encoder layer [Wq;Wk;0], per decoder layer [Wk_cross;0]
+  Lin mem_kv;                        // N = Ld*2d: per decoder layer [Wk_cross;Wv_cross]
+  float* dim_t = nullptr; float* dim_s = nullptr;
+  // class branch
+  Lin ct_in, ct_out, cs_in, cs_out, c_lin1, c_lin2, x_q, x_kv, x_out;
+  LnP c_n1t, c_n1s, c_n2;
+  Lin head_b, bbox0, bbox1, bbox2, class_fc;
+
+  // run-time state
+  char* ws = nullptr; size_t ws_cap = 0;
+  char* stage_in = nullptr; size_t stage_in_cap = 0;      // forward_host staging
+  char* stage_out = nullptr; size_t stage_out_cap = 0;
+  bool force_simt = false;
+  bool profiling = false, debug_keep = false, use_graph = false;
+  cudaEvent_t ev[TUBER_NUM_STAGES + 1] = {};
+  bool ev_valid = false;
+  std::map<std::string, Tap> taps;
+  int launches = 0;
+  bool kprof = false;
+  std::vector<KernelRec> kp; int kp_used = 0;
+  struct GraphEntry { std::vector<uintptr_t> key; cudaGraphExec_t exec; };
+  std::vector<GraphEntry> graphs;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// weight ingest helpers
+// ------------------------------------------------------------------------------------------
+struct Packer {
+  TuberPlan* p;
+  std::string missing;
+  int status = TUBER_OK;
+
+  const HostTensor* get(const std::string& name, std::initializer_list<int64_t> shape) {
+    auto it = p->host.find(name);
+    if (it == p->host.end()) {
+      if (status == TUBER_OK) { status = fail(TUBER_ERR_MISSING, "weight '%s' was never set", name.c_str()); }
+      return nullptr;
+    }
+    if (shape.size()) {
+      int64_t want = 1, have = 1;
+      for (auto s : shape) want *= s;
+      for (auto s : it->second.shape) have *= s;
+      if (want != have) {
+        if (status == TUBER_OK) status = fail(TUBER_ERR_SHAPE, "weight '%s' has %lld elements, expected %lld", name.c_str(), (long long)have, (long long)want);
+        return nullptr;
+      }
+    }
+    return &it->second;
+  }
+
+  template <typename T>
+  T* upload(const std::vector<T>& v) {
+    void* d = nullptr;
+    if (cudaMalloc(&d, v.size() * sizeof(T) + 16) != cudaSuccess) {
+      if (status == TUBER_OK) status = fail(TUBER_ERR_CUDA, "cudaMalloc of %zu bytes failed", v.size() * sizeof(T));
+      return nullptr;
+    }
+    p->owned.push_back(d);
+    cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return reinterpret_cast<T*>(d);
+  }
+
+  // fp32 [N,K] host rows -> Lin (both the fp32 copy and the packed split planes)
+  Lin make_lin(const std::vector<float>& w, int N, int K, const std::vector<float>* scale, const std::vector<float>* shift) {
+    Lin l;
+    l.N = N; l.K = K;
+    l.wf = upload(w);
+    void* wp = nullptr;
+    if (cudaMalloc(&wp, (size_t)N * K * 4 + 16) != cudaSuccess) {
+      if (status == TUBER_OK) status = fail(TUBER_ERR_CUDA, "cudaMalloc failed");
+      return l;
+    }
+    p->owned.push_back(wp);
+    l.wp = wp;
+    if (l.wf) launch_pack_weight(l.wf, wp, N, K, 0);
+    if (scale) l.scale = upload(*scale);
+    if (shift) l.shift = upload(*shift);
+    return l;
+  }
+
+  // eval-mode BatchNorm3d folded to y = x*scale + shift
+  bool bn(const std::string& prefix, int C, std::vector<float>& scale, std::vector<float>& shift) {
+    const HostTensor* g = get(prefix + ".weight", {C});
+    const HostTensor* b = get(prefix + ".bias", {C});
+    const HostTensor* m = get(prefix + ".running_mean", {C});
+    const HostTensor* v = get(prefix + ".running_var", {C});
+    if (!g || !b || !m || !v) return false;
+    scale.resize(C); shift.resize(C);
+    for (int i = 0; i < C; ++i) {
+      double s = (double)g->data[i] / sqrt((double)v->data[i] + (double)BN_EPS);
+      scale[i] = (float)s;
+      shift[i] = (float)((double)b->data[i] - (double)m->data[i] * s);
+    }
+    return true;
+  }
+
+  Lin conv_bn(const std::string& conv, const std::string& bnp, int N, int K) {
+    const HostTensor* w = get(conv + ".weight", {N, K});
+    std::vector<float> sc, sh;
+    if (!w || !bn(bnp, N, sc, sh)) return Lin();
+    return make_lin(w->data, N, K, &sc, &sh);
+  }
+
+  // rows [r0, r0+n) of a [R,K] weight (+ the same slice of its bias)
+  Lin linear_rows(const std::string& wname, const std::string& bname, int R, int K, int r0, int n) {
+    const HostTensor* w = get(wname, {R, K});
+    const HostTensor* b = bname.empty() ? nullptr : get(bname, {R});
+    if (!w || (!bname.empty() && !b)) return Lin();
+    std::vector<float> ws(w->data.begin() + (size_t)r0 * K, w->data.begin() + (size_t)(r0 + n) * K);
+    if (b) {
+      std::vector<float> bs(b->data.begin() + r0, b->data.begin() + r0 + n);
+      return make_lin(ws, n, K, nullptr, &bs);
+    }
+    return make_lin(ws, n, K, nullptr, nullptr);
+  }
+  Lin linear(const std::string& prefix, int N, int K) { return linear_rows(prefix + ".weight", prefix + ".bias", N, K, 0, N); }
+
+  LnP ln(const std::string& prefix, int C) {
+    LnP l;
+    const HostTensor* g = get(prefix + ".weight", {C});
+    const HostTensor* b = get(prefix + ".bias", {C});
+    if (!g || !b) return l;
+    l.g = upload(g->data); l.b = upload(b->data); l.C = C;
+    return l;
+  }
+};
+
+void host_layernorm(std::vector<double>& x, const std::vector<float>& g, const std::vector<float>& b) {
+  const size_t n = x.size();
+  double mean = 0, var = 0;
+  for (double v : x) mean += v;
+  mean /= (double)n;
+  for (double v : x) var += (v - mean) * (v - mean);
+  var /= (double)n;
+  const double rstd = 1.0 / sqrt(var + (double)LN_EPS);
+  for (size_t i = 0; i < n; ++i) x[i] = (x[i] - mean) * rstd * (double)g[i] + (double)b[i];
+}
+
+// y[n] = sum_k W[r0+n, k] x[k] (+ b[r0+n])
+std::vector<double> host_matvec(const HostTensor& w, const HostTensor* b, int r0, int N, int K, const std::vector<double>& x) {
+  std::vector<double> y(N);
+  for (int n = 0; n < N; ++n) {
+    const float* row = w.data.data() + (size_t)(r0 + n) * K;
+    double acc = 0;
+    for (int k = 0; k < K; ++k) acc += (double)row[k] * x[k];
+    y[n] = acc + (b ? (double)b->data[r0 + n] : 0.0);
+  }
+  return y;
+}
+
+// out[q, n] = sum_k E[q,k] W[r0+n,k]   (fp64 accumulate, fp32 result)
+void host_embed_proj(const HostTensor& e, int Q, int K, const HostTensor& w, int r0, int N, float* out, int ldo) {
+  for (int q = 0; q < Q; ++q) {
+    const float* er = e.data.data() + (size_t)q * K;
+    for (int n = 0; n < N; ++n) {
+      const float* wr = w.data.data() + (size_t)(r0 + n) * K;
+      double acc = 0;
+      for (int k = 0; k < K; ++k) acc += (double)er[k] * (double)wr[k];
+      out[(size_t)q * ldo + n] = (float)acc;
+    }
+  }
+}
+
+int do_finalize(TuberPlan* p) {
+  const TuberConfig& c = p->cfg;
+  Packer pk{p};
+  const int d = c.d_model, ff = c.dim_ff, Q = c.num_queries;
+  const std::string bb = "backbone.body";
+
+  // ---- stem (ir_CSN_152.py:109-120): weight (64,3,3,7,7) -> [441][64] ----
+  {
+    const HostTensor* w = pk.get(bb + ".conv1.weight", {64, 441});
+    std::vector<float> sc, sh;
+    if (w && pk.bn(bb + ".bn1", 64, sc, sh)) {
+      std::vector<float> t((size_t)441 * 64);
+      for (int oc = 0; oc < 64; ++oc)
+        for (int k = 0; k < 441; ++k) t[(size_t)k * 64 + oc] = w->data[(size_t)oc * 441 + k];
+      p->stem_w = pk.upload(t);
+      p->stem_scale = pk.upload(sc);
+      p->stem_shift = pk.upload(sh);
+    }
+  }
+  // ---- bottlenecks (ir_CSN_152.py:36-68,124-170) ----
+  const int planes_of[4] = {64, 128, 256, 512};
+  const int tstr[4] = {1, 2, 2, 2};
+  const int sstr[4] = {1, 2, 2, c.last_stride ? 2 : 1};
+  int in_planes = 64;
+  for (int li = 0; li < 4 && pk.status == TUBER_OK; ++li) {
+    const int planes = planes_of[li], outp = planes * 4;
+    p->blocks[li].clear();
+    for (int bi = 0; bi < c.blocks[li] && pk.status == TUBER_OK; ++bi) {
+      Block b;
+      char pre[96];
+      snprintf(pre, sizeof pre, "%s.layer%d.%d", bb.c_str(), li + 1, bi);
+      const std::string P = pre;
+      b.cin = bi == 0 ? in_planes : outp;
+      b.planes = planes; b.cout = outp;
+      b.has_ds = bi == 0;
+      b.st_t = bi == 0 ? tstr[li] : 1;
+      b.st_s = bi == 0 ? sstr[li] : 1;
+      b.conv1 = pk.conv_bn(P + ".conv1", P + ".bn1", planes, b.cin);
+      {
+        const HostTensor* w = pk.get(P + ".conv3.weight", {planes, 27});
+        std::vector<float> sc, sh;
+        if (w && pk.bn(P + ".bn3", planes, sc, sh)) {
+          std::vector<float> t((size_t)27 * planes);
+          for (int ch = 0; ch < planes; ++ch)
+            for (int k = 0; k < 27; ++k) t[(size_t)k * planes + ch] = w->data[(size_t)ch * 27 + k];
+          b.dw.w = pk.upload(t); b.dw.scale = pk.upload(sc); b.dw.shift = pk.upload(sh); b.dw.C = planes;
+        }
+      }
+      b.conv4 = pk.conv_bn(P + ".conv4", P + ".bn4", outp, planes);
+      if (b.has_ds) b.ds = pk.conv_bn(P + ".down_sample.0", P + ".down_sample.1", outp, b.cin);
+      p->blocks[li].push_back(b);
+    }
+    in_planes = outp;
+  }
+  if (pk.status != TUBER_OK) return pk.status;
+  if (in_planes != POOL_DIM) return fail(TUBER_ERR_INVALID, "backbone width %d != 2048", in_planes);
+
+  // ---- decode pool (backbone_builder.py:49-53; transformer_layers.py:407-448) ----
+  if (c.pool == TUBER_POOL_DECODE) {
+    const int D = POOL_DIM;
+    const std::string L = "backbone.pool_decoder.layers.0";
+    const HostTensor* qp = pk.get("backbone.query_pool.weight", {D});
+    const HostTensor* sa_w = pk.get(L + ".self_attn.in_proj_weight", {3 * D, D});
+    const HostTensor* sa_b = pk.get(L + ".self_attn.in_proj_bias", {3 * D});
+    const HostTensor* so_w = pk.get(L + ".self_attn.out_proj.weight", {D, D});
+    const HostTensor* so_b = pk.get(L + ".self_attn.out_proj.bias", {D});
+    const HostTensor* n1g = pk.get(L + ".norm1.weight", {D});
+    const HostTensor* n1b = pk.get(L + ".norm1.bias", {D});
+    const HostTensor* ca_w = pk.get(L + ".multihead_attn.in_proj_weight", {3 * D, D});
+    const HostTensor* ca_b = pk.get(L + ".multihead_attn.in_proj_bias", {3 * D});
+    if (pk.status != TUBER_OK) return pk.status;
+    // the pooled query is one token per pixel, so its self-attention softmax is identically 1 and the
+    // whole first sub-layer is input independent: tgt1 = LN1(q + Wo (Wv q + bv) + bo)
+    std::vector<double> q0(qp->data.begin(), qp->data.end());
+    std::vector<double> v = host_matvec(*sa_w, sa_b, 2 * D, D, D, q0);
+    std::vector<double> o = host_matvec(*so_w, so_b, 0, D, D, v);
+    for (int i = 0; i < D; ++i) o[i] += q0[i];
+    host_layernorm(o, n1g->data, n1b->data);
+    std::vector<double> qc = host_matvec(*ca_w, ca_b, 0, D, D, o);
+    std::vector<float> tgt1(o.begin(), o.end()), qcf(qc.begin(), qc.end());
+    p->pool_tgt1 = pk.upload(tgt1);
+    p->pool_q = pk.upload(qcf);
+    p->pool_kv = pk.linear_rows(L + ".multihead_attn.in_proj_weight", L + ".multihead_attn.in_proj_bias", 3 * D, D, D, 2 * D);
+    p->pool_out = pk.linear(L + ".multihead_attn.out_proj", D, D);
+    p->pool_lin1 = pk.linear(L + ".linear1", 2048, D);
+    p->pool_lin2 = pk.linear(L + ".linear2", D, 2048);
+    p->pool_n2 = pk.ln(L + ".norm2", D);
+    p->pool_n3 = pk.ln(L + ".norm3", D);
+    p->pool_nf = pk.ln("backbone.pool_decoder.norm", D);
+  }
+
+  // ---- projections (tuber_ava.py:57-58) ----
+  p->input_proj = pk.linear("input_proj", d, c.dim_ff);   // backbone.num_channels := DIM_FEEDFORWARD (backbone_builder.py:111)
+  p->class_proj = pk.linear("class_proj", d, c.dim_ff);
+  if (c.dim_ff != POOL_DIM) return fail(TUBER_ERR_INVALID, "DIM_FEEDFORWARD must equal the backbone width 2048");
+
+  // ---- DETR encoder / decoder (transformer.py:131-149,193-211) ----
+  p->enc.clear();
+  p->dec.clear();
+  const int NP = c.enc_layers * 3 * d + c.dec_layers * 2 * d;
+  std::vector<float> posw((size_t)NP * d, 0.f);
+  for (int i = 0; i < c.enc_layers && pk.status == TUBER_OK; ++i) {
+    char pre[96];
+    snprintf(pre, sizeof pre, "transformer.encoder.layers.%d", i);
+    const std::string P = pre;
+    EncLayer e;
+    e.in = pk.linear_rows(P + ".self_attn.in_proj_weight", P + ".self_attn.in_proj_bias", 3 * d, d, 0, 3 * d);
+    e.out = pk.linear(P + ".self_attn.out_proj", d, d);
+    e.lin1 = pk.linear(P + ".linear1", ff, d);
+    e.lin2 = pk.linear(P + ".linear2", d, ff);
+    e.n1 = pk.ln(P + ".norm1", d);
+    e.n2 = pk.ln(P + ".norm2", d);
+    const HostTensor* w = pk.get(P + ".self_attn.in_proj_weight", {3 * d, d});
+    if (w) memcpy(posw.data() + (size_t)i * 3 * d * d, w->data.data(), (size_t)2 * d * d * sizeof(float));   // Wq, Wk rows
+    p->enc.push_back(e);
+  }
+  const HostTensor* qe = pk.get("query_embed.weight", {Q, d});
+  std::vector<float> memw((size_t)c.dec_layers * 2 * d * d), memb((size_t)c.dec_layers * 2 * d);
+  for (int i = 0; i < c.dec_layers && pk.status == TUBER_OK; ++i) {
+    char pre[96];
+    snprintf(pre, sizeof pre, "transformer.decoder.layers.%d", i);
+    const std::string P = pre;
+    DecLayer l;
+    l.sa_in = pk.linear_rows(P + ".self_attn.in_proj_weight", P + ".self_attn.in_proj_bias", 3 * d, d, 0, 3 * d);
+    l.sa_out = pk.linear(P + ".self_attn.out_proj", d, d);
+    l.ca_q = pk.linear_rows(P + ".multihead_attn.in_proj_weight", P + ".multihead_attn.in_proj_bias", 3 * d, d, 0, d);
+    l.ca_out = pk.linear(P + ".multihead_attn.out_proj", d, d);
+    l.lin1 = pk.linear(P + ".linear1", ff, d);
+    l.lin2 = pk.linear(P + ".linear2", d, ff);
+    l.n1 = pk.ln(P + ".norm1", d);
+    l.n2 = pk.ln(P + ".norm2", d);
+    l.n3 = pk.ln(P + ".norm3", d);
+    const HostTensor* sw = pk.get(P + ".self_attn.in_proj_weight", {3 * d, d});
+    const HostTensor* cw = pk.get(P + ".multihead_attn.in_proj_weight", {3 * d, d});
+    const HostTensor* cb = pk.get(P + ".multihead_attn.in_proj_bias", {3 * d});
+    if (sw && cw && cb && qe) {
+      std::vector<float> pq((size_t)Q * 3 * d, 0.f), pc((size_t)Q * d);
+      host_embed_proj(*qe, Q, d, *sw, 0, 2 * d, pq.data(), 3 * d);
+      host_embed_proj(*qe, Q, d, *cw, 0, d, pc.data(), d);
+      l.pq_sa = pk.upload(pq);
+      l.pq_ca = pk.upload(pc);
+      memcpy(memw.data() + (size_t)i * 2 * d * d, cw->data.data() + (size_t)d * d, (size_t)2 * d * d * sizeof(float));
+      memcpy(memb.data() + (size_t)i * 2 * d, cb->data.data() + d, (size_t)2 * d * sizeof(float));
+      // position term of the cross-attention keys: k = (memory + pos) Wk^T
+      memcpy(posw.data() + ((size_t)c.enc_layers * 3 * d + (size_t)i * 2 * d) * d, cw->data.data() + (size_t)d * d,
+             (size_t)d * d * sizeof(float));
+    }
+    p->dec.push_back(l);
+  }
+  if (pk.status != TUBER_OK) return pk.status;
+  p->dec_norm = pk.ln("transformer.decoder.norm", d);
+  p->pos_proj = pk.make_lin(posw, NP, d, nullptr, nullptr);
+  p->mem_kv = pk.make_lin(memw, c.dec_layers * 2 * d, d, nullptr, &memb);
+  {
+    // position_encoding.py:22-23,52-57: temperature ** (2 * (i // 2) / n), n = d/4 (t) and 3d/8 (y, x)
+    const int nt = d / 8 * 2, ns = d / 8 * 3;
+    std::vector<float> dt(nt), ds(ns);
+    for (int i = 0; i < nt; ++i) dt[i] = powf(10000.f, (float)(2 * (i / 2)) / (float)nt);
+    for (int i = 0; i < ns; ++i) ds[i] = powf(10000.f, (float)(2 * (i / 2)) / (float)ns);
+    p->dim_t = pk.upload(dt);
+    p->dim_s = pk.upload(ds);
+  }
+
+  // ---- class branch (transformer_layers.py:46-64; tuber_ava.py:60-62) ----
+  {
+    const std::string P = "encoder.layers.0";
+    p->ct_in = pk.linear_rows(P + ".self_attn_t.in_proj_weight", P + ".self_attn_t.in_proj_bias", 3 * d, d, 0, 3 * d);
+    p->ct_out = pk.linear(P + ".self_attn_t.out_proj", d, d);
+    p->cs_in = pk.linear_rows(P + ".self_attn_s.in_proj_weight", P + ".self_attn_s.in_proj_bias", 3 * d, d, 0, 3 * d);
+    p->cs_out = pk.linear(P + ".self_attn_s.out_proj", d, d);
+    p->c_lin1 = pk.linear(P + ".linear1", CLS_FF, 2 * d);
+    p->c_lin2 = pk.linear(P + ".linear2", d, CLS_FF);
+    p->c_n1t = pk.ln(P + ".norm1_t", d);
+    p->c_n1s = pk.ln(P + ".norm1_s", d);
+    p->c_n2 = pk.ln(P + ".norm2", d);
+    p->x_q = pk.linear_rows("cross_attn.in_proj_weight", "cross_attn.in_proj_bias", 3 * d, d, 0, d);
+    p->x_kv = pk.linear_rows("cross_attn.in_proj_weight", "cross_attn.in_proj_bias", 3 * d, d, d, 2 * d);
+    p->x_out = pk.linear("cross_attn.out_proj", d, d);
+  }
+  // ---- heads (tuber_ava.py:64-73; criterion.py:485-492) ----
+  p->head_b = c.ava_mode ? pk.linear("class_embed_b", 3, d) : pk.linear("class_embed_b", 2, POOL_DIM);
+  p->bbox0 = pk.linear("bbox_embed.layers.0", d, d);
+  p->bbox1 = pk.linear("bbox_embed.layers.1", d, d);
+  p->bbox2 = pk.linear("bbox_embed.layers.2", 4, d);
+  p->class_fc = pk.linear("class_fc", c.num_classes, d);
+  if (pk.status != TUBER_OK) return pk.status;
+  CK(cudaDeviceSynchronize());
+  CK(cudaGetLastError());
+  p->host.clear();
+  p->finalized = true;
+  return TUBER_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+struct Ctx {
+  TuberPlan* p;
+  Ws ws;
+  cudaStream_t st;
+  bool dry;
+  int launches = 0;
+  int status = TUBER_OK;
+
+  bool ok() const { return status == TUBER_OK; }
+  // every device operation of a forward goes through here: counted, optionally bracketed by CUDA events
+  // (per-kernel profiling), skipped in the dry (sizing) pass
+  template <class F>
+  void launch(const char* name, double bytes, double flops, F&& f) {
+    if (!ok()) return;
+    ++launches;
+    if (dry) return;
+    const int idx = p->kprof ? kp_begin(name, bytes, flops) : -1;
+    cudaError_t e = f();
+    if (idx >= 0) cudaEventRecord(p->kp[idx].e1, st);
+    if (e != cudaSuccess) status = fail(TUBER_ERR_CUDA, "%s: %s %s", name, cudaGetErrorString(e), gemm_tc_last_error());
+  }
+  int kp_begin(const char* name, double bytes, double flops) {
+    if (p->kp_used == (int)p->kp.size()) {
+      KernelRec r{};
+      if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+      p->kp.push_back(r);
+    }
+    KernelRec& r = p->kp[p->kp_used];
+    r.name = name; r.bytes = bytes; r.flops = flops;
+    cudaEventRecord(r.e0, st);
+    return p->kp_used++;
+  }
+  float* f32(long long rows, int cols) { return reinterpret_cast<float*>(ws.alloc((size_t)rows * cols * 4)); }
+  void* split(long long rows, int cols) { return ws.alloc((size_t)rows * cols * 4); }
+
+  // C = act(scale * A W^T + shift + res)
+  void gemm(const void* A, int a_fmt, int lda, long long M, const Lin& w, const void* res, int res_fmt, int ldr, int res_mod,
+            void* C, int c_fmt, int ldc, void* C2, int ldc2, int act) {
+    if (!ok()) return;
+    GemmArgs a{};
+    a.A = A; a.a_fmt = a_fmt; a.lda = lda;
+    a.Wf = w.wf; a.Wp = w.wp; a.scale = w.scale; a.shift = w.shift;
+    a.res = res; a.res_fmt = res_fmt; a.ldr = ldr; a.res_mod = res_mod;
+    a.C = C; a.c_fmt = c_fmt; a.ldc = ldc; a.C2 = C2; a.ldc2 = ldc2;
+    a.M = (int)M; a.N = w.N; a.K = w.K; a.act = act;
+    const bool tc_ok = a_fmt == FMT_SPLIT && w.N % 64 == 0 && w.K % 64 == 0 && act != ACT_SIGMOID && lda % 8 == 0;
+    const bool tc = tc_ok && !p->force_simt;
+    const double mn = (double)M * w.N;
+    const double bytes = 4.0 * ((double)M * w.K + (double)w.N * w.K + mn * (C2 ? 2 : 1) +
+                                (res ? (res_mod > 0 ? (double)res_mod * w.N : mn) : 0.0));
+    launch(tc ? "gemm_bf16x3_tcgen05" : "sgemm_fp32", bytes, 2.0 * mn * w.K,
+           [&] { return tc ? launch_gemm_tc(a, st) : launch_sgemm(a, st); });
+  }
+
+  void layernorm(const float* x, int ldx, const void* res, int res_fmt, int ldr, const LnP& ln, long long rows,
+                 float* out_f32, int ldo, void* out_split, int lds, int split_col_off = 0, int rpg = 0,
+                 long long group_stride = 0, long long row_off = 0) {
+    if (!ok()) return;
+    LnArgs a{};
+    a.x = x; a.ldx = ldx; a.res = res; a.res_fmt = res_fmt; a.ldr = ldr;
+    a.gamma = ln.g; a.beta = ln.b; a.eps = LN_EPS; a.rows = (int)rows; a.C = ln.C;
+    a.out_f32 = out_f32; a.ldo = ldo; a.rpg = rpg; a.group_stride = group_stride; a.row_off = row_off;
+    a.out_split = out_split; a.lds = lds; a.split_col_off = split_col_off;
+    const double n = (double)rows * ln.C;
+    launch("layernorm", 4.0 * n * (1 + (res ? 1 : 0) + (out_f32 ? 1 : 0) + (out_split ? 1 : 0)), 8.0 * n,
+           [&] { return launch_layernorm(a, st); });
+  }
+
+  void attention(const float* q, int ldq, SeqMap qm, const float* k, const float* v, int ldkv, SeqMap km, void* o_split, int ldo,
+                 SeqMap om, const uint8_t* kpm, int NB, int H, int L, int S, int D) {
+    if (!ok()) return;
+    AttnArgs a{};
+    a.q = q; a.ldq = ldq; a.qm = qm; a.k = k; a.v = v; a.ldk = ldkv; a.ldv = ldkv; a.km = km;
+    a.o_f32 = nullptr; a.o_split = o_split; a.ldo = ldo; a.om = om;
+    a.kpm = kpm; a.kpm_div = 1; a.NB = NB; a.H = H; a.L = L; a.S = S; a.D = D;
+    a.scale = 1.f / sqrtf((float)D);
+    const double e = (double)H * D;
+    launch("attention", 4.0 * e * ((double)NB * L * 2 + (double)NB * S * 2), 4.0 * (double)NB * H * L * S * D,
+           [&] { return launch_attention(a, st); });
+  }
+
+  void tap(const char* name, const void* ptr, int fmt, long long rows, int cols) {
+    if (dry || !ok()) return;
+    Tap t{ptr, fmt, rows, cols, nullptr};
+    auto it = p->taps.find(name);
+    if (it != p->taps.end() && it->second.keep) { cudaFree(it->second.keep); }
+    if (p->debug_keep) {
+      void* keep = nullptr;
+      size_t bytes = (size_t)rows * cols * 4;
+      if (cudaMalloc(&keep, bytes) == cudaSuccess) {
+        cudaMemcpyAsync(keep, ptr, bytes, cudaMemcpyDeviceToDevice, st);
+        t.keep = keep;
+        t.ptr = keep;
+      }
+    }
+    p->taps[name] = t;
+  }
+
+  void stage_mark(int i) {
+    if (dry || !p->profiling || !ok()) return;
+    cudaEventRecord(p->ev[i], st);
+  }
+};
+
+inline SeqMap seqmap(int inner, long long outer, long long inner_stride, long long step) {
+  SeqMap m; m.inner = inner; m.outer = outer; m.inner_stride = inner_stride; m.step = step;
+  return m;
+}
+
+struct Geometry {
+  int H1, W1, H2, W2;
+  int Ti[4], Hi[4], Wi[4];       // stage INPUT dims
+  int Tf, Hf, Wf, Tp;
+};
+
+int compute_geometry(const TuberConfig& c, int T, int H, int W, Geometry& g) {
+  if (T < 1 || H < 7 || W < 7) return fail(TUBER_ERR_SHAPE, "clip %dx%dx%d too small", T, H, W);
+  g.H1 = (H + 6 - 7) / 2 + 1; g.W1 = (W + 6 - 7) / 2 + 1;
+  g.H2 = (g.H1 + 2 - 3) / 2 + 1; g.W2 = (g.W1 + 2 - 3) / 2 + 1;
+  int t = T, h = g.H2, w = g.W2;
+  const int tstr[4] = {1, 2, 2, 2};
+  const int sstr[4] = {1, 2, 2, c.last_stride ? 2 : 1};
+  for (int li = 0; li < 4; ++li) {
+    g.Ti[li] = t; g.Hi[li] = h; g.Wi[li] = w;
+    t = (t - 1) / tstr[li] + 1; h = (h - 1) / sstr[li] + 1; w = (w - 1) / sstr[li] + 1;
+  }
+  g.Tf = t; g.Hf = h; g.Wf = w;
+  switch (c.pool) {
+    case TUBER_POOL_AVG: case TUBER_POOL_MAX:
+      if (c.pool_kernel < 1 || g.Tf < c.pool_kernel)
+        return fail(TUBER_ERR_SHAPE, "temporal pool window %d exceeds the %d feature frames (input T=%d)", c.pool_kernel, g.Tf, T);
+      g.Tp = g.Tf / c.pool_kernel;
+      break;
+    case TUBER_POOL_DECODE: case TUBER_POOL_CENTER: g.Tp = 1; break;
+    default: g.Tp = g.Tf;
+  }
+  return TUBER_OK;
+}
+
+int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, int H, int W, float* logits, float* boxes,
+                float* logits_b) {
+  TuberPlan* p = cx.p;
+  const TuberConfig& c = p->cfg;
+  const bool dry = cx.dry;
+  cudaStream_t st = cx.st;
+  Geometry g;
+  TRY(compute_geometry(c, T, H, W, g));
+  const int d = c.d_model, nh = c.nhead, hd = d / nh, Q = c.num_queries, Le = c.enc_layers, Ld = c.dec_layers;
+
+  // ---- backbone buffers (ping-pong block outputs, conv1 / depthwise / shortcut scratch) ----
+  size_t max_out = (size_t)B * T * g.H1 * g.W1 * 64, max_t1 = 0, max_t2 = 0, max_res = 0, max_xg = 0;
+  {
+    size_t x0 = (size_t)B * T * g.H2 * g.W2 * 64;
+    if (x0 > max_out) max_out = x0;
+    int t = T, h = g.H2, w = g.W2;
+    for (int li = 0; li < 4; ++li)
+      for (const Block& b : p->blocks[li]) {
+        const int to = (t - 1) / b.st_t + 1, ho = (h - 1) / b.st_s + 1, wo = (w - 1) / b.st_s + 1;
+        const size_t vin = (size_t)B * t * h * w, vout = (size_t)B * to * ho * wo;
+        max_t1 = std::max(max_t1, vin * b.planes);
+        max_t2 = std::max(max_t2, vout * b.planes);
+        max_out = std::max(max_out, vout * b.cout);
+        if (b.has_ds) {
+          max_res = std::max(max_res, vout * b.cout);
+          if (b.st_t != 1 || b.st_s != 1) max_xg = std::max(max_xg, vout * b.cin);
+        }
+        t = to; h = ho; w = wo;
+      }
+  }
+  char* bufA = (char*)cx.ws.alloc(max_out * 4);
+  char* bufB = (char*)cx.ws.alloc(max_out * 4);
+  float* t1 = (float*)cx.ws.alloc(max_t1 * 4);
+  void* t2 = cx.ws.alloc(max_t2 * 4);
+  float* resb = (float*)cx.ws.alloc(max_res * 4);
+  void* xg = cx.ws.alloc(max_xg * 4 + 16);
+
+  // ---- stem: conv + BN + ReLU (F, NDHWC) then the (1,3,3) max pool (S) ----
+  cx.stage_mark(0);
+  {
+    const double vin = (double)B * 3 * T * H * W, v1 = (double)B * T * g.H1 * g.W1 * 64, v2 = (double)B * T * g.H2 * g.W2 * 64;
+    cx.launch("stem_conv", 4.0 * (vin + v1), 2.0 * 441 * v1,
+              [&] { return launch_stem_conv(clips, p->stem_w, p->stem_scale, p->stem_shift, (float*)bufA, B, T, H, W, g.H1, g.W1, st); });
+    cx.launch("maxpool", 4.0 * (v1 + v2), 9.0 * v2,
+              [&] { return launch_maxpool_hw((const float*)bufA, bufB, B * T, g.H1, g.W1, g.H2, g.W2, 64, st); });
+  }
+  char* cur = bufB;
+  char* nxt = bufA;
+  int t = T, h = g.H2, w = g.W2;
+  cx.tap("stem", cur, FMT_SPLIT, (long long)B * t * h * w, 64);
+
+  // ---- bottlenecks: 1x1x1 -> depthwise 3x3x3 (stride) -> 1x1x1 (+ shortcut) -> ReLU ----
+  for (int li = 0; li < 4; ++li) {
+    cx.stage_mark(1 + li);
+    for (const Block& b : p->blocks[li]) {
+      const int to = (t - 1) / b.st_t + 1, ho = (h - 1) / b.st_s + 1, wo = (w - 1) / b.st_s + 1;
+      const long long vin = (long long)B * t * h * w, vout = (long long)B * to * ho * wo;
+      cx.gemm(cur, FMT_SPLIT, b.cin, vin, b.conv1, nullptr, 0, 0, 0, t1, FMT_F32, b.planes, nullptr, 0, ACT_RELU);
+      cx.launch("dwconv3x3x3", 4.0 * ((double)vin + vout) * b.planes, 54.0 * vout * b.planes,
+                [&] { return launch_dwconv(t1, b.dw.w, b.dw.scale, b.dw.shift, t2, B, t, h, w, b.planes, b.st_t, b.st_s, to, ho, wo, st); });
+      const void* res = cur;
+      int res_fmt = FMT_SPLIT, ldr = b.cin;
+      if (b.has_ds) {
+        const void* a = cur;
+        if (b.st_t != 1 || b.st_s != 1) {
+          cx.launch("gather_rows", 8.0 * vout * b.cin, 0.0,
+                    [&] { return launch_gather_rows(cur, xg, b.cin * 4, B, t, h, w, b.st_t, b.st_s, to, ho, wo, st); });
+          a = xg;
+        }
+        cx.gemm(a, FMT_SPLIT, b.cin, vout, b.ds, nullptr, 0, 0, 0, resb, FMT_F32, b.cout, nullptr, 0, ACT_NONE);
+        res = resb; res_fmt = FMT_F32; ldr = b.cout;
+      }
+      cx.gemm(t2, FMT_SPLIT, b.planes, vout, b.conv4, res, res_fmt, ldr, 0, nxt, FMT_SPLIT, b.cout, nullptr, 0, ACT_RELU);
+      std::swap(cur, nxt);
+      t = to; h = ho; w = wo;
+    }
+    static const char* names[4] = {"layer1", "layer2", "layer3", "layer4"};
+    cx.tap(names[li], cur, FMT_SPLIT, (long long)B * t * h * w, p->blocks[li].back().cout);
+  }
+  if (!cx.ok()) return cx.status;
+  const int Tf = g.Tf, HW = g.Hf * g.Wf, Tp = g.Tp, CB = POOL_DIM;
+  const void* xt = cur;                                    // S [B*Tf*HW, 2048]
+  const long long Mc = (long long)B * Tf * HW;             // class-branch tokens
+  const int Ntok = Tp * HW;
+  const long long Mtok = (long long)B * Ntok;              // DETR encoder tokens
+  cx.tap("xt", xt, FMT_SPLIT, Mc, CB);
+
+  // ---- temporal pooling (backbone_builder.py:70-80) ----
+  cx.stage_mark(5);
+  const void* xs = xt;
+  if (c.pool == TUBER_POOL_AVG || c.pool == TUBER_POOL_MAX) {
+    void* o = cx.split(Mtok, CB);
+    cx.launch("tpool", 4.0 * ((double)Mc + Mtok) * CB, (double)Mc * CB,
+              [&] { return launch_tpool(xt, o, B, Tf, HW, CB, c.pool_kernel, Tp, c.pool == TUBER_POOL_MAX, st); });
+    xs = o;
+  } else if (c.pool == TUBER_POOL_CENTER) {
+    void* o = cx.split(Mtok, CB);
+    cx.launch("slice_frames", 8.0 * Mtok * CB, 0.0, [&] { return launch_slice_frames(xt, o, CB * 4, B, Tf, HW, Tf / 2, 1, st); });
+    xs = o;
+  } else if (c.pool == TUBER_POOL_DECODE) {
+    // per pixel: one learned query attends over the Tf frame tokens (d = 2048, 8 heads x 256)
+    const long long Mp = (long long)B * HW;
+    float* kv = cx.f32(Mc, 2 * CB);
+    cx.gemm(xt, FMT_SPLIT, CB, Mc, p->pool_kv, nullptr, 0, 0, 0, kv, FMT_F32, 2 * CB, nullptr, 0, ACT_NONE);
+    void* att = cx.split(Mp, CB);
+    cx.attention(p->pool_q, CB, seqmap(1, 0, 0, 0), kv, kv + CB, 2 * CB, seqmap(HW, (long long)Tf * HW, 1, HW), att, CB,
+                 seqmap(1, 1, 0, 1), nullptr, (int)Mp, 8, 1, Tf, CB / 8);
+    float* o1 = cx.f32(Mp, CB);
+    cx.gemm(att, FMT_SPLIT, CB, Mp, p->pool_out, nullptr, 0, 0, 0, o1, FMT_F32, CB, nullptr, 0, ACT_NONE);
+    float* t2f = cx.f32(Mp, CB);
+    void* t2s = cx.split(Mp, CB);
+    cx.layernorm(o1, CB, p->pool_tgt1, FMT_F32, 0, p->pool_n2, Mp, t2f, CB, t2s, CB);
+    void* hdn = cx.split(Mp, 2048);
+    cx.gemm(t2s, FMT_SPLIT, CB, Mp, p->pool_lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, 2048, nullptr, 0, ACT_RELU);
+    float* o2 = cx.f32(Mp, CB);
+    cx.gemm(hdn, FMT_SPLIT, 2048, Mp, p->pool_lin2, t2f, FMT_F32, CB, 0, o2, FMT_F32, CB, nullptr, 0, ACT_NONE);
+    float* t3 = cx.f32(Mp, CB);
+    cx.layernorm(o2, CB, nullptr, 0, 0, p->pool_n3, Mp, t3, CB, nullptr, 0);
+    void* o = cx.split(Mp, CB);
+    cx.layernorm(t3, CB, nullptr, 0, 0, p->pool_nf, Mp, nullptr, 0, o, CB);
+    xs = o;
+  }
+  cx.tap("xs", xs, FMT_SPLIT, Mtok, CB);
+
+  // ---- padding mask at feature resolution, 3-D sine position code and its projections ----
+  cx.stage_mark(6);
+  const int Bp = mask ? B : 1;                              // without padding every clip has the same code
+  uint8_t* fmask = (uint8_t*)cx.ws.alloc((size_t)Bp * Ntok);
+  float* pos = cx.f32((long long)Bp * Ntok, d);
+  void* pos_s = cx.split((long long)Bp * Ntok, d);
+  const int NP = Le * 3 * d + Ld * 2 * d;
+  float* posp = cx.f32((long long)Bp * Ntok, NP);
+  {
+    const double n = (double)Bp * Ntok * d;
+    cx.launch("mask_resize", (double)Bp * Ntok, 0.0, [&] { return launch_mask_resize(mask, fmask, Bp, H, W, Tp, g.Hf, g.Wf, st); });
+    cx.launch("posenc", 4.0 * n, 8.0 * n,
+              [&] { return launch_posenc(fmask, p->dim_t, p->dim_s, pos, Bp, Tp, g.Hf, g.Wf, d / 8 * 2, d / 8 * 3, st); });
+    cx.launch("to_split", 8.0 * n, 0.0, [&] { return launch_to_split(pos, d, pos_s, d, (long long)Bp * Ntok, d, st); });
+  }
+  cx.gemm(pos_s, FMT_SPLIT, d, (long long)Bp * Ntok, p->pos_proj, nullptr, 0, 0, 0, posp, FMT_F32, NP, nullptr, 0, ACT_NONE);
+  const uint8_t* kpm = mask ? fmask : nullptr;
+  const int pos_mod = mask ? 0 : Ntok;
+  cx.tap("pos", pos, FMT_F32, (long long)Bp * Ntok, d);
+
+  // input_proj / class_proj (tuber_ava.py:119,129)
+  float* src_f = cx.f32(Mtok, d);
+  void* src_s = cx.split(Mtok, d);
+  cx.gemm(xs, FMT_SPLIT, CB, Mtok, p->input_proj, nullptr, 0, 0, 0, src_f, FMT_F32, d, src_s, d, ACT_NONE);
+  float* srcc_f = cx.f32(Mc, d);
+  void* srcc_s = cx.split(Mc, d);
+  cx.gemm(xt, FMT_SPLIT, CB, Mc, p->class_proj, nullptr, 0, 0, 0, srcc_f, FMT_F32, d, srcc_s, d, ACT_NONE);
+  cx.tap("src", src_f, FMT_F32, Mtok, d);
+
+  // ---- DETR encoder (transformer.py:153-168): post-norm, q = k = src + pos, v = src ----
+  cx.stage_mark(7);
+  {
+    float* qkv = cx.f32(Mtok, 3 * d);
+    void* att = cx.split(Mtok, d);
+    float* o = cx.f32(Mtok, d);
+    void* hdn = cx.split(Mtok, c.dim_ff);
+    for (int i = 0; i < Le; ++i) {
+      const EncLayer& e = p->enc[i];
+      cx.gemm(src_s, FMT_SPLIT, d, Mtok, e.in, posp + (size_t)i * 3 * d, FMT_F32, NP, pos_mod, qkv, FMT_F32, 3 * d, nullptr, 0, ACT_NONE);
+      cx.attention(qkv, 3 * d, seqmap(1, Ntok, 0, 1), qkv + d, qkv + 2 * d, 3 * d, seqmap(1, Ntok, 0, 1), att, d,
+                   seqmap(1, Ntok, 0, 1), kpm, B, nh, Ntok, Ntok, hd);
+      cx.gemm(att, FMT_SPLIT, d, Mtok, e.out, src_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
+      cx.layernorm(o, d, nullptr, 0, 0, e.n1, Mtok, src_f, d, src_s, d);
+      cx.gemm(src_s, FMT_SPLIT, d, Mtok, e.lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, c.dim_ff, nullptr, 0, ACT_RELU);
+      cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mtok, e.lin2, src_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
+      cx.layernorm(o, d, nullptr, 0, 0, e.n2, Mtok, src_f, d, src_s, d);
+    }
+  }
+  cx.tap("memory", src_f, FMT_F32, Mtok, d);
+
+  // ---- DETR decoder (transformer.py:218-249), all layers' outputs kept (return_intermediate) ----
+  cx.stage_mark(8);
+  const long long Mq = (long long)B * Q, Mh = (long long)B * Ld * Q;
+  float* hs_f = cx.f32(Mh, d);                              // [B, Ld, Q, d]
+  void* hs_s = cx.split(Mh, d);
+  {
+    float* memkv = cx.f32(Mtok, Ld * 2 * d);                // per layer [K | V] of the cross attention
+    cx.gemm(src_s, FMT_SPLIT, d, Mtok, p->mem_kv, posp + (size_t)Le * 3 * d, FMT_F32, NP, pos_mod, memkv, FMT_F32, Ld * 2 * d,
+            nullptr, 0, ACT_NONE);
+    float* tgt_f = cx.f32(Mq, d);
+    void* tgt_s = cx.split(Mq, d);
+    // tgt = zeros_like(query_embed), transformer.py:60 (all-zero bits are zero in both formats)
+    cx.launch("memset", 4.0 * Mq * d, 0.0, [&] { return cudaMemsetAsync(tgt_f, 0, (size_t)Mq * d * 4, st); });
+    cx.launch("memset", 4.0 * Mq * d, 0.0, [&] { return cudaMemsetAsync(tgt_s, 0, (size_t)Mq * d * 4, st); });
+    float* qkv = cx.f32(Mq, 3 * d);
+    float* qc = cx.f32(Mq, d);
+    void* att = cx.split(Mq, d);
+    float* o = cx.f32(Mq, d);
+    void* hdn = cx.split(Mq, c.dim_ff);
+    for (int i = 0; i < Ld; ++i) {
+      const DecLayer& l = p->dec[i];
+      cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.sa_in, l.pq_sa, FMT_F32, 3 * d, Q, qkv, FMT_F32, 3 * d, nullptr, 0, ACT_NONE);
+      cx.attention(qkv, 3 * d, seqmap(1, Q, 0, 1), qkv + d, qkv + 2 * d, 3 * d, seqmap(1, Q, 0, 1), att, d, seqmap(1, Q, 0, 1),
+                   nullptr, B, nh, Q, Q, hd);
+      cx.gemm(att, FMT_SPLIT, d, Mq, l.sa_out, tgt_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
+      cx.layernorm(o, d, nullptr, 0, 0, l.n1, Mq, tgt_f, d, tgt_s, d);
+      cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.ca_q, l.pq_ca, FMT_F32, d, Q, qc, FMT_F32, d, nullptr, 0, ACT_NONE);
+      cx.attention(qc, d, seqmap(1, Q, 0, 1), memkv + (size_t)i * 2 * d, memkv + (size_t)i * 2 * d + d, Ld * 2 * d,
+                   seqmap(1, Ntok, 0, 1), att, d, seqmap(1, Q, 0, 1), kpm, B, nh, Q, Ntok, hd);
+      cx.gemm(att, FMT_SPLIT, d, Mq, l.ca_out, tgt_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
+      cx.layernorm(o, d, nullptr, 0, 0, l.n2, Mq, tgt_f, d, tgt_s, d);
+      cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, c.dim_ff, nullptr, 0, ACT_RELU);
+      cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mq, l.lin2, tgt_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
+      cx.layernorm(o, d, nullptr, 0, 0, l.n3, Mq, tgt_f, d, tgt_s, d);
+      // shared final norm on every layer's output (transformer.py:116-126), row (b, q) -> (b, i, q)
+      cx.layernorm(tgt_f, d, nullptr, 0, 0, p->dec_norm, Mq, hs_f, d, hs_s, d, 0, Q, (long long)Ld * Q, (long long)i * Q);
+    }
+  }
+  cx.tap("hs", hs_f, FMT_F32, Mh, d);
+
+  // ---- class branch + heads ----
+  cx.stage_mark(9);
+  // actor-ness head (tuber_ava.py:121-125)
+  if (c.ava_mode) {
+    cx.gemm(hs_f, FMT_F32, d, Mh, p->head_b, nullptr, 0, 0, 0, logits_b, FMT_F32, 3, nullptr, 0, ACT_NONE);
+  } else {
+    float* gap = cx.f32(B, CB);
+    cx.launch("global_avgpool", 4.0 * Mc * CB, (double)Mc * CB, [&] { return launch_global_avgpool(xt, gap, B, Tf * HW, CB, st); });
+    cx.gemm(gap, FMT_F32, CB, B, p->head_b, nullptr, 0, 0, 0, logits_b, FMT_F32, 2, nullptr, 0, ACT_NONE);
+  }
+  // box head (criterion.py:494-497) + sigmoid (tuber_ava.py:142)
+  {
+    void* h1 = cx.split(Mh, d);
+    void* h2 = cx.split(Mh, d);
+    cx.gemm(hs_s, FMT_SPLIT, d, Mh, p->bbox0, nullptr, 0, 0, 0, h1, FMT_SPLIT, d, nullptr, 0, ACT_RELU);
+    cx.gemm(h1, FMT_SPLIT, d, Mh, p->bbox1, nullptr, 0, 0, 0, h2, FMT_SPLIT, d, nullptr, 0, ACT_RELU);
+    cx.gemm(h2, FMT_SPLIT, d, Mh, p->bbox2, nullptr, 0, 0, 0, boxes, FMT_F32, 4, nullptr, 0, ACT_SIGMOID);
+  }
+  // class-branch encoder layer (transformer_layers.py:71-97), evaluated once per clip: the reference runs
+  // DEC_LAYERS identical replicas of it (tuber_ava.py:133-135)
+  float* memc_f = cx.f32(Mc, d);
+  void* memc_s = cx.split(Mc, d);
+  {
+    float* qkv = cx.f32(Mc, 3 * d);
+    void* att = cx.split(Mc, d);
+    float* o = cx.f32(Mc, d);
+    void* cat = cx.split(Mc, 2 * d);
+    void* hdn = cx.split(Mc, CLS_FF);
+    const int ch = d / CLS_HEADS;
+    // "_t": attention inside a frame over its HW positions
+    cx.gemm(srcc_s, FMT_SPLIT, d, Mc, p->ct_in, nullptr, 0, 0, 0, qkv, FMT_F32, 3 * d, nullptr, 0, ACT_NONE);
+    cx.attention(qkv, 3 * d, seqmap(1, HW, 0, 1), qkv + d, qkv + 2 * d, 3 * d, seqmap(1, HW, 0, 1), att, d, seqmap(1, HW, 0, 1),
+                 nullptr, B * Tf, CLS_HEADS, HW, HW, ch);
+    cx.gemm(att, FMT_SPLIT, d, Mc, p->ct_out, srcc_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
+    cx.layernorm(o, d, nullptr, 0, 0, p->c_n1t, Mc, nullptr, 0, cat, 2 * d, 0);
+    // "_s": attention inside a pixel over its Tf frames
+    cx.gemm(srcc_s, FMT_SPLIT, d, Mc, p->cs_in, nullptr, 0, 0, 0, qkv, FMT_F32, 3 * d, nullptr, 0, ACT_NONE);
+    const SeqMap pix = seqmap(HW, (long long)Tf * HW, 1, HW);
+    cx.attention(qkv, 3 * d, pix, qkv + d, qkv + 2 * d, 3 * d, pix, att, d, pix, nullptr, B * HW, CLS_HEADS, Tf, Tf, ch);
+    cx.gemm(att, FMT_SPLIT, d, Mc, p->cs_out, srcc_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
+    cx.layernorm(o, d, nullptr, 0, 0, p->c_n1s, Mc, nullptr, 0, cat, 2 * d, d);
+    cx.gemm(cat, FMT_SPLIT, 2 * d, Mc, p->c_lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, CLS_FF, nullptr, 0, ACT_RELU);
+    cx.gemm(hdn, FMT_SPLIT, CLS_FF, Mc, p->c_lin2, srcc_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
+    cx.layernorm(o, d, nullptr, 0, 0, p->c_n2, Mc, memc_f, d, memc_s, d);
+  }
+  cx.tap("mem_c", memc_f, FMT_F32, Mc, d);
+  // class cross-attention (tuber_ava.py:137-139) + class_fc (:141; Dropout(0.5) is the identity in eval)
+  {
+    const int Nc = Tf * HW, LQ = Ld * Q;
+    float* qx = cx.f32(Mh, d);
+    float* kvx = cx.f32(Mc, 2 * d);
+    void* att = cx.split(Mh, d);
+    void* oc = cx.split(Mh, d);
+    cx.gemm(hs_s, FMT_SPLIT, d, Mh, p->x_q, nullptr, 0, 0, 0, qx, FMT_F32, d, nullptr, 0, ACT_NONE);
+    cx.gemm(memc_s, FMT_SPLIT, d, Mc, p->x_kv, nullptr, 0, 0, 0, kvx, FMT_F32, 2 * d, nullptr, 0, ACT_NONE);
+    cx.attention(qx, d, seqmap(1, LQ, 0, 1), kvx, kvx + d, 2 * d, seqmap(1, Nc, 0, 1), att, d, seqmap(1, LQ, 0, 1), nullptr, B,
+                 CLS_HEADS, LQ, Nc, d / CLS_HEADS);
+    cx.gemm(att, FMT_SPLIT, d, Mh, p->x_out, nullptr, 0, 0, 0, oc, FMT_SPLIT, d, nullptr, 0, ACT_NONE);
+    cx.gemm(oc, FMT_SPLIT, d, Mh, p->class_fc, nullptr, 0, 0, 0, logits, FMT_F32, c.num_classes, nullptr, 0, ACT_NONE);
+  }
+  cx.stage_mark(TUBER_NUM_STAGES);
+  return cx.status;
+}
+
+int ensure_workspace(TuberPlan* p, int B, int T, int H, int W, size_t* need_out, int* launches_out) {
+  Ctx cx{p};
+  cx.dry = true;
+  cx.ws.dry = true;
+  cx.st = 0;
+  TRY(run_forward(cx, nullptr, nullptr, B, T, H, W, nullptr, nullptr, nullptr));
+  size_t need = cx.ws.peak + 4096;
+  if (need_out) *need_out = need;
+  if (launches_out) *launches_out = cx.launches;
+  return TUBER_OK;
+}
+
+int check_forward_args(TuberPlan* p, int B, int T, int H, int W) {
+  if (!p) return fail(TUBER_ERR_INVALID, "null plan");
+  if (!p->finalized) return fail(TUBER_ERR_STATE, "tuber_forward before tuber_plan_finalize");
+  if (B < 1) return fail(TUBER_ERR_INVALID, "batch %d", B);
+  (void)T; (void)H; (void)W;
+  return TUBER_OK;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+int tuber_abi_version(void) { return TUBER_ABI_VERSION; }
+const char* tuber_last_error(void) { return g_last_error; }
+
+int tuber_plan_create(const TuberConfig* cfg, TuberPlan** out_plan) {
+  if (!cfg || !out_plan) return fail(TUBER_ERR_INVALID, "null argument");
+  if (cfg->abi_version != TUBER_ABI_VERSION) return fail(TUBER_ERR_INVALID, "ABI version %d != %d", cfg->abi_version, TUBER_ABI_VERSION);
+  if (cfg->d_model != 256 || cfg->nhead != 8)
+    return fail(TUBER_ERR_INVALID, "d_model %d / nhead %d unsupported (kernels are built for 256 / 8)", cfg->d_model, cfg->nhead);
+  if (cfg->dim_ff % 64 != 0 || cfg->enc_layers < 1 || cfg->dec_layers < 1 || cfg->num_queries < 1 || cfg->num_classes < 1)
+    return fail(TUBER_ERR_INVALID, "bad transformer dimensions");
+  if (cfg->pool < TUBER_POOL_AVG || cfg->pool > TUBER_POOL_NONE) return fail(TUBER_ERR_INVALID, "bad pool mode %d", cfg->pool);
+  for (int i = 0; i < 4; ++i)
+    if (cfg->blocks[i] < 1) return fail(TUBER_ERR_INVALID, "stage %d has no blocks", i);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TUBER_ERR_CUDA, "no CUDA device: the tuber_b200 path has no CPU fallback");
+  cudaDeviceProp prop;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(TUBER_ERR_CUDA, "device '%s' is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+  TuberPlan* p = new TuberPlan();
+  p->cfg = *cfg;
+  p->device = dev;
+  const char* fs = getenv("TUBER_FORCE_SIMT");
+  p->force_simt = fs && fs[0] == '1';
+  *out_plan = p;
+  return TUBER_OK;
+}
+
+void tuber_plan_destroy(TuberPlan* p) {
+  if (!p) return;
+  for (void* d : p->owned) cudaFree(d);
+  for (auto& kv : p->taps) if (kv.second.keep) cudaFree(kv.second.keep);
+  for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);
+  if (p->ws) cudaFree(p->ws);
+  if (p->stage_in) cudaFree(p->stage_in);
+  if (p->stage_out) cudaFree(p->stage_out);
+  if (p->ev_valid) for (auto& e : p->ev) cudaEventDestroy(e);
+  for (auto& r : p->kp) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  delete p;
+}
+
+int tuber_plan_set_weight(TuberPlan* p, const char* name, const float* host_data, const int64_t* shape, int32_t ndim) {
+  if (!p || !name || !host_data || ndim < 0 || (ndim > 0 && !shape)) return fail(TUBER_ERR_INVALID, "null argument");
+  if (p->finalized) return fail(TUBER_ERR_STATE, "plan already finalized");
+  HostTensor t;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= shape[i]; }
+  t.data.assign(host_data, host_data + n);
+  p->host[name] = std::move(t);
+  return TUBER_OK;
+}
+
+int tuber_plan_finalize(TuberPlan* p) {
+  if (!p) return fail(TUBER_ERR_INVALID, "null plan");
+  if (p->finalized) return fail(TUBER_ERR_STATE, "plan already finalized");
+  CK(cudaSetDevice(p->device));
+  return do_finalize(p);
+}
+
+int tuber_query_shapes(TuberPlan* p, int32_t B, int32_t T, int32_t H, int32_t W, TuberShapeInfo* out) {
+  if (!out) return fail(TUBER_ERR_INVALID, "null argument");
+  TRY(check_forward_args(p, B, T, H, W));
+  Geometry g;
+  TRY(compute_geometry(p->cfg, T, H, W, g));
+  size_t need = 0;
+  int launches = 0;
+  TRY(ensure_workspace(p, B, T, H, W, &need, &launches));
+  out->Tf = g.Tf; out->Hf = g.Hf; out->Wf = g.Wf; out->Tp = g.Tp;
+  out->enc_tokens = g.Tp * g.Hf * g.Wf; out->cls_tokens = g.Tf * g.Hf * g.Wf;
+  out->launches = launches; out->workspace_bytes = (int64_t)need;
+  return TUBER_OK;
+}
+
+int tuber_forward(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev, int32_t B, int32_t T, int32_t H, int32_t W,
+                  float* logits_dev, float* boxes_dev, float* logits_b_dev, void* stream) {
+  TRY(check_forward_args(p, B, T, H, W));
+  if (!clips_dev || !logits_dev || !boxes_dev || !logits_b_dev) return fail(TUBER_ERR_INVALID, "null device pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  size_t need = 0;
+  TRY(ensure_workspace(p, B, T, H, W, &need, nullptr));
+  if (need > p->ws_cap) {
+    CK(cudaDeviceSynchronize());
+    if (p->ws) cudaFree(p->ws);
+    p->ws = nullptr; p->ws_cap = 0;
+    for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);     // captured pointers are stale now
+    p->graphs.clear();
+    void* w = nullptr;
+    cudaError_t e = cudaMalloc(&w, need);
+    if (e != cudaSuccess) return fail(TUBER_ERR_CUDA, "workspace of %zu bytes: %s", need, cudaGetErrorString(e));
+    p->ws = (char*)w; p->ws_cap = need;
+  }
+  if (p->profiling && !p->ev_valid) {
+    for (auto& e : p->ev) CK(cudaEventCreate(&e));
+    p->ev_valid = true;
+  }
+  Ctx cx{p};
+  cx.dry = false;
+  cx.ws.base = p->ws; cx.ws.cap = p->ws_cap;
+  cx.st = st;
+  p->kp_used = 0;
+  const bool graph = p->use_graph && !p->profiling && !p->debug_keep && !p->kprof;
+  if (!graph) {
+    int s = run_forward(cx, clips_dev, mask_dev, B, T, H, W, logits_dev, boxes_dev, logits_b_dev);
+    p->launches = cx.launches;
+    return s;
+  }
+  std::vector<uintptr_t> key = {(uintptr_t)clips_dev, (uintptr_t)mask_dev, (uintptr_t)B, (uintptr_t)T, (uintptr_t)H, (uintptr_t)W,
+                                (uintptr_t)logits_dev, (uintptr_t)boxes_dev, (uintptr_t)logits_b_dev};
+  for (auto& g : p->graphs)
+    if (g.key == key) { CK(cudaGraphLaunch(g.exec, st)); return TUBER_OK; }
+  // first call for this (shape, buffers): run eagerly (this call's result; also performs the one-time
+  // function-attribute set-up), then record the same launch sequence for the following calls
+  {
+    int s0 = run_forward(cx, clips_dev, mask_dev, B, T, H, W, logits_dev, boxes_dev, logits_b_dev);
+    p->launches = cx.launches;
+    if (s0 != TUBER_OK) return s0;
+  }
+  Ctx cap{p};
+  cap.dry = false;
+  cap.ws.base = p->ws; cap.ws.cap = p->ws_cap;
+  cap.st = st;
+  cudaGraph_t graph_obj = nullptr;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int s = run_forward(cap, clips_dev, mask_dev, B, T, H, W, logits_dev, boxes_dev, logits_b_dev);
+  cudaError_t e = cudaStreamEndCapture(st, &graph_obj);
+  if (s != TUBER_OK) { if (graph_obj) cudaGraphDestroy(graph_obj); return s; }
+  if (e != cudaSuccess) return fail(TUBER_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph_obj, 0);
+  cudaGraphDestroy(graph_obj);
+  if (e != cudaSuccess) return fail(TUBER_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+  if (p->graphs.size() >= 8) { cudaGraphExecDestroy(p->graphs.front().exec); p->graphs.erase(p->graphs.begin()); }
+  p->graphs.push_back({key, exec});
+  return TUBER_OK;
+}
+
+int tuber_forward_host(TuberPlan* p, const float* clips_host, const uint8_t* mask_host, int32_t B, int32_t T, int32_t H,
+                       int32_t W, float* logits_host, float* boxes_host, float* logits_b_host, void* stream) {
+  TRY(check_forward_args(p, B, T, H, W));
+  if (!clips_host || !logits_host || !boxes_host || !logits_b_host) return fail(TUBER_ERR_INVALID, "null host pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const TuberConfig& c = p->cfg;
+  const size_t clip_bytes = (size_t)B * 3 * T * H * W * 4, mask_bytes = mask_host ? (size_t)B * H * W : 0;
+  const size_t in_need = clip_bytes + ((mask_bytes + 255) & ~(size_t)255) + 256;
+  const size_t n_logits = (size_t)B * c.dec_layers * c.num_queries * c.num_classes, n_boxes = (size_t)B * c.dec_layers * c.num_queries * 4;
+  const size_t n_lb = c.ava_mode ? (size_t)B * c.dec_layers * c.num_queries * 3 : (size_t)B * 2;
+  const size_t out_need = (n_logits + n_boxes + n_lb) * 4 + 1024;
+  if (in_need > p->stage_in_cap) {
+    CK(cudaDeviceSynchronize());
+    if (p->stage_in) cudaFree(p->stage_in);
+    p->stage_in = nullptr; p->stage_in_cap = 0;
+    void* q = nullptr;
+    CK(cudaMalloc(&q, in_need));
+    p->stage_in = (char*)q; p->stage_in_cap = in_need;
+  }
+  if (out_need > p->stage_out_cap) {
+    CK(cudaDeviceSynchronize());
+    if (p->stage_out) cudaFree(p->stage_out);
+    p->stage_out = nullptr; p->stage_out_cap = 0;
+    void* q = nullptr;
+    CK(cudaMalloc(&q, out_need));
+    p->stage_out = (char*)q; p->stage_out_cap = out_need;
+  }
+  float* d_clips = (float*)p->stage_in;
+  uint8_t* d_mask = mask_host ? (uint8_t*)(p->stage_in + clip_bytes) : nullptr;
+  float* d_logits = (float*)p->stage_out;
+  float* d_boxes = d_logits + ((n_logits + 63) & ~(size_t)63);
+  float* d_lb = d_boxes + ((n_boxes + 63) & ~(size_t)63);
+  CK(cudaMemcpyAsync(d_clips, clips_host, clip_bytes, cudaMemcpyHostToDevice, st));
+  if (mask_host) CK(cudaMemcpyAsync(d_mask, mask_host, mask_bytes, cudaMemcpyHostToDevice, st));
+  TRY(tuber_forward(p, d_clips, d_mask, B, T, H, W, d_logits, d_boxes, d_lb, stream));
+  CK(cudaMemcpyAsync(logits_host, d_logits, n_logits * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(boxes_host, d_boxes, n_boxes * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(logits_b_host, d_lb, n_lb * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return TUBER_OK;
+}
+
+int tuber_set_profiling(TuberPlan* p, int32_t enabled) {
+  if (!p) return fail(TUBER_ERR_INVALID, "null plan");
+  p->profiling = enabled != 0;
+  return TUBER_OK;
+}
+int tuber_set_debug_keep(TuberPlan* p, int32_t enabled) {
+  if (!p) return fail(TUBER_ERR_INVALID, "null plan");
+  p->debug_keep = enabled != 0;
+  return TUBER_OK;
+}
+int tuber_set_graph(TuberPlan* p, int32_t enabled) {
+  if (!p) return fail(TUBER_ERR_INVALID, "null plan");
+  p->use_graph = enabled != 0;
+  return TUBER_OK;
+}
+int tuber_set_force_simt(TuberPlan* p, int32_t enabled) {
+  if (!p) return fail(TUBER_ERR_INVALID, "null plan");
+  p->force_simt = enabled != 0;
+  return TUBER_OK;
+}
+int tuber_last_launches(TuberPlan* p) { return p ? p->launches : 0; }
+
+int tuber_set_kernel_profiling(TuberPlan* p, int32_t enabled) {
+  if (!p) return fail(TUBER_ERR_INVALID, "null plan");
+  p->kprof = enabled != 0;
+  return TUBER_OK;
+}
+
+int tuber_get_kernel_profile(TuberPlan* p, TuberKernelStat* out, int32_t capacity, int32_t* n_out) {
+  if (!p || !n_out) return fail(TUBER_ERR_INVALID, "null argument");
+  std::vector<TuberKernelStat> agg;
+  for (int i = 0; i < p->kp_used; ++i) {
+    const KernelRec& r = p->kp[i];
+    CK(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    TuberKernelStat* s = nullptr;
+    for (auto& a : agg) if (strcmp(a.name, r.name) == 0) s = &a;
+    if (!s) {
+      TuberKernelStat z{};
+      snprintf(z.name, sizeof z.name, "%s", r.name);
+      agg.push_back(z);
+      s = &agg.back();
+    }
+    s->launches += 1; s->ms += ms; s->bytes += r.bytes; s->flops += r.flops;
+  }
+  *n_out = (int32_t)agg.size();
+  if (out) for (int i = 0; i < (int)agg.size() && i < capacity; ++i) out[i] = agg[i];
+  return TUBER_OK;
+}
+
+static const char* kStageNames[TUBER_NUM_STAGES] = {"stem", "layer1", "layer2", "layer3", "layer4", "pool", "proj", "encoder", "decoder", "class+heads"};
+const char* tuber_stage_name(int32_t i) { return (i >= 0 && i < TUBER_NUM_STAGES) ? kStageNames[i] : ""; }
+
+int tuber_get_stage_ms(TuberPlan* p, float* ms_out) {
+  if (!p || !ms_out) return fail(TUBER_ERR_INVALID, "null argument");
+  if (!p->ev_valid) return fail(TUBER_ERR_STATE, "no profiled forward yet");
+  CK(cudaEventSynchronize(p->ev[TUBER_NUM_STAGES]));
+  for (int i = 0; i < TUBER_NUM_STAGES; ++i) CK(cudaEventElapsedTime(ms_out + i, p->ev[i], p->ev[i + 1]));
+  return TUBER_OK;
+}
+
+int tuber_debug_fetch(TuberPlan* p, const char* what, float* dst_dev, int64_t* n_out, void* stream) {
+  if (!p || !what) return fail(TUBER_ERR_INVALID, "null argument");
+  auto it = p->taps.find(what);
+  if (it == p->taps.end()) return fail(TUBER_ERR_INVALID, "no intermediate named '%s'", what);
+  const Tap& t = it->second;
+  if (n_out) *n_out = t.rows * t.cols;
+  if (!dst_dev) return TUBER_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (t.fmt == FMT_F32) CK(cudaMemcpyAsync(dst_dev, t.ptr, (size_t)t.rows * t.cols * 4, cudaMemcpyDeviceToDevice, st));
+  else CK(launch_from_split(t.ptr, t.cols, dst_dev, t.cols, t.rows, t.cols, st));
+  return TUBER_OK;
+}
+
+// ---- single operators ------------------------------------------------------------------------
+int tuber_op_to_split(const float* in, void* out, int64_t rows, int32_t cols, void* stream) {
+  CK(launch_to_split(in, cols, out, cols, rows, cols, (cudaStream_t)stream));
+  return TUBER_OK;
+}
+int tuber_op_from_split(const void* in, float* out, int64_t rows, int32_t cols, void* stream) {
+  CK(launch_from_split(in, cols, out, cols, rows, cols, (cudaStream_t)stream));
+  return TUBER_OK;
+}
+int tuber_op_pack_weight(const float* w, void* out, int32_t N, int32_t K, void* stream) {
+  CK(launch_pack_weight(w, out, N, K, (cudaStream_t)stream));
+  return TUBER_OK;
+}
+int tuber_op_gemm_tc(const void* a_split, const void* w_packed, const float* scale, const float* shift, const void* res,
+                     int32_t res_fmt, int32_t res_mod, void* c, int32_t c_fmt, int32_t M, int32_t N, int32_t K, int32_t relu,
+                     void* stream) {
+  GemmArgs a{};
+  a.A = a_split; a.a_fmt = FMT_SPLIT; a.lda = K; a.Wp = w_packed; a.scale = scale; a.shift = shift;
+  a.res = res; a.res_fmt = res_fmt; a.ldr = N; a.res_mod = res_mod; a.C = c; a.c_fmt = c_fmt; a.ldc = N;
+  a.M = M; a.N = N; a.K = K; a.act = relu ? ACT_RELU : ACT_NONE;
+  CK(launch_gemm_tc(a, (cudaStream_t)stream));
+  return TUBER_OK;
+}
+int tuber_op_sgemm(const float* A, const float* W, const float* bias, const float* res, float* C, int32_t M, int32_t N, int32_t K,
+                   int32_t act, void* stream) {
+  GemmArgs a{};
+  a.A = A; a.a_fmt = FMT_F32; a.lda = K; a.Wf = W; a.shift = bias; a.res = res; a.res_fmt = FMT_F32; a.ldr = N;
+  a.C = C; a.c_fmt = FMT_F32; a.ldc = N; a.M = M; a.N = N; a.K = K; a.act = act;
+  CK(launch_sgemm(a, (cudaStream_t)stream));
+  return TUBER_OK;
+}
+int tuber_op_dwconv(const float* in, const float* w27c, const float* scale, const float* shift, void* out_split, int32_t B, int32_t Ti,
+                    int32_t Hi, int32_t Wi, int32_t C, int32_t stride_t, int32_t stride_s, void* stream) {
+  const int To = (Ti - 1) / stride_t + 1, Ho = (Hi - 1) / stride_s + 1, Wo = (Wi - 1) / stride_s + 1;
+  CK(launch_dwconv(in, w27c, scale, shift, out_split, B, Ti, Hi, Wi, C, stride_t, stride_s, To, Ho, Wo, (cudaStream_t)stream));
+  return TUBER_OK;
+}
+int tuber_op_stem(const float* x, const float* w441x64, const float* scale, const float* shift, float* conv_out, void* pooled_split,
+                  int32_t B, int32_t T, int32_t H, int32_t W, void* stream) {
+  const int H1 = (H - 1) / 2 + 1, W1 = (W - 1) / 2 + 1, H2 = (H1 - 1) / 2 + 1, W2 = (W1 - 1) / 2 + 1;
+  CK(launch_stem_conv(x, w441x64, scale, shift, conv_out, B, T, H, W, H1, W1, (cudaStream_t)stream));
+  if (pooled_split) CK(launch_maxpool_hw(conv_out, pooled_split, B * T, H1, W1, H2, W2, 64, (cudaStream_t)stream));
+  return TUBER_OK;
+}
+int tuber_op_layernorm(const float* x, const float* res, const float* gamma, const float* beta, float* out, int64_t rows, int32_t C,
+                       void* stream) {
+  LnArgs a{};
+  a.x = x; a.ldx = C; a.res = res; a.res_fmt = FMT_F32; a.ldr = C; a.gamma = gamma; a.beta = beta; a.eps = LN_EPS;
+  a.rows = (int)rows; a.C = C; a.out_f32 = out; a.ldo = C;
+  CK(launch_layernorm(a, (cudaStream_t)stream));
+  return TUBER_OK;
+}
+int tuber_op_attention(const float* q, const float* k, const float* v, const uint8_t* kpm, float* out, int32_t NB, int32_t H, int32_t L,
+                       int32_t S, int32_t D, float scale, void* stream) {
+  AttnArgs a{};
+  const int E = H * D;
+  a.q = q; a.ldq = E; a.qm = seqmap(1, L, 0, 1);
+  a.k = k; a.v = v; a.ldk = E; a.ldv = E; a.km = seqmap(1, S, 0, 1);
+  a.o_f32 = out; a.ldo = E; a.om = seqmap(1, L, 0, 1);
+  a.kpm = kpm; a.kpm_div = 1; a.NB = NB; a.H = H; a.L = L; a.S = S; a.D = D; a.scale = scale;
+  CK(launch_attention(a, (cudaStream_t)stream));
+  return TUBER_OK;
+}
+int tuber_op_posenc(const uint8_t* fmask, float* pos, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d_model, void* stream) {
+  const int nt = d_model / 8 * 2, ns = d_model / 8 * 3;
+  std::vector<float> dt(nt), ds(ns);
+  for (int i = 0; i < nt; ++i) dt[i] = powf(10000.f, (float)(2 * (i / 2)) / (float)nt);
+  for (int i = 0; i < ns; ++i) ds[i] = powf(10000.f, (float)(2 * (i / 2)) / (float)ns);
+  float *ddt = nullptr, *dds = nullptr;
+  CK(cudaMalloc((void**)&ddt, nt * 4));
+  CK(cudaMalloc((void**)&dds, ns * 4));
+  CK(cudaMemcpy(ddt, dt.data(), nt * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dds, ds.data(), ns * 4, cudaMemcpyHostToDevice));
+  cudaError_t e = launch_posenc(fmask, ddt, dds, pos, B, T, H, W, nt, ns, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(ddt);
+  cudaFree(dds);
+  CK(e);
+  return TUBER_OK;
+}
+
+}  // extern "C"
