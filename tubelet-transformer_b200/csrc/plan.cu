@@ -84,12 +84,13 @@ struct KernelRec { const char* name; double bytes, flops; cudaEvent_t e0, e1; };
 struct Tap { const void* ptr; int fmt; long long rows; int cols; void* keep; };
 
 struct Ws {   // bump allocator over one device buffer; in dry mode only counts
-  char* base = nullptr; size_t cap = 0, off = 0, peak = 0; bool dry = false;
+  char* base = nullptr; size_t cap = 0, off = 0, peak = 0; bool dry = false, overflow = false;
   void* alloc(size_t bytes) {
     size_t o = (off + 255) & ~(size_t)255;
     off = o + bytes;
     if (off > peak) peak = off;
     if (dry) return reinterpret_cast<void*>((uintptr_t)0x1000 + o);
+    if (off > cap) { overflow = true; return base; }      // never hand out memory past the buffer
     return base + o;
   }
 };
@@ -134,6 +135,7 @@ struct TuberPlan {
   std::map<std::string, Tap> taps;
   int launches = 0;
   bool kprof = false;
+  cudaStream_t cap_stream = nullptr;
   std::vector<KernelRec> kp; int kp_used = 0;
   struct GraphEntry { std::vector<uintptr_t> key; cudaGraphExec_t exec; };
   std::vector<GraphEntry> graphs;
@@ -492,6 +494,7 @@ struct Ctx {
     if (!ok()) return;
     ++launches;
     if (dry) return;
+    if (ws.overflow) { status = fail(TUBER_ERR_STATE, "workspace overflow before %s (sizing pass disagrees with the forward)", name); return; }
     const int idx = p->kprof ? kp_begin(name, bytes, flops) : -1;
     cudaError_t e = f();
     if (idx >= 0) cudaEventRecord(p->kp[idx].e1, st);
@@ -893,12 +896,14 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
   return cx.status;
 }
 
-int ensure_workspace(TuberPlan* p, int B, int T, int H, int W, size_t* need_out, int* launches_out) {
+int ensure_workspace(TuberPlan* p, int B, int T, int H, int W, bool has_mask, size_t* need_out, int* launches_out) {
   Ctx cx{p};
   cx.dry = true;
   cx.ws.dry = true;
   cx.st = 0;
-  TRY(run_forward(cx, nullptr, nullptr, B, T, H, W, nullptr, nullptr, nullptr));
+  // the sizing pass must see the same mask / no-mask choice as the real one (per-clip position codes)
+  const uint8_t* mask_tag = has_mask ? reinterpret_cast<const uint8_t*>((uintptr_t)0x1000) : nullptr;
+  TRY(run_forward(cx, nullptr, mask_tag, B, T, H, W, nullptr, nullptr, nullptr));
   size_t need = cx.ws.peak + 4096;
   if (need_out) *need_out = need;
   if (launches_out) *launches_out = cx.launches;
@@ -954,6 +959,7 @@ void tuber_plan_destroy(TuberPlan* p) {
   for (void* d : p->owned) cudaFree(d);
   for (auto& kv : p->taps) if (kv.second.keep) cudaFree(kv.second.keep);
   for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);
+  if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   if (p->ws) cudaFree(p->ws);
   if (p->stage_in) cudaFree(p->stage_in);
   if (p->stage_out) cudaFree(p->stage_out);
@@ -987,7 +993,7 @@ int tuber_query_shapes(TuberPlan* p, int32_t B, int32_t T, int32_t H, int32_t W,
   TRY(compute_geometry(p->cfg, T, H, W, g));
   size_t need = 0;
   int launches = 0;
-  TRY(ensure_workspace(p, B, T, H, W, &need, &launches));
+  TRY(ensure_workspace(p, B, T, H, W, true, &need, &launches));
   out->Tf = g.Tf; out->Hf = g.Hf; out->Wf = g.Wf; out->Tp = g.Tp;
   out->enc_tokens = g.Tp * g.Hf * g.Wf; out->cls_tokens = g.Tf * g.Hf * g.Wf;
   out->launches = launches; out->workspace_bytes = (int64_t)need;
@@ -1000,7 +1006,7 @@ int tuber_forward(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev,
   if (!clips_dev || !logits_dev || !boxes_dev || !logits_b_dev) return fail(TUBER_ERR_INVALID, "null device pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   size_t need = 0;
-  TRY(ensure_workspace(p, B, T, H, W, &need, nullptr));
+  TRY(ensure_workspace(p, B, T, H, W, mask_dev != nullptr, &need, nullptr));
   if (need > p->ws_cap) {
     CK(cudaDeviceSynchronize());
     if (p->ws) cudaFree(p->ws);
@@ -1042,10 +1048,14 @@ int tuber_forward(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev,
   cap.dry = false;
   cap.ws.base = p->ws; cap.ws.cap = p->ws_cap;
   cap.st = st;
+  // record on a private stream (the caller's may be the legacy default stream, which cannot capture);
+  // the instantiated graph is launched on the caller's stream
+  if (!p->cap_stream) CK(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+  cap.st = p->cap_stream;
   cudaGraph_t graph_obj = nullptr;
-  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  CK(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
   int s = run_forward(cap, clips_dev, mask_dev, B, T, H, W, logits_dev, boxes_dev, logits_b_dev);
-  cudaError_t e = cudaStreamEndCapture(st, &graph_obj);
+  cudaError_t e = cudaStreamEndCapture(p->cap_stream, &graph_obj);
   if (s != TUBER_OK) { if (graph_obj) cudaGraphDestroy(graph_obj); return s; }
   if (e != cudaSuccess) return fail(TUBER_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
   cudaGraphExec_t exec = nullptr;
