@@ -28,7 +28,7 @@ def test_split_roundtrip(abi):
 
 @pytest.mark.parametrize("m,n,k", [(300, 64, 64), (128, 128, 256), (1000, 256, 2048), (4096, 512, 128), (77, 192, 512),
                                    (20000, 256, 64)])
-@pytest.mark.parametrize("variant", ["plain", "bn_relu_res", "split_out_split_res", "res_mod"])
+@pytest.mark.parametrize("variant", ["plain", "bn_relu_res", "split_out_split_res", "res_mod", "mixed_res_f32_out_split", "split_out"])
 def test_gemm_tc(abi, m, n, k, variant):
     g = torch.Generator(device="cuda").manual_seed(m * 7 + n + k)
     a = torch.randn(m, k, device="cuda", generator=g)
@@ -44,6 +44,13 @@ def test_gemm_tc(abi, m, n, k, variant):
         res = torch.randn(m, n, device="cuda", generator=g)
         ref = torch.relu(ref + res.double())
         kw = dict(relu=True, res_split=variant == "split_out_split_res", c_split=variant == "split_out_split_res")
+    if variant == "mixed_res_f32_out_split":
+        res = torch.randn(m, n, device="cuda", generator=g)
+        ref = ref + res.double()
+        kw = dict(c_split=True)
+    if variant == "split_out":
+        ref = torch.relu(ref)
+        kw = dict(relu=True, c_split=True)
     if variant == "res_mod":
         mod = 13
         res = torch.randn(mod, n, device="cuda", generator=g)

@@ -1,19 +1,29 @@
 // tcgen05 "bf16x3" GEMM for sm_100a: the pointwise (1x1x1) convolutions of the CSN backbone, the
-// 2048->256 projections and the decode-pool linear layers.
+// 2048->256 projections, the decode-pool and transformer linear layers.
 //
-//   C[M,N] = act( scale[n] * sum_k A[m,k] W[n,k] + shift[n] + res[m % res_mod, n] )
+//   C[M,N] = act( scale[n] * sum_k A[m,k] W[n,k] + shift[n] + res[m, n] )
 //
 // Operands are split-bf16 (common.cuh): A = A_hi + A_mid, W = W_hi + W_mid, and the kernel issues
-// three tensor-core passes per k-block  A_hi*W_hi + A_hi*W_mid + A_mid*W_hi  into one fp32 TMEM
-// accumulator (dropped terms are O(2^-16) relative).  Structure (one CTA per SM, persistent over
-// output tiles, 192 threads):
-//   warp 0      TMA producer: one cp.async.bulk.tensor.3d per operand and k-block brings the hi and
+// three tensor-core passes per k-block  A_mid*W_hi + A_hi*W_mid + A_hi*W_hi  into one fp32 TMEM
+// accumulator (dropped terms are O(2^-16) relative).  All global traffic is TMA:
+//
+//   warp 0      operand producer: one cp.async.bulk.tensor.3d per operand and k-block brings the hi and
 //               mid planes of a 128 x 64 (A) / BN x 64 (W) tile into 128B-swizzled shared memory.
-//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16),
-//               12 per k-block; tcgen05.commit releases the smem stage / publishes the accumulator.
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), folded-BN scale/shift or
-//               bias, residual add, ReLU, fp32 or split-bf16 store.  The accumulator is double
-//               buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps tile i+1's MMAs.
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16), 12 per
+//               k-block; tcgen05.commit frees the operand stage / publishes the accumulator (TMEM,
+//               double buffered: 2 x BN columns, so the epilogue of tile i overlaps the MMAs of i+1).
+//   warp 2      panel producer: for every 128 x 64 output panel it claims a 32 KB shared-memory panel
+//               buffer and, when there is a residual, TMA-loads the residual panel into it.
+//   warps 3..6  epilogue: tcgen05.ld (thread = accumulator row), folded-BN scale/shift or bias, residual
+//               from the panel, ReLU, written back IN PLACE into the panel (fp32 or split-bf16, in the
+//               128B-swizzled layout the tensor map expects), then one thread issues the TMA store.
+//
+// A panel is 128 rows x 64 columns = 32 KB in either format, as two 16 KB sub-tiles of 128-byte rows:
+//   fp32  : sub-tile s = columns [32s, 32s+32) of the panel  (tensor map: {32, rows, N/32} view of the matrix)
+//   split : sub-tile 0 = hi plane, sub-tile 1 = mid plane   (tensor map: {N, rows, 2 planes})
+// so thread r owns exactly row r of both sub-tiles in both formats and the in-place update is race free.
+// The TMA residual path needs res format == output format; other cases (row-periodic residuals, mixed
+// formats) use per-thread global loads (small token-sized GEMMs only).
 #include <cuda.h>
 #include <stdio.h>
 #include <string.h>
@@ -23,22 +33,31 @@
 namespace tc {
 
 constexpr int BM = 128, BK = 64;            // BK bf16 = 128 bytes = one swizzle-128B row
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 224;            // 7 warps
+constexpr int EPI_WARP0 = 3;                // warps 3..6 (warp % 4 = 3,0,1,2: all four TMEM lane groups)
 constexpr int A_PLANE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int PANEL_BYTES = 32768, SUB_BYTES = 16384;
 
-template <int BN> struct Cfg {
+enum ResMode { RES_NONE = 0, RES_TMA = 1, RES_DIRECT = 2 };
+
+template <int BN_, int STAGES_, int PANELS_> struct Cfg {
+  static constexpr int BN = BN_, STAGES = STAGES_, PANELS = PANELS_;
   static constexpr int W_PLANE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * W_PLANE_BYTES;
-  static constexpr int STAGES = (BN == 64) ? 4 : 3;
   static constexpr int TMEM_COLS = 2 * BN;                      // power of two >= 32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * BN * 4 /*scale,shift x2*/;
+  static constexpr int PANELS_PER_TILE = BN / 64;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SS_BYTES = 4 * BN * 4;                   // scale, shift x 2 accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PANELS * PANEL_BYTES + BAR_BYTES + SS_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared-memory limit");
+  static_assert(2 * STAGES + 4 + 2 * PANELS + 1 <= BAR_BYTES / 8, "barrier area too small");
 };
 
 struct Params {
   const float* scale; const float* shift;
-  const void* res; int res_fmt; int ldr; int res_mod;
-  float* Cf; int ldcf;          // fp32 output (nullable)
-  void* Cs; int ldcs;           // split output (nullable)
+  const void* res; int res_fmt; int ldr; int res_mod;   // RES_DIRECT only
+  int res_mode;
+  int out_fmt;
   int M, N, K, act;
 };
 
@@ -70,6 +89,14 @@ TB_DEVINL void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, i
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+TB_DEVINL void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+TB_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> TB_DEVINL void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+TB_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+TB_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 TB_DEVINL void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 TB_DEVINL void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 TB_DEVINL void umma_commit(uint32_t bar) {
@@ -97,6 +124,14 @@ TB_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+TB_DEVINL uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+TB_DEVINL void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // Shared-memory matrix descriptor, K-major operand, 128B swizzle (cute::UMMA::SmemDescriptor):
 // start address >> 4 in [0,14), LBO (unused for swizzled K-major, = 1) in [16,30), SBO = 1024 B
@@ -116,22 +151,28 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN>
+// 16-byte chunk j of row r in a 128B-swizzled sub-tile
+TB_DEVINL uint32_t swz(uint32_t sub_base, int r, int j) { return sub_base + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4); }
+
+template <class C>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, Params p) {
-  using C = Cfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // swizzle-128B needs 1024 B alignment
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, Params p) {
+  constexpr int BN = C::BN;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);            // swizzle-128B tiles need 1024 B alignment
+  const uint32_t panel_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = panel_base + C::PANELS * PANEL_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 4 + s); };
+  auto pfree_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 4 + C::PANELS + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4 + 2 * C::PANELS);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_base));
   // per-accumulator-stage copies of this tile's scale / shift columns: [2][2][BN] floats
-  float* s_ss = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+  float* s_ss = reinterpret_cast<float*>(smem_raw + (bar_base + C::BAR_BYTES - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / BN;
@@ -139,8 +180,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int kblocks = p.K / BK;
 
   if (warp == 0 && lane == 0) {
+    if (smem_base & 1023u) __trap();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    if (p.res_mode == RES_TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -148,6 +192,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4);
+    }
+    for (int s = 0; s < C::PANELS; ++s) {
+      mbar_init(pfull_bar(s), 1);
+      mbar_init(pfree_bar(s), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -162,7 +210,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= operand producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -212,83 +260,162 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
     }
+  } else if (warp == 2) {
+    // ================= panel producer =================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int j = 0; j < C::PANELS_PER_TILE; ++j) {
+          mbar_wait(pfree_bar(slot), phase ^ 1);         // the store that last read this buffer has drained
+          if (p.res_mode == RES_TMA) {
+            const int col = n_blk * BN + j * 64;
+            mbar_expect_tx(pfull_bar(slot), PANEL_BYTES);
+            if (p.out_fmt == FMT_F32) tma_load_3d(panel_base + slot * PANEL_BYTES, &tmR, pfull_bar(slot), 0, m_blk * BM, col >> 5);
+            else tma_load_3d(panel_base + slot * PANEL_BYTES, &tmR, pfull_bar(slot), col, m_blk * BM, 0);
+          } else {
+            mbar_arrive(pfull_bar(slot));
+          }
+          if (++slot == C::PANELS) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 3..6) =================
     const int lg = warp & 3;                              // TMEM lane group this warp may access
-    int it = 0;
+    const int et = threadIdx.x - EPI_WARP0 * 32;          // 0..127
+    const int r = lg * 32 + lane;                         // accumulator row = panel row of this thread
+    int it = 0, slot = 0, prev_slot = -1;
+    uint32_t pphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       float* s_scale = s_ss + as * 2 * BN;
       float* s_shift = s_scale + BN;
-      {
-        const int t = threadIdx.x - 64;                   // 0..127 over the four epilogue warps
-        if (t < BN) {
-          s_scale[t] = p.scale ? __ldg(p.scale + n_blk * BN + t) : 1.f;
-          s_shift[t] = p.shift ? __ldg(p.shift + n_blk * BN + t) : 0.f;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");    // epilogue warps only
+      if (et < BN) {
+        s_scale[et] = p.scale ? __ldg(p.scale + n_blk * BN + et) : 1.f;
+        s_shift[et] = p.shift ? __ldg(p.shift + n_blk * BN + et) : 0.f;
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
       mbar_wait(tfull_bar(as), aphase);
       tcgen05_fence_after();
-      const long long row = (long long)m_blk * BM + lg * 32 + lane;
+      const long long row = (long long)m_blk * BM + r;
       const bool row_ok = row < p.M;
       const long long rrow = p.res_mod > 0 ? row % p.res_mod : row;
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + cc * 32), r);
-        const int n0 = n_blk * BN + cc * 32;
-        float v[32];
+      for (int j = 0; j < C::PANELS_PER_TILE; ++j) {
+        mbar_wait(pfull_bar(slot), pphase);
+        const uint32_t pb = panel_base + slot * PANEL_BYTES;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {                     // 32-column halves of the panel
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + j * 64 + h * 32), acc);
+          const int cl = j * 64 + h * 32;                 // column inside the tile
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 sc = *reinterpret_cast<const float4*>(s_scale + cc * 32 + 4 * j);
-          const float4 sh = *reinterpret_cast<const float4*>(s_shift + cc * 32 + 4 * j);
-          v[4 * j] = fmaf(__uint_as_float(r[4 * j]), sc.x, sh.x);
-          v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
-          v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
-          v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
-        }
-        if (row_ok) {
-          if (p.res) {
+          for (int q = 0; q < 8; ++q) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + cl + 4 * q);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + cl + 4 * q);
+            v[4 * q] = fmaf(__uint_as_float(acc[4 * q]), sc.x, sh.x);
+            v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), sc.y, sh.y);
+            v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), sc.z, sh.z);
+            v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), sc.w, sh.w);
+          }
+          if (p.res_mode == RES_TMA) {
+            if (p.out_fmt == FMT_F32) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const uint4 t = lds128(swz(pb + h * SUB_BYTES, r, q));
+                v[4 * q] += __uint_as_float(t.x); v[4 * q + 1] += __uint_as_float(t.y);
+                v[4 * q + 2] += __uint_as_float(t.z); v[4 * q + 3] += __uint_as_float(t.w);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {               // 8 columns per 16-byte chunk of each plane
+                const uint4 a = lds128(swz(pb, r, 4 * h + q));
+                const uint4 b = lds128(swz(pb + SUB_BYTES, r, 4 * h + q));
+                v[8 * q] += bf16_lo_to_f32(a.x) + bf16_lo_to_f32(b.x); v[8 * q + 1] += bf16_hi_to_f32(a.x) + bf16_hi_to_f32(b.x);
+                v[8 * q + 2] += bf16_lo_to_f32(a.y) + bf16_lo_to_f32(b.y); v[8 * q + 3] += bf16_hi_to_f32(a.y) + bf16_hi_to_f32(b.y);
+                v[8 * q + 4] += bf16_lo_to_f32(a.z) + bf16_lo_to_f32(b.z); v[8 * q + 5] += bf16_hi_to_f32(a.z) + bf16_hi_to_f32(b.z);
+                v[8 * q + 6] += bf16_lo_to_f32(a.w) + bf16_lo_to_f32(b.w); v[8 * q + 7] += bf16_hi_to_f32(a.w) + bf16_hi_to_f32(b.w);
+              }
+            }
+          } else if (p.res_mode == RES_DIRECT && row_ok) {
+            const int n0 = n_blk * BN + cl;
             if (p.res_fmt == FMT_F32) {
               const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + rrow * p.ldr + n0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 t = __ldg(rp + j);
-                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+              for (int q = 0; q < 8; ++q) {
+                const float4 t = __ldg(rp + q);
+                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
               }
             } else {
               const __nv_bfloat16* hp = split_hi(p.res, rrow, p.ldr) + n0;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 t = load_split4(hp + 4 * j, hp + p.ldr + 4 * j);
-                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+              for (int q = 0; q < 8; ++q) {
+                const float4 t = load_split4(hp + 4 * q, hp + p.ldr + 4 * q);
+                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
               }
             }
           }
           if (p.act == ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
           }
-          if (p.Cf) {
-            float4* op = reinterpret_cast<float4*>(p.Cf + row * p.ldcf + n0);
+          if (p.out_fmt == FMT_F32) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (p.Cs) {
-            __nv_bfloat16* hp = split_hi(p.Cs, row, p.ldcs) + n0;
+            for (int q = 0; q < 8; ++q)
+              sts128(swz(pb + h * SUB_BYTES, r, q), make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                                                               __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3])));
+          } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              store_split4(hp + 4 * j, hp + p.ldcs + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            for (int q = 0; q < 4; ++q) {
+              uint32_t hi[4], mid[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat16 h0, m0, h1, m1;
+                split_bf16(v[8 * q + 2 * e], h0, m0);
+                split_bf16(v[8 * q + 2 * e + 1], h1, m1);
+                hi[e] = pack_bf16x2(h0, h1);
+                mid[e] = pack_bf16x2(m0, m1);
+              }
+              sts128(swz(pb, r, 4 * h + q), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+              sts128(swz(pb + SUB_BYTES, r, 4 * h + q), make_uint4(mid[0], mid[1], mid[2], mid[3]));
+            }
           }
         }
+        if (j == C::PANELS_PER_TILE - 1) {                // accumulator fully read: hand it back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        fence_proxy_async();                              // generic-proxy writes -> visible to the TMA store
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const int col = n_blk * BN + j * 64;
+          if (p.out_fmt == FMT_F32) tma_store_3d(&tmC, pb, 0, m_blk * BM, col >> 5);
+          else tma_store_3d(&tmC, pb, col, m_blk * BM, 0);
+          bulk_commit();
+          // keep at most PANELS-2 stores in flight, then recycle the buffer(s) whose store has drained
+          if constexpr (C::PANELS == 1) {
+            bulk_wait_read<0>();
+            mbar_arrive(pfree_bar(slot));
+          } else {
+            bulk_wait_read<C::PANELS - 2>();
+            if constexpr (C::PANELS == 2) {
+              mbar_arrive(pfree_bar(slot));
+            } else {
+              if (prev_slot >= 0) mbar_arrive(pfree_bar(prev_slot));
+              prev_slot = slot;
+            }
+          }
+        }
+        if (++slot == C::PANELS) { slot = 0; pphase ^= 1; }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
     }
+    if (et == 0) bulk_wait_all();                         // shared memory must outlive the last stores
   }
 
   tcgen05_fence_before();
@@ -304,6 +431,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+using CfgWide = Cfg<128, 2, 3>;   // memory-bound shapes: panels pipelined (load residual | compute | store)
+using CfgDeep = Cfg<128, 3, 1>;   // K >= 512: deeper operand ring, one panel buffer
+using CfgN64 = Cfg<64, 3, 2>;     // N == 64 (or N % 128 != 0)
 
 static char g_err[256] = "";
 static EncodeTiledFn g_encode = nullptr;
@@ -321,31 +452,49 @@ static cudaError_t init_once() {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaFuncSetAttribute(gemm_bf16x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES);
+  e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES);
+  e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDeep::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgN64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgN64::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return cudaSuccess;
 }
 
-// 3-D map over a split tensor: dims {K, rows, plane}, box {64, box_rows, 2}
-static bool encode_split_map(CUtensorMap* map, const void* base, uint64_t k, uint64_t rows, uint64_t row_stride_bytes,
-                             uint64_t plane_stride_bytes, uint32_t box_rows) {
-  cuuint64_t dims[3] = {k, rows, 2};
-  cuuint64_t strides[2] = {row_stride_bytes, plane_stride_bytes};
-  cuuint32_t box[3] = {(cuuint32_t)BK, box_rows, 2};
+static bool encode3(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                    uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1_bytes, s2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_encode(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled failed (%d): k=%llu rows=%llu rs=%llu ps=%llu", (int)r,
-             (unsigned long long)k, (unsigned long long)rows, (unsigned long long)row_stride_bytes,
-             (unsigned long long)plane_stride_bytes);
+    snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u", (int)r,
+             (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1_bytes,
+             (unsigned long long)s2_bytes, b0, b1, b2);
     return false;
   }
   return true;
+}
+
+// split tensor [rows, ld] restricted to `cols` columns: dims {cols, rows, plane}, box {64, box_rows, 2}
+static bool encode_split_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+  return encode3(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, cols, rows, 2, ld * 4, ld * 2, 64, box_rows, 2);
+}
+// fp32 matrix [rows, ld] restricted to `cols` columns, as {32, rows, cols/32}: box {32, 128, 2} = one 64-column panel
+static bool encode_f32_panel_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld) {
+  return encode3(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, 32, rows, cols / 32, ld * 4, 128, 32, BM, 2);
+}
+
+template <class C>
+static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                              const Params& p, cudaStream_t st) {
+  const int tiles = ceil_div(p.M, BM) * (p.N / C::BN);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  gemm_bf16x3_kernel<C><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmW, tmC, tmR, p);
+  return cudaGetLastError();
 }
 
 }  // namespace tc
@@ -356,33 +505,39 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   using namespace tc;
   cudaError_t e = init_once();
   if (e != cudaSuccess) return e;
-  if (a.M <= 0 || a.N % 64 != 0 || a.K % 64 != 0 || a.lda % 8 != 0 || a.K > a.lda || a.a_fmt != FMT_SPLIT ||
-      a.A2 != nullptr || a.Wp == nullptr || a.act == ACT_SIGMOID || (reinterpret_cast<uintptr_t>(a.A) & 15) ||
-      (reinterpret_cast<uintptr_t>(a.Wp) & 15)) {
-    snprintf(g_err, sizeof g_err, "gemm_tc: unsupported problem M=%d N=%d K=%d lda=%d a_fmt=%d", a.M, a.N, a.K,
-             a.lda, a.a_fmt);
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (a.M <= 0 || a.N % 64 != 0 || a.K % 64 != 0 || a.lda % 8 != 0 || a.K > a.lda || a.a_fmt != FMT_SPLIT || a.A2 != nullptr ||
+      a.Wp == nullptr || a.act == ACT_SIGMOID || a.C2 != nullptr || !aligned16(a.A) || !aligned16(a.Wp) || !aligned16(a.C) ||
+      a.ldc % 8 != 0 || a.N > a.ldc) {
+    snprintf(g_err, sizeof g_err, "gemm_tc: unsupported problem M=%d N=%d K=%d lda=%d ldc=%d a_fmt=%d", a.M, a.N, a.K, a.lda, a.ldc,
+             a.a_fmt);
     return cudaErrorInvalidValue;
   }
   const int bn = (a.N % 128 == 0) ? 128 : 64;
-  CUtensorMap tmA, tmW;
-  if (!encode_split_map(&tmA, a.A, a.K, a.M, (uint64_t)a.lda * 4, (uint64_t)a.lda * 2, BM)) return cudaErrorInvalidValue;
-  if (!encode_split_map(&tmW, a.Wp, a.K, a.N, (uint64_t)a.K * 2, (uint64_t)a.N * a.K * 2, bn)) return cudaErrorInvalidValue;
-  Params p;
+  Params p{};
   p.scale = a.scale; p.shift = a.shift;
-  p.res = a.res; p.res_fmt = a.res_fmt; p.ldr = a.ldr; p.res_mod = a.res_mod;
-  if (a.c_fmt == FMT_F32) {
-    p.Cf = reinterpret_cast<float*>(a.C); p.ldcf = a.ldc; p.Cs = a.C2; p.ldcs = a.ldc2;
-  } else {
-    p.Cs = a.C; p.ldcs = a.ldc; p.Cf = reinterpret_cast<float*>(a.C2); p.ldcf = a.ldc2;
-  }
+  p.out_fmt = a.c_fmt;
   p.M = a.M; p.N = a.N; p.K = a.K; p.act = a.act;
-  const int tiles = ceil_div(a.M, BM) * (a.N / bn);
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  if (bn == 128)
-    gemm_bf16x3_kernel<128><<<grid, NUM_THREADS, Cfg<128>::SMEM_BYTES, st>>>(tmA, tmW, p);
-  else
-    gemm_bf16x3_kernel<64><<<grid, NUM_THREADS, Cfg<64>::SMEM_BYTES, st>>>(tmA, tmW, p);
-  return cudaGetLastError();
+  p.res_mode = RES_NONE;
+  if (a.res) {
+    const bool tma_ok = a.res_mod <= 0 && a.res_fmt == a.c_fmt && aligned16(a.res) && a.ldr % 8 == 0 && a.N <= a.ldr;
+    p.res_mode = tma_ok ? RES_TMA : RES_DIRECT;
+    p.res = a.res; p.res_fmt = a.res_fmt; p.ldr = a.ldr; p.res_mod = a.res_mod;
+  }
+  CUtensorMap tmA, tmW, tmC, tmR;
+  if (!encode_split_map(&tmA, a.A, a.K, a.M, a.lda, BM)) return cudaErrorInvalidValue;
+  if (!encode3(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.Wp, a.K, a.N, 2, (uint64_t)a.K * 2, (uint64_t)a.N * a.K * 2, 64, bn, 2))
+    return cudaErrorInvalidValue;
+  bool ok = a.c_fmt == FMT_F32 ? encode_f32_panel_map(&tmC, a.C, a.N, a.M, a.ldc) : encode_split_map(&tmC, a.C, a.N, a.M, a.ldc, BM);
+  if (!ok) return cudaErrorInvalidValue;
+  tmR = tmC;
+  if (p.res_mode == RES_TMA) {
+    ok = a.c_fmt == FMT_F32 ? encode_f32_panel_map(&tmR, a.res, a.N, a.M, a.ldr) : encode_split_map(&tmR, a.res, a.N, a.M, a.ldr, BM);
+    if (!ok) return cudaErrorInvalidValue;
+  }
+  if (bn == 64) return launch_cfg<CfgN64>(tmA, tmW, tmC, tmR, p, st);
+  if (a.K >= 512) return launch_cfg<CfgDeep>(tmA, tmW, tmC, tmR, p, st);
+  return launch_cfg<CfgWide>(tmA, tmW, tmC, tmR, p, st);
 }
 
 // fp32 [N,K] -> bf16 [2][N][K] (hi plane, mid plane)

@@ -58,7 +58,7 @@ cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st);
 
 // ---- LayerNorm over the last dim (C in {256, 2048}) of x (+ res) ---------------------------
 struct LnArgs {
-  const float* x; int ldx;
+  const void* x; int x_fmt; int ldx;         // fp32 or split
   const void* res; int res_fmt; int ldr;     // optional: normalise x + res (fp32 or split; ldr 0 = broadcast row)
   const float* gamma; const float* beta; float eps;
   int rows, C;

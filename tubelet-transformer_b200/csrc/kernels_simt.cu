@@ -461,7 +461,12 @@ layernorm_kernel(LnArgs p) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     int c = i * 128 + lane * 4;
-    v[i] = __ldg(reinterpret_cast<const float4*>(p.x + r * p.ldx + c));
+    if (p.x_fmt == FMT_F32) {
+      v[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + r * p.ldx + c));
+    } else {
+      const __nv_bfloat16* h = split_hi(p.x, r, p.ldx) + c;
+      v[i] = load_split4(h, h + p.ldx);
+    }
     if (p.res) {
       float4 u;
       if (p.res_fmt == FMT_F32) {

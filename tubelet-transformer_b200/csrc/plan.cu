@@ -516,29 +516,29 @@ struct Ctx {
 
   // C = act(scale * A W^T + shift + res)
   void gemm(const void* A, int a_fmt, int lda, long long M, const Lin& w, const void* res, int res_fmt, int ldr, int res_mod,
-            void* C, int c_fmt, int ldc, void* C2, int ldc2, int act) {
+            void* C, int c_fmt, int ldc, int act) {
     if (!ok()) return;
     GemmArgs a{};
     a.A = A; a.a_fmt = a_fmt; a.lda = lda;
     a.Wf = w.wf; a.Wp = w.wp; a.scale = w.scale; a.shift = w.shift;
     a.res = res; a.res_fmt = res_fmt; a.ldr = ldr; a.res_mod = res_mod;
-    a.C = C; a.c_fmt = c_fmt; a.ldc = ldc; a.C2 = C2; a.ldc2 = ldc2;
+    a.C = C; a.c_fmt = c_fmt; a.ldc = ldc;
     a.M = (int)M; a.N = w.N; a.K = w.K; a.act = act;
-    const bool tc_ok = a_fmt == FMT_SPLIT && w.N % 64 == 0 && w.K % 64 == 0 && act != ACT_SIGMOID && lda % 8 == 0;
+    const bool tc_ok = a_fmt == FMT_SPLIT && w.N % 64 == 0 && w.K % 64 == 0 && act != ACT_SIGMOID && lda % 8 == 0 && ldc % 8 == 0;
     const bool tc = tc_ok && !p->force_simt;
     const double mn = (double)M * w.N;
-    const double bytes = 4.0 * ((double)M * w.K + (double)w.N * w.K + mn * (C2 ? 2 : 1) +
-                                (res ? (res_mod > 0 ? (double)res_mod * w.N : mn) : 0.0));
+    const double bytes = 4.0 * ((double)M * w.K + (double)w.N * w.K + mn + (res ? (res_mod > 0 ? (double)res_mod * w.N : mn) : 0.0));
     launch(tc ? "gemm_bf16x3_tcgen05" : "sgemm_fp32", bytes, 2.0 * mn * w.K,
            [&] { return tc ? launch_gemm_tc(a, st) : launch_sgemm(a, st); });
   }
 
-  void layernorm(const float* x, int ldx, const void* res, int res_fmt, int ldr, const LnP& ln, long long rows,
+  // out = LayerNorm(x + res); x fp32 or split; fp32 and / or split outputs
+  void layernorm(const void* x, int x_fmt, int ldx, const void* res, int res_fmt, int ldr, const LnP& ln, long long rows,
                  float* out_f32, int ldo, void* out_split, int lds, int split_col_off = 0, int rpg = 0,
                  long long group_stride = 0, long long row_off = 0) {
     if (!ok()) return;
     LnArgs a{};
-    a.x = x; a.ldx = ldx; a.res = res; a.res_fmt = res_fmt; a.ldr = ldr;
+    a.x = x; a.x_fmt = x_fmt; a.ldx = ldx; a.res = res; a.res_fmt = res_fmt; a.ldr = ldr;
     a.gamma = ln.g; a.beta = ln.b; a.eps = LN_EPS; a.rows = (int)rows; a.C = ln.C;
     a.out_f32 = out_f32; a.ldo = ldo; a.rpg = rpg; a.group_stride = group_stride; a.row_off = row_off;
     a.out_split = out_split; a.lds = lds; a.split_col_off = split_col_off;
@@ -652,7 +652,7 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
   char* bufB = (char*)cx.ws.alloc(max_out * 4);
   float* t1 = (float*)cx.ws.alloc(max_t1 * 4);
   void* t2 = cx.ws.alloc(max_t2 * 4);
-  float* resb = (float*)cx.ws.alloc(max_res * 4);
+  void* resb = cx.ws.alloc(max_res * 4);
   void* xg = cx.ws.alloc(max_xg * 4 + 16);
 
   // ---- stem: conv + BN + ReLU (F, NDHWC) then the (1,3,3) max pool (S) ----
@@ -675,7 +675,7 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     for (const Block& b : p->blocks[li]) {
       const int to = (t - 1) / b.st_t + 1, ho = (h - 1) / b.st_s + 1, wo = (w - 1) / b.st_s + 1;
       const long long vin = (long long)B * t * h * w, vout = (long long)B * to * ho * wo;
-      cx.gemm(cur, FMT_SPLIT, b.cin, vin, b.conv1, nullptr, 0, 0, 0, t1, FMT_F32, b.planes, nullptr, 0, ACT_RELU);
+      cx.gemm(cur, FMT_SPLIT, b.cin, vin, b.conv1, nullptr, 0, 0, 0, t1, FMT_F32, b.planes, ACT_RELU);
       cx.launch("dwconv3x3x3", 4.0 * ((double)vin + vout) * b.planes, 54.0 * vout * b.planes,
                 [&] { return launch_dwconv(t1, b.dw.w, b.dw.scale, b.dw.shift, t2, B, t, h, w, b.planes, b.st_t, b.st_s, to, ho, wo, st); });
       const void* res = cur;
@@ -687,10 +687,10 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
                     [&] { return launch_gather_rows(cur, xg, b.cin * 4, B, t, h, w, b.st_t, b.st_s, to, ho, wo, st); });
           a = xg;
         }
-        cx.gemm(a, FMT_SPLIT, b.cin, vout, b.ds, nullptr, 0, 0, 0, resb, FMT_F32, b.cout, nullptr, 0, ACT_NONE);
-        res = resb; res_fmt = FMT_F32; ldr = b.cout;
+        cx.gemm(a, FMT_SPLIT, b.cin, vout, b.ds, nullptr, 0, 0, 0, resb, FMT_SPLIT, b.cout, ACT_NONE);
+        res = resb; res_fmt = FMT_SPLIT; ldr = b.cout;
       }
-      cx.gemm(t2, FMT_SPLIT, b.planes, vout, b.conv4, res, res_fmt, ldr, 0, nxt, FMT_SPLIT, b.cout, nullptr, 0, ACT_RELU);
+      cx.gemm(t2, FMT_SPLIT, b.planes, vout, b.conv4, res, res_fmt, ldr, 0, nxt, FMT_SPLIT, b.cout, ACT_RELU);
       std::swap(cur, nxt);
       t = to; h = ho; w = wo;
     }
@@ -721,23 +721,21 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     // per pixel: one learned query attends over the Tf frame tokens (d = 2048, 8 heads x 256)
     const long long Mp = (long long)B * HW;
     float* kv = cx.f32(Mc, 2 * CB);
-    cx.gemm(xt, FMT_SPLIT, CB, Mc, p->pool_kv, nullptr, 0, 0, 0, kv, FMT_F32, 2 * CB, nullptr, 0, ACT_NONE);
+    cx.gemm(xt, FMT_SPLIT, CB, Mc, p->pool_kv, nullptr, 0, 0, 0, kv, FMT_F32, 2 * CB, ACT_NONE);
     void* att = cx.split(Mp, CB);
     cx.attention(p->pool_q, CB, seqmap(1, 0, 0, 0), kv, kv + CB, 2 * CB, seqmap(HW, (long long)Tf * HW, 1, HW), att, CB,
                  seqmap(1, 1, 0, 1), nullptr, (int)Mp, 8, 1, Tf, CB / 8);
-    float* o1 = cx.f32(Mp, CB);
-    cx.gemm(att, FMT_SPLIT, CB, Mp, p->pool_out, nullptr, 0, 0, 0, o1, FMT_F32, CB, nullptr, 0, ACT_NONE);
-    float* t2f = cx.f32(Mp, CB);
+    void* o1 = cx.split(Mp, CB);
+    cx.gemm(att, FMT_SPLIT, CB, Mp, p->pool_out, nullptr, 0, 0, 0, o1, FMT_SPLIT, CB, ACT_NONE);
     void* t2s = cx.split(Mp, CB);
-    cx.layernorm(o1, CB, p->pool_tgt1, FMT_F32, 0, p->pool_n2, Mp, t2f, CB, t2s, CB);
+    cx.layernorm(o1, FMT_SPLIT, CB, p->pool_tgt1, FMT_F32, 0, p->pool_n2, Mp, nullptr, 0, t2s, CB);
     void* hdn = cx.split(Mp, 2048);
-    cx.gemm(t2s, FMT_SPLIT, CB, Mp, p->pool_lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, 2048, nullptr, 0, ACT_RELU);
-    float* o2 = cx.f32(Mp, CB);
-    cx.gemm(hdn, FMT_SPLIT, 2048, Mp, p->pool_lin2, t2f, FMT_F32, CB, 0, o2, FMT_F32, CB, nullptr, 0, ACT_NONE);
-    float* t3 = cx.f32(Mp, CB);
-    cx.layernorm(o2, CB, nullptr, 0, 0, p->pool_n3, Mp, t3, CB, nullptr, 0);
+    cx.gemm(t2s, FMT_SPLIT, CB, Mp, p->pool_lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, 2048, ACT_RELU);
+    cx.gemm(hdn, FMT_SPLIT, 2048, Mp, p->pool_lin2, t2s, FMT_SPLIT, CB, 0, o1, FMT_SPLIT, CB, ACT_NONE);
+    void* t3 = cx.split(Mp, CB);
+    cx.layernorm(o1, FMT_SPLIT, CB, nullptr, 0, 0, p->pool_n3, Mp, nullptr, 0, t3, CB);
     void* o = cx.split(Mp, CB);
-    cx.layernorm(t3, CB, nullptr, 0, 0, p->pool_nf, Mp, nullptr, 0, o, CB);
+    cx.layernorm(t3, FMT_SPLIT, CB, nullptr, 0, 0, p->pool_nf, Mp, nullptr, 0, o, CB);
     xs = o;
   }
   cx.tap("xs", xs, FMT_SPLIT, Mtok, CB);
@@ -757,127 +755,121 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
               [&] { return launch_posenc(fmask, p->dim_t, p->dim_s, pos, Bp, Tp, g.Hf, g.Wf, d / 8 * 2, d / 8 * 3, st); });
     cx.launch("to_split", 8.0 * n, 0.0, [&] { return launch_to_split(pos, d, pos_s, d, (long long)Bp * Ntok, d, st); });
   }
-  cx.gemm(pos_s, FMT_SPLIT, d, (long long)Bp * Ntok, p->pos_proj, nullptr, 0, 0, 0, posp, FMT_F32, NP, nullptr, 0, ACT_NONE);
+  cx.gemm(pos_s, FMT_SPLIT, d, (long long)Bp * Ntok, p->pos_proj, nullptr, 0, 0, 0, posp, FMT_F32, NP, ACT_NONE);
   const uint8_t* kpm = mask ? fmask : nullptr;
   const int pos_mod = mask ? 0 : Ntok;
   cx.tap("pos", pos, FMT_F32, (long long)Bp * Ntok, d);
 
-  // input_proj / class_proj (tuber_ava.py:119,129)
-  float* src_f = cx.f32(Mtok, d);
+  // input_proj / class_proj (tuber_ava.py:119,129); token activations live in split format from here on
   void* src_s = cx.split(Mtok, d);
-  cx.gemm(xs, FMT_SPLIT, CB, Mtok, p->input_proj, nullptr, 0, 0, 0, src_f, FMT_F32, d, src_s, d, ACT_NONE);
-  float* srcc_f = cx.f32(Mc, d);
+  cx.gemm(xs, FMT_SPLIT, CB, Mtok, p->input_proj, nullptr, 0, 0, 0, src_s, FMT_SPLIT, d, ACT_NONE);
   void* srcc_s = cx.split(Mc, d);
-  cx.gemm(xt, FMT_SPLIT, CB, Mc, p->class_proj, nullptr, 0, 0, 0, srcc_f, FMT_F32, d, srcc_s, d, ACT_NONE);
-  cx.tap("src", src_f, FMT_F32, Mtok, d);
+  cx.gemm(xt, FMT_SPLIT, CB, Mc, p->class_proj, nullptr, 0, 0, 0, srcc_s, FMT_SPLIT, d, ACT_NONE);
+  cx.tap("src", src_s, FMT_SPLIT, Mtok, d);
 
   // ---- DETR encoder (transformer.py:153-168): post-norm, q = k = src + pos, v = src ----
   cx.stage_mark(7);
   {
     float* qkv = cx.f32(Mtok, 3 * d);
     void* att = cx.split(Mtok, d);
-    float* o = cx.f32(Mtok, d);
+    void* o = cx.split(Mtok, d);
     void* hdn = cx.split(Mtok, c.dim_ff);
     for (int i = 0; i < Le; ++i) {
       const EncLayer& e = p->enc[i];
-      cx.gemm(src_s, FMT_SPLIT, d, Mtok, e.in, posp + (size_t)i * 3 * d, FMT_F32, NP, pos_mod, qkv, FMT_F32, 3 * d, nullptr, 0, ACT_NONE);
+      cx.gemm(src_s, FMT_SPLIT, d, Mtok, e.in, posp + (size_t)i * 3 * d, FMT_F32, NP, pos_mod, qkv, FMT_F32, 3 * d, ACT_NONE);
       cx.attention(qkv, 3 * d, seqmap(1, Ntok, 0, 1), qkv + d, qkv + 2 * d, 3 * d, seqmap(1, Ntok, 0, 1), att, d,
                    seqmap(1, Ntok, 0, 1), kpm, B, nh, Ntok, Ntok, hd);
-      cx.gemm(att, FMT_SPLIT, d, Mtok, e.out, src_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
-      cx.layernorm(o, d, nullptr, 0, 0, e.n1, Mtok, src_f, d, src_s, d);
-      cx.gemm(src_s, FMT_SPLIT, d, Mtok, e.lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, c.dim_ff, nullptr, 0, ACT_RELU);
-      cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mtok, e.lin2, src_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
-      cx.layernorm(o, d, nullptr, 0, 0, e.n2, Mtok, src_f, d, src_s, d);
+      cx.gemm(att, FMT_SPLIT, d, Mtok, e.out, src_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, e.n1, Mtok, nullptr, 0, src_s, d);
+      cx.gemm(src_s, FMT_SPLIT, d, Mtok, e.lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, c.dim_ff, ACT_RELU);
+      cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mtok, e.lin2, src_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, e.n2, Mtok, nullptr, 0, src_s, d);
     }
   }
-  cx.tap("memory", src_f, FMT_F32, Mtok, d);
+  cx.tap("memory", src_s, FMT_SPLIT, Mtok, d);
 
   // ---- DETR decoder (transformer.py:218-249), all layers' outputs kept (return_intermediate) ----
   cx.stage_mark(8);
   const long long Mq = (long long)B * Q, Mh = (long long)B * Ld * Q;
-  float* hs_f = cx.f32(Mh, d);                              // [B, Ld, Q, d]
-  void* hs_s = cx.split(Mh, d);
+  void* hs_s = cx.split(Mh, d);                             // [B, Ld, Q, d]
   {
     float* memkv = cx.f32(Mtok, Ld * 2 * d);                // per layer [K | V] of the cross attention
     cx.gemm(src_s, FMT_SPLIT, d, Mtok, p->mem_kv, posp + (size_t)Le * 3 * d, FMT_F32, NP, pos_mod, memkv, FMT_F32, Ld * 2 * d,
-            nullptr, 0, ACT_NONE);
-    float* tgt_f = cx.f32(Mq, d);
+            ACT_NONE);
     void* tgt_s = cx.split(Mq, d);
-    // tgt = zeros_like(query_embed), transformer.py:60 (all-zero bits are zero in both formats)
-    cx.launch("memset", 4.0 * Mq * d, 0.0, [&] { return cudaMemsetAsync(tgt_f, 0, (size_t)Mq * d * 4, st); });
+    // tgt = zeros_like(query_embed), transformer.py:60 (all-zero bits are zero in split format too)
     cx.launch("memset", 4.0 * Mq * d, 0.0, [&] { return cudaMemsetAsync(tgt_s, 0, (size_t)Mq * d * 4, st); });
     float* qkv = cx.f32(Mq, 3 * d);
     float* qc = cx.f32(Mq, d);
     void* att = cx.split(Mq, d);
-    float* o = cx.f32(Mq, d);
+    void* o = cx.split(Mq, d);
     void* hdn = cx.split(Mq, c.dim_ff);
     for (int i = 0; i < Ld; ++i) {
       const DecLayer& l = p->dec[i];
-      cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.sa_in, l.pq_sa, FMT_F32, 3 * d, Q, qkv, FMT_F32, 3 * d, nullptr, 0, ACT_NONE);
+      cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.sa_in, l.pq_sa, FMT_F32, 3 * d, Q, qkv, FMT_F32, 3 * d, ACT_NONE);
       cx.attention(qkv, 3 * d, seqmap(1, Q, 0, 1), qkv + d, qkv + 2 * d, 3 * d, seqmap(1, Q, 0, 1), att, d, seqmap(1, Q, 0, 1),
                    nullptr, B, nh, Q, Q, hd);
-      cx.gemm(att, FMT_SPLIT, d, Mq, l.sa_out, tgt_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
-      cx.layernorm(o, d, nullptr, 0, 0, l.n1, Mq, tgt_f, d, tgt_s, d);
-      cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.ca_q, l.pq_ca, FMT_F32, d, Q, qc, FMT_F32, d, nullptr, 0, ACT_NONE);
+      cx.gemm(att, FMT_SPLIT, d, Mq, l.sa_out, tgt_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, l.n1, Mq, nullptr, 0, tgt_s, d);
+      cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.ca_q, l.pq_ca, FMT_F32, d, Q, qc, FMT_F32, d, ACT_NONE);
       cx.attention(qc, d, seqmap(1, Q, 0, 1), memkv + (size_t)i * 2 * d, memkv + (size_t)i * 2 * d + d, Ld * 2 * d,
                    seqmap(1, Ntok, 0, 1), att, d, seqmap(1, Q, 0, 1), kpm, B, nh, Q, Ntok, hd);
-      cx.gemm(att, FMT_SPLIT, d, Mq, l.ca_out, tgt_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
-      cx.layernorm(o, d, nullptr, 0, 0, l.n2, Mq, tgt_f, d, tgt_s, d);
-      cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, c.dim_ff, nullptr, 0, ACT_RELU);
-      cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mq, l.lin2, tgt_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
-      cx.layernorm(o, d, nullptr, 0, 0, l.n3, Mq, tgt_f, d, tgt_s, d);
+      cx.gemm(att, FMT_SPLIT, d, Mq, l.ca_out, tgt_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, l.n2, Mq, nullptr, 0, tgt_s, d);
+      cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, c.dim_ff, ACT_RELU);
+      cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mq, l.lin2, tgt_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, l.n3, Mq, nullptr, 0, tgt_s, d);
       // shared final norm on every layer's output (transformer.py:116-126), row (b, q) -> (b, i, q)
-      cx.layernorm(tgt_f, d, nullptr, 0, 0, p->dec_norm, Mq, hs_f, d, hs_s, d, 0, Q, (long long)Ld * Q, (long long)i * Q);
+      cx.layernorm(tgt_s, FMT_SPLIT, d, nullptr, 0, 0, p->dec_norm, Mq, nullptr, 0, hs_s, d, 0, Q, (long long)Ld * Q, (long long)i * Q);
     }
   }
-  cx.tap("hs", hs_f, FMT_F32, Mh, d);
+  cx.tap("hs", hs_s, FMT_SPLIT, Mh, d);
 
   // ---- class branch + heads ----
   cx.stage_mark(9);
   // actor-ness head (tuber_ava.py:121-125)
   if (c.ava_mode) {
-    cx.gemm(hs_f, FMT_F32, d, Mh, p->head_b, nullptr, 0, 0, 0, logits_b, FMT_F32, 3, nullptr, 0, ACT_NONE);
+    cx.gemm(hs_s, FMT_SPLIT, d, Mh, p->head_b, nullptr, 0, 0, 0, logits_b, FMT_F32, 3, ACT_NONE);
   } else {
     float* gap = cx.f32(B, CB);
     cx.launch("global_avgpool", 4.0 * Mc * CB, (double)Mc * CB, [&] { return launch_global_avgpool(xt, gap, B, Tf * HW, CB, st); });
-    cx.gemm(gap, FMT_F32, CB, B, p->head_b, nullptr, 0, 0, 0, logits_b, FMT_F32, 2, nullptr, 0, ACT_NONE);
+    cx.gemm(gap, FMT_F32, CB, B, p->head_b, nullptr, 0, 0, 0, logits_b, FMT_F32, 2, ACT_NONE);
   }
   // box head (criterion.py:494-497) + sigmoid (tuber_ava.py:142)
   {
     void* h1 = cx.split(Mh, d);
     void* h2 = cx.split(Mh, d);
-    cx.gemm(hs_s, FMT_SPLIT, d, Mh, p->bbox0, nullptr, 0, 0, 0, h1, FMT_SPLIT, d, nullptr, 0, ACT_RELU);
-    cx.gemm(h1, FMT_SPLIT, d, Mh, p->bbox1, nullptr, 0, 0, 0, h2, FMT_SPLIT, d, nullptr, 0, ACT_RELU);
-    cx.gemm(h2, FMT_SPLIT, d, Mh, p->bbox2, nullptr, 0, 0, 0, boxes, FMT_F32, 4, nullptr, 0, ACT_SIGMOID);
+    cx.gemm(hs_s, FMT_SPLIT, d, Mh, p->bbox0, nullptr, 0, 0, 0, h1, FMT_SPLIT, d, ACT_RELU);
+    cx.gemm(h1, FMT_SPLIT, d, Mh, p->bbox1, nullptr, 0, 0, 0, h2, FMT_SPLIT, d, ACT_RELU);
+    cx.gemm(h2, FMT_SPLIT, d, Mh, p->bbox2, nullptr, 0, 0, 0, boxes, FMT_F32, 4, ACT_SIGMOID);
   }
   // class-branch encoder layer (transformer_layers.py:71-97), evaluated once per clip: the reference runs
   // DEC_LAYERS identical replicas of it (tuber_ava.py:133-135)
-  float* memc_f = cx.f32(Mc, d);
   void* memc_s = cx.split(Mc, d);
   {
     float* qkv = cx.f32(Mc, 3 * d);
     void* att = cx.split(Mc, d);
-    float* o = cx.f32(Mc, d);
+    void* o = cx.split(Mc, d);
     void* cat = cx.split(Mc, 2 * d);
     void* hdn = cx.split(Mc, CLS_FF);
     const int ch = d / CLS_HEADS;
     // "_t": attention inside a frame over its HW positions
-    cx.gemm(srcc_s, FMT_SPLIT, d, Mc, p->ct_in, nullptr, 0, 0, 0, qkv, FMT_F32, 3 * d, nullptr, 0, ACT_NONE);
+    cx.gemm(srcc_s, FMT_SPLIT, d, Mc, p->ct_in, nullptr, 0, 0, 0, qkv, FMT_F32, 3 * d, ACT_NONE);
     cx.attention(qkv, 3 * d, seqmap(1, HW, 0, 1), qkv + d, qkv + 2 * d, 3 * d, seqmap(1, HW, 0, 1), att, d, seqmap(1, HW, 0, 1),
                  nullptr, B * Tf, CLS_HEADS, HW, HW, ch);
-    cx.gemm(att, FMT_SPLIT, d, Mc, p->ct_out, srcc_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
-    cx.layernorm(o, d, nullptr, 0, 0, p->c_n1t, Mc, nullptr, 0, cat, 2 * d, 0);
+    cx.gemm(att, FMT_SPLIT, d, Mc, p->ct_out, srcc_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+    cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->c_n1t, Mc, nullptr, 0, cat, 2 * d, 0);
     // "_s": attention inside a pixel over its Tf frames
-    cx.gemm(srcc_s, FMT_SPLIT, d, Mc, p->cs_in, nullptr, 0, 0, 0, qkv, FMT_F32, 3 * d, nullptr, 0, ACT_NONE);
+    cx.gemm(srcc_s, FMT_SPLIT, d, Mc, p->cs_in, nullptr, 0, 0, 0, qkv, FMT_F32, 3 * d, ACT_NONE);
     const SeqMap pix = seqmap(HW, (long long)Tf * HW, 1, HW);
     cx.attention(qkv, 3 * d, pix, qkv + d, qkv + 2 * d, 3 * d, pix, att, d, pix, nullptr, B * HW, CLS_HEADS, Tf, Tf, ch);
-    cx.gemm(att, FMT_SPLIT, d, Mc, p->cs_out, srcc_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
-    cx.layernorm(o, d, nullptr, 0, 0, p->c_n1s, Mc, nullptr, 0, cat, 2 * d, d);
-    cx.gemm(cat, FMT_SPLIT, 2 * d, Mc, p->c_lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, CLS_FF, nullptr, 0, ACT_RELU);
-    cx.gemm(hdn, FMT_SPLIT, CLS_FF, Mc, p->c_lin2, srcc_f, FMT_F32, d, 0, o, FMT_F32, d, nullptr, 0, ACT_NONE);
-    cx.layernorm(o, d, nullptr, 0, 0, p->c_n2, Mc, memc_f, d, memc_s, d);
+    cx.gemm(att, FMT_SPLIT, d, Mc, p->cs_out, srcc_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+    cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->c_n1s, Mc, nullptr, 0, cat, 2 * d, d);
+    cx.gemm(cat, FMT_SPLIT, 2 * d, Mc, p->c_lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, CLS_FF, ACT_RELU);
+    cx.gemm(hdn, FMT_SPLIT, CLS_FF, Mc, p->c_lin2, srcc_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+    cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->c_n2, Mc, nullptr, 0, memc_s, d);
   }
-  cx.tap("mem_c", memc_f, FMT_F32, Mc, d);
+  cx.tap("mem_c", memc_s, FMT_SPLIT, Mc, d);
   // class cross-attention (tuber_ava.py:137-139) + class_fc (:141; Dropout(0.5) is the identity in eval)
   {
     const int Nc = Tf * HW, LQ = Ld * Q;
@@ -885,12 +877,12 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     float* kvx = cx.f32(Mc, 2 * d);
     void* att = cx.split(Mh, d);
     void* oc = cx.split(Mh, d);
-    cx.gemm(hs_s, FMT_SPLIT, d, Mh, p->x_q, nullptr, 0, 0, 0, qx, FMT_F32, d, nullptr, 0, ACT_NONE);
-    cx.gemm(memc_s, FMT_SPLIT, d, Mc, p->x_kv, nullptr, 0, 0, 0, kvx, FMT_F32, 2 * d, nullptr, 0, ACT_NONE);
+    cx.gemm(hs_s, FMT_SPLIT, d, Mh, p->x_q, nullptr, 0, 0, 0, qx, FMT_F32, d, ACT_NONE);
+    cx.gemm(memc_s, FMT_SPLIT, d, Mc, p->x_kv, nullptr, 0, 0, 0, kvx, FMT_F32, 2 * d, ACT_NONE);
     cx.attention(qx, d, seqmap(1, LQ, 0, 1), kvx, kvx + d, 2 * d, seqmap(1, Nc, 0, 1), att, d, seqmap(1, LQ, 0, 1), nullptr, B,
                  CLS_HEADS, LQ, Nc, d / CLS_HEADS);
-    cx.gemm(att, FMT_SPLIT, d, Mh, p->x_out, nullptr, 0, 0, 0, oc, FMT_SPLIT, d, nullptr, 0, ACT_NONE);
-    cx.gemm(oc, FMT_SPLIT, d, Mh, p->class_fc, nullptr, 0, 0, 0, logits, FMT_F32, c.num_classes, nullptr, 0, ACT_NONE);
+    cx.gemm(att, FMT_SPLIT, d, Mh, p->x_out, nullptr, 0, 0, 0, oc, FMT_SPLIT, d, ACT_NONE);
+    cx.gemm(oc, FMT_SPLIT, d, Mh, p->class_fc, nullptr, 0, 0, 0, logits, FMT_F32, c.num_classes, ACT_NONE);
   }
   cx.stage_mark(TUBER_NUM_STAGES);
   return cx.status;
@@ -1231,7 +1223,7 @@ int tuber_op_stem(const float* x, const float* w441x64, const float* scale, cons
 int tuber_op_layernorm(const float* x, const float* res, const float* gamma, const float* beta, float* out, int64_t rows, int32_t C,
                        void* stream) {
   LnArgs a{};
-  a.x = x; a.ldx = C; a.res = res; a.res_fmt = FMT_F32; a.ldr = C; a.gamma = gamma; a.beta = beta; a.eps = LN_EPS;
+  a.x = x; a.x_fmt = FMT_F32; a.ldx = C; a.res = res; a.res_fmt = FMT_F32; a.ldr = C; a.gamma = gamma; a.beta = beta; a.eps = LN_EPS;
   a.rows = (int)rows; a.C = C; a.out_f32 = out; a.ldo = C;
   CK(launch_layernorm(a, (cudaStream_t)stream));
   return TUBER_OK;
