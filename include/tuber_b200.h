@@ -157,8 +157,9 @@ int tuber_op_sgemm(const float* a_dev, const float* w_dev, const float* bias_dev
 int tuber_op_dwconv(const float* in_dev, const float* w27c_dev, const float* scale_dev, const float* shift_dev,
                     void* out_split_dev, int32_t B, int32_t Ti, int32_t Hi, int32_t Wi, int32_t C, int32_t stride_t,
                     int32_t stride_s, void* stream);
-/* stem conv + scale/shift + ReLU (fp32 NDHWC out) and the (1,3,3) max pool (split out) */
-int tuber_op_stem(const float* x_ncdhw_dev, const float* w441x64_dev, const float* scale_dev, const float* shift_dev,
+/* stem conv + scale/shift + ReLU (fp32 NDHWC out) and the (1,3,3) max pool (split out); w = the reference's
+ * conv1.weight (64,3,3,7,7) fp32 on the device.  Synchronises the stream. */
+int tuber_op_stem(const float* x_ncdhw_dev, const float* w_oc441_dev, const float* scale_dev, const float* shift_dev,
                   float* conv_out_dev, void* pooled_split_dev, int32_t B, int32_t T, int32_t H, int32_t W, void* stream);
 /* LayerNorm(x + res) over C in {256, 2048} */
 int tuber_op_layernorm(const float* x_dev, const float* res_dev, const float* gamma_dev, const float* beta_dev,

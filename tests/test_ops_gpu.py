@@ -91,7 +91,7 @@ def test_dwconv(abi, c, st_t, st_s, dims):
     assert _rel(got, ref) < 3e-5
 
 
-@pytest.mark.parametrize("dims", [(1, 4, 32, 32), (2, 3, 45, 70)])
+@pytest.mark.parametrize("dims", [(1, 4, 32, 32), (2, 3, 45, 70), (1, 2, 64, 300), (1, 3, 130, 256)])
 def test_stem(abi, dims):
     from tuber_b200 import _lib
     b, t, h, w = dims
@@ -102,12 +102,12 @@ def test_stem(abi, dims):
     ref = torch.relu(ref * scale.double()[None, :, None, None, None] + shift.double()[None, :, None, None, None])
     refp = F.max_pool3d(ref, (1, 3, 3), (1, 2, 2), (0, 1, 1))
     h1, w1, h2, w2 = ref.shape[3], ref.shape[4], refp.shape[3], refp.shape[4]
-    wpk = wt.reshape(64, 441).t().contiguous()
+    wpk = wt.reshape(64, 441).contiguous()
     conv = torch.empty((b, t, h1, w1, 64), device="cuda")
     pooled = torch.empty((b * t * h2 * w2, 64), device="cuda")
     _lib.check(_lib.load().tuber_op_stem(abi.P(x), abi.P(wpk), abi.P(scale), abi.P(shift), abi.P(conv), abi.P(pooled), b, t, h, w,
                                          abi.stream()))
-    assert _rel(conv.permute(0, 4, 1, 2, 3), ref) < 1e-5
+    assert _rel(conv.permute(0, 4, 1, 2, 3), ref) < 3e-5
     got = abi.from_split(pooled, b * t * h2 * w2, 64).view(b, t, h2, w2, 64).permute(0, 4, 1, 2, 3)
     assert _rel(got, refp) < 3e-5
 

@@ -63,6 +63,13 @@ struct Params {
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 TB_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one lane of the (converged) warp; keeps the surrounding control flow warp-uniform so that descriptors and
+// addresses stay in uniform registers instead of being moved there (R2UR) before every tcgen05.mma
+TB_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 
 TB_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -227,37 +234,39 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(as), aphase ^ 1);          // epilogue has drained this accumulator
+    // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
+    constexpr uint32_t idesc = make_idesc(BM, BN);
+    const uint64_t desc0 = make_smem_desc(smem_base);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(as), aphase ^ 1);            // epilogue has drained this accumulator
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint64_t a_hi = make_smem_desc(sa), a_mid = make_smem_desc(sa + A_PLANE_BYTES);
-          const uint64_t w_hi = make_smem_desc(sa + 2 * A_PLANE_BYTES);
-          const uint64_t w_mid = make_smem_desc(sa + 2 * A_PLANE_BYTES + C::W_PLANE_BYTES);
+        if (elect_one()) {
+          // descriptor address field is in 16-byte units
+          const uint64_t a_hi = desc0 + (uint64_t)(stage * (C::STAGE_BYTES >> 4)), a_mid = a_hi + (A_PLANE_BYTES >> 4);
+          const uint64_t w_hi = a_hi + ((2 * A_PLANE_BYTES) >> 4), w_mid = w_hi + (C::W_PLANE_BYTES >> 4);
+          const uint32_t first = kb == 0 ? 0u : 1u;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {            // +32 bytes per K=16 step: +2 in the >>4 address field
-            umma_bf16(tmem_d, a_mid + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < BK / 16; ++k)              // +32 bytes per K=16 step: +2 in the >>4 address field
+            umma_bf16(tmem_d, a_mid + 2 * k, w_hi + 2 * k, idesc, k == 0 ? first : 1u);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, a_hi + 2 * k, w_mid + 2 * k, idesc, 1);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, a_hi + 2 * k, w_hi + 2 * k, idesc, 1);
           umma_commit(empty_bar(stage));                 // smem stage reusable once these MMAs retire
           if (kb == kblocks - 1) umma_commit(tfull_bar(as));
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 2) {

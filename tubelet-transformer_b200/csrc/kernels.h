@@ -8,10 +8,11 @@
 
 #include "common.cuh"
 
-// ---- stem (ir_CSN_152.py:109-122,176-179) ------------------------------------------------
-// x NCDHW fp32 (B,3,T,H,W); wpk [441][64] (k = ((c*3+kt)*7+kh)*7+kw, oc fastest);
-// y NDHWC fp32 [B,T,H1,W1,64] = relu(conv*scale+shift)
-cudaError_t launch_stem_conv(const float* x, const float* wpk, const float* scale, const float* shift,
+// ---- stem (ir_CSN_152.py:109-122,176-179), stem_tc.cu --------------------------------------
+// filter (64,3,3,7,7) fp32 = [oc][441] -> packed split bf16 [2][64][576] in the kernel's K order
+cudaError_t launch_stem_pack_weight(const float* w_oc441, void* out, cudaStream_t st);
+// x NCDHW fp32 (B,3,T,H,W); wpk from launch_stem_pack_weight; y NDHWC fp32 [B,T,H1,W1,64] = relu(conv*scale+shift)
+cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale, const float* shift,
                              float* y, int B, int T, int H, int W, int H1, int W1, cudaStream_t st);
 // (1,3,3)/s(1,2,2)/p(0,1,1) max pool, fp32 [BT,H1,W1,C] -> split [BT,H2,W2,C]
 cudaError_t launch_maxpool_hw(const float* in, void* out_split, int BT, int H1, int W1, int H2, int W2,

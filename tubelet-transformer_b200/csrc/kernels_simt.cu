@@ -1,4 +1,4 @@
-// CUDA-core kernels of the TubeR forward path (sm_100a): stem convolution, max pool,
+// CUDA-core kernels of the TubeR forward path (sm_100a): stem max pool,
 // depthwise 3x3x3 stencil, strided gathers, temporal pooling, fp32 GEMM for the token-sized
 // linear layers, LayerNorm, attention cores, padding-mask resize and the 3-D sine position code.
 // The tensor-core GEMM lives in gemm_tc.cu.  All activations are channels-last (NDHWC).
@@ -6,105 +6,6 @@
 #include <math.h>
 
 #include "kernels.h"
-
-// =============================================================================================
-// Stem: Conv3d(3->64,(3,7,7),s(1,2,2),p(1,3,3)) + BN + ReLU     (ir_CSN_152.py:109-120,176-178)
-// One CTA = an 8x32 tile of conv outputs of one frame, all 64 channels.  The whole filter bank
-// (441x64 fp32 = 110 KB) and the 3-frame input patch live in shared memory; a thread keeps
-// 8 output columns x 4 channels in registers and slides the 7-tap window over a 21-wide row.
-// =============================================================================================
-namespace stem {
-constexpr int TH = 8, TW = 32, KVOL = 441, OC = 64;
-constexpr int PH = 2 * TH + 5, PW = 72;   // patch rows 21, cols 69 padded to 72
-constexpr int SMEM_BYTES = (KVOL * OC + 9 * PH * PW) * 4;
-}  // namespace stem
-
-__global__ void __launch_bounds__(512, 1)
-stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ wpk, const float* __restrict__ scale,
-                 const float* __restrict__ shift, float* __restrict__ y, int B, int T, int H, int W, int H1,
-                 int W1) {
-  using namespace stem;
-  extern __shared__ __align__(16) float smem[];
-  float* wsm = smem;                 // [441][64]
-  float* ism = smem + KVOL * OC;     // [9][PH][PW]
-  const int tid = threadIdx.x;
-  const int bt = blockIdx.z, b = bt / T, t = bt % T;
-  const int oh0 = blockIdx.y * TH, ow0 = blockIdx.x * TW;
-
-  for (int i = tid; i < KVOL * OC / 4; i += 512)
-    reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(wpk) + i);
-  const int ih0 = 2 * oh0 - 3, iw0 = 2 * ow0 - 3;
-  for (int i = tid; i < 9 * PH * PW; i += 512) {
-    int q = i % PW, r = (i / PW) % PH, ck = i / (PW * PH);
-    int c = ck / 3, kt = ck % 3;
-    int it = t + kt - 1, ih = ih0 + r, iw = iw0 + q;
-    float v = 0.f;
-    if (it >= 0 && it < T && ih >= 0 && ih < H && iw >= 0 && iw < W)
-      v = __ldg(x + ((((long long)b * 3 + c) * T + it) * H + ih) * W + iw);
-    ism[i] = v;
-  }
-  __syncthreads();
-
-  const int chg = tid & 15, seg = (tid >> 4) & 3, row = tid >> 6;
-  float acc[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-
-  for (int ck = 0; ck < 9; ++ck) {
-#pragma unroll 1
-    for (int kh = 0; kh < 7; ++kh) {
-      const float* irow = ism + (ck * PH + 2 * row + kh) * PW + 16 * seg;
-      float in[24];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        float4 v4 = reinterpret_cast<const float4*>(irow)[i];
-        in[4 * i] = v4.x; in[4 * i + 1] = v4.y; in[4 * i + 2] = v4.z; in[4 * i + 3] = v4.w;
-      }
-      const float* wrow = wsm + ((ck * 7 + kh) * 7) * OC + chg * 4;
-#pragma unroll
-      for (int kw = 0; kw < 7; ++kw) {
-        float4 w4 = *reinterpret_cast<const float4*>(wrow + kw * OC);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float a = in[2 * j + kw];
-          acc[j][0] = fmaf(a, w4.x, acc[j][0]);
-          acc[j][1] = fmaf(a, w4.y, acc[j][1]);
-          acc[j][2] = fmaf(a, w4.z, acc[j][2]);
-          acc[j][3] = fmaf(a, w4.w, acc[j][3]);
-        }
-      }
-    }
-  }
-  const int oh = oh0 + row;
-  if (oh >= H1) return;
-  float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + chg);
-  float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + chg);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    int ow = ow0 + seg * 8 + j;
-    if (ow >= W1) continue;
-    float4 o;
-    o.x = fmaxf(fmaf(acc[j][0], sc.x, sh.x), 0.f);
-    o.y = fmaxf(fmaf(acc[j][1], sc.y, sh.y), 0.f);
-    o.z = fmaxf(fmaf(acc[j][2], sc.z, sh.z), 0.f);
-    o.w = fmaxf(fmaf(acc[j][3], sc.w, sh.w), 0.f);
-    reinterpret_cast<float4*>(y + (((long long)bt * H1 + oh) * W1 + ow) * OC)[chg] = o;
-  }
-}
-
-cudaError_t launch_stem_conv(const float* x, const float* wpk, const float* scale, const float* shift, float* y,
-                             int B, int T, int H, int W, int H1, int W1, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         stem::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  dim3 grid(ceil_div(W1, stem::TW), ceil_div(H1, stem::TH), B * T);
-  stem_conv_kernel<<<grid, 512, stem::SMEM_BYTES, st>>>(x, wpk, scale, shift, y, B, T, H, W, H1, W1);
-  return cudaGetLastError();
-}
 
 // MaxPool3d((1,3,3),s(1,2,2),p(0,1,1))  (ir_CSN_152.py:122,179): fp32 -> split
 __global__ void maxpool_hw_kernel(const float* __restrict__ in, void* __restrict__ out, int BT, int H1, int W1,

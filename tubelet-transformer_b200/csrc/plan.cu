@@ -105,7 +105,7 @@ struct TuberPlan {
   std::vector<void*> owned;          // device allocations of packed weights
 
   // packed model
-  float* stem_w = nullptr; float* stem_scale = nullptr; float* stem_shift = nullptr;
+  void* stem_w = nullptr; float* stem_scale = nullptr; float* stem_shift = nullptr;
   std::vector<Block> blocks[4];
   // decode pool (input-independent parts folded at finalize)
   float* pool_tgt1 = nullptr;        // [2048] LN1(query_pool + self_attn(query_pool))
@@ -288,15 +288,17 @@ int do_finalize(TuberPlan* p) {
   const int d = c.d_model, ff = c.dim_ff, Q = c.num_queries;
   const std::string bb = "backbone.body";
 
-  // ---- stem (ir_CSN_152.py:109-120): weight (64,3,3,7,7) -> [441][64] ----
+  // ---- stem (ir_CSN_152.py:109-120): filter (64,3,3,7,7) -> packed split bf16 [2][64][576] ----
   {
     const HostTensor* w = pk.get(bb + ".conv1.weight", {64, 441});
     std::vector<float> sc, sh;
     if (w && pk.bn(bb + ".bn1", 64, sc, sh)) {
-      std::vector<float> t((size_t)441 * 64);
-      for (int oc = 0; oc < 64; ++oc)
-        for (int k = 0; k < 441; ++k) t[(size_t)k * 64 + oc] = w->data[(size_t)oc * 441 + k];
-      p->stem_w = pk.upload(t);
+      float* wf = pk.upload(w->data);
+      void* wp = nullptr;
+      if (cudaMalloc(&wp, 2 * 64 * 576 * 2) != cudaSuccess) return fail(TUBER_ERR_CUDA, "cudaMalloc failed");
+      p->owned.push_back(wp);
+      if (wf) launch_stem_pack_weight(wf, wp, 0);
+      p->stem_w = wp;
       p->stem_scale = pk.upload(sc);
       p->stem_shift = pk.upload(sh);
     }
@@ -1213,11 +1215,18 @@ int tuber_op_dwconv(const float* in, const float* w27c, const float* scale, cons
   CK(launch_dwconv(in, w27c, scale, shift, out_split, B, Ti, Hi, Wi, C, stride_t, stride_s, To, Ho, Wo, (cudaStream_t)stream));
   return TUBER_OK;
 }
-int tuber_op_stem(const float* x, const float* w441x64, const float* scale, const float* shift, float* conv_out, void* pooled_split,
+int tuber_op_stem(const float* x, const float* w_oc441, const float* scale, const float* shift, float* conv_out, void* pooled_split,
                   int32_t B, int32_t T, int32_t H, int32_t W, void* stream) {
   const int H1 = (H - 1) / 2 + 1, W1 = (W - 1) / 2 + 1, H2 = (H1 - 1) / 2 + 1, W2 = (W1 - 1) / 2 + 1;
-  CK(launch_stem_conv(x, w441x64, scale, shift, conv_out, B, T, H, W, H1, W1, (cudaStream_t)stream));
-  if (pooled_split) CK(launch_maxpool_hw(conv_out, pooled_split, B * T, H1, W1, H2, W2, 64, (cudaStream_t)stream));
+  cudaStream_t st = (cudaStream_t)stream;
+  void* wp = nullptr;
+  CK(cudaMalloc(&wp, 2 * 64 * 576 * 2));
+  cudaError_t e = launch_stem_pack_weight(w_oc441, wp, st);
+  if (e == cudaSuccess) e = launch_stem_conv(x, wp, scale, shift, conv_out, B, T, H, W, H1, W1, st);
+  if (e == cudaSuccess && pooled_split) e = launch_maxpool_hw(conv_out, pooled_split, B * T, H1, W1, H2, W2, 64, st);
+  cudaStreamSynchronize(st);
+  cudaFree(wp);
+  CK(e);
   return TUBER_OK;
 }
 int tuber_op_layernorm(const float* x, const float* res, const float* gamma, const float* beta, float* out, int64_t rows, int32_t C,

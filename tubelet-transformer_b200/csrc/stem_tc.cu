@@ -1,0 +1,481 @@
+// Stem convolution on the tensor cores (sm_100a): Conv3d(3->64,(3,7,7),s(1,2,2),p(1,3,3)) + BN + ReLU
+// (reference models/backbones/ir_CSN_152.py:109-120,176-178) as an implicit GEMM with tcgen05.
+//
+//   out[pos, oc] = relu(scale[oc] * sum_k patch[pos, k] * w[oc, k] + shift[oc])
+//
+// GEMM view per tile: M = 128 consecutive output columns of one output row (b, t, oh), N = 32 output
+// channels (a CTA owns one half of the 64 channels so that its packed filter bank, 64 KB, stays resident
+// in shared memory), K = 576 = 9 k-blocks x 8 groups x 8: k-block = input plane (c, kt), group = filter row kh
+// (group 7 is all zero), and a group holds the 7 taps kw = 0..6 of that filter row plus one zero tap.  The patch
+// row of a group is simply 8 consecutive pixels in[c, t+kt-1, 2*oh+kh-3, 2*ow-3 .. 2*ow+4], so the A operand is
+// built by threads from a ring of input rows kept in shared memory:
+//
+//   ring      [9 (c,kt) planes][8 row slots][264 pixels], each pixel pre-split into (bf16 hi | bf16 mid << 16);
+//             a new output row needs only two new input rows per plane (slot = input row & 7).
+//   builders  8 warps: stage the ring (global fp32 -> split, zero padding applied here), then for each of the
+//             9 k-blocks write the 128 x 64 hi and mid A tiles (K-major, 128B swizzle) with 16-byte stores.
+//   MMA       1 thread: three bf16 passes (mid*hi + hi*mid + hi*hi) of tcgen05.mma M=128, N=32, K=16 into six
+//             independent fp32 TMEM accumulators (pass x K-step parity; an N=32 MMA is latency- not
+//             throughput-bound, so dependent accumulation chains are kept short), double buffered per tile.
+//   epilogue  4 warps: tcgen05.ld, BN scale/shift + ReLU, 128B-swizzled panel in shared memory, TMA store
+//             into the channels-last fp32 output [B*T*H1, W1, 64].
+#include <cuda.h>
+#include <stdio.h>
+
+#include "kernels.h"
+
+namespace stemtc {
+
+constexpr int KB = 9;                       // k-blocks of 64 = input planes (c, kt)
+constexpr int KTOT = KB * 64;
+constexpr int NCH = 32;                     // output channels per CTA
+constexpr int A_PLANE = 128 * 128;          // 16 KB: 128 rows x 64 bf16
+constexpr int A_STAGE = 2 * A_PLANE;        // hi + mid
+constexpr int A_STAGES = 2;
+constexpr int W_KB_BYTES = 2 * NCH * 128;   // 8 KB per k-block (hi 4 KB + mid 4 KB)
+constexpr int W_BYTES = KB * W_KB_BYTES;    // 72 KB
+constexpr int RING_PX = 264;
+constexpr int RING_BYTES = 9 * 8 * RING_PX * 4;   // 76032
+constexpr int OUT_BYTES = 128 * 128;        // 128 positions x 32 fp32
+constexpr int OFF_W = 0;
+constexpr int OFF_A = OFF_W + W_BYTES;
+constexpr int OFF_OUT = OFF_A + A_STAGES * A_STAGE;
+constexpr int OFF_RING = OFF_OUT + OUT_BYTES;
+constexpr int OFF_BAR = OFF_RING + ((RING_BYTES + 127) / 128) * 128;
+constexpr int OFF_SS = OFF_BAR + 128;              // scale[32], shift[32] of this CTA's channels
+constexpr int SMEM_BYTES = OFF_SS + 256;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+constexpr int NUM_THREADS = 416;            // warp 0 MMA, warps 1-4 epilogue, warps 5-12 builders
+constexpr int NBUILD = 256;
+constexpr int NACC = 6;                     // independent TMEM accumulators per tile (3 passes x K-step parity): short MMA dependency chains
+constexpr int TMEM_COLS = 512;              // 2 tile buffers x NACC x 32 columns = 384 -> next power of two
+constexpr int ROWS_PER_UNIT = 16;
+
+struct Params {
+  const float* x;                           // (B,3,T,H,W) fp32
+  const float* scale; const float* shift;   // [64]
+  int B, T, H, W, H1, W1;
+};
+
+TB_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one lane of the (converged) warp; keeps the surrounding control flow warp-uniform so that descriptors and
+// addresses stay in uniform registers instead of being moved there (R2UR) before every tcgen05.mma
+TB_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+TB_DEVINL void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+TB_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+TB_DEVINL void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+TB_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+TB_DEVINL void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+TB_DEVINL void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+TB_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+TB_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+TB_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+TB_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+TB_DEVINL void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+TB_DEVINL void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+TB_DEVINL void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+TB_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+TB_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+TB_DEVINL void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+TB_DEVINL uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+TB_DEVINL void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// K-major, 128B-swizzle shared-memory matrix descriptor (same encoding as gemm_tc.cu)
+TB_DEVINL uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+TB_DEVINL uint32_t swz(uint32_t base, int r, int j) { return base + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4); }
+
+// pixel -> (bf16 hi) | (bf16 mid) << 16
+TB_DEVINL uint32_t split_pack(float v) {
+  __nv_bfloat16 hi, mid;
+  split_bf16(v, hi, mid);
+  return pack_bf16x2(hi, mid);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bar = sb + OFF_BAR;
+  auto full_bar = [&](int s) { return bar + 8u * s; };            // A stage written by the builders
+  auto empty_bar = [&](int s) { return bar + 8u * (2 + s); };     // A stage consumed by the MMAs
+  auto tfull_bar = [&](int s) { return bar + 8u * (4 + s); };
+  auto tempty_bar = [&](int s) { return bar + 8u * (6 + s); };
+  const uint32_t w_bar = bar + 64;
+  const uint32_t tmem_slot = bar + 72;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = blockIdx.x & 1;                                 // which 32 output channels
+  const int owb_n = (p.W1 + 127) / 128;
+  const int rb_n = (p.H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+  const int units = p.B * p.T * owb_n * rb_n;
+  const int cta = blockIdx.x >> 1, ncta = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    if (sb & 1023u) __trap();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full_bar(s), NBUILD / 32);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= filter bank load + MMA issuer (whole warp, one elected lane issues) =================
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, W_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_3d(sb + OFF_W + kb * W_KB_BYTES, &tmW, w_bar, kb * 64, half * NCH, 0);
+    }
+    __syncwarp();
+    mbar_wait(w_bar, 0);
+    constexpr uint32_t idesc = make_idesc(128, NCH);
+    const uint64_t a_desc0 = make_smem_desc(sb + OFF_A), w_desc0 = make_smem_desc(sb + OFF_W);
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    for (int u = cta; u < units; u += ncta) {
+      const int rb = u % rb_n;
+      const int r0 = rb * ROWS_PER_UNIT, r1 = min(p.H1, r0 + ROWS_PER_UNIT);
+      for (int oh = r0; oh < r1; ++oh, ++it) {
+        const int as = it & 1;
+        mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * NACC * NCH);
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            // descriptor address field is in 16-byte units: stage stride 32 KB = 2048, plane 16 KB = 1024, K=16 step = 2
+            const uint64_t a_hi = a_desc0 + (uint64_t)(stage * (A_STAGE >> 4)), a_mid = a_hi + (A_PLANE >> 4);
+            const uint64_t w_hi = w_desc0 + (uint64_t)(kb * (W_KB_BYTES >> 4)), w_mid = w_hi + ((NCH * 128) >> 4);
+            const uint32_t first = kb == 0 ? 0u : 1u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                      // consecutive MMAs go to different accumulators
+              const uint32_t acc = k < 2 ? first : 1u;
+              umma_bf16(tmem_d + (uint32_t)((0 + (k & 1)) * NCH), a_mid + 2 * k, w_hi + 2 * k, idesc, acc);
+              umma_bf16(tmem_d + (uint32_t)((2 + (k & 1)) * NCH), a_hi + 2 * k, w_mid + 2 * k, idesc, acc);
+              umma_bf16(tmem_d + (uint32_t)((4 + (k & 1)) * NCH), a_hi + 2 * k, w_hi + 2 * k, idesc, acc);
+            }
+            umma_commit(empty_bar(stage));
+            if (kb == KB - 1) umma_commit(tfull_bar(as));
+          }
+          __syncwarp();
+          if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp <= 4) {
+    // ================= epilogue =================
+    const int lg = warp & 3;
+    const int m = lg * 32 + lane;                                  // output column inside the tile
+    const int et = threadIdx.x - 32;
+    float* s_sc = reinterpret_cast<float*>(smem + OFF_SS);
+    float* s_sh = s_sc + NCH;
+    if (et < NCH) {
+      s_sc[et] = __ldg(p.scale + half * NCH + et);
+      s_sh[et] = __ldg(p.shift + half * NCH + et);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    int it = 0;
+    for (int u = cta; u < units; u += ncta) {
+      const int rb = u % rb_n, owb = (u / rb_n) % owb_n, bt = u / (rb_n * owb_n);
+      const int r0 = rb * ROWS_PER_UNIT, r1 = min(p.H1, r0 + ROWS_PER_UNIT);
+      for (int oh = r0; oh < r1; ++oh, ++it) {
+        const int as = it & 1;
+        mbar_wait(tfull_bar(as), (it >> 1) & 1);
+        tcgen05_fence_after();
+        float acc[32];
+        {
+          const uint32_t t0 = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * NACC * NCH);
+          uint32_t part[32];
+          tmem_ld32(t0, part);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(part[q]);
+#pragma unroll 1
+          for (int a = 1; a < NACC; ++a) {                         // small terms first would be ideal; fp32 adds of 6 partials
+            tmem_ld32(t0 + (uint32_t)(a * NCH), part);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(part[q]);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (et == 0) bulk_wait_read0();                            // previous store has finished reading the panel
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_sc + 4 * q), sh = *reinterpret_cast<const float4*>(s_sh + 4 * q);
+          uint4 o;
+          o.x = __float_as_uint(fmaxf(fmaf(acc[4 * q], sc.x, sh.x), 0.f));
+          o.y = __float_as_uint(fmaxf(fmaf(acc[4 * q + 1], sc.y, sh.y), 0.f));
+          o.z = __float_as_uint(fmaxf(fmaf(acc[4 * q + 2], sc.z, sh.z), 0.f));
+          o.w = __float_as_uint(fmaxf(fmaf(acc[4 * q + 3], sc.w, sh.w), 0.f));
+          sts128(swz(sb + OFF_OUT, m, q), o);
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          tma_store_3d(&tmOut, sb + OFF_OUT, half * NCH, owb * 128, bt * p.H1 + oh);
+          bulk_commit();
+        }
+      }
+    }
+    if (et == 0) bulk_wait_all();
+  } else {
+    // ================= ring staging + A-tile builders =================
+    const int bt_ = threadIdx.x - 160;                             // 0..255 = ring pixel this thread stages
+    const int m = bt_ & 127, gh = bt_ >> 7;                        // tile row, which 4 of the 8 groups of a k-block
+    const uint32_t ring = sb + OFF_RING;
+    const int xr = bt_ >> 3, xj = 256 + (bt_ & 7);                 // the 8 extra pixels (256..263) of row xr
+    for (int i = bt_; i < RING_BYTES / 4; i += NBUILD) sts32(ring + 4u * i, 0u);   // never feed stale NaN bits to the MMA
+    uint32_t dst[4];                                               // swizzled chunk offsets of this thread's groups
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) dst[jj] = (uint32_t)m * 128u + (uint32_t)(((gh * 4 + jj) ^ (m & 7)) << 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = cta; u < units; u += ncta) {
+      const int rb = u % rb_n, owb = (u / rb_n) % owb_n, bt = u / (rb_n * owb_n);
+      const int b = bt / p.T, t = bt % p.T;
+      const int r0 = rb * ROWS_PER_UNIT, r1 = min(p.H1, r0 + ROWS_PER_UNIT);
+      const int iw0 = 2 * owb * 128 - 3;
+      const bool ok_a = iw0 + bt_ >= 0 && iw0 + bt_ < p.W, ok_x = iw0 + xj < p.W;
+      // ring pixel (plane, ih, j) <- x[b, c, t+kt-1, ih, iw0+j], 0 outside the clip (the conv's zero padding)
+      auto row_ptr = [&](int plane, int ih) -> const float* {
+        const int c = plane / 3, f = t + plane % 3 - 1;
+        if (f < 0 || f >= p.T || ih < 0 || ih >= p.H) return nullptr;
+        return p.x + ((((long long)b * 3 + c) * p.T + f) * p.H + ih) * (long long)p.W + iw0;
+      };
+      asm volatile("bar.sync 2, 256;" ::: "memory");               // previous unit's readers are done
+      for (int plane = 0; plane < 9; ++plane) {                    // rows 2*r0-3 .. 2*r0+3 of every plane
+        float v[7];
+#pragma unroll
+        for (int rr = 0; rr < 7; ++rr) {
+          const float* rp = row_ptr(plane, 2 * r0 - 3 + rr);
+          v[rr] = (rp && ok_a) ? __ldg(rp + bt_) : 0.f;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 7; ++rr)
+          sts32(ring + (uint32_t)(((plane * 8 + ((2 * r0 - 3 + rr) & 7)) * RING_PX + bt_) * 4), split_pack(v[rr]));
+      }
+      for (int i = bt_; i < 63 * 8; i += NBUILD) {
+        const int plane = (i >> 3) / 7, rr = (i >> 3) % 7, j = 256 + (i & 7), ih = 2 * r0 - 3 + rr;
+        const float* rp = row_ptr(plane, ih);
+        const float v = (rp && iw0 + j < p.W) ? __ldg(rp + j) : 0.f;
+        sts32(ring + (uint32_t)(((plane * 8 + (ih & 7)) * RING_PX + j) * 4), split_pack(v));
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      for (int oh = r0; oh < r1; ++oh) {
+        // prefetch the two input rows the next output row adds (ih = 2*oh+4, 2*oh+5) into registers
+        float pf[18], pfx = 0.f;
+        const bool more = oh + 1 < r1;
+        if (more) {
+#pragma unroll
+          for (int q = 0; q < 18; ++q) {
+            const float* rp = row_ptr(q >> 1, 2 * oh + 4 + (q & 1));
+            pf[q] = (rp && ok_a) ? __ldg(rp + bt_) : 0.f;
+          }
+          if (xr < 18) {
+            const float* rp = row_ptr(xr >> 1, 2 * oh + 4 + (xr & 1));
+            pfx = (rp && ok_x) ? __ldg(rp + xj) : 0.f;
+          }
+        }
+        const uint32_t src0 = ring + (uint32_t)(2 * m * 4);
+        uint32_t slot_off[4];                                      // ring row of filter row kh = 4*gh + jj (kh = 7: zero weights)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) slot_off[jj] = (uint32_t)(((2 * oh - 3 + gh * 4 + jj) & 7) * RING_PX * 4);
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = sb + OFF_A + stage * A_STAGE;
+          const uint32_t srck = src0 + (uint32_t)(kb * 8 * RING_PX * 4);
+          uint2 w[4][4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[jj][e] = lds64(srck + slot_off[jj] + 8u * e);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            uint4 hi, mid;
+            hi.x = __byte_perm(w[jj][0].x, w[jj][0].y, 0x5410); mid.x = __byte_perm(w[jj][0].x, w[jj][0].y, 0x7632);
+            hi.y = __byte_perm(w[jj][1].x, w[jj][1].y, 0x5410); mid.y = __byte_perm(w[jj][1].x, w[jj][1].y, 0x7632);
+            hi.z = __byte_perm(w[jj][2].x, w[jj][2].y, 0x5410); mid.z = __byte_perm(w[jj][2].x, w[jj][2].y, 0x7632);
+            hi.w = __byte_perm(w[jj][3].x, w[jj][3].y, 0x5410); mid.w = __byte_perm(w[jj][3].x, w[jj][3].y, 0x7632);
+            sts128(sa + dst[jj], hi);
+            sts128(sa + A_PLANE + dst[jj], mid);
+          }
+          fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar(stage));
+          if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");             // every builder has finished reading this row's window
+        if (more) {
+#pragma unroll
+          for (int q = 0; q < 18; ++q) {
+            const int ih = 2 * oh + 4 + (q & 1);
+            sts32(ring + (uint32_t)((((q >> 1) * 8 + (ih & 7)) * RING_PX + bt_) * 4), split_pack(pf[q]));
+          }
+          if (xr < 18) {
+            const int ih = 2 * oh + 4 + (xr & 1);
+            sts32(ring + (uint32_t)((((xr >> 1) * 8 + (ih & 7)) * RING_PX + xj) * 4), split_pack(pfx));
+          }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// reference filter (64,3,3,7,7) = [oc][441] fp32 -> packed split [2][64][576] bf16 in the kernel's K order
+__global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * KTOT) return;
+  const int oc = i / KTOT, k = i % KTOT, plane = k / 64, kh = (k % 64) / 8, kw = k % 8;
+  const float v = (kh < 7 && kw < 7) ? w[oc * 441 + (plane * 7 + kh) * 7 + kw] : 0.f;
+  __nv_bfloat16 hi, mid;
+  split_bf16(v, hi, mid);
+  out[i] = hi;
+  out[64 * KTOT + i] = mid;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 0;
+
+static cudaError_t init_once() {
+  if (g_encode) return cudaSuccess;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) return e != cudaSuccess ? e : cudaErrorNotSupported;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return cudaSuccess;
+}
+
+}  // namespace stemtc
+
+cudaError_t launch_stem_pack_weight(const float* w_oc441, void* out, cudaStream_t st) {
+  stemtc::stem_pack_weight_kernel<<<(64 * stemtc::KTOT + 255) / 256, 256, 0, st>>>(w_oc441, reinterpret_cast<__nv_bfloat16*>(out));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale, const float* shift, float* y, int B, int T, int H,
+                             int W, int H1, int W1, cudaStream_t st) {
+  using namespace stemtc;
+  cudaError_t e = init_once();
+  if (e != cudaSuccess) return e;
+  CUtensorMap tmW, tmOut;
+  {
+    cuuint64_t dims[3] = {KTOT, 64, 2};
+    cuuint64_t strides[2] = {KTOT * 2, 64 * KTOT * 2};
+    cuuint32_t box[3] = {64, NCH, 2}, es[3] = {1, 1, 1};
+    if (g_encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpk), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  {
+    cuuint64_t dims[3] = {64, (cuuint64_t)W1, (cuuint64_t)B * T * H1};
+    cuuint64_t strides[2] = {64 * 4, (cuuint64_t)W1 * 64 * 4};
+    cuuint32_t box[3] = {NCH, 128, 1}, es[3] = {1, 1, 1};
+    if (g_encode(&tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  Params p{x, scale, shift, B, T, H, W, H1, W1};
+  const int units = B * T * ((W1 + 127) / 128) * ((H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT);
+  int pairs = g_num_sms / 2;
+  if (pairs > units) pairs = units;
+  if (pairs < 1) pairs = 1;
+  stem_tc_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmOut, p);
+  return cudaGetLastError();
+}
