@@ -13,10 +13,11 @@
 //   ring      [9 (c,kt) planes][8 row slots][264 pixels], each pixel pre-split into (bf16 hi | bf16 mid << 16);
 //             a new output row needs only two new input rows per plane (slot = input row & 7).
 //   builders  8 warps: stage the ring (global fp32 -> split, zero padding applied here), then for each of the
-//             9 k-blocks write the 128 x 64 hi and mid A tiles (K-major, 128B swizzle) with 16-byte stores.
-//   MMA       1 thread: three bf16 passes (mid*hi + hi*mid + hi*hi) of tcgen05.mma M=128, N=32, K=16 into six
-//             independent fp32 TMEM accumulators (pass x K-step parity; an N=32 MMA is latency- not
-//             throughput-bound, so dependent accumulation chains are kept short), double buffered per tile.
+//             9 k-blocks write the 128 x 64 hi and mid A tiles straight into TENSOR MEMORY (tcgen05.st, thread =
+//             row): the A operand never touches shared memory, whose bandwidth is what bounds this kernel.
+//   MMA       1 thread: three bf16 passes (mid*hi + hi*mid + hi*hi) of tcgen05.mma M=128, N=32, K=16 with A from
+//             tensor memory and the filter bank from shared memory, into two fp32 TMEM accumulators (K-step
+//             parity), double buffered per tile.
 //   epilogue  4 warps: tcgen05.ld, BN scale/shift + ReLU, 128B-swizzled panel in shared memory, TMA store
 //             into the channels-last fp32 output [B*T*H1, W1, 64].
 #include <cuda.h>
@@ -29,17 +30,14 @@ namespace stemtc {
 constexpr int KB = 9;                       // k-blocks of 64 = input planes (c, kt)
 constexpr int KTOT = KB * 64;
 constexpr int NCH = 32;                     // output channels per CTA
-constexpr int A_PLANE = 128 * 128;          // 16 KB: 128 rows x 64 bf16
-constexpr int A_STAGE = 2 * A_PLANE;        // hi + mid
-constexpr int A_STAGES = 2;
+constexpr int A_STAGES = 4;                 // A k-block stages in TENSOR MEMORY (64 columns each: hi 32 + mid 32)
 constexpr int W_KB_BYTES = 2 * NCH * 128;   // 8 KB per k-block (hi 4 KB + mid 4 KB)
 constexpr int W_BYTES = KB * W_KB_BYTES;    // 72 KB
 constexpr int RING_PX = 264;
 constexpr int RING_BYTES = 9 * 8 * RING_PX * 4;   // 76032
 constexpr int OUT_BYTES = 128 * 128;        // 128 positions x 32 fp32
 constexpr int OFF_W = 0;
-constexpr int OFF_A = OFF_W + W_BYTES;
-constexpr int OFF_OUT = OFF_A + A_STAGES * A_STAGE;
+constexpr int OFF_OUT = OFF_W + W_BYTES;
 constexpr int OFF_RING = OFF_OUT + OUT_BYTES;
 constexpr int OFF_BAR = OFF_RING + ((RING_BYTES + 127) / 128) * 128;
 constexpr int OFF_SS = OFF_BAR + 128;              // scale[32], shift[32] of this CTA's channels
@@ -47,8 +45,9 @@ constexpr int SMEM_BYTES = OFF_SS + 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int NUM_THREADS = 416;            // warp 0 MMA, warps 1-4 epilogue, warps 5-12 builders
 constexpr int NBUILD = 256;
-constexpr int NACC = 6;                     // independent TMEM accumulators per tile (3 passes x K-step parity): short MMA dependency chains
-constexpr int TMEM_COLS = 512;              // 2 tile buffers x NACC x 32 columns = 384 -> next power of two
+constexpr int NACC = 2;                     // independent TMEM accumulators per tile (K-step parity)
+constexpr int A_COL0 = 2 * NACC * NCH;      // TMEM columns: [0, 128) accumulators (2 tile buffers), then the A stages
+constexpr int TMEM_COLS = 512;              // 128 + 4 x 64 = 384 -> next power of two
 constexpr int ROWS_PER_UNIT = 16;
 
 struct Params {
@@ -107,6 +106,25 @@ TB_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: A = 128 lanes (rows) x 8 columns, two bf16 per 32-bit column
+TB_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// thread (lane L of the warp) -> TMEM lane (quadrant base + L), 16 consecutive columns
+TB_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+TB_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 TB_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -157,13 +175,13 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
   const uint32_t bar = sb + OFF_BAR;
-  auto full_bar = [&](int s) { return bar + 8u * s; };            // A stage written by the builders
-  auto empty_bar = [&](int s) { return bar + 8u * (2 + s); };     // A stage consumed by the MMAs
-  auto tfull_bar = [&](int s) { return bar + 8u * (4 + s); };
-  auto tempty_bar = [&](int s) { return bar + 8u * (6 + s); };
-  const uint32_t w_bar = bar + 64;
-  const uint32_t tmem_slot = bar + 72;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 72);
+  auto full_bar = [&](int s) { return bar + 8u * s; };                       // A stage written by the builders
+  auto empty_bar = [&](int s) { return bar + 8u * (A_STAGES + s); };         // A stage consumed by the MMAs
+  auto tfull_bar = [&](int s) { return bar + 8u * (2 * A_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar + 8u * (2 * A_STAGES + 2 + s); };
+  const uint32_t w_bar = bar + 8u * (2 * A_STAGES + 4);
+  const uint32_t tmem_slot = bar + 8u * (2 * A_STAGES + 5);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * A_STAGES + 5));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = blockIdx.x & 1;                                 // which 32 output channels
@@ -176,9 +194,11 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     if (sb & 1023u) __trap();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(full_bar(s), NBUILD / 32);
       mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4);
     }
@@ -203,7 +223,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     __syncwarp();
     mbar_wait(w_bar, 0);
     constexpr uint32_t idesc = make_idesc(128, NCH);
-    const uint64_t a_desc0 = make_smem_desc(sb + OFF_A), w_desc0 = make_smem_desc(sb + OFF_W);
+    const uint64_t w_desc0 = make_smem_desc(sb + OFF_W);
     int stage = 0, it = 0;
     uint32_t phase = 0;
     for (int u = cta; u < units; u += ncta) {
@@ -219,16 +239,15 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           if (elect_one()) {
-            // descriptor address field is in 16-byte units: stage stride 32 KB = 2048, plane 16 KB = 1024, K=16 step = 2
-            const uint64_t a_hi = a_desc0 + (uint64_t)(stage * (A_STAGE >> 4)), a_mid = a_hi + (A_PLANE >> 4);
+            const uint32_t a_hi = tmem_base + (uint32_t)(A_COL0 + stage * 64), a_mid = a_hi + 32;   // 8 columns per K=16 step
             const uint64_t w_hi = w_desc0 + (uint64_t)(kb * (W_KB_BYTES >> 4)), w_mid = w_hi + ((NCH * 128) >> 4);
             const uint32_t first = kb == 0 ? 0u : 1u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {                      // consecutive MMAs go to different accumulators
-              const uint32_t acc = k < 2 ? first : 1u;
-              umma_bf16(tmem_d + (uint32_t)((0 + (k & 1)) * NCH), a_mid + 2 * k, w_hi + 2 * k, idesc, acc);
-              umma_bf16(tmem_d + (uint32_t)((2 + (k & 1)) * NCH), a_hi + 2 * k, w_mid + 2 * k, idesc, acc);
-              umma_bf16(tmem_d + (uint32_t)((4 + (k & 1)) * NCH), a_hi + 2 * k, w_hi + 2 * k, idesc, acc);
+            for (int k = 0; k < 4; ++k) {                      // even / odd K-steps accumulate separately
+              const uint32_t d = tmem_d + (uint32_t)((k & 1) * NCH);
+              umma_bf16_ts(d, a_mid + 8 * k, w_hi + 2 * k, idesc, k < 2 ? first : 1u);
+              umma_bf16_ts(d, a_hi + 8 * k, w_mid + 2 * k, idesc, 1u);
+              umma_bf16_ts(d, a_hi + 8 * k, w_hi + 2 * k, idesc, 1u);
             }
             umma_commit(empty_bar(stage));
             if (kb == KB - 1) umma_commit(tfull_bar(as));
@@ -299,13 +318,12 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   } else {
     // ================= ring staging + A-tile builders =================
     const int bt_ = threadIdx.x - 160;                             // 0..255 = ring pixel this thread stages
-    const int m = bt_ & 127, gh = bt_ >> 7;                        // tile row, which 4 of the 8 groups of a k-block
+    const int m = (warp & 3) * 32 + lane;                          // tile row = TMEM lane this thread may write
+    const int gh = (warp - 5) >> 2;                                // which 4 of the 8 groups (filter rows) of a k-block
     const uint32_t ring = sb + OFF_RING;
     const int xr = bt_ >> 3, xj = 256 + (bt_ & 7);                 // the 8 extra pixels (256..263) of row xr
     for (int i = bt_; i < RING_BYTES / 4; i += NBUILD) sts32(ring + 4u * i, 0u);   // never feed stale NaN bits to the MMA
-    uint32_t dst[4];                                               // swizzled chunk offsets of this thread's groups
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) dst[jj] = (uint32_t)m * 128u + (uint32_t)(((gh * 4 + jj) ^ (m & 7)) << 4);
+    const uint32_t a_dst = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(A_COL0 + gh * 16);
     int stage = 0;
     uint32_t phase = 0;
     for (int u = cta; u < units; u += ncta) {
@@ -361,7 +379,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 #pragma unroll 1
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = sb + OFF_A + stage * A_STAGE;
+          tcgen05_fence_after();
           const uint32_t srck = src0 + (uint32_t)(kb * 8 * RING_PX * 4);
           uint2 w[4][4];
 #pragma unroll
@@ -369,17 +387,19 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 #pragma unroll
             for (int e = 0; e < 4; ++e) w[jj][e] = lds64(srck + slot_off[jj] + 8u * e);
           }
+          uint32_t hi[16], mid[16];                                // group jj -> columns 4*jj .. 4*jj+3 (two bf16 per column)
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            uint4 hi, mid;
-            hi.x = __byte_perm(w[jj][0].x, w[jj][0].y, 0x5410); mid.x = __byte_perm(w[jj][0].x, w[jj][0].y, 0x7632);
-            hi.y = __byte_perm(w[jj][1].x, w[jj][1].y, 0x5410); mid.y = __byte_perm(w[jj][1].x, w[jj][1].y, 0x7632);
-            hi.z = __byte_perm(w[jj][2].x, w[jj][2].y, 0x5410); mid.z = __byte_perm(w[jj][2].x, w[jj][2].y, 0x7632);
-            hi.w = __byte_perm(w[jj][3].x, w[jj][3].y, 0x5410); mid.w = __byte_perm(w[jj][3].x, w[jj][3].y, 0x7632);
-            sts128(sa + dst[jj], hi);
-            sts128(sa + A_PLANE + dst[jj], mid);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hi[4 * jj + e] = __byte_perm(w[jj][e].x, w[jj][e].y, 0x5410);
+              mid[4 * jj + e] = __byte_perm(w[jj][e].x, w[jj][e].y, 0x7632);
+            }
           }
-          fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core
+          tmem_st16(a_dst + (uint32_t)(stage * 64), hi);
+          tmem_st16(a_dst + (uint32_t)(stage * 64 + 32), mid);
+          tmem_st_wait();
+          tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(full_bar(stage));
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
