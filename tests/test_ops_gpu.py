@@ -72,7 +72,8 @@ def test_sgemm(abi, m, n, k, act):
 
 
 @pytest.mark.parametrize("c,st_t,st_s,dims", [(64, 1, 1, (2, 4, 9, 10)), (128, 2, 2, (1, 8, 16, 16)), (512, 2, 1, (2, 3, 5, 7)),
-                                              (256, 2, 2, (1, 5, 7, 9))])
+                                              (256, 2, 2, (1, 5, 7, 9)), (64, 1, 1, (1, 8, 32, 32)), (128, 1, 1, (2, 5, 16, 17)),
+                                              (512, 1, 1, (1, 1, 3, 3)), (256, 1, 1, (1, 2, 8, 8))])
 def test_dwconv(abi, c, st_t, st_s, dims):
     from tuber_b200 import _lib
     b, t, h, w = dims
@@ -124,7 +125,8 @@ def test_layernorm(abi, c):
 
 
 @pytest.mark.parametrize("nb,h,l,s,d,masked", [(2, 8, 256, 256, 32, True), (3, 8, 15, 15, 32, False), (2, 8, 15, 300, 32, True),
-                                               (5, 8, 1, 4, 256, False), (2, 8, 90, 1024, 32, False), (4, 8, 4, 4, 32, False)])
+                                               (5, 8, 1, 4, 256, False), (2, 8, 90, 1024, 32, False), (4, 8, 4, 4, 32, False),
+                                               (2, 8, 40, 33, 32, True), (1, 8, 320, 320, 32, False), (3, 8, 7, 17, 32, True)])
 def test_attention(abi, nb, h, l, s, d, masked):
     from tuber_b200 import _lib
     e = h * d

@@ -118,9 +118,112 @@ dwconv_kernel(const float* __restrict__ in, const float* __restrict__ wpk, const
   }
 }
 
+// Stride-1 variant with a shared-memory halo tile (the 24 stride-1 blocks of CSN-152 / 13 of CSN-50 are the
+// ones that matter): a CTA produces a TT x TH x TW block of outputs for CC = 32 channels from a
+// (TT+2) x (TH+2) x (TW+2) input block staged once with cp.async (zero-filled outside the volume), so every
+// input element leaves L2 ~2.3x instead of 9x.  A thread owns one output row of TW = 8 voxels x 4 channels.
+namespace dwt {
+constexpr int TT = 4, TH = 8, TW = 8, CC = 32;
+constexpr int IT = TT + 2, IH = TH + 2, IW = TW + 2;
+constexpr int IN_F4 = IT * IH * IW * (CC / 4);            // float4 slots of the input tile
+constexpr int SMEM_BYTES = IN_F4 * 16 + 27 * CC * 4;      // + this chunk's 27 x CC weights
+constexpr int THREADS = TT * TH * (CC / 4);               // 256
+}  // namespace dwt
+
+__global__ void __launch_bounds__(dwt::THREADS, 2)
+dwconv_s1_tiled_kernel(const float* __restrict__ in, const float* __restrict__ wpk, const float* __restrict__ scale,
+                       const float* __restrict__ shift, void* __restrict__ out, int B, int T, int H, int W, int C) {
+  using namespace dwt;
+  extern __shared__ __align__(16) float4 dw_smem[];
+  float4* tile = dw_smem;                                   // [IT][IH][IW][CC/4]
+  float4* wsm = dw_smem + IN_F4;                            // [27][CC/4]
+  const int tid = threadIdx.x;
+  const int wt = (W + TW - 1) / TW, ht = (H + TH - 1) / TH, tt = (T + TT - 1) / TT;
+  int bid = blockIdx.x;
+  const int cb = (blockIdx.y) * CC;                         // channel chunk
+  const int w0 = (bid % wt) * TW; bid /= wt;
+  const int h0 = (bid % ht) * TH; bid /= ht;
+  const int t0 = (bid % tt) * TT;
+  const int b = bid / tt;
+
+  for (int i = tid; i < IN_F4; i += THREADS) {
+    const int c4 = i % (CC / 4);
+    int r = i / (CC / 4);
+    const int iw = w0 - 1 + r % IW; r /= IW;
+    const int ih = h0 - 1 + r % IH;
+    const int it = t0 - 1 + r / IH;
+    const bool ok = it >= 0 && it < T && ih >= 0 && ih < H && iw >= 0 && iw < W;
+    const float* src = ok ? in + ((((long long)b * T + it) * H + ih) * W + iw) * (long long)C + cb + c4 * 4 : in;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + i);
+    const int nbytes = ok ? 16 : 0;                         // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+  }
+  for (int i = tid; i < 27 * (CC / 4); i += THREADS) {
+    const int c4 = i % (CC / 4), tap = i / (CC / 4);
+    wsm[i] = __ldg(reinterpret_cast<const float4*>(wpk + (long long)tap * C + cb) + c4);
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int c4 = tid % (CC / 4);
+  const int lh = (tid / (CC / 4)) % TH, lt = tid / ((CC / 4) * TH);
+  const int oh = h0 + lh, ot = t0 + lt;
+  if (oh >= H || ot >= T) return;
+  float4 acc[TW];
+#pragma unroll
+  for (int j = 0; j < TW; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int kt = 0; kt < 3; ++kt) {
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const float4* row = tile + (((lt + kt) * IH + lh + kh) * IW) * (CC / 4) + c4;
+      float4 x[IW];
+#pragma unroll
+      for (int q = 0; q < IW; ++q) x[q] = row[q * (CC / 4)];
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float4 wv = wsm[((kt * 3 + kh) * 3 + kw) * (CC / 4) + c4];
+#pragma unroll
+        for (int j = 0; j < TW; ++j) {
+          acc[j].x = fmaf(x[j + kw].x, wv.x, acc[j].x);
+          acc[j].y = fmaf(x[j + kw].y, wv.y, acc[j].y);
+          acc[j].z = fmaf(x[j + kw].z, wv.z, acc[j].z);
+          acc[j].w = fmaf(x[j + kw].w, wv.w, acc[j].w);
+        }
+      }
+    }
+  }
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cb) + c4);
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cb) + c4);
+  const long long orow0 = (((long long)b * T + ot) * H + oh) * W + w0;
+#pragma unroll
+  for (int j = 0; j < TW; ++j) {
+    if (w0 + j >= W) break;
+    float4 o;
+    o.x = fmaxf(fmaf(acc[j].x, sc.x, sh.x), 0.f);
+    o.y = fmaxf(fmaf(acc[j].y, sc.y, sh.y), 0.f);
+    o.z = fmaxf(fmaf(acc[j].z, sc.z, sh.z), 0.f);
+    o.w = fmaxf(fmaf(acc[j].w, sc.w, sh.w), 0.f);
+    __nv_bfloat16* hi = split_hi(out, orow0 + j, C) + cb + c4 * 4;
+    store_split4(hi, hi + C, o);
+  }
+}
+
 cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale, const float* shift,
                           void* out_split, int B, int Ti, int Hi, int Wi, int C, int st_t, int st_s, int To,
                           int Ho, int Wo, cudaStream_t st) {
+  if (st_t == 1 && st_s == 1 && C % dwt::CC == 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(dwconv_s1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dwt::SMEM_BYTES);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    const long long tiles = (long long)B * ceil_div(Ti, dwt::TT) * ceil_div(Hi, dwt::TH) * ceil_div(Wi, dwt::TW);
+    dim3 grid((unsigned)tiles, C / dwt::CC);
+    dwconv_s1_tiled_kernel<<<grid, dwt::THREADS, dwt::SMEM_BYTES, st>>>(in, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C);
+    return cudaGetLastError();
+  }
   long long total = (long long)B * To * Ho * ((Wo + 3) / 4) * (C / 4);
   int grid = ceil_div(total, 256);
   if (st_s == 1)
@@ -426,109 +529,6 @@ __device__ __forceinline__ long long seq_row0(const SeqMap& m, int n) {
   return (long long)(n / m.inner) * m.outer + (long long)(n % m.inner) * m.inner_stride;
 }
 
-// (a) head_dim 32, one thread per query, K/V tiles of 128 keys staged in shared memory,
-//     online softmax in chunks of 4 keys.  grid = (ceil(L/blockDim), H, NB).
-__global__ void __launch_bounds__(128)
-attn_smem_kernel(AttnArgs p) {
-  constexpr int D = 32, TS = 128;
-  __shared__ __align__(16) float Ks[TS][D];
-  __shared__ __align__(16) float Vs[TS][D];
-  __shared__ uint8_t Ms[TS];
-  const int n = blockIdx.z, h = blockIdx.y;
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = l < p.L;
-  const long long q0 = seq_row0(p.qm, n), k0 = seq_row0(p.km, n);
-
-  float q[D], acc[D];
-  float m = -INFINITY, lsum = 0.f;
-#pragma unroll
-  for (int d = 0; d < D; ++d) acc[d] = 0.f;
-  if (active) {
-    const float* qp = p.q + (q0 + (long long)l * p.qm.step) * p.ldq + h * D;
-#pragma unroll
-    for (int d4 = 0; d4 < D / 4; ++d4) {
-      float4 t = __ldg(reinterpret_cast<const float4*>(qp) + d4);
-      q[4 * d4] = t.x * p.scale; q[4 * d4 + 1] = t.y * p.scale;
-      q[4 * d4 + 2] = t.z * p.scale; q[4 * d4 + 3] = t.w * p.scale;
-    }
-  }
-  const uint8_t* mrow = p.kpm ? p.kpm + (long long)(n / p.kpm_div) * p.S : nullptr;
-
-  for (int s0 = 0; s0 < p.S; s0 += TS) {
-    const int ts = min(TS, p.S - s0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < ts * (D / 4); i += blockDim.x) {
-      int j = i / (D / 4), d4 = i % (D / 4);
-      long long krow = k0 + (long long)(s0 + j) * p.km.step;
-      reinterpret_cast<float4*>(&Ks[j][0])[d4] = __ldg(reinterpret_cast<const float4*>(p.k + krow * p.ldk + h * D) + d4);
-      reinterpret_cast<float4*>(&Vs[j][0])[d4] = __ldg(reinterpret_cast<const float4*>(p.v + krow * p.ldv + h * D) + d4);
-    }
-    for (int j = threadIdx.x; j < ts; j += blockDim.x) Ms[j] = mrow ? mrow[s0 + j] : 0;
-    __syncthreads();
-    if (!active) continue;
-    for (int j0 = 0; j0 < ts; j0 += 4) {
-      float s[4];
-      float cmax = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int j = j0 + i;
-        float dot = -INFINITY;
-        if (j < ts && !Ms[j]) {
-          dot = 0.f;
-#pragma unroll
-          for (int d4 = 0; d4 < D / 4; ++d4) {
-            float4 kk = reinterpret_cast<const float4*>(&Ks[j][0])[d4];
-            dot = fmaf(q[4 * d4], kk.x, dot);
-            dot = fmaf(q[4 * d4 + 1], kk.y, dot);
-            dot = fmaf(q[4 * d4 + 2], kk.z, dot);
-            dot = fmaf(q[4 * d4 + 3], kk.w, dot);
-          }
-        }
-        s[i] = dot;
-        cmax = fmaxf(cmax, dot);
-      }
-      if (cmax == -INFINITY) continue;
-      const float mnew = fmaxf(m, cmax);
-      const float corr = expf(m - mnew);      // m = -inf -> 0
-      float pr[4];
-      float psum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        pr[i] = expf(s[i] - mnew);             // masked -> 0
-        psum += pr[i];
-      }
-      lsum = lsum * corr + psum;
-      m = mnew;
-#pragma unroll
-      for (int d4 = 0; d4 < D / 4; ++d4) {
-        float4 a = make_float4(acc[4 * d4] * corr, acc[4 * d4 + 1] * corr, acc[4 * d4 + 2] * corr,
-                               acc[4 * d4 + 3] * corr);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (j0 + i < ts) {
-            float4 vv = reinterpret_cast<const float4*>(&Vs[j0 + i][0])[d4];
-            a.x = fmaf(pr[i], vv.x, a.x); a.y = fmaf(pr[i], vv.y, a.y);
-            a.z = fmaf(pr[i], vv.z, a.z); a.w = fmaf(pr[i], vv.w, a.w);
-          }
-        }
-        acc[4 * d4] = a.x; acc[4 * d4 + 1] = a.y; acc[4 * d4 + 2] = a.z; acc[4 * d4 + 3] = a.w;
-      }
-    }
-  }
-  if (!active) return;
-  const float inv = 1.f / lsum;
-  const long long orow = seq_row0(p.om, n) + (long long)l * p.om.step;
-#pragma unroll
-  for (int d4 = 0; d4 < D / 4; ++d4) {
-    float4 o = make_float4(acc[4 * d4] * inv, acc[4 * d4 + 1] * inv, acc[4 * d4 + 2] * inv, acc[4 * d4 + 3] * inv);
-    if (p.o_f32) reinterpret_cast<float4*>(p.o_f32 + orow * p.ldo + h * D)[d4] = o;
-    if (p.o_split) {
-      __nv_bfloat16* hi = split_hi(p.o_split, orow, p.ldo) + h * D + d4 * 4;
-      store_split4(hi, hi + p.ldo, o);
-    }
-  }
-}
-
 // (b) any head_dim = 32*DPL, one warp per (sequence, head, query), keys streamed from global:
 //     for the tiny-S sites (S = T' = 4 temporal attention, 15-query decoder self-attention,
 //     the decode pool's 1x4 cross-attention with head_dim 256).
@@ -587,13 +587,140 @@ attn_warp_kernel(AttnArgs p) {
   }
 }
 
+// (c) head_dim 32, L and S beyond a handful: a CTA = one (sequence, head, 32-query tile), 4 warps x 8 queries.
+//     Keys / values stream through shared memory in chunks of 32 (cp.async, double buffered).  Scores: lane =
+//     key, the key's 32 dims live in registers and the 8 queries are broadcast from shared memory; online
+//     softmax with warp reductions; P.V: lane = output dim, the chunk's V column lives in registers and the
+//     probabilities are broadcast from shared memory.  ~3.5 instructions per (query, key) pair.
+namespace attile {
+constexpr int QT = 32, KC = 32, D = 32, QW = 8;           // queries per CTA, keys per chunk, head dim, queries per warp
+}
+__global__ void __launch_bounds__(128)
+attn_tile_kernel(AttnArgs p) {
+  using namespace attile;
+  __shared__ __align__(16) float Qs[QT][D];
+  __shared__ __align__(16) float Ks[2][KC][D + 4];         // +4: lane-strided row reads stay conflict free with 16 B alignment
+  __shared__ __align__(16) float Vs[2][KC][D];
+  __shared__ __align__(16) float Ps[4][QW][KC];
+  __shared__ uint8_t Ms[2][KC];
+  const int n = blockIdx.z, h = blockIdx.y, l0 = blockIdx.x * QT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long q0 = seq_row0(p.qm, n), k0 = seq_row0(p.km, n);
+  const uint8_t* mrow = p.kpm ? p.kpm + (long long)(n / p.kpm_div) * p.S : nullptr;
+
+  for (int i = tid; i < QT * (D / 4); i += 128) {
+    const int q = i / (D / 4), d4 = i % (D / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l0 + q < p.L) {
+      v = __ldg(reinterpret_cast<const float4*>(p.q + (q0 + (long long)(l0 + q) * p.qm.step) * p.ldq + h * D) + d4);
+      v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
+    }
+    *reinterpret_cast<float4*>(&Qs[q][d4 * 4]) = v;
+  }
+  auto load_chunk = [&](int c, int buf) {
+    const int s0 = c * KC;
+    for (int i = tid; i < KC * (D / 4); i += 128) {
+      const int j = i / (D / 4), d4 = i % (D / 4);
+      const bool ok = s0 + j < p.S;
+      const long long krow = k0 + (long long)(ok ? s0 + j : 0) * p.km.step;
+      const int nb = ok ? 16 : 0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(&Ks[buf][j][d4 * 4])),
+                   "l"(p.k + krow * p.ldk + h * D + d4 * 4), "r"(nb) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(&Vs[buf][j][d4 * 4])),
+                   "l"(p.v + krow * p.ldv + h * D + d4 * 4), "r"(nb) : "memory");
+    }
+    if (tid < KC) Ms[buf][tid] = (s0 + tid >= p.S) || (mrow && mrow[s0 + tid]);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int nchunks = (p.S + KC - 1) / KC;
+  load_chunk(0, 0);
+  float acc[QW], mx[QW], ls[QW];
+#pragma unroll
+  for (int q = 0; q < QW; ++q) { acc[q] = 0.f; mx[q] = -INFINITY; ls[q] = 0.f; }
+  const bool warp_active = l0 + warp * QW < p.L;
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    if (c + 1 < nchunks) {
+      load_chunk(c + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp_active) {
+      float kr[D];
+#pragma unroll
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 t = *reinterpret_cast<const float4*>(&Ks[buf][lane][d4 * 4]);
+        kr[4 * d4] = t.x; kr[4 * d4 + 1] = t.y; kr[4 * d4 + 2] = t.z; kr[4 * d4 + 3] = t.w;
+      }
+      const bool masked = Ms[buf][lane];
+#pragma unroll
+      for (int q = 0; q < QW; ++q) {
+        const float* qv = &Qs[warp * QW + q][0];
+        float sdot = 0.f;
+#pragma unroll
+        for (int d4 = 0; d4 < D / 4; ++d4) {
+          const float4 t = *reinterpret_cast<const float4*>(qv + d4 * 4);
+          sdot = fmaf(t.x, kr[4 * d4], sdot); sdot = fmaf(t.y, kr[4 * d4 + 1], sdot);
+          sdot = fmaf(t.z, kr[4 * d4 + 2], sdot); sdot = fmaf(t.w, kr[4 * d4 + 3], sdot);
+        }
+        if (masked) sdot = -INFINITY;
+        const float cm = warp_max(sdot);
+        const float mnew = fmaxf(mx[q], cm);
+        const float pr = (mnew == -INFINITY) ? 0.f : expf(sdot - mnew);      // whole row masked so far: nothing to add
+        const float corr = (mnew == -INFINITY) ? 1.f : expf(mx[q] - mnew);    // mx = -inf -> 0
+        ls[q] = ls[q] * corr + warp_sum(pr);
+        acc[q] *= corr;
+        mx[q] = mnew;
+        Ps[warp][q][lane] = pr;
+      }
+      __syncwarp();
+      float vr[KC];
+#pragma unroll
+      for (int j = 0; j < KC; ++j) vr[j] = Vs[buf][j][lane];
+#pragma unroll
+      for (int q = 0; q < QW; ++q) {
+        float a = acc[q];
+#pragma unroll
+        for (int j4 = 0; j4 < KC / 4; ++j4) {
+          const float4 t = *reinterpret_cast<const float4*>(&Ps[warp][q][j4 * 4]);
+          a = fmaf(t.x, vr[4 * j4], a); a = fmaf(t.y, vr[4 * j4 + 1], a);
+          a = fmaf(t.z, vr[4 * j4 + 2], a); a = fmaf(t.w, vr[4 * j4 + 3], a);
+        }
+        acc[q] = a;
+      }
+    }
+    __syncthreads();
+  }
+  if (!warp_active) return;
+  const long long o0 = seq_row0(p.om, n);
+#pragma unroll
+  for (int q = 0; q < QW; ++q) {
+    const int l = l0 + warp * QW + q;
+    if (l >= p.L) break;
+    const float o = acc[q] / ls[q];
+    const long long orow = o0 + (long long)l * p.om.step;
+    const int cidx = h * D + lane;
+    if (p.o_f32) p.o_f32[orow * p.ldo + cidx] = o;
+    if (p.o_split) {
+      __nv_bfloat16 hi, mid;
+      split_bf16(o, hi, mid);
+      __nv_bfloat16* hp = split_hi(p.o_split, orow, p.ldo);
+      hp[cidx] = hi;
+      hp[p.ldo + cidx] = mid;
+    }
+  }
+}
+
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st) {
   if (a.D % 32 != 0 || a.NB <= 0 || a.L <= 0 || a.S <= 0) return cudaErrorInvalidValue;
   const bool small = a.S <= 16 || a.D != 32;
   if (!small) {
-    int threads = a.L >= 128 ? 128 : ((a.L + 31) / 32) * 32;
-    dim3 grid(ceil_div(a.L, threads), a.H, a.NB);
-    attn_smem_kernel<<<grid, threads, 0, st>>>(a);
+    dim3 grid(ceil_div(a.L, attile::QT), a.H, a.NB);
+    attn_tile_kernel<<<grid, 128, 0, st>>>(a);
   } else {
     long long warps = (long long)a.NB * a.H * a.L;
     int grid = ceil_div(warps * 32, 128);

@@ -80,7 +80,7 @@ struct DecLayer {
   float* pq_ca = nullptr;   // [Q, d] : query_embed x Wq^T           (query = tgt + query_pos, :232)
 };
 
-struct KernelRec { const char* name; double bytes, flops; cudaEvent_t e0, e1; };
+struct KernelRec { const char* name; double bytes, flops; cudaEvent_t e0, e1; char tag[64]; };
 struct Tap { const void* ptr; int fmt; long long rows; int cols; void* keep; };
 
 struct Ws {   // bump allocator over one device buffer; in dry mode only counts
@@ -487,6 +487,7 @@ struct Ctx {
   bool dry;
   int launches = 0;
   int status = TUBER_OK;
+  char tag[64] = "";     // optional shape note for the next launch (per-kernel profile dump)
 
   bool ok() const { return status == TUBER_OK; }
   // every device operation of a forward goes through here: counted, optionally bracketed by CUDA events
@@ -510,6 +511,8 @@ struct Ctx {
     }
     KernelRec& r = p->kp[p->kp_used];
     r.name = name; r.bytes = bytes; r.flops = flops;
+    snprintf(r.tag, sizeof r.tag, "%s", tag);
+    tag[0] = 0;
     cudaEventRecord(r.e0, st);
     return p->kp_used++;
   }
@@ -528,6 +531,7 @@ struct Ctx {
     a.M = (int)M; a.N = w.N; a.K = w.K; a.act = act;
     const bool tc_ok = a_fmt == FMT_SPLIT && w.N % 64 == 0 && w.K % 64 == 0 && act != ACT_SIGMOID && lda % 8 == 0 && ldc % 8 == 0;
     const bool tc = tc_ok && !p->force_simt;
+    if (p->kprof) snprintf(tag, sizeof tag, "M=%lld N=%d K=%d res=%d/%d out=%d act=%d", M, w.N, w.K, res ? 1 + res_fmt : 0, res_mod, c_fmt, act);
     const double mn = (double)M * w.N;
     const double bytes = 4.0 * ((double)M * w.K + (double)w.N * w.K + mn + (res ? (res_mod > 0 ? (double)res_mod * w.N : mn) : 0.0));
     launch(tc ? "gemm_bf16x3_tcgen05" : "sgemm_fp32", bytes, 2.0 * mn * w.K,
@@ -557,6 +561,7 @@ struct Ctx {
     a.o_f32 = nullptr; a.o_split = o_split; a.ldo = ldo; a.om = om;
     a.kpm = kpm; a.kpm_div = 1; a.NB = NB; a.H = H; a.L = L; a.S = S; a.D = D;
     a.scale = 1.f / sqrtf((float)D);
+    if (p->kprof) snprintf(tag, sizeof tag, "NB=%d H=%d L=%d S=%d D=%d", NB, H, L, S, D);
     const double e = (double)H * D;
     launch("attention", 4.0 * e * ((double)NB * L * 2 + (double)NB * S * 2), 4.0 * (double)NB * H * L * S * D,
            [&] { return launch_attention(a, st); });
@@ -1134,11 +1139,15 @@ int tuber_set_kernel_profiling(TuberPlan* p, int32_t enabled) {
 int tuber_get_kernel_profile(TuberPlan* p, TuberKernelStat* out, int32_t capacity, int32_t* n_out) {
   if (!p || !n_out) return fail(TUBER_ERR_INVALID, "null argument");
   std::vector<TuberKernelStat> agg;
+  const char* dump = getenv("TUBER_KPROF_DUMP");
   for (int i = 0; i < p->kp_used; ++i) {
     const KernelRec& r = p->kp[i];
     CK(cudaEventSynchronize(r.e1));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    if (dump && dump[0] == '1')
+      fprintf(stderr, "kprof %3d %-22s %8.1f us %8.1f GB/s %8.1f TFLOP/s  %s\n", i, r.name, ms * 1e3, r.bytes / (ms * 1e-3) / 1e9,
+              r.flops / (ms * 1e-3) / 1e12, r.tag);
     TuberKernelStat* s = nullptr;
     for (auto& a : agg) if (strcmp(a.name, r.name) == 0) s = &a;
     if (!s) {
