@@ -10,8 +10,8 @@ A step = one forward over one batch of synthetic clips.  Workload at every N: BA
 over ranks with no data-path collective inside the forward and one all-gather of packed detections per
 step ("weak" scaling: per-GPU batch fixed).
   value    whole-job clips/s, inputs resident in HBM, CUDA-graph replay of the launch sequence
-  e2e      the same through the C-ABI host entry point (tuber_forward_host): pinned host clips -> H2D ->
-           forward -> D2H of the detections, every step
+  e2e      the same through the host entry points (tuber_forward_host_submit/_wait): pinned host clips -> H2D ->
+           forward -> D2H of the detections, every step; two slots, so step i+1's copy overlaps step i's kernels
   roofline the kernel with the largest share of device time, from a per-launch CUDA-event profile of
            one extra forward (algorithmic bytes / flops per launch over the summed event time)
   cpu_baseline  the CPU oracle (a restatement of the reference on the same torch CPU ops) on a bounded
@@ -208,31 +208,39 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches_per_step = lib.tuber_last_launches(model.plan())
 
-    # ---- e2e: host buffers through the C-ABI host entry point
-    h_clips = torch.empty((B, 3, T, H, W), dtype=torch.float32).pin_memory()
-    h_clips.copy_(clips)
-    h_out = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in out.items()}
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # ---- e2e: host buffers through the public host entry points (tuber_forward_host_submit / _wait): every step
+    # copies that step's clips from pinned host memory (two alternating buffers) and reads its detections back;
+    # the copy of step i+1 is in flight while step i computes
+    h_clips = [torch.empty((B, 3, T, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for hc in h_clips:
+        hc.copy_(clips)
+    h_out = [model._host_out(B) for _ in range(2)]
 
-    def e2e_step():
-        _lib.check(lib.tuber_forward_host(model.plan(), C.c_void_p(h_clips.data_ptr()), None, B, T, H, W,
-                                          C.c_void_p(h_out["pred_logits"].data_ptr()), C.c_void_p(h_out["pred_boxes"].data_ptr()),
-                                          C.c_void_p(h_out["pred_logits_b"].data_ptr()), stream))
+    def e2e_run(n):
+        model.forward_host_submit(0, h_clips[0], None, h_out[0])
+        for i in range(1, n):
+            model.forward_host_submit(i & 1, h_clips[i & 1], None, h_out[i & 1])
+            model.forward_host_wait((i - 1) & 1)
+        model.forward_host_wait((n - 1) & 1)
 
-    for _ in range(2):
-        e2e_step()
+    e2e_run(3)
     sync_all()
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(4, args.steps)
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()                                  # returns after the D2H copies have completed
-    sync_all()
+    e2e_run(e2e_steps)                              # returns after the last step's D2H copies have completed
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = B * world * e2e_steps / float(e2e_s.item())
-    h2d = h_clips.numel() * 4
-    d2h = sum(v.numel() for v in h_out.values()) * 4
+    h2d = h_clips[0].numel() * 4
+    d2h = sum(v.numel() for v in h_out[0].values()) * 4
+    # the same, one synchronous call per step (no overlap), for reference
+    for _ in range(2):
+        model.forward_host(h_clips[0], None, h_out[0])
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        model.forward_host(h_clips[0], None, h_out[0])
+    e2e_sync_val = B * e2e_steps / (time.perf_counter() - t0)
 
     if rank != 0:
         if world > 1:
@@ -280,7 +288,9 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload, "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "forward_host_submit/_wait (double-buffered: H2D of step i+1 overlaps step i)",
+                    "synchronous_per_call_rank0": e2e_sync_val},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "cuda_graph": not args.no_graph, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},

@@ -92,6 +92,15 @@ int tuber_forward_host(TuberPlan* plan, const float* clips_host, const uint8_t* 
                        int32_t H, int32_t W, float* logits_host, float* boxes_host, float* logits_b_host,
                        void* stream);
 
+/* Pipelined form of tuber_forward_host for a stream of batches: submit() enqueues the H2D copies of `slot`
+ * (0 or 1) on a private copy stream and the forward + D2H copies on a private compute stream and returns at once;
+ * wait() blocks until that slot's outputs are in host memory.  Submitting slot 1 while slot 0 computes overlaps
+ * the next batch's input copy with the current batch's kernels (host buffers must be pinned for the overlap and
+ * must stay valid until wait()).  A slot must be waited on before it is submitted again. */
+int tuber_forward_host_submit(TuberPlan* plan, int32_t slot, const float* clips_host, const uint8_t* mask_host, int32_t B,
+                              int32_t T, int32_t H, int32_t W, float* logits_host, float* boxes_host, float* logits_b_host);
+int tuber_forward_host_wait(TuberPlan* plan, int32_t slot);
+
 /* Output geometry for an input shape: feature-map size after the backbone (T',H',W'), tokens seen
  * by the DETR encoder, number of kernel launches one forward issues. */
 typedef struct TuberShapeInfo {

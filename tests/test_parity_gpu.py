@@ -136,6 +136,30 @@ def test_cuda_graph_replay_is_bit_identical():
             assert torch.equal(out[k], eager[k]), k
 
 
+def test_host_entry_points_match_device_path():
+    """tuber_forward_host and the pipelined submit/wait pair give the device path's numbers."""
+    cfg, sd, clips, _ = build_case("A_csn50_avg_bnrand")
+    model = _model(cfg, sd)
+    ref = {k: v.cpu() for k, v in model.forward_raw(clips.cuda()).items()}
+    pinned = clips.pin_memory()
+    out = model.forward_host(pinned)
+    for k in ref:
+        assert torch.equal(out[k], ref[k]), k
+    other = (clips * 0.5).contiguous().pin_memory()
+    ref2 = {k: v.cpu() for k, v in model.forward_raw(other.cuda()).items()}
+    o0 = model.forward_host_submit(0, pinned)
+    o1 = model.forward_host_submit(1, other)
+    model.forward_host_wait(0)
+    o0b = {k: v.clone() for k, v in o0.items()}
+    o0 = model.forward_host_submit(0, other, None, o0)
+    model.forward_host_wait(1)
+    model.forward_host_wait(0)
+    for k in ref:
+        assert torch.equal(o0b[k], ref[k]) and torch.equal(o1[k], ref2[k]) and torch.equal(o0[k], ref2[k]), k
+    with pytest.raises(RuntimeError):
+        model.forward_host_wait(0)                            # nothing in flight
+
+
 def test_no_fallback_off_device():
     import tuber_b200
     cfg, sd, clips, _ = build_case("A_csn50")

@@ -52,6 +52,8 @@ PROTOTYPES = {
     "tuber_plan_finalize": (_I, [_P]),
     "tuber_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "tuber_forward_host": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "tuber_forward_host_submit": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "tuber_forward_host_wait": (_I, [_P, _I]),
     "tuber_query_shapes": (_I, [_P, _I, _I, _I, _I, C.POINTER(TuberShapeInfo)]),
     "tuber_set_graph": (_I, [_P, _I]),
     "tuber_set_force_simt": (_I, [_P, _I]),

@@ -126,8 +126,12 @@ struct TuberPlan {
 
   // run-time state
   char* ws = nullptr; size_t ws_cap = 0;
-  char* stage_in = nullptr; size_t stage_in_cap = 0;      // forward_host staging
-  char* stage_out = nullptr; size_t stage_out_cap = 0;
+  // forward_host staging: two slots so that the host copies of step i+1 overlap the kernels of step i
+  char* stage_in[2] = {nullptr, nullptr}; size_t stage_in_cap[2] = {0, 0};
+  char* stage_out[2] = {nullptr, nullptr}; size_t stage_out_cap[2] = {0, 0};
+  cudaStream_t copy_stream = nullptr, run_stream = nullptr;
+  cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
+  bool slot_busy[2] = {false, false};
   bool force_simt = false;
   bool profiling = false, debug_keep = false, use_graph = false;
   cudaEvent_t ev[TUBER_NUM_STAGES + 1] = {};
@@ -960,8 +964,14 @@ void tuber_plan_destroy(TuberPlan* p) {
   for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   if (p->ws) cudaFree(p->ws);
-  if (p->stage_in) cudaFree(p->stage_in);
-  if (p->stage_out) cudaFree(p->stage_out);
+  for (int i = 0; i < 2; ++i) {
+    if (p->stage_in[i]) cudaFree(p->stage_in[i]);
+    if (p->stage_out[i]) cudaFree(p->stage_out[i]);
+    if (p->h2d_done[i]) cudaEventDestroy(p->h2d_done[i]);
+    if (p->slot_done[i]) cudaEventDestroy(p->slot_done[i]);
+  }
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+  if (p->run_stream) cudaStreamDestroy(p->run_stream);
   if (p->ev_valid) for (auto& e : p->ev) cudaEventDestroy(e);
   for (auto& r : p->kp) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   delete p;
@@ -1066,45 +1076,96 @@ int tuber_forward(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev,
   return TUBER_OK;
 }
 
-int tuber_forward_host(TuberPlan* p, const float* clips_host, const uint8_t* mask_host, int32_t B, int32_t T, int32_t H,
-                       int32_t W, float* logits_host, float* boxes_host, float* logits_b_host, void* stream) {
-  TRY(check_forward_args(p, B, T, H, W));
-  if (!clips_host || !logits_host || !boxes_host || !logits_b_host) return fail(TUBER_ERR_INVALID, "null host pointer");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+namespace {
+
+// H2D (+mask) -> forward -> D2H of one batch through staging slot `slot`.  `in_st` carries the input copies,
+// `st` the kernels and the output copies; the caller decides whether they are the same stream.
+int host_step(TuberPlan* p, int slot, const float* clips_host, const uint8_t* mask_host, int B, int T, int H, int W,
+              float* logits_host, float* boxes_host, float* logits_b_host, cudaStream_t in_st, cudaStream_t st) {
   const TuberConfig& c = p->cfg;
   const size_t clip_bytes = (size_t)B * 3 * T * H * W * 4, mask_bytes = mask_host ? (size_t)B * H * W : 0;
   const size_t in_need = clip_bytes + ((mask_bytes + 255) & ~(size_t)255) + 256;
   const size_t n_logits = (size_t)B * c.dec_layers * c.num_queries * c.num_classes, n_boxes = (size_t)B * c.dec_layers * c.num_queries * 4;
   const size_t n_lb = c.ava_mode ? (size_t)B * c.dec_layers * c.num_queries * 3 : (size_t)B * 2;
   const size_t out_need = (n_logits + n_boxes + n_lb) * 4 + 1024;
-  if (in_need > p->stage_in_cap) {
+  if (in_need > p->stage_in_cap[slot]) {
     CK(cudaDeviceSynchronize());
-    if (p->stage_in) cudaFree(p->stage_in);
-    p->stage_in = nullptr; p->stage_in_cap = 0;
+    if (p->stage_in[slot]) cudaFree(p->stage_in[slot]);
+    p->stage_in[slot] = nullptr; p->stage_in_cap[slot] = 0;
     void* q = nullptr;
     CK(cudaMalloc(&q, in_need));
-    p->stage_in = (char*)q; p->stage_in_cap = in_need;
+    p->stage_in[slot] = (char*)q; p->stage_in_cap[slot] = in_need;
   }
-  if (out_need > p->stage_out_cap) {
+  if (out_need > p->stage_out_cap[slot]) {
     CK(cudaDeviceSynchronize());
-    if (p->stage_out) cudaFree(p->stage_out);
-    p->stage_out = nullptr; p->stage_out_cap = 0;
+    if (p->stage_out[slot]) cudaFree(p->stage_out[slot]);
+    p->stage_out[slot] = nullptr; p->stage_out_cap[slot] = 0;
     void* q = nullptr;
     CK(cudaMalloc(&q, out_need));
-    p->stage_out = (char*)q; p->stage_out_cap = out_need;
+    p->stage_out[slot] = (char*)q; p->stage_out_cap[slot] = out_need;
   }
-  float* d_clips = (float*)p->stage_in;
-  uint8_t* d_mask = mask_host ? (uint8_t*)(p->stage_in + clip_bytes) : nullptr;
-  float* d_logits = (float*)p->stage_out;
+  float* d_clips = (float*)p->stage_in[slot];
+  uint8_t* d_mask = mask_host ? (uint8_t*)(p->stage_in[slot] + clip_bytes) : nullptr;
+  float* d_logits = (float*)p->stage_out[slot];
   float* d_boxes = d_logits + ((n_logits + 63) & ~(size_t)63);
   float* d_lb = d_boxes + ((n_boxes + 63) & ~(size_t)63);
-  CK(cudaMemcpyAsync(d_clips, clips_host, clip_bytes, cudaMemcpyHostToDevice, st));
-  if (mask_host) CK(cudaMemcpyAsync(d_mask, mask_host, mask_bytes, cudaMemcpyHostToDevice, st));
-  TRY(tuber_forward(p, d_clips, d_mask, B, T, H, W, d_logits, d_boxes, d_lb, stream));
+  CK(cudaMemcpyAsync(d_clips, clips_host, clip_bytes, cudaMemcpyHostToDevice, in_st));
+  if (mask_host) CK(cudaMemcpyAsync(d_mask, mask_host, mask_bytes, cudaMemcpyHostToDevice, in_st));
+  if (in_st != st) {
+    CK(cudaEventRecord(p->h2d_done[slot], in_st));
+    CK(cudaStreamWaitEvent(st, p->h2d_done[slot], 0));
+  }
+  TRY(tuber_forward(p, d_clips, d_mask, B, T, H, W, d_logits, d_boxes, d_lb, st));
   CK(cudaMemcpyAsync(logits_host, d_logits, n_logits * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(boxes_host, d_boxes, n_boxes * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(logits_b_host, d_lb, n_lb * 4, cudaMemcpyDeviceToHost, st));
+  return TUBER_OK;
+}
+
+int ensure_host_pipeline(TuberPlan* p) {
+  if (p->copy_stream) return TUBER_OK;
+  CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&p->run_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&p->h2d_done[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&p->slot_done[i], cudaEventDisableTiming));
+  }
+  return TUBER_OK;
+}
+
+}  // namespace
+
+int tuber_forward_host(TuberPlan* p, const float* clips_host, const uint8_t* mask_host, int32_t B, int32_t T, int32_t H,
+                       int32_t W, float* logits_host, float* boxes_host, float* logits_b_host, void* stream) {
+  TRY(check_forward_args(p, B, T, H, W));
+  if (!clips_host || !logits_host || !boxes_host || !logits_b_host) return fail(TUBER_ERR_INVALID, "null host pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int i = 0; i < 2; ++i)
+    if (p->slot_busy[i]) return fail(TUBER_ERR_STATE, "tuber_forward_host while an asynchronous submission is in flight");
+  TRY(host_step(p, 0, clips_host, mask_host, B, T, H, W, logits_host, boxes_host, logits_b_host, st, st));
   CK(cudaStreamSynchronize(st));
+  return TUBER_OK;
+}
+
+int tuber_forward_host_submit(TuberPlan* p, int32_t slot, const float* clips_host, const uint8_t* mask_host, int32_t B, int32_t T,
+                              int32_t H, int32_t W, float* logits_host, float* boxes_host, float* logits_b_host) {
+  TRY(check_forward_args(p, B, T, H, W));
+  if (slot < 0 || slot > 1) return fail(TUBER_ERR_INVALID, "slot must be 0 or 1");
+  if (!clips_host || !logits_host || !boxes_host || !logits_b_host) return fail(TUBER_ERR_INVALID, "null host pointer");
+  if (p->slot_busy[slot]) return fail(TUBER_ERR_STATE, "slot %d still in flight: call tuber_forward_host_wait first", slot);
+  TRY(ensure_host_pipeline(p));
+  TRY(host_step(p, slot, clips_host, mask_host, B, T, H, W, logits_host, boxes_host, logits_b_host, p->copy_stream, p->run_stream));
+  CK(cudaEventRecord(p->slot_done[slot], p->run_stream));
+  p->slot_busy[slot] = true;
+  return TUBER_OK;
+}
+
+int tuber_forward_host_wait(TuberPlan* p, int32_t slot) {
+  if (!p) return fail(TUBER_ERR_INVALID, "null plan");
+  if (slot < 0 || slot > 1) return fail(TUBER_ERR_INVALID, "slot must be 0 or 1");
+  if (!p->slot_busy[slot]) return fail(TUBER_ERR_STATE, "slot %d has no submission in flight", slot);
+  CK(cudaEventSynchronize(p->slot_done[slot]));
+  p->slot_busy[slot] = false;
   return TUBER_OK;
 }
 

@@ -274,6 +274,47 @@ class DETR(nn.Module):
                                                  C.c_void_p(out["pred_logits_b"].data_ptr()), C.c_void_p(stream)))
         return out
 
+    # -- host-memory entry points (tuber_forward_host*, include/tuber_b200.h) ----------------
+    def _host_out(self, B: int) -> Dict[str, Tensor]:
+        L, Q = self.dec_layers, self.num_queries
+        return {"pred_logits": torch.empty((B, L, Q, self.num_class_out), dtype=torch.float32).pin_memory(),
+                "pred_boxes": torch.empty((B, L, Q, 4), dtype=torch.float32).pin_memory(),
+                "pred_logits_b": torch.empty((B, L, Q, 3) if self.dataset_mode == "ava" else (B, 2), dtype=torch.float32).pin_memory()}
+
+    def _host_args(self, clips: Tensor, mask: Optional[Tensor], out: Dict[str, Tensor]):
+        if clips.device.type != "cpu" or clips.dtype != torch.float32 or not clips.is_contiguous() or clips.dim() != 5:
+            raise ValueError("clips must be a contiguous fp32 (B,3,T,H,W) tensor in (pinned) host memory")
+        B, _, T, H, W = clips.shape
+        mptr = None
+        if mask is not None:
+            if mask.device.type != "cpu" or mask.dtype != torch.uint8 or not mask.is_contiguous() or tuple(mask.shape) != (B, H, W):
+                raise ValueError("mask must be a contiguous uint8 (B,H,W) host tensor")
+            mptr = C.c_void_p(mask.data_ptr())
+        return (C.c_void_p(clips.data_ptr()), mptr, B, T, H, W, C.c_void_p(out["pred_logits"].data_ptr()),
+                C.c_void_p(out["pred_boxes"].data_ptr()), C.c_void_p(out["pred_logits_b"].data_ptr()))
+
+    @torch.no_grad()
+    def forward_host(self, clips: Tensor, mask: Optional[Tensor] = None, out: Optional[Dict[str, Tensor]] = None):
+        """Host clips -> H2D -> forward -> D2H, synchronous; returns all-layer outputs in host memory."""
+        out = out if out is not None else self._host_out(clips.shape[0])
+        with torch.cuda.device(self._device()):
+            stream = C.c_void_p(torch.cuda.current_stream(self._device()).cuda_stream)
+            _lib.check(_lib.load().tuber_forward_host(self.plan(), *self._host_args(clips, mask, out), stream))
+        return out
+
+    @torch.no_grad()
+    def forward_host_submit(self, slot: int, clips: Tensor, mask: Optional[Tensor] = None,
+                            out: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+        """Pipelined form: enqueue batch `slot` (0/1) and return at once; `forward_host_wait(slot)` makes `out` valid.
+        The input copy of one slot overlaps the kernels of the other.  Buffers must stay alive until the wait."""
+        out = out if out is not None else self._host_out(clips.shape[0])
+        with torch.cuda.device(self._device()):
+            _lib.check(_lib.load().tuber_forward_host_submit(self.plan(), slot, *self._host_args(clips, mask, out)))
+        return out
+
+    def forward_host_wait(self, slot: int) -> None:
+        _lib.check(_lib.load().tuber_forward_host_wait(self.plan(), slot))
+
     def forward(self, samples: Union[NestedTensor, List[Tensor], Tensor]):
         if isinstance(samples, (list, tuple)):
             samples = nested_tensor_from_tensor_list(list(samples))            # tuber_ava.py:112-113
