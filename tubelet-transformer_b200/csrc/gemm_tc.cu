@@ -59,6 +59,7 @@ struct Params {
   int res_mode;
   int out_fmt;
   int M, N, K, act;
+  int kb1;                                              // k-blocks taken from the first A operand (the rest from the second)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -163,8 +164,9 @@ TB_DEVINL uint32_t swz(uint32_t sub_base, int r, int j) { return sub_base + (uin
 
 template <class C>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, Params p) {
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
+                   const __grid_constant__ CUtensorMap tmR, Params p) {
   constexpr int BN = C::BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);            // swizzle-128B tiles need 1024 B alignment
@@ -189,6 +191,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0 && lane == 0) {
     if (smem_base & 1023u) __trap();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    if (p.kb1 < kblocks) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     if (p.res_mode == RES_TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
@@ -227,7 +230,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM, 0);
+          if (kb < p.kb1) tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM, 0);
+          else tma_load_3d(sa, &tmA2, full_bar(stage), (kb - p.kb1) * BK, m_blk * BM, 0);
           tma_load_3d(sa + 2 * A_PLANE_BYTES, &tmW, full_bar(stage), kb * BK, n_blk * BN, 0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -498,11 +502,11 @@ static bool encode_f32_panel_map(CUtensorMap* map, const void* base, uint64_t co
 }
 
 template <class C>
-static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
+static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
                               const Params& p, cudaStream_t st) {
   const int tiles = ceil_div(p.M, BM) * (p.N / C::BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_bf16x3_kernel<C><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmW, tmC, tmR, p);
+  gemm_bf16x3_kernel<C><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmA2, tmW, tmC, tmR, p);
   return cudaGetLastError();
 }
 
@@ -515,27 +519,31 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   cudaError_t e = init_once();
   if (e != cudaSuccess) return e;
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (a.M <= 0 || a.N % 64 != 0 || a.K % 64 != 0 || a.lda % 8 != 0 || a.K > a.lda || a.a_fmt != FMT_SPLIT || a.A2 != nullptr ||
-      a.Wp == nullptr || a.act == ACT_SIGMOID || a.C2 != nullptr || !aligned16(a.A) || !aligned16(a.Wp) || !aligned16(a.C) ||
-      a.ldc % 8 != 0 || a.N > a.ldc) {
-    snprintf(g_err, sizeof g_err, "gemm_tc: unsupported problem M=%d N=%d K=%d lda=%d ldc=%d a_fmt=%d", a.M, a.N, a.K, a.lda, a.ldc,
-             a.a_fmt);
+  const int KT = a.K + (a.Ab ? a.Kb : 0);
+  if (a.M <= 0 || a.N % 64 != 0 || a.K % 64 != 0 || a.lda % 8 != 0 || a.K > a.lda || a.a_fmt != FMT_SPLIT || a.Wp == nullptr ||
+      a.act == ACT_SIGMOID || a.C2 != nullptr || !aligned16(a.A) || !aligned16(a.Wp) || !aligned16(a.C) || a.ldc % 8 != 0 ||
+      a.N > a.ldc || (a.Ab && (a.Kb % 64 != 0 || a.Kb <= 0 || a.ldb % 8 != 0 || a.Kb > a.ldb || !aligned16(a.Ab)))) {
+    snprintf(g_err, sizeof g_err, "gemm_tc: unsupported problem M=%d N=%d K=%d+%d lda=%d ldc=%d a_fmt=%d", a.M, a.N, a.K, a.Ab ? a.Kb : 0,
+             a.lda, a.ldc, a.a_fmt);
     return cudaErrorInvalidValue;
   }
   const int bn = (a.N % 128 == 0) ? 128 : 64;
   Params p{};
   p.scale = a.scale; p.shift = a.shift;
   p.out_fmt = a.c_fmt;
-  p.M = a.M; p.N = a.N; p.K = a.K; p.act = a.act;
+  p.M = a.M; p.N = a.N; p.K = KT; p.act = a.act;
+  p.kb1 = a.K / BK;
   p.res_mode = RES_NONE;
   if (a.res) {
     const bool tma_ok = a.res_mod <= 0 && a.res_fmt == a.c_fmt && aligned16(a.res) && a.ldr % 8 == 0 && a.N <= a.ldr;
     p.res_mode = tma_ok ? RES_TMA : RES_DIRECT;
     p.res = a.res; p.res_fmt = a.res_fmt; p.ldr = a.ldr; p.res_mod = a.res_mod;
   }
-  CUtensorMap tmA, tmW, tmC, tmR;
+  CUtensorMap tmA, tmA2, tmW, tmC, tmR;
   if (!encode_split_map(&tmA, a.A, a.K, a.M, a.lda, BM)) return cudaErrorInvalidValue;
-  if (!encode3(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.Wp, a.K, a.N, 2, (uint64_t)a.K * 2, (uint64_t)a.N * a.K * 2, 64, bn, 2))
+  tmA2 = tmA;
+  if (a.Ab && !encode_split_map(&tmA2, a.Ab, a.Kb, a.M, a.ldb, BM)) return cudaErrorInvalidValue;
+  if (!encode3(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.Wp, KT, a.N, 2, (uint64_t)KT * 2, (uint64_t)a.N * KT * 2, 64, bn, 2))
     return cudaErrorInvalidValue;
   bool ok = a.c_fmt == FMT_F32 ? encode_f32_panel_map(&tmC, a.C, a.N, a.M, a.ldc) : encode_split_map(&tmC, a.C, a.N, a.M, a.ldc, BM);
   if (!ok) return cudaErrorInvalidValue;
@@ -544,9 +552,9 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
     ok = a.c_fmt == FMT_F32 ? encode_f32_panel_map(&tmR, a.res, a.N, a.M, a.ldr) : encode_split_map(&tmR, a.res, a.N, a.M, a.ldr, BM);
     if (!ok) return cudaErrorInvalidValue;
   }
-  if (bn == 64) return launch_cfg<CfgN64>(tmA, tmW, tmC, tmR, p, st);
-  if (a.K >= 512) return launch_cfg<CfgDeep>(tmA, tmW, tmC, tmR, p, st);
-  return launch_cfg<CfgWide>(tmA, tmW, tmC, tmR, p, st);
+  if (bn == 64) return launch_cfg<CfgN64>(tmA, tmA2, tmW, tmC, tmR, p, st);
+  if (KT >= 512) return launch_cfg<CfgDeep>(tmA, tmA2, tmW, tmC, tmR, p, st);
+  return launch_cfg<CfgWide>(tmA, tmA2, tmW, tmC, tmR, p, st);
 }
 
 // fp32 [N,K] -> bf16 [2][N][K] (hi plane, mid plane)

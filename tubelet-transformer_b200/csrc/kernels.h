@@ -37,17 +37,17 @@ cudaError_t launch_tpool(const void* in_split, void* out_split, int B, int Tin, 
 // mean over N rows of a split tensor [B,N,C] -> fp32 [B,C]
 cudaError_t launch_global_avgpool(const void* in_split, float* out, int B, int N, int C, cudaStream_t st);
 
-// ---- GEMM: C = act( scale[n] * ((A (+A2[row % a2_mod])) W^T)[m,n] + shift[n] + res[m % res_mod, n] ) ------
+// ---- GEMM: C = act( scale[n] * ([A | Ab] W^T)[m,n] + shift[n] + res[m % res_mod, n] ) -----------------------
 // One argument block for both implementations:
 //   launch_gemm_tc   tcgen05 bf16x3 tensor-core kernel (gemm_tc.cu): A must be FMT_SPLIT, needs Wp,
-//                    N % 64 == 0, K % 64 == 0, no A2.
+//                    N % 64 == 0, K % 64 == 0, Kb % 64 == 0.
 //   launch_sgemm     fp32 CUDA-core kernel (kernels_simt.cu): any A format, needs Wf, K % 16 == 0; used for
 //                    the tiny-N heads (N = 2, 3, 4, 80) and as the debugging cross-check of the TC kernel.
 struct GemmArgs {
   const void* A; int a_fmt; int lda;         // [M, lda] fp32 or split
-  const float* A2; int lda2; int a2_mod;     // optional fp32 addend on A rows (SIMT only; a2_mod <= 0: same row)
-  const float* Wf;                           // fp32 [N, K] row-major
-  const void* Wp;                            // packed split weights: bf16 [2][N][K]
+  const void* Ab; int ldb; int Kb;           // optional second operand concatenated along K (same format as A): W is [N, K+Kb]
+  const float* Wf;                           // fp32 [N, K+Kb] row-major
+  const void* Wp;                            // packed split weights: bf16 [2][N][K+Kb]
   const float* scale; const float* shift;    // [N] each, nullable (1 / 0)
   const void* res; int res_fmt; int ldr; int res_mod;   // nullable residual, added before act
   void* C; int c_fmt; int ldc;

@@ -352,27 +352,25 @@ sgemm_kernel(GemmArgs p) {
 
   const int am = m0 + lr, wn = n0 + lr;
   const bool a_ok = am < p.M, w_ok = wn < p.N;
+  const int KT = p.K + p.Kb;                     // [A | Ab] along K
   const float* a_ptr = nullptr;
   const __nv_bfloat16* a_hi = nullptr;
-  if (p.a_fmt == FMT_F32)
+  const float* b_ptr = nullptr;
+  const __nv_bfloat16* b_hi = nullptr;
+  if (p.a_fmt == FMT_F32) {
     a_ptr = reinterpret_cast<const float*>(p.A) + (long long)am * p.lda + lk;
-  else
+    if (p.Ab) b_ptr = reinterpret_cast<const float*>(p.Ab) + (long long)am * p.ldb + lk;
+  } else {
     a_hi = split_hi(p.A, am, p.lda) + lk;
-  const float* a2_ptr = nullptr;
-  if (p.A2) {
-    int r2 = p.a2_mod > 0 ? am % p.a2_mod : am;
-    a2_ptr = p.A2 + (long long)r2 * p.lda2 + lk;
+    if (p.Ab) b_hi = split_hi(p.Ab, am, p.ldb) + lk;
   }
-  const float* w_ptr = p.Wf + (long long)wn * p.K + lk;
+  const float* w_ptr = p.Wf + (long long)wn * KT + lk;
 
   auto load_a = [&](int k0) -> float4 {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a_ok) {
-      v = a_ptr ? __ldg(reinterpret_cast<const float4*>(a_ptr + k0)) : load_split4(a_hi + k0, a_hi + p.lda + k0);
-      if (a2_ptr) {
-        float4 u = __ldg(reinterpret_cast<const float4*>(a2_ptr + k0));
-        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-      }
+      if (k0 < p.K) v = a_ptr ? __ldg(reinterpret_cast<const float4*>(a_ptr + k0)) : load_split4(a_hi + k0, a_hi + p.lda + k0);
+      else v = b_ptr ? __ldg(reinterpret_cast<const float4*>(b_ptr + k0 - p.K)) : load_split4(b_hi + k0 - p.K, b_hi + p.ldb + k0 - p.K);
     }
     return v;
   };
@@ -387,11 +385,11 @@ sgemm_kernel(GemmArgs p) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   float4 ra = load_a(0), rw = load_w(0);
-  for (int k0 = 0; k0 < p.K; k0 += BK) {
+  for (int k0 = 0; k0 < KT; k0 += BK) {
     As[lk + 0][lr] = ra.x; As[lk + 1][lr] = ra.y; As[lk + 2][lr] = ra.z; As[lk + 3][lr] = ra.w;
     Ws[lk + 0][lr] = rw.x; Ws[lk + 1][lr] = rw.y; Ws[lk + 2][lr] = rw.z; Ws[lk + 3][lr] = rw.w;
     __syncthreads();
-    if (k0 + BK < p.K) {
+    if (k0 + BK < KT) {
       ra = load_a(k0 + BK);
       rw = load_w(k0 + BK);
     }
@@ -444,7 +442,7 @@ sgemm_kernel(GemmArgs p) {
 }
 
 cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st) {
-  if (a.K % 16 != 0 || a.M <= 0 || a.N <= 0 || a.Wf == nullptr) return cudaErrorInvalidValue;
+  if (a.K % 16 != 0 || a.Kb % 16 != 0 || a.M <= 0 || a.N <= 0 || a.Wf == nullptr) return cudaErrorInvalidValue;
   dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64));
   sgemm_kernel<<<grid, 256, 0, st>>>(a);
   return cudaGetLastError();

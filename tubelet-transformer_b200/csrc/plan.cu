@@ -67,7 +67,8 @@ struct Dw { float* w = nullptr; float* scale = nullptr; float* shift = nullptr; 
 struct LnP { float* g = nullptr; float* b = nullptr; int C = 0; };
 
 struct Block {
-  Lin conv1, conv4, ds;
+  Lin conv1, conv4;
+  Lin c4ds;                 // first block of a stage: [s4*W4 | sd*Wd] with shift b4 + bd (conv4 and the shortcut as one GEMM)
   Dw dw;
   bool has_ds = false;
   int st_t = 1, st_s = 1, cin = 0, planes = 0, cout = 0;
@@ -337,7 +338,22 @@ int do_finalize(TuberPlan* p) {
         }
       }
       b.conv4 = pk.conv_bn(P + ".conv4", P + ".bn4", outp, planes);
-      if (b.has_ds) b.ds = pk.conv_bn(P + ".down_sample.0", P + ".down_sample.1", outp, b.cin);
+      if (b.has_ds) {
+        // relu(bn4(W4 t2) + bn_d(Wd x)) = relu([t2 | x] [s4*W4 | sd*Wd]^T + (b4 + bd)): one GEMM, no shortcut tensor in HBM
+        const HostTensor* w4 = pk.get(P + ".conv4.weight", {outp, planes});
+        const HostTensor* wd = pk.get(P + ".down_sample.0.weight", {outp, b.cin});
+        std::vector<float> s4, b4, sd, bd;
+        if (w4 && wd && pk.bn(P + ".bn4", outp, s4, b4) && pk.bn(P + ".down_sample.1", outp, sd, bd)) {
+          const int kt = planes + b.cin;
+          std::vector<float> wcat((size_t)outp * kt), bias(outp);
+          for (int n = 0; n < outp; ++n) {
+            for (int k = 0; k < planes; ++k) wcat[(size_t)n * kt + k] = s4[n] * w4->data[(size_t)n * planes + k];
+            for (int k = 0; k < b.cin; ++k) wcat[(size_t)n * kt + planes + k] = sd[n] * wd->data[(size_t)n * b.cin + k];
+            bias[n] = b4[n] + bd[n];
+          }
+          b.c4ds = pk.make_lin(wcat, outp, kt, nullptr, &bias);
+        }
+      }
       p->blocks[li].push_back(b);
     }
     in_planes = outp;
@@ -525,14 +541,15 @@ struct Ctx {
 
   // C = act(scale * A W^T + shift + res)
   void gemm(const void* A, int a_fmt, int lda, long long M, const Lin& w, const void* res, int res_fmt, int ldr, int res_mod,
-            void* C, int c_fmt, int ldc, int act) {
+            void* C, int c_fmt, int ldc, int act, const void* Ab = nullptr, int ldb = 0, int Kb = 0) {
     if (!ok()) return;
     GemmArgs a{};
     a.A = A; a.a_fmt = a_fmt; a.lda = lda;
+    a.Ab = Ab; a.ldb = ldb; a.Kb = Ab ? Kb : 0;
     a.Wf = w.wf; a.Wp = w.wp; a.scale = w.scale; a.shift = w.shift;
     a.res = res; a.res_fmt = res_fmt; a.ldr = ldr; a.res_mod = res_mod;
     a.C = C; a.c_fmt = c_fmt; a.ldc = ldc;
-    a.M = (int)M; a.N = w.N; a.K = w.K; a.act = act;
+    a.M = (int)M; a.N = w.N; a.K = w.K - a.Kb; a.act = act;
     const bool tc_ok = a_fmt == FMT_SPLIT && w.N % 64 == 0 && w.K % 64 == 0 && act != ACT_SIGMOID && lda % 8 == 0 && ldc % 8 == 0;
     const bool tc = tc_ok && !p->force_simt;
     if (p->kprof) snprintf(tag, sizeof tag, "M=%lld N=%d K=%d res=%d/%d out=%d act=%d", M, w.N, w.K, res ? 1 + res_fmt : 0, res_mod, c_fmt, act);
@@ -640,7 +657,7 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
   const int d = c.d_model, nh = c.nhead, hd = d / nh, Q = c.num_queries, Le = c.enc_layers, Ld = c.dec_layers;
 
   // ---- backbone buffers (ping-pong block outputs, conv1 / depthwise / shortcut scratch) ----
-  size_t max_out = (size_t)B * T * g.H1 * g.W1 * 64, max_t1 = 0, max_t2 = 0, max_res = 0, max_xg = 0;
+  size_t max_out = (size_t)B * T * g.H1 * g.W1 * 64, max_t1 = 0, max_t2 = 0, max_xg = 0;
   {
     size_t x0 = (size_t)B * T * g.H2 * g.W2 * 64;
     if (x0 > max_out) max_out = x0;
@@ -653,7 +670,6 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
         max_t2 = std::max(max_t2, vout * b.planes);
         max_out = std::max(max_out, vout * b.cout);
         if (b.has_ds) {
-          max_res = std::max(max_res, vout * b.cout);
           if (b.st_t != 1 || b.st_s != 1) max_xg = std::max(max_xg, vout * b.cin);
         }
         t = to; h = ho; w = wo;
@@ -663,7 +679,6 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
   char* bufB = (char*)cx.ws.alloc(max_out * 4);
   float* t1 = (float*)cx.ws.alloc(max_t1 * 4);
   void* t2 = cx.ws.alloc(max_t2 * 4);
-  void* resb = cx.ws.alloc(max_res * 4);
   void* xg = cx.ws.alloc(max_xg * 4 + 16);
 
   // ---- stem: conv + BN + ReLU (F, NDHWC) then the (1,3,3) max pool (S) ----
@@ -689,19 +704,17 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
       cx.gemm(cur, FMT_SPLIT, b.cin, vin, b.conv1, nullptr, 0, 0, 0, t1, FMT_F32, b.planes, ACT_RELU);
       cx.launch("dwconv3x3x3", 4.0 * ((double)vin + vout) * b.planes, 54.0 * vout * b.planes,
                 [&] { return launch_dwconv(t1, b.dw.w, b.dw.scale, b.dw.shift, t2, B, t, h, w, b.planes, b.st_t, b.st_s, to, ho, wo, st); });
-      const void* res = cur;
-      int res_fmt = FMT_SPLIT, ldr = b.cin;
       if (b.has_ds) {
-        const void* a = cur;
+        const void* xa = cur;                                // the shortcut's input rows (strided voxel gather when the block strides)
         if (b.st_t != 1 || b.st_s != 1) {
           cx.launch("gather_rows", 8.0 * vout * b.cin, 0.0,
                     [&] { return launch_gather_rows(cur, xg, b.cin * 4, B, t, h, w, b.st_t, b.st_s, to, ho, wo, st); });
-          a = xg;
+          xa = xg;
         }
-        cx.gemm(a, FMT_SPLIT, b.cin, vout, b.ds, nullptr, 0, 0, 0, resb, FMT_SPLIT, b.cout, ACT_NONE);
-        res = resb; res_fmt = FMT_SPLIT; ldr = b.cout;
+        cx.gemm(t2, FMT_SPLIT, b.planes, vout, b.c4ds, nullptr, 0, 0, 0, nxt, FMT_SPLIT, b.cout, ACT_RELU, xa, b.cin, b.cin);
+      } else {
+        cx.gemm(t2, FMT_SPLIT, b.planes, vout, b.conv4, cur, FMT_SPLIT, b.cin, 0, nxt, FMT_SPLIT, b.cout, ACT_RELU);
       }
-      cx.gemm(t2, FMT_SPLIT, b.planes, vout, b.conv4, res, res_fmt, ldr, 0, nxt, FMT_SPLIT, b.cout, ACT_RELU);
       std::swap(cur, nxt);
       t = to; h = ho; w = wo;
     }
