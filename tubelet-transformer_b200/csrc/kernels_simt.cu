@@ -2,6 +2,7 @@
 // depthwise 3x3x3 stencil, strided gathers, temporal pooling, fp32 GEMM for the token-sized
 // linear layers, LayerNorm, attention cores, padding-mask resize and the 3-D sine position code.
 // The tensor-core GEMM lives in gemm_tc.cu.  All activations are channels-last (NDHWC).
+#include <cuda.h>
 #include <float.h>
 #include <math.h>
 
@@ -119,109 +120,172 @@ dwconv_kernel(const float* __restrict__ in, const float* __restrict__ wpk, const
 }
 
 // Stride-1 variant with a shared-memory halo tile (the 24 stride-1 blocks of CSN-152 / 13 of CSN-50 are the
-// ones that matter): a CTA produces a TT x TH x TW block of outputs for CC = 32 channels from a
-// (TT+2) x (TH+2) x (TW+2) input block staged once with cp.async (zero-filled outside the volume), so every
-// input element leaves L2 ~2.3x instead of 9x.  A thread owns one output row of TW = 8 voxels x 4 channels.
+// ones that matter): a tile = TT x TH x TW outputs for CC = 32 channels, computed from a (TT+2) x (TH+2) x (TW+2)
+// input block that ONE 5-D TMA load brings in (out-of-volume voxels are zero-filled by the TMA unit = the conv's
+// padding), so every input element leaves L2 ~2.3x instead of 9x and no thread computes a load address.
+// CTAs are persistent (one per SM) and double buffered: the halo block of tile i+1 streams in while tile i is
+// computed.  A thread owns one output row of TW = 8 voxels x 4 channels.
 namespace dwt {
 constexpr int TT = 4, TH = 8, TW = 8, CC = 32;
 constexpr int IT = TT + 2, IH = TH + 2, IW = TW + 2;
 constexpr int IN_F4 = IT * IH * IW * (CC / 4);            // float4 slots of the input tile
-constexpr int SMEM_BYTES = IN_F4 * 16 + 27 * CC * 4;      // + this chunk's 27 x CC weights
+constexpr int W_F4 = 27 * (CC / 4);                       // this chunk's 27 x CC weights
+constexpr int STAGE_F4 = IN_F4 + W_F4 + 8;                // keep stages 128-byte aligned
+constexpr int STAGE_TX = (IN_F4 + W_F4) * 16;
+constexpr int SMEM_BYTES = 2 * STAGE_F4 * 16 + 16;        // + two mbarriers
 constexpr int THREADS = TT * TH * (CC / 4);               // 256
 }  // namespace dwt
 
-__global__ void __launch_bounds__(dwt::THREADS, 2)
-dwconv_s1_tiled_kernel(const float* __restrict__ in, const float* __restrict__ wpk, const float* __restrict__ scale,
-                       const float* __restrict__ shift, void* __restrict__ out, int B, int T, int H, int W, int C) {
+__global__ void __launch_bounds__(dwt::THREADS, 1)
+dwconv_s1_tiled_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
+                       const float* __restrict__ scale, const float* __restrict__ shift, void* __restrict__ out, int B, int T,
+                       int H, int W, int C, int ntiles) {
   using namespace dwt;
-  extern __shared__ __align__(16) float4 dw_smem[];
-  float4* tile = dw_smem;                                   // [IT][IH][IW][CC/4]
-  float4* wsm = dw_smem + IN_F4;                            // [27][CC/4]
+  extern __shared__ __align__(128) float4 dw_smem[];
   const int tid = threadIdx.x;
-  const int wt = (W + TW - 1) / TW, ht = (H + TH - 1) / TH, tt = (T + TT - 1) / TT;
-  int bid = blockIdx.x;
-  const int cb = (blockIdx.y) * CC;                         // channel chunk
-  const int w0 = (bid % wt) * TW; bid /= wt;
-  const int h0 = (bid % ht) * TH; bid /= ht;
-  const int t0 = (bid % tt) * TT;
-  const int b = bid / tt;
+  const int wt = (W + TW - 1) / TW, ht = (H + TH - 1) / TH, tt = (T + TT - 1) / TT, nch = C / CC;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(dw_smem);
+  const uint32_t bar0 = sbase + 2 * STAGE_F4 * 16;
 
-  for (int i = tid; i < IN_F4; i += THREADS) {
-    const int c4 = i % (CC / 4);
-    int r = i / (CC / 4);
-    const int iw = w0 - 1 + r % IW; r /= IW;
-    const int ih = h0 - 1 + r % IH;
-    const int it = t0 - 1 + r / IH;
-    const bool ok = it >= 0 && it < T && ih >= 0 && ih < H && iw >= 0 && iw < W;
-    const float* src = ok ? in + ((((long long)b * T + it) * H + ih) * W + iw) * (long long)C + cb + c4 * 4 : in;
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + i);
-    const int nbytes = ok ? 16 : 0;                         // src-size 0: the 16 destination bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+  auto decode = [&](int tile, int& b, int& t0, int& h0, int& w0, int& cb) {
+    cb = (tile % nch) * CC; tile /= nch;                    // channel chunks of one spatial tile are neighbours (L2 reuse)
+    w0 = (tile % wt) * TW; tile /= wt;
+    h0 = (tile % ht) * TH; tile /= ht;
+    t0 = (tile % tt) * TT;
+    b = tile / tt;
+  };
+  auto prefetch = [&](int tile, int buf) {                  // one thread: two bulk tensor loads onto the stage's mbarrier
+    int b, t0, h0, w0, cb;
+    decode(tile, b, t0, h0, w0, cb);
+    const uint32_t dst = sbase + buf * STAGE_F4 * 16, bar = bar0 + 8 * buf;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)STAGE_TX) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(&tmIn), "r"(bar), "r"(cb), "r"(w0 - 1), "r"(h0 - 1), "r"(t0 - 1), "r"(b) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst + IN_F4 * 16), "l"(&tmW), "r"(bar), "r"(cb), "r"(0) : "memory");
+  };
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 27 * (CC / 4); i += THREADS) {
-    const int c4 = i % (CC / 4), tap = i / (CC / 4);
-    wsm[i] = __ldg(reinterpret_cast<const float4*>(wpk + (long long)tap * C + cb) + c4);
-  }
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   const int c4 = tid % (CC / 4);
   const int lh = (tid / (CC / 4)) % TH, lt = tid / ((CC / 4) * TH);
-  const int oh = h0 + lh, ot = t0 + lt;
-  if (oh >= H || ot >= T) return;
-  float4 acc[TW];
+  int tile = blockIdx.x, buf = 0;
+  uint32_t phase[2] = {0, 0};
+  if (tid == 0 && tile < ntiles) prefetch(tile, 0);
+  for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) prefetch(next, buf ^ 1);   // that stage was released by the barrier ending the last iteration
+    {
+      const uint32_t bar = bar0 + 8 * buf, par = phase[buf];
+      asm volatile(
+          "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n"
+          ::"r"(bar), "r"(par) : "memory");
+      phase[buf] ^= 1;
+    }
+    int b, t0, h0, w0, cb;
+    decode(tile, b, t0, h0, w0, cb);
+    const float4* tsm = dw_smem + buf * STAGE_F4;
+    const float4* wsm = tsm + IN_F4;
+    const int oh = h0 + lh, ot = t0 + lt;
+    if (oh < H && ot < T) {
+      float4 acc[TW];
 #pragma unroll
-  for (int j = 0; j < TW; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < TW; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int kt = 0; kt < 3; ++kt) {
+      for (int kt = 0; kt < 3; ++kt) {
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const float4* row = tile + (((lt + kt) * IH + lh + kh) * IW) * (CC / 4) + c4;
-      float4 x[IW];
+        for (int kh = 0; kh < 3; ++kh) {
+          const float4* row = tsm + (((lt + kt) * IH + lh + kh) * IW) * (CC / 4) + c4;
+          float4 x[IW];
 #pragma unroll
-      for (int q = 0; q < IW; ++q) x[q] = row[q * (CC / 4)];
+          for (int q = 0; q < IW; ++q) x[q] = row[q * (CC / 4)];
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const float4 wv = wsm[((kt * 3 + kh) * 3 + kw) * (CC / 4) + c4];
+          for (int kw = 0; kw < 3; ++kw) {
+            const float4 wv = wsm[((kt * 3 + kh) * 3 + kw) * (CC / 4) + c4];
 #pragma unroll
-        for (int j = 0; j < TW; ++j) {
-          acc[j].x = fmaf(x[j + kw].x, wv.x, acc[j].x);
-          acc[j].y = fmaf(x[j + kw].y, wv.y, acc[j].y);
-          acc[j].z = fmaf(x[j + kw].z, wv.z, acc[j].z);
-          acc[j].w = fmaf(x[j + kw].w, wv.w, acc[j].w);
+            for (int j = 0; j < TW; ++j) {
+              acc[j].x = fmaf(x[j + kw].x, wv.x, acc[j].x);
+              acc[j].y = fmaf(x[j + kw].y, wv.y, acc[j].y);
+              acc[j].z = fmaf(x[j + kw].z, wv.z, acc[j].z);
+              acc[j].w = fmaf(x[j + kw].w, wv.w, acc[j].w);
+            }
+          }
         }
       }
-    }
-  }
-  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cb) + c4);
-  const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cb) + c4);
-  const long long orow0 = (((long long)b * T + ot) * H + oh) * W + w0;
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cb) + c4);
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cb) + c4);
+      const long long orow0 = (((long long)b * T + ot) * H + oh) * W + w0;
 #pragma unroll
-  for (int j = 0; j < TW; ++j) {
-    if (w0 + j >= W) break;
-    float4 o;
-    o.x = fmaxf(fmaf(acc[j].x, sc.x, sh.x), 0.f);
-    o.y = fmaxf(fmaf(acc[j].y, sc.y, sh.y), 0.f);
-    o.z = fmaxf(fmaf(acc[j].z, sc.z, sh.z), 0.f);
-    o.w = fmaxf(fmaf(acc[j].w, sc.w, sh.w), 0.f);
-    __nv_bfloat16* hi = split_hi(out, orow0 + j, C) + cb + c4 * 4;
-    store_split4(hi, hi + C, o);
+      for (int j = 0; j < TW; ++j) {
+        if (w0 + j >= W) break;
+        float4 o;
+        o.x = fmaxf(fmaf(acc[j].x, sc.x, sh.x), 0.f);
+        o.y = fmaxf(fmaf(acc[j].y, sc.y, sh.y), 0.f);
+        o.z = fmaxf(fmaf(acc[j].z, sc.z, sh.z), 0.f);
+        o.w = fmaxf(fmaf(acc[j].w, sc.w, sh.w), 0.f);
+        __nv_bfloat16* hi = split_hi(out, orow0 + j, C) + cb + c4 * 4;
+        store_split4(hi, hi + C, o);
+      }
+    }
+    __syncthreads();                                        // every reader is done: the stage may be refilled
   }
 }
+
+namespace dwt {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 0;
+static cudaError_t init_once() {
+  if (g_encode) return cudaSuccess;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) return e != cudaSuccess ? e : cudaErrorNotSupported;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaFuncSetAttribute(dwconv_s1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return cudaSuccess;
+}
+}  // namespace dwt
 
 cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale, const float* shift,
                           void* out_split, int B, int Ti, int Hi, int Wi, int C, int st_t, int st_s, int To,
                           int Ho, int Wo, cudaStream_t st) {
   if (st_t == 1 && st_s == 1 && C % dwt::CC == 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(dwconv_s1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dwt::SMEM_BYTES);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
+    using namespace dwt;
+    cudaError_t e = init_once();
+    if (e != cudaSuccess) return e;
+    CUtensorMap tmIn, tmW;
+    {
+      cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Ti, (cuuint64_t)B};
+      cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)Wi * C * 4, (cuuint64_t)Hi * Wi * C * 4, (cuuint64_t)Ti * Hi * Wi * C * 4};
+      cuuint32_t box[5] = {CC, IW, IH, IT, 1}, es[5] = {1, 1, 1, 1, 1};
+      if (g_encode(&tmIn, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
     }
-    const long long tiles = (long long)B * ceil_div(Ti, dwt::TT) * ceil_div(Hi, dwt::TH) * ceil_div(Wi, dwt::TW);
-    dim3 grid((unsigned)tiles, C / dwt::CC);
-    dwconv_s1_tiled_kernel<<<grid, dwt::THREADS, dwt::SMEM_BYTES, st>>>(in, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C);
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)C, 27};
+      cuuint64_t strides[1] = {(cuuint64_t)C * 4};
+      cuuint32_t box[2] = {CC, 27}, es[2] = {1, 1};
+      if (g_encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(wpk), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+    }
+    const long long tiles = (long long)B * ceil_div(Ti, TT) * ceil_div(Hi, TH) * ceil_div(Wi, TW) * (C / CC);
+    const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+    dwconv_s1_tiled_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmIn, tmW, scale, shift, out_split, B, Ti, Hi, Wi, C, (int)tiles);
     return cudaGetLastError();
   }
   long long total = (long long)B * To * Ho * ((Wo + 3) / 4) * (C / 4);
