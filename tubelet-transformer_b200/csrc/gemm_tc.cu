@@ -527,7 +527,9 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
              a.lda, a.ldc, a.a_fmt);
     return cudaErrorInvalidValue;
   }
-  const int bn = (a.N % 128 == 0) ? 128 : 64;
+  // 128-wide tiles unless that leaves most of the machine idle (token-sized GEMMs): then 64-wide tiles double the CTA count
+  int bn = (a.N % 128 == 0) ? 128 : 64;
+  if (bn == 128 && (long long)ceil_div(a.M, BM) * (a.N / 128) * 2 <= g_num_sms) bn = 64;
   Params p{};
   p.scale = a.scale; p.shift = a.shift;
   p.out_fmt = a.c_fmt;

@@ -132,7 +132,8 @@ constexpr int IN_F4 = IT * IH * IW * (CC / 4);            // float4 slots of the
 constexpr int W_F4 = 27 * (CC / 4);                       // this chunk's 27 x CC weights
 constexpr int STAGE_F4 = IN_F4 + W_F4 + 8;                // keep stages 128-byte aligned
 constexpr int STAGE_TX = (IN_F4 + W_F4) * 16;
-constexpr int SMEM_BYTES = 2 * STAGE_F4 * 16 + 16;        // + two mbarriers
+constexpr int NSTAGE = 2;                                 // double buffered, one CTA per SM (two single-stage CTAs measured slower)
+constexpr int SMEM_BYTES = NSTAGE * STAGE_F4 * 16 + 16;   // + mbarriers
 constexpr int THREADS = TT * TH * (CC / 4);               // 256
 }  // namespace dwt
 
@@ -145,7 +146,7 @@ dwconv_s1_tiled_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_co
   const int tid = threadIdx.x;
   const int wt = (W + TW - 1) / TW, ht = (H + TH - 1) / TH, tt = (T + TT - 1) / TT, nch = C / CC;
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(dw_smem);
-  const uint32_t bar0 = sbase + 2 * STAGE_F4 * 16;
+  const uint32_t bar0 = sbase + NSTAGE * STAGE_F4 * 16;
 
   auto decode = [&](int tile, int& b, int& t0, int& h0, int& w0, int& cb) {
     cb = (tile % nch) * CC; tile /= nch;                    // channel chunks of one spatial tile are neighbours (L2 reuse)
@@ -178,9 +179,9 @@ dwconv_s1_tiled_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_co
   int tile = blockIdx.x, buf = 0;
   uint32_t phase[2] = {0, 0};
   if (tid == 0 && tile < ntiles) prefetch(tile, 0);
-  for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+  for (; tile < ntiles; tile += gridDim.x, buf = (buf + 1) % NSTAGE) {
     const int next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) prefetch(next, buf ^ 1);   // that stage was released by the barrier ending the last iteration
+    if (NSTAGE == 2 && tid == 0 && next < ntiles) prefetch(next, buf ^ 1);   // that stage was released by the barrier ending the last iteration
     {
       const uint32_t bar = bar0 + 8 * buf, par = phase[buf];
       asm volatile(
@@ -234,6 +235,7 @@ dwconv_s1_tiled_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_co
       }
     }
     __syncthreads();                                        // every reader is done: the stage may be refilled
+    if (NSTAGE == 1 && tid == 0 && next < ntiles) prefetch(next, 0);
   }
 }
 
@@ -284,7 +286,8 @@ cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale,
         return cudaErrorInvalidValue;
     }
     const long long tiles = (long long)B * ceil_div(Ti, TT) * ceil_div(Hi, TH) * ceil_div(Wi, TW) * (C / CC);
-    const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+    const long long slots = (long long)g_num_sms * (NSTAGE == 1 ? 2 : 1);
+    const int grid = (int)(tiles < slots ? tiles : slots);
     dwconv_s1_tiled_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmIn, tmW, scale, shift, out_split, B, Ti, Hi, Wi, C, (int)tiles);
     return cudaGetLastError();
   }
