@@ -11,9 +11,12 @@
 // ---- stem (ir_CSN_152.py:109-122,176-179), stem_tc.cu --------------------------------------
 // filter (64,3,3,7,7) fp32 = [oc][441] -> packed split bf16 [2][64][576] in the kernel's K order
 cudaError_t launch_stem_pack_weight(const float* w_oc441, void* out, cudaStream_t st);
-// x NCDHW fp32 (B,3,T,H,W); wpk from launch_stem_pack_weight; y NDHWC fp32 [B,T,H1,W1,64] = relu(conv*scale+shift)
-cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale, const float* shift,
-                             float* y, int B, int T, int H, int W, int H1, int W1, cudaStream_t st);
+// x NCDHW fp32 (B,3,T,H,W); wpk from launch_stem_pack_weight.  When stem_pool_is_fused(W1) the kernel writes the
+// max-pooled result (split [B,T,H2,W2,64]) itself and y is not touched; otherwise it writes the conv rows
+// y = relu(conv*scale+shift) (fp32 NDHWC [B,T,H1,W1,64]) and launch_maxpool_hw must follow.
+bool stem_pool_is_fused(int W1);
+cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale, const float* shift, float* y, void* pooled,
+                             int B, int T, int H, int W, int H1, int W1, cudaStream_t st);
 // (1,3,3)/s(1,2,2)/p(0,1,1) max pool, fp32 [BT,H1,W1,C] -> split [BT,H2,W2,C]
 cudaError_t launch_maxpool_hw(const float* in, void* out_split, int BT, int H1, int W1, int H2, int W2,
                               int C, cudaStream_t st);

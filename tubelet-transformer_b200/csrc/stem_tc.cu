@@ -1,25 +1,29 @@
-// Stem convolution on the tensor cores (sm_100a): Conv3d(3->64,(3,7,7),s(1,2,2),p(1,3,3)) + BN + ReLU
-// (reference models/backbones/ir_CSN_152.py:109-120,176-178) as an implicit GEMM with tcgen05.
+// Stem of the CSN backbone on the tensor cores (sm_100a): Conv3d(3->64,(3,7,7),s(1,2,2),p(1,3,3)) + BN + ReLU +
+// MaxPool3d((1,3,3),s(1,2,2),p(0,1,1))  (reference models/backbones/ir_CSN_152.py:109-122,176-179) as an
+// implicit GEMM with tcgen05 and the max pool fused into the epilogue.
 //
-//   out[pos, oc] = relu(scale[oc] * sum_k patch[pos, k] * w[oc, k] + shift[oc])
+//   conv[pos, oc] = relu(scale[oc] * sum_k patch[pos, k] * w[oc, k] + shift[oc])
 //
-// GEMM view per tile: M = 128 consecutive output columns of one output row (b, t, oh), N = 32 output
-// channels (a CTA owns one half of the 64 channels so that its packed filter bank, 64 KB, stays resident
-// in shared memory), K = 576 = 9 k-blocks x 8 groups x 8: k-block = input plane (c, kt), group = filter row kh
-// (group 7 is all zero), and a group holds the 7 taps kw = 0..6 of that filter row plus one zero tap.  The patch
-// row of a group is simply 8 consecutive pixels in[c, t+kt-1, 2*oh+kh-3, 2*ow-3 .. 2*ow+4], so the A operand is
-// built by threads from a ring of input rows kept in shared memory:
+// GEMM view per tile: M = 128 consecutive output columns of one conv row (b, t, oh), N = 32 output channels (a CTA
+// owns one half of the 64 channels so that its packed filter bank, 72 KB, stays resident in shared memory),
+// K = 576 = 9 k-blocks x 8 groups x 8: k-block = input plane (c, kt), group = filter row kh (group 7 is all zero),
+// and a group holds the 7 taps kw = 0..6 of that filter row plus one zero tap.  The patch row of a group is simply 8
+// consecutive pixels in[c, t+kt-1, 2*oh+kh-3, 2*ow-3 .. 2*ow+4], so the A operand is built by threads from a ring of
+// input rows kept in shared memory:
 //
-//   ring      [9 (c,kt) planes][8 row slots][264 pixels], each pixel pre-split into (bf16 hi | bf16 mid << 16);
-//             a new output row needs only two new input rows per plane (slot = input row & 7).
-//   builders  8 warps: stage the ring (global fp32 -> split, zero padding applied here), then for each of the
-//             9 k-blocks write the 128 x 64 hi and mid A tiles straight into TENSOR MEMORY (tcgen05.st, thread =
-//             row): the A operand never touches shared memory, whose bandwidth is what bounds this kernel.
-//   MMA       1 thread: three bf16 passes (mid*hi + hi*mid + hi*hi) of tcgen05.mma M=128, N=32, K=16 with A from
-//             tensor memory and the filter bank from shared memory, into two fp32 TMEM accumulators (K-step
+//   ring      two planar arrays (bf16 hi, bf16 mid) of [9 (c,kt) planes][8 row slots][132 pixel pairs]; a new conv row
+//             needs only two new input rows per plane (slot = input row & 7); zero padding is applied at staging.
+//   builders  8 warps: stage the ring (global fp32 -> split), then write the 128 x 64 hi and mid A tiles of each
+//             k-block straight into TENSOR MEMORY (tcgen05.st, thread = row; 4 x LDS.32 per plane and group, no
+//             shuffling): the im2col expansion never touches shared memory.  A stage = the 3 k-blocks of one input
+//             channel (192 TMEM columns), two stages.
+//   MMA       1 elected lane: three bf16 passes (mid*hi + hi*mid + hi*hi) of tcgen05.mma M=128, N=32, K=16 with A
+//             from tensor memory and the filter bank from shared memory, into two fp32 TMEM accumulators (K-step
 //             parity), double buffered per tile.
-//   epilogue  4 warps: tcgen05.ld, BN scale/shift + ReLU, 128B-swizzled panel in shared memory, TMA store
-//             into the channels-last fp32 output [B*T*H1, W1, 64].
+//   epilogue  4 warps: tcgen05.ld, BN scale/shift + ReLU into a 3-row ring of conv rows in shared memory; every
+//             second row the 3x3/s2 max pool of the last three rows is written in split-bf16 to [B*T, H2, W2, 64].
+//             A unit of 16 conv rows recomputes the one conv row above it that its first pooled row needs.
+//             (When W1 > 128 the conv rows go to HBM through TMA instead and a separate kernel pools.)
 #include <cuda.h>
 #include <stdio.h>
 
@@ -30,30 +34,36 @@ namespace stemtc {
 constexpr int KB = 9;                       // k-blocks of 64 = input planes (c, kt)
 constexpr int KTOT = KB * 64;
 constexpr int NCH = 32;                     // output channels per CTA
-constexpr int A_STAGES = 4;                 // A k-block stages in TENSOR MEMORY (64 columns each: hi 32 + mid 32)
+constexpr int A_STAGES = 2;                 // A stages in TENSOR MEMORY: 3 k-blocks (one input channel) = 192 columns each
+constexpr int KB_PER_STAGE = 3;
+constexpr int STAGE_COLS = KB_PER_STAGE * 64;
 constexpr int W_KB_BYTES = 2 * NCH * 128;   // 8 KB per k-block (hi 4 KB + mid 4 KB)
 constexpr int W_BYTES = KB * W_KB_BYTES;    // 72 KB
-constexpr int RING_PX = 264;
-constexpr int RING_BYTES = 9 * 8 * RING_PX * 4;   // 76032
-constexpr int OUT_BYTES = 128 * 128;        // 128 positions x 32 fp32
+constexpr int RING_PX = 264, RING_PAIRS = RING_PX / 2;
+constexpr int RING_PLANE_BYTES = 9 * 8 * RING_PAIRS * 4;      // 38016: one of the two planar arrays (hi / mid)
+constexpr int ROWBUF_BYTES = 128 * 128;     // one conv row: 128 positions x 32 fp32, 128B-swizzled
 constexpr int OFF_W = 0;
-constexpr int OFF_OUT = OFF_W + W_BYTES;
-constexpr int OFF_RING = OFF_OUT + OUT_BYTES;
-constexpr int OFF_BAR = OFF_RING + ((RING_BYTES + 127) / 128) * 128;
-constexpr int OFF_SS = OFF_BAR + 128;              // scale[32], shift[32] of this CTA's channels
+constexpr int OFF_ROWS = OFF_W + W_BYTES;                     // 3 conv rows
+constexpr int OFF_RING_HI = OFF_ROWS + 3 * ROWBUF_BYTES;
+constexpr int OFF_RING_MID = OFF_RING_HI + RING_PLANE_BYTES;
+constexpr int OFF_BAR = OFF_RING_MID + ((RING_PLANE_BYTES + 127) / 128) * 128;
+constexpr int OFF_SS = OFF_BAR + 128;       // scale[32], shift[32] of this CTA's channels
 constexpr int SMEM_BYTES = OFF_SS + 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(OFF_RING_HI % 128 == 0 && OFF_RING_MID % 4 == 0, "alignment");
 constexpr int NUM_THREADS = 416;            // warp 0 MMA, warps 1-4 epilogue, warps 5-12 builders
 constexpr int NBUILD = 256;
 constexpr int NACC = 2;                     // independent TMEM accumulators per tile (K-step parity)
 constexpr int A_COL0 = 2 * NACC * NCH;      // TMEM columns: [0, 128) accumulators (2 tile buffers), then the A stages
-constexpr int TMEM_COLS = 512;              // 128 + 4 x 64 = 384 -> next power of two
-constexpr int ROWS_PER_UNIT = 16;
+constexpr int TMEM_COLS = 512;              // 128 + 2 x 192
+constexpr int ROWS_PER_UNIT = 32;
 
 struct Params {
   const float* x;                           // (B,3,T,H,W) fp32
   const float* scale; const float* shift;   // [64]
-  int B, T, H, W, H1, W1;
+  void* pooled;                             // split [B*T*H2*W2, 64] (fused pool) or null
+  int B, T, H, W, H1, W1, H2, W2;
+  int fuse_pool;
 };
 
 TB_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -163,11 +173,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 TB_DEVINL uint32_t swz(uint32_t base, int r, int j) { return base + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4); }
 
-// pixel -> (bf16 hi) | (bf16 mid) << 16
-TB_DEVINL uint32_t split_pack(float v) {
-  __nv_bfloat16 hi, mid;
-  split_bf16(v, hi, mid);
-  return pack_bf16x2(hi, mid);
+TB_DEVINL uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+TB_DEVINL uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -189,11 +203,17 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   const int rb_n = (p.H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
   const int units = p.B * p.T * owb_n * rb_n;
   const int cta = blockIdx.x >> 1, ncta = gridDim.x >> 1;
+  // conv rows of unit row-block rb: [first, r1); with the fused pool the row above the block is recomputed
+  auto unit_rows = [&](int rb, int& first, int& r0, int& r1) {
+    r0 = rb * ROWS_PER_UNIT;
+    r1 = min(p.H1, r0 + ROWS_PER_UNIT);
+    first = (p.fuse_pool && r0 > 0) ? r0 - 1 : r0;
+  };
 
   if (threadIdx.x == 0) {
     if (sb & 1023u) __trap();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+    if (!p.fuse_pool) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
     for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(full_bar(s), NBUILD / 32);
       mbar_init(empty_bar(s), 1);
@@ -227,30 +247,34 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     int stage = 0, it = 0;
     uint32_t phase = 0;
     for (int u = cta; u < units; u += ncta) {
-      const int rb = u % rb_n;
-      const int r0 = rb * ROWS_PER_UNIT, r1 = min(p.H1, r0 + ROWS_PER_UNIT);
-      for (int oh = r0; oh < r1; ++oh, ++it) {
+      int first, r0, r1;
+      unit_rows(u % rb_n, first, r0, r1);
+      for (int oh = first; oh < r1; ++oh, ++it) {
         const int as = it & 1;
         mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * NACC * NCH);
 #pragma unroll 1
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int c = 0; c < 3; ++c) {                           // one A stage = the three planes of input channel c
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           if (elect_one()) {
-            const uint32_t a_hi = tmem_base + (uint32_t)(A_COL0 + stage * 64), a_mid = a_hi + 32;   // 8 columns per K=16 step
-            const uint64_t w_hi = w_desc0 + (uint64_t)(kb * (W_KB_BYTES >> 4)), w_mid = w_hi + ((NCH * 128) >> 4);
-            const uint32_t first = kb == 0 ? 0u : 1u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {                      // even / odd K-steps accumulate separately
-              const uint32_t d = tmem_d + (uint32_t)((k & 1) * NCH);
-              umma_bf16_ts(d, a_mid + 8 * k, w_hi + 2 * k, idesc, k < 2 ? first : 1u);
-              umma_bf16_ts(d, a_hi + 8 * k, w_mid + 2 * k, idesc, 1u);
-              umma_bf16_ts(d, a_hi + 8 * k, w_hi + 2 * k, idesc, 1u);
+            for (int q = 0; q < KB_PER_STAGE; ++q) {
+              const int kb = c * KB_PER_STAGE + q;
+              const uint32_t a_hi = tmem_base + (uint32_t)(A_COL0 + stage * STAGE_COLS + q * 64), a_mid = a_hi + 32;   // 8 columns per K=16 step
+              const uint64_t w_hi = w_desc0 + (uint64_t)(kb * (W_KB_BYTES >> 4)), w_mid = w_hi + ((NCH * 128) >> 4);
+              const uint32_t first_k = kb == 0 ? 0u : 1u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {                    // even / odd K-steps accumulate separately
+                const uint32_t d = tmem_d + (uint32_t)((k & 1) * NCH);
+                umma_bf16_ts(d, a_mid + 8 * k, w_hi + 2 * k, idesc, k < 2 ? first_k : 1u);
+                umma_bf16_ts(d, a_hi + 8 * k, w_mid + 2 * k, idesc, 1u);
+                umma_bf16_ts(d, a_hi + 8 * k, w_hi + 2 * k, idesc, 1u);
+              }
             }
             umma_commit(empty_bar(stage));
-            if (kb == KB - 1) umma_commit(tfull_bar(as));
+            if (c == 2) umma_commit(tfull_bar(as));
           }
           __syncwarp();
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
@@ -260,7 +284,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   } else if (warp <= 4) {
     // ================= epilogue =================
     const int lg = warp & 3;
-    const int m = lg * 32 + lane;                                  // output column inside the tile
+    const int m = lg * 32 + lane;                                  // conv column inside the tile
     const int et = threadIdx.x - 32;
     float* s_sc = reinterpret_cast<float*>(smem + OFF_SS);
     float* s_sh = s_sc + NCH;
@@ -269,11 +293,13 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       s_sh[et] = __ldg(p.shift + half * NCH + et);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int pw = et >> 1, hq = et & 1;                           // pooled column, which 16 of the 32 channels
     int it = 0;
     for (int u = cta; u < units; u += ncta) {
       const int rb = u % rb_n, owb = (u / rb_n) % owb_n, bt = u / (rb_n * owb_n);
-      const int r0 = rb * ROWS_PER_UNIT, r1 = min(p.H1, r0 + ROWS_PER_UNIT);
-      for (int oh = r0; oh < r1; ++oh, ++it) {
+      int first, r0, r1;
+      unit_rows(rb, first, r0, r1);
+      for (int oh = first; oh < r1; ++oh, ++it) {
         const int as = it & 1;
         mbar_wait(tfull_bar(as), (it >> 1) & 1);
         tcgen05_fence_after();
@@ -284,18 +310,18 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
           tmem_ld32(t0, part);
 #pragma unroll
           for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(part[q]);
-#pragma unroll 1
-          for (int a = 1; a < NACC; ++a) {                         // small terms first would be ideal; fp32 adds of 6 partials
-            tmem_ld32(t0 + (uint32_t)(a * NCH), part);
+          tmem_ld32(t0 + NCH, part);
 #pragma unroll
-            for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(part[q]);
-          }
+          for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(part[q]);
         }
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
-        if (et == 0) bulk_wait_read0();                            // previous store has finished reading the panel
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint32_t rowb = sb + OFF_ROWS + (uint32_t)((p.fuse_pool ? (oh % 3) : 0) * ROWBUF_BYTES);
+        if (!p.fuse_pool) {
+          if (et == 0) bulk_wait_read0();                          // previous store has finished reading the panel
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 sc = *reinterpret_cast<const float4*>(s_sc + 4 * q), sh = *reinterpret_cast<const float4*>(s_sh + 4 * q);
@@ -304,100 +330,154 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
           o.y = __float_as_uint(fmaxf(fmaf(acc[4 * q + 1], sc.y, sh.y), 0.f));
           o.z = __float_as_uint(fmaxf(fmaf(acc[4 * q + 2], sc.z, sh.z), 0.f));
           o.w = __float_as_uint(fmaxf(fmaf(acc[4 * q + 3], sc.w, sh.w), 0.f));
-          sts128(swz(sb + OFF_OUT, m, q), o);
+          sts128(swz(rowb, m, q), o);
         }
-        fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0) {
-          tma_store_3d(&tmOut, sb + OFF_OUT, half * NCH, owb * 128, bt * p.H1 + oh);
-          bulk_commit();
+        if (!p.fuse_pool) {
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            tma_store_3d(&tmOut, rowb, half * NCH, owb * 128, bt * p.H1 + oh);
+            bulk_commit();
+          }
+          continue;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");             // the conv row is complete in shared memory
+        // pooled row ph (centre conv row 2*ph) is emitted by the unit that owns its centre, once row 2*ph+1 (or the
+        // last conv row) is in: max over conv rows {2ph-1, 2ph, 2ph+1} x columns {2pw-1, 2pw, 2pw+1}, missing = skipped
+        const bool last_row = oh == p.H1 - 1;
+        if ((oh & 1) || last_row) {
+          const int ph = (oh & 1) ? (oh - 1) >> 1 : oh >> 1;
+          if (2 * ph >= r0 && pw < p.W2) {
+            float4 mx[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) mx[e] = make_float4(0.f, 0.f, 0.f, 0.f);   // post-ReLU values are >= 0
+#pragma unroll
+            for (int dr = -1; dr <= 1; ++dr) {
+              const int cr = 2 * ph + dr;
+              if (cr < 0 || cr >= p.H1 || cr > oh) continue;
+              const uint32_t rsrc = sb + OFF_ROWS + (uint32_t)((cr % 3) * ROWBUF_BYTES);
+#pragma unroll
+              for (int dc = -1; dc <= 1; ++dc) {
+                const int cc = 2 * pw + dc;
+                if (cc < 0 || cc >= p.W1) continue;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const uint4 v = lds128(swz(rsrc, cc, hq * 4 + e));
+                  mx[e].x = fmaxf(mx[e].x, __uint_as_float(v.x)); mx[e].y = fmaxf(mx[e].y, __uint_as_float(v.y));
+                  mx[e].z = fmaxf(mx[e].z, __uint_as_float(v.z)); mx[e].w = fmaxf(mx[e].w, __uint_as_float(v.w));
+                }
+              }
+            }
+            const long long vox = ((long long)bt * p.H2 + ph) * p.W2 + pw;
+            __nv_bfloat16* hi = split_hi(p.pooled, vox, 64) + half * NCH + hq * 16;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) store_split4(hi + 4 * e, hi + 64 + 4 * e, mx[e]);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");           // pool reads done before a row slot is rewritten
         }
       }
     }
-    if (et == 0) bulk_wait_all();
+    if (!p.fuse_pool && et == 0) bulk_wait_all();
   } else {
     // ================= ring staging + A-tile builders =================
-    const int bt_ = threadIdx.x - 160;                             // 0..255 = ring pixel this thread stages
+    const int bt_ = threadIdx.x - 160;                             // 0..255
     const int m = (warp & 3) * 32 + lane;                          // tile row = TMEM lane this thread may write
     const int gh = (warp - 5) >> 2;                                // which 4 of the 8 groups (filter rows) of a k-block
-    const uint32_t ring = sb + OFF_RING;
-    const int xr = bt_ >> 3, xj = 256 + (bt_ & 7);                 // the 8 extra pixels (256..263) of row xr
-    for (int i = bt_; i < RING_BYTES / 4; i += NBUILD) sts32(ring + 4u * i, 0u);   // never feed stale NaN bits to the MMA
+    const uint32_t ring_hi = sb + OFF_RING_HI, ring_mid = sb + OFF_RING_MID;
+    for (int i = bt_; i < RING_PLANE_BYTES / 4; i += NBUILD) {      // never feed stale NaN bits to the MMA
+      sts32(ring_hi + 4u * i, 0u);
+      sts32(ring_mid + 4u * i, 0u);
+    }
     const uint32_t a_dst = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(A_COL0 + gh * 16);
     int stage = 0;
     uint32_t phase = 0;
     for (int u = cta; u < units; u += ncta) {
       const int rb = u % rb_n, owb = (u / rb_n) % owb_n, bt = u / (rb_n * owb_n);
       const int b = bt / p.T, t = bt % p.T;
-      const int r0 = rb * ROWS_PER_UNIT, r1 = min(p.H1, r0 + ROWS_PER_UNIT);
+      int first, r0, r1;
+      unit_rows(rb, first, r0, r1);
       const int iw0 = 2 * owb * 128 - 3;
-      const bool ok_a = iw0 + bt_ >= 0 && iw0 + bt_ < p.W, ok_x = iw0 + xj < p.W;
-      // ring pixel (plane, ih, j) <- x[b, c, t+kt-1, ih, iw0+j], 0 outside the clip (the conv's zero padding)
+      // ring pixel (plane, ih, j) <- x[b, c, t+kt-1, ih, iw0+j], 0 outside the clip (the conv's zero padding).
+      // Staging map: thread = (pixel pair spr in [0,128), row parity srr); the 4 pairs 128..131 of each row are a
+      // second, mostly idle step.  Row pointers are warp-uniform, column validity is a per-thread constant.
+      const int spr = bt_ & 127, srr = bt_ >> 7;
+      const int xpr = 128 + (bt_ & 3), xrow = bt_ >> 2;             // extra step: row xrow of the 18 (or 63) staged rows
+      auto col_ok = [&](int j) { return iw0 + j >= 0 && iw0 + j < p.W; };
+      const bool ok0 = col_ok(2 * spr), ok1 = col_ok(2 * spr + 1), xok0 = col_ok(2 * xpr), xok1 = col_ok(2 * xpr + 1);
+      const float* xb = p.x + (long long)b * 3 * p.T * p.H * p.W + iw0;
+      const long long plane_stride = (long long)p.H * p.W;
       auto row_ptr = [&](int plane, int ih) -> const float* {
         const int c = plane / 3, f = t + plane % 3 - 1;
         if (f < 0 || f >= p.T || ih < 0 || ih >= p.H) return nullptr;
-        return p.x + ((((long long)b * 3 + c) * p.T + f) * p.H + ih) * (long long)p.W + iw0;
+        return xb + ((long long)c * p.T + f) * plane_stride + (long long)ih * p.W;
+      };
+      auto store_pair = [&](int plane, int ih, int pr, float v0, float v1) {
+        __nv_bfloat16 h0, m0, h1, m1;
+        split_bf16(v0, h0, m0);
+        split_bf16(v1, h1, m1);
+        const uint32_t off = (uint32_t)(((plane * 8 + (ih & 7)) * RING_PAIRS + pr) * 4);
+        sts32(ring_hi + off, pack_bf16x2(h0, h1));
+        sts32(ring_mid + off, pack_bf16x2(m0, m1));
       };
       asm volatile("bar.sync 2, 256;" ::: "memory");               // previous unit's readers are done
-      for (int plane = 0; plane < 9; ++plane) {                    // rows 2*r0-3 .. 2*r0+3 of every plane
-        float v[7];
+      for (int plane = 0; plane < 9; ++plane) {                     // rows 2*first-3 .. 2*first+3 of every plane
+        float v0[4], v1[4];
 #pragma unroll
-        for (int rr = 0; rr < 7; ++rr) {
-          const float* rp = row_ptr(plane, 2 * r0 - 3 + rr);
-          v[rr] = (rp && ok_a) ? __ldg(rp + bt_) : 0.f;
+        for (int g2 = 0; g2 < 4; ++g2) {
+          const int rr = 2 * g2 + srr;
+          const float* rp = rr < 7 ? row_ptr(plane, 2 * first - 3 + rr) : nullptr;
+          v0[g2] = (rp && ok0) ? __ldg(rp + 2 * spr) : 0.f;
+          v1[g2] = (rp && ok1) ? __ldg(rp + 2 * spr + 1) : 0.f;
         }
 #pragma unroll
-        for (int rr = 0; rr < 7; ++rr)
-          sts32(ring + (uint32_t)(((plane * 8 + ((2 * r0 - 3 + rr) & 7)) * RING_PX + bt_) * 4), split_pack(v[rr]));
+        for (int g2 = 0; g2 < 4; ++g2)
+          if (2 * g2 + srr < 7) store_pair(plane, 2 * first - 3 + 2 * g2 + srr, spr, v0[g2], v1[g2]);
       }
-      for (int i = bt_; i < 63 * 8; i += NBUILD) {
-        const int plane = (i >> 3) / 7, rr = (i >> 3) % 7, j = 256 + (i & 7), ih = 2 * r0 - 3 + rr;
+      if (xrow < 63) {
+        const int plane = xrow / 7, ih = 2 * first - 3 + xrow % 7;
         const float* rp = row_ptr(plane, ih);
-        const float v = (rp && iw0 + j < p.W) ? __ldg(rp + j) : 0.f;
-        sts32(ring + (uint32_t)(((plane * 8 + (ih & 7)) * RING_PX + j) * 4), split_pack(v));
+        store_pair(plane, ih, xpr, (rp && xok0) ? __ldg(rp + 2 * xpr) : 0.f, (rp && xok1) ? __ldg(rp + 2 * xpr + 1) : 0.f);
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");
-      for (int oh = r0; oh < r1; ++oh) {
-        // prefetch the two input rows the next output row adds (ih = 2*oh+4, 2*oh+5) into registers
-        float pf[18], pfx = 0.f;
+      for (int oh = first; oh < r1; ++oh) {
+        // prefetch the two input rows the next conv row adds (ih = 2*oh+4, 2*oh+5) into registers
+        float pf0[9], pf1[9], px0 = 0.f, px1 = 0.f;
         const bool more = oh + 1 < r1;
         if (more) {
 #pragma unroll
-          for (int q = 0; q < 18; ++q) {
-            const float* rp = row_ptr(q >> 1, 2 * oh + 4 + (q & 1));
-            pf[q] = (rp && ok_a) ? __ldg(rp + bt_) : 0.f;
+          for (int plane = 0; plane < 9; ++plane) {
+            const float* rp = row_ptr(plane, 2 * oh + 4 + srr);
+            pf0[plane] = (rp && ok0) ? __ldg(rp + 2 * spr) : 0.f;
+            pf1[plane] = (rp && ok1) ? __ldg(rp + 2 * spr + 1) : 0.f;
           }
-          if (xr < 18) {
-            const float* rp = row_ptr(xr >> 1, 2 * oh + 4 + (xr & 1));
-            pfx = (rp && ok_x) ? __ldg(rp + xj) : 0.f;
+          if (xrow < 18) {
+            const float* rp = row_ptr(xrow >> 1, 2 * oh + 4 + (xrow & 1));
+            px0 = (rp && xok0) ? __ldg(rp + 2 * xpr) : 0.f;
+            px1 = (rp && xok1) ? __ldg(rp + 2 * xpr + 1) : 0.f;
           }
         }
-        const uint32_t src0 = ring + (uint32_t)(2 * m * 4);
         uint32_t slot_off[4];                                      // ring row of filter row kh = 4*gh + jj (kh = 7: zero weights)
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) slot_off[jj] = (uint32_t)(((2 * oh - 3 + gh * 4 + jj) & 7) * RING_PX * 4);
+        for (int jj = 0; jj < 4; ++jj) slot_off[jj] = (uint32_t)((((2 * oh - 3 + gh * 4 + jj) & 7) * RING_PAIRS + m) * 4);
 #pragma unroll 1
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int c = 0; c < 3; ++c) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           tcgen05_fence_after();
-          const uint32_t srck = src0 + (uint32_t)(kb * 8 * RING_PX * 4);
-          uint2 w[4][4];
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
+          for (int q = 0; q < KB_PER_STAGE; ++q) {
+            const uint32_t pl = (uint32_t)((c * KB_PER_STAGE + q) * 8 * RING_PAIRS * 4);
+            uint32_t hi[16], mid[16];                              // group jj -> columns 4*jj .. 4*jj+3 (two bf16 per column)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) w[jj][e] = lds64(srck + slot_off[jj] + 8u * e);
-          }
-          uint32_t hi[16], mid[16];                                // group jj -> columns 4*jj .. 4*jj+3 (two bf16 per column)
+            for (int jj = 0; jj < 4; ++jj) {
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              hi[4 * jj + e] = __byte_perm(w[jj][e].x, w[jj][e].y, 0x5410);
-              mid[4 * jj + e] = __byte_perm(w[jj][e].x, w[jj][e].y, 0x7632);
+              for (int e = 0; e < 4; ++e) {
+                hi[4 * jj + e] = lds32(ring_hi + pl + slot_off[jj] + 4u * e);
+                mid[4 * jj + e] = lds32(ring_mid + pl + slot_off[jj] + 4u * e);
+              }
             }
+            tmem_st16(a_dst + (uint32_t)(stage * STAGE_COLS + q * 64), hi);
+            tmem_st16(a_dst + (uint32_t)(stage * STAGE_COLS + q * 64 + 32), mid);
           }
-          tmem_st16(a_dst + (uint32_t)(stage * 64), hi);
-          tmem_st16(a_dst + (uint32_t)(stage * 64 + 32), mid);
           tmem_st_wait();
           tcgen05_fence_before();
           __syncwarp();
@@ -407,14 +487,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         asm volatile("bar.sync 2, 256;" ::: "memory");             // every builder has finished reading this row's window
         if (more) {
 #pragma unroll
-          for (int q = 0; q < 18; ++q) {
-            const int ih = 2 * oh + 4 + (q & 1);
-            sts32(ring + (uint32_t)((((q >> 1) * 8 + (ih & 7)) * RING_PX + bt_) * 4), split_pack(pf[q]));
-          }
-          if (xr < 18) {
-            const int ih = 2 * oh + 4 + (xr & 1);
-            sts32(ring + (uint32_t)((((xr >> 1) * 8 + (ih & 7)) * RING_PX + xj) * 4), split_pack(pfx));
-          }
+          for (int plane = 0; plane < 9; ++plane) store_pair(plane, 2 * oh + 4 + srr, spr, pf0[plane], pf1[plane]);
+          if (xrow < 18) store_pair(xrow >> 1, 2 * oh + 4 + (xrow & 1), xpr, px0, px1);
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");
       }
@@ -469,8 +543,12 @@ cudaError_t launch_stem_pack_weight(const float* w_oc441, void* out, cudaStream_
   return cudaGetLastError();
 }
 
-cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale, const float* shift, float* y, int B, int T, int H,
-                             int W, int H1, int W1, cudaStream_t st) {
+bool stem_pool_is_fused(int W1) { return W1 <= 128; }
+
+// y: fp32 conv rows [B,T,H1,W1,64] (only written when the pool is not fused; may be null otherwise);
+// pooled: split [B,T,H2,W2,64] (only written when stem_pool_is_fused(W1))
+cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale, const float* shift, float* y, void* pooled, int B,
+                             int T, int H, int W, int H1, int W1, cudaStream_t st) {
   using namespace stemtc;
   cudaError_t e = init_once();
   if (e != cudaSuccess) return e;
@@ -483,7 +561,10 @@ cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
   }
-  {
+  const bool fuse = stem_pool_is_fused(W1) && pooled != nullptr;
+  tmOut = tmW;
+  if (!fuse) {
+    if (y == nullptr) return cudaErrorInvalidValue;
     cuuint64_t dims[3] = {64, (cuuint64_t)W1, (cuuint64_t)B * T * H1};
     cuuint64_t strides[2] = {64 * 4, (cuuint64_t)W1 * 64 * 4};
     cuuint32_t box[3] = {NCH, 128, 1}, es[3] = {1, 1, 1};
@@ -491,7 +572,7 @@ cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
   }
-  Params p{x, scale, shift, B, T, H, W, H1, W1};
+  Params p{x, scale, shift, fuse ? pooled : nullptr, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, (W1 - 1) / 2 + 1, fuse ? 1 : 0};
   const int units = B * T * ((W1 + 127) / 128) * ((H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT);
   int pairs = g_num_sms / 2;
   if (pairs > units) pairs = units;
