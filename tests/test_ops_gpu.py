@@ -126,7 +126,9 @@ def test_layernorm(abi, c):
 
 @pytest.mark.parametrize("nb,h,l,s,d,masked", [(2, 8, 256, 256, 32, True), (3, 8, 15, 15, 32, False), (2, 8, 15, 300, 32, True),
                                                (5, 8, 1, 4, 256, False), (2, 8, 90, 1024, 32, False), (4, 8, 4, 4, 32, False),
-                                               (2, 8, 40, 33, 32, True), (1, 8, 320, 320, 32, False), (3, 8, 7, 17, 32, True)])
+                                               (2, 8, 40, 33, 32, True), (1, 8, 320, 320, 32, False), (3, 8, 7, 17, 32, True),
+                                               (2, 8, 64, 64, 32, False), (2, 8, 130, 70, 32, True), (3, 8, 8, 8, 32, True),
+                                               (2, 16, 2, 2, 32, False), (2, 8, 16, 129, 32, False)])
 def test_attention(abi, nb, h, l, s, d, masked):
     from tuber_b200 import _lib
     e = h * d

@@ -84,7 +84,12 @@ struct AttnArgs {
   int NB, H, L, S, D;                        // D = head dim (32, or any multiple of 32 for the warp kernel)
   float scale;
 };
+// dispatcher: head_dim 32 -> the mma.sync kernels of attn_mma.cu (TUBER_ATTN_SIMT=1 in the environment forces the
+// CUDA-core kernels, the cross-check of the tests); other head dims -> the CUDA-core warp kernel
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st);
+cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t st);
+// attn_mma.cu; cudaErrorNotSupported when the shape is outside what it covers
+cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);
 
 // ---- masks and position code (backbone_builder.py:85-86, position_encoding.py:32-72) ------
 cudaError_t launch_mask_resize(const uint8_t* mask, uint8_t* fmask, int B, int H, int W, int T, int Hf,

@@ -781,6 +781,15 @@ attn_tile_kernel(AttnArgs p) {
 }
 
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st) {
+  static const bool force_simt = [] { const char* e = getenv("TUBER_ATTN_SIMT"); return e && e[0] == '1'; }();
+  if (!force_simt && a.D == 32) {
+    cudaError_t e = launch_attention_mma(a, st);
+    if (e != cudaErrorNotSupported) return e;
+  }
+  return launch_attention_simt(a, st);
+}
+
+cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t st) {
   if (a.D % 32 != 0 || a.NB <= 0 || a.L <= 0 || a.S <= 0) return cudaErrorInvalidValue;
   const bool small = a.S <= 16 || a.D != 32;
   if (!small) {
