@@ -503,6 +503,391 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   }
 }
 
+// =============================================================================================================
+// Fused-pool variant on CTA PAIRS (tcgen05 cta_group::2): the kernel above lets both CTAs of an SM pair build the
+// same A tile (each multiplies it with its own 32 of the 64 filters), and it is bound by exactly that build (shared
+// memory reads + tcgen05.st; ncu: tensor pipe 27 % busy, LSU/L1 68 %).  Here the two CTAs of a cluster form one
+// M = 256 x N = 64 MMA: each CTA builds the A rows of ITS OWN conv row (128 positions) in its own tensor memory and
+// keeps its own half of the filter bank (32 channels, 72 KB) in shared memory; the leader CTA's elected lane issues
+// tcgen05.mma.cta_group::2, which reads A from both CTAs' tensor memory and B from both CTAs' shared memory and leaves
+// D[128 positions x 64 channels] in each CTA's tensor memory.  Every A element is now built once per 64 channels.
+//
+//   unit      (frame bt, block of 32 conv rows); the pair works on two units at a time (rank r takes unit 2i + r).
+//             A unit always walks 33 rows (its first pooled row needs the conv row above the block); rows outside the
+//             image are dummies: built from zero padding, ignored by the epilogue.
+//   barriers  full[s]   builders of BOTH CTAs -> leader's MMA warp (remote mbarrier.arrive for rank 1)
+//             empty[s]  tcgen05.commit (multicast to both CTAs) -> each CTA's builders
+//             tfull[a]  tcgen05.commit (multicast)              -> each CTA's epilogue
+//             tempty[a] epilogue warps of BOTH CTAs -> leader's MMA warp
+//   epilogue  tcgen05.ld 64 channels, BN + ReLU into ONE conv-row buffer in shared memory, then the 3x3/s2 max pool as
+//             a running maximum held in registers (thread = pooled column x 32 channels): horizontal 3-max of the
+//             row from shared memory, vertical combination across rows {2ph-1, 2ph, 2ph+1} in registers.
+// =============================================================================================================
+namespace p2 {
+constexpr int NCH2 = 64;                    // channels per pair (N of the MMA); NCH = 32 per CTA (B operand half)
+constexpr int ROW2_BYTES = 128 * NCH2 * 4;  // conv row buffer: 128 positions x 64 fp32
+constexpr int OFF_W2 = 0;
+constexpr int OFF_ROW2 = OFF_W2 + W_BYTES;
+constexpr int OFF_RING_HI2 = OFF_ROW2 + ROW2_BYTES;
+constexpr int OFF_RING_MID2 = OFF_RING_HI2 + RING_PLANE_BYTES;
+constexpr int OFF_BAR2 = OFF_RING_MID2 + ((RING_PLANE_BYTES + 127) / 128) * 128;
+constexpr int OFF_SS2 = OFF_BAR2 + 128;     // scale[64], shift[64]
+constexpr int SMEM2_BYTES = OFF_SS2 + 512;
+static_assert(SMEM2_BYTES <= 232448, "shared memory budget");
+static_assert(OFF_RING_HI2 % 128 == 0, "alignment");
+constexpr int A_COL0_2 = 2 * NCH2;          // TMEM columns: [0, 128) two accumulator buffers, then the two A stages
+constexpr int UNIT_ROWS = ROWS_PER_UNIT + 1;
+}  // namespace p2
+
+TB_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+TB_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+TB_DEVINL uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+TB_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+TB_DEVINL void mbar_wait_cluster(uint32_t bar, uint32_t parity) {          // waits on a barrier that remote CTAs arrive on
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+TB_DEVINL void umma2_commit_mc(uint32_t bar) {                             // arrives on `bar` of both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+TB_DEVINL void umma2_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
+  using namespace p2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bar = sb + OFF_BAR2;
+  auto full_bar = [&](int s) { return bar + 8u * s; };                       // leader: A stage written by both CTAs' builders
+  auto empty_bar = [&](int s) { return bar + 8u * (A_STAGES + s); };         // each CTA: A stage consumed by the MMAs
+  auto tfull_bar = [&](int s) { return bar + 8u * (2 * A_STAGES + s); };     // each CTA: accumulator complete
+  auto tempty_bar = [&](int s) { return bar + 8u * (2 * A_STAGES + 2 + s); };  // leader: accumulator drained by both epilogues
+  const uint32_t w_bar = bar + 8u * (2 * A_STAGES + 4);
+  const uint32_t tmem_slot = bar + 8u * (2 * A_STAGES + 5);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR2 + 8 * (2 * A_STAGES + 5));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                         // = which 32 output channels this CTA's filter half holds
+  const int rb_n = (p.H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+  const int units = p.B * p.T * rb_n;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int steps = (units + 1) / 2;                               // pair steps; step i = units 2i (rank 0) and 2i+1 (rank 1)
+
+  if (threadIdx.x == 0) {
+    if (sb & 1023u) __trap();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    for (int s = 0; s < A_STAGES; ++s) {
+      mbar_init(full_bar(s), 2 * NBUILD / 32);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);
+    }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                              // both CTAs' barriers exist before anyone arrives remotely
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= filter half load (both CTAs) + MMA issuer (leader CTA only) =================
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, W_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_3d(sb + OFF_W2 + kb * W_KB_BYTES, &tmW, w_bar, kb * 64, (int)rank * NCH, 0);
+    }
+    __syncwarp();
+    if (rank == 0) {
+      mbar_wait(w_bar, 0);                                         // (rank 1's half: its builders wait for it before their first arrive)
+      constexpr uint32_t idesc = make_idesc(256, NCH2);
+      const uint64_t w_desc0 = make_smem_desc(sb + OFF_W2);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int i = pair; i < steps; i += npairs) {
+        for (int r = 0; r < UNIT_ROWS; ++r, ++it) {
+          const int as = it & 1;
+          mbar_wait_cluster(tempty_bar(as), ((it >> 1) & 1) ^ 1);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(as * NCH2);
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c) {
+            mbar_wait_cluster(full_bar(stage), phase);
+            tcgen05_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int q = 0; q < KB_PER_STAGE; ++q) {
+                const int kb = c * KB_PER_STAGE + q;
+                const uint32_t a_hi = tmem_base + (uint32_t)(A_COL0_2 + stage * STAGE_COLS + q * 64), a_mid = a_hi + 32;
+                const uint64_t w_hi = w_desc0 + (uint64_t)(kb * (W_KB_BYTES >> 4)), w_mid = w_hi + ((NCH * 128) >> 4);
+                const uint32_t first_k = kb == 0 ? 0u : 1u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma2_bf16_ts(tmem_d, a_mid + 8 * k, w_hi + 2 * k, idesc, k == 0 ? first_k : 1u);
+                  umma2_bf16_ts(tmem_d, a_hi + 8 * k, w_mid + 2 * k, idesc, 1u);
+                  umma2_bf16_ts(tmem_d, a_hi + 8 * k, w_hi + 2 * k, idesc, 1u);
+                }
+              }
+              umma2_commit_mc(empty_bar(stage));
+              if (c == 2) umma2_commit_mc(tfull_bar(as));
+            }
+            __syncwarp();
+            if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp <= 4) {
+    // ================= epilogue: BN + ReLU + 3x3/s2 max pool =================
+    const int lg = warp & 3;
+    const int m = lg * 32 + lane;                                  // conv column = TMEM lane
+    const int et = threadIdx.x - 32;
+    float* s_sc = reinterpret_cast<float*>(smem + OFF_SS2);
+    float* s_sh = s_sc + NCH2;
+    if (et < NCH2) {
+      s_sc[et] = __ldg(p.scale + et);
+      s_sh[et] = __ldg(p.shift + et);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int pw = et >> 1, hq = et & 1;                           // pooled column, which 32 of the 64 channels
+    const uint32_t rowb = sb + OFF_ROW2;
+    auto rswz = [&](int pos, int chunk) { return rowb + (uint32_t)pos * 256u + (uint32_t)(((chunk ^ (pos >> 1)) & 15) << 4); };
+    const uint32_t tempty_remote0 = mapa_rank(tempty_bar(0), 0), tempty_remote1 = mapa_rank(tempty_bar(1), 0);
+    int it = 0;
+    for (int i = pair; i < steps; i += npairs) {
+      const int u = min(2 * i + (int)rank, units - 1);             // odd unit count: the last step's rank 1 repeats the last unit
+      const int rb = u % rb_n, bt = u / rb_n;
+      const int r0 = rb * ROWS_PER_UNIT;
+      float4 run[8];                                               // running maximum over the rows seen so far (post-ReLU: >= 0)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) run[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < UNIT_ROWS; ++r, ++it) {
+        const int oh = r0 - 1 + r;
+        const int as = it & 1;
+        mbar_wait(tfull_bar(as), (it >> 1) & 1);
+        tcgen05_fence_after();
+        const bool valid = oh >= 0 && oh < p.H1;                   // uniform over the CTA
+        if (valid) {
+          const uint32_t t0 = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * NCH2);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t part[32];
+            tmem_ld32(t0 + 32 * hh, part);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 sc = *reinterpret_cast<const float4*>(s_sc + 32 * hh + 4 * q), sh = *reinterpret_cast<const float4*>(s_sh + 32 * hh + 4 * q);
+              uint4 o;
+              o.x = __float_as_uint(fmaxf(fmaf(__uint_as_float(part[4 * q]), sc.x, sh.x), 0.f));
+              o.y = __float_as_uint(fmaxf(fmaf(__uint_as_float(part[4 * q + 1]), sc.y, sh.y), 0.f));
+              o.z = __float_as_uint(fmaxf(fmaf(__uint_as_float(part[4 * q + 2]), sc.z, sh.z), 0.f));
+              o.w = __float_as_uint(fmaxf(fmaf(__uint_as_float(part[4 * q + 3]), sc.w, sh.w), 0.f));
+              sts128(rswz(m, 8 * hh + q), o);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(as ? tempty_remote1 : tempty_remote0);
+        if (!valid) continue;                                      // dummy row (above / below the image): contributes nothing
+        asm volatile("bar.sync 1, 128;" ::: "memory");             // the conv row is complete in shared memory
+        // horizontal 3-max at stride 2 of this conv row: columns 2pw-1, 2pw, 2pw+1
+        float4 hm[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hm[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pw < p.W2) {
+#pragma unroll
+          for (int dc = -1; dc <= 1; ++dc) {
+            const int cc = 2 * pw + dc;
+            if (cc < 0 || cc >= p.W1) continue;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint4 v = lds128(rswz(cc, hq * 8 + e));
+              hm[e].x = fmaxf(hm[e].x, __uint_as_float(v.x)); hm[e].y = fmaxf(hm[e].y, __uint_as_float(v.y));
+              hm[e].z = fmaxf(hm[e].z, __uint_as_float(v.z)); hm[e].w = fmaxf(hm[e].w, __uint_as_float(v.w));
+            }
+          }
+        }
+        // vertical: pooled row ph = max(rows 2ph-1, 2ph, 2ph+1); emitted at row 2ph+1, or at row 2ph when it is the last one
+        const bool odd = oh & 1;
+        const bool emit = r > 0 && (odd || oh == p.H1 - 1);
+        if (!odd || r > 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            run[e].x = fmaxf(run[e].x, hm[e].x); run[e].y = fmaxf(run[e].y, hm[e].y);
+            run[e].z = fmaxf(run[e].z, hm[e].z); run[e].w = fmaxf(run[e].w, hm[e].w);
+          }
+        }
+        if (emit && pw < p.W2) {
+          const int ph = oh >> 1;
+          const long long vox = ((long long)bt * p.H2 + ph) * p.W2 + pw;
+          __nv_bfloat16* hi = split_hi(p.pooled, vox, 64) + hq * 32;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) store_split4(hi + 4 * e, hi + 64 + 4 * e, run[e]);
+        }
+        if (odd) {                                                 // this row is row 2(ph+1)-1 of the next pooled row
+#pragma unroll
+          for (int e = 0; e < 8; ++e) run[e] = hm[e];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");             // pool reads done before the row buffer is rewritten
+      }
+    }
+  } else {
+    // ================= ring staging + A-tile builders (as in stem_tc_kernel; one unit per CTA) =================
+    const int bt_ = threadIdx.x - 160;                             // 0..255
+    const int m = (warp & 3) * 32 + lane;
+    const int gh = (warp - 5) >> 2;
+    const uint32_t ring_hi = sb + OFF_RING_HI2, ring_mid = sb + OFF_RING_MID2;
+    for (int i = bt_; i < RING_PLANE_BYTES / 4; i += NBUILD) {
+      sts32(ring_hi + 4u * i, 0u);
+      sts32(ring_mid + 4u * i, 0u);
+    }
+    const uint32_t a_dst = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(A_COL0_2 + gh * 16);
+    const uint32_t full_remote0 = mapa_rank(full_bar(0), 0), full_remote1 = mapa_rank(full_bar(1), 0);
+    mbar_wait(w_bar, 0);                                           // this CTA's filter half has landed before its first "full" arrive
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = pair; i < steps; i += npairs) {
+      const int u = min(2 * i + (int)rank, units - 1);
+      const int rb = u % rb_n, bt = u / rb_n;
+      const int b = bt / p.T, t = bt % p.T;
+      const int first = rb * ROWS_PER_UNIT - 1, r1 = first + UNIT_ROWS;
+      const int iw0 = -3;
+      const int spr = bt_ & 127, srr = bt_ >> 7;
+      const int xpr = 128 + (bt_ & 3), xrow = bt_ >> 2;
+      auto col_ok = [&](int j) { return iw0 + j >= 0 && iw0 + j < p.W; };
+      const bool ok0 = col_ok(2 * spr), ok1 = col_ok(2 * spr + 1), xok0 = col_ok(2 * xpr), xok1 = col_ok(2 * xpr + 1);
+      const float* xb = p.x + (long long)b * 3 * p.T * p.H * p.W + iw0;
+      const long long plane_stride = (long long)p.H * p.W;
+      auto row_ptr = [&](int plane, int ih) -> const float* {
+        const int c = plane / 3, f = t + plane % 3 - 1;
+        if (f < 0 || f >= p.T || ih < 0 || ih >= p.H) return nullptr;
+        return xb + ((long long)c * p.T + f) * plane_stride + (long long)ih * p.W;
+      };
+      auto store_pair = [&](int plane, int ih, int pr, float v0, float v1) {
+        __nv_bfloat16 h0, m0, h1, m1;
+        split_bf16(v0, h0, m0);
+        split_bf16(v1, h1, m1);
+        const uint32_t off = (uint32_t)(((plane * 8 + (ih & 7)) * RING_PAIRS + pr) * 4);
+        sts32(ring_hi + off, pack_bf16x2(h0, h1));
+        sts32(ring_mid + off, pack_bf16x2(m0, m1));
+      };
+      asm volatile("bar.sync 2, 256;" ::: "memory");               // previous unit's readers are done
+      for (int plane = 0; plane < 9; ++plane) {                     // rows 2*first-3 .. 2*first+3 of every plane
+        float v0[4], v1[4];
+#pragma unroll
+        for (int g2 = 0; g2 < 4; ++g2) {
+          const int rr = 2 * g2 + srr;
+          const float* rp = rr < 7 ? row_ptr(plane, 2 * first - 3 + rr) : nullptr;
+          v0[g2] = (rp && ok0) ? __ldg(rp + 2 * spr) : 0.f;
+          v1[g2] = (rp && ok1) ? __ldg(rp + 2 * spr + 1) : 0.f;
+        }
+#pragma unroll
+        for (int g2 = 0; g2 < 4; ++g2)
+          if (2 * g2 + srr < 7) store_pair(plane, 2 * first - 3 + 2 * g2 + srr, spr, v0[g2], v1[g2]);
+      }
+      if (xrow < 63) {
+        const int plane = xrow / 7, ih = 2 * first - 3 + xrow % 7;
+        const float* rp = row_ptr(plane, ih);
+        store_pair(plane, ih, xpr, (rp && xok0) ? __ldg(rp + 2 * xpr) : 0.f, (rp && xok1) ? __ldg(rp + 2 * xpr + 1) : 0.f);
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      for (int oh = first; oh < r1; ++oh) {
+        float pf0[9], pf1[9], px0 = 0.f, px1 = 0.f;
+        const bool more = oh + 1 < r1;
+        if (more) {
+#pragma unroll
+          for (int plane = 0; plane < 9; ++plane) {
+            const float* rp = row_ptr(plane, 2 * oh + 4 + srr);
+            pf0[plane] = (rp && ok0) ? __ldg(rp + 2 * spr) : 0.f;
+            pf1[plane] = (rp && ok1) ? __ldg(rp + 2 * spr + 1) : 0.f;
+          }
+          if (xrow < 18) {
+            const float* rp = row_ptr(xrow >> 1, 2 * oh + 4 + (xrow & 1));
+            px0 = (rp && xok0) ? __ldg(rp + 2 * xpr) : 0.f;
+            px1 = (rp && xok1) ? __ldg(rp + 2 * xpr + 1) : 0.f;
+          }
+        }
+        uint32_t slot_off[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) slot_off[jj] = (uint32_t)((((2 * oh - 3 + gh * 4 + jj) & 7) * RING_PAIRS + m) * 4);
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int q = 0; q < KB_PER_STAGE; ++q) {
+            const uint32_t pl = (uint32_t)((c * KB_PER_STAGE + q) * 8 * RING_PAIRS * 4);
+            uint32_t hi[16], mid[16];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                hi[4 * jj + e] = lds32(ring_hi + pl + slot_off[jj] + 4u * e);
+                mid[4 * jj + e] = lds32(ring_mid + pl + slot_off[jj] + 4u * e);
+              }
+            }
+            tmem_st16(a_dst + (uint32_t)(stage * STAGE_COLS + q * 64), hi);
+            tmem_st16(a_dst + (uint32_t)(stage * STAGE_COLS + q * 64 + 32), mid);
+          }
+          tmem_st_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(stage ? full_remote1 : full_remote0);
+          if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (more) {
+#pragma unroll
+          for (int plane = 0; plane < 9; ++plane) store_pair(plane, 2 * oh + 4 + srr, spr, pf0[plane], pf1[plane]);
+          if (xrow < 18) store_pair(xrow >> 1, 2 * oh + 4 + (xrow & 1), xpr, px0, px1);
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                              // the leader's MMAs read this CTA's memories until its last commit
+  if (warp == 0) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
 // reference filter (64,3,3,7,7) = [oc][441] fp32 -> packed split [2][64][576] bf16 in the kernel's K order
 __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -531,6 +916,8 @@ static cudaError_t init_once() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(stem_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p2::SMEM2_BYTES);
   if (e != cudaSuccess) return e;
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return cudaSuccess;
@@ -562,6 +949,15 @@ cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale
       return cudaErrorInvalidValue;
   }
   const bool fuse = stem_pool_is_fused(W1) && pooled != nullptr;
+  if (fuse) {                                                      // CTA pairs (cta_group::2), pool fused
+    Params p{x, scale, shift, pooled, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, (W1 - 1) / 2 + 1, 1};
+    const int units = B * T * ((H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT);
+    int pairs = g_num_sms / 2;
+    if (pairs > (units + 1) / 2) pairs = (units + 1) / 2;
+    if (pairs < 1) pairs = 1;
+    stem_tc2_kernel<<<2 * pairs, NUM_THREADS, p2::SMEM2_BYTES, st>>>(tmW, p);
+    return cudaGetLastError();
+  }
   tmOut = tmW;
   if (!fuse) {
     if (y == nullptr) return cudaErrorInvalidValue;
