@@ -48,6 +48,22 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "src": "fallback"}
 
 
+def _ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu launch-list summary (profiles/*_summary.json,
+    written by tools/ncu_launches_summary.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_summary.json")), key=os.path.getmtime)
+    for f in reversed(files):
+        try:
+            with open(f) as fh:
+                k = json.load(fh)["kernels"].get(kernel)
+            if k:
+                return k["dram_bytes_per_launch"], os.path.relpath(f, ROOT)
+        except (OSError, ValueError, KeyError):
+            continue
+    return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -106,6 +122,15 @@ def _cpu_reference(cfg, sd, T, H, W, budget_s: float, max_clips: int):
 
 
 def main():
+    # stdout carries exactly one line, the JSON result: libraries that print to fd 1 (NCCL's version banner, ...) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -150,11 +175,11 @@ def main():
         dt = time.perf_counter() - t0
         v = per_step * steps / dt
         sample = f"{steps} steps of {per_step} clips {T}x{H}x{W} (bounded sample of the {args.batch}-clip step), {dt:.1f} s"
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        emit({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
                           "warmup": 1, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload,
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     # ---------------------------------------------------------------- this repo's arm (B200)
@@ -274,8 +299,10 @@ def main():
     else:
         ach = 3.0 * top.flops / (top.ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"]}
+    traffic, traffic_src = _ncu_traffic(top.name.decode())
     roof.update({"kernel": top.name.decode(), "launches_per_step": top.launches, "avg_launch_ms": top.ms / max(1, top.launches),
-                 "algorithmic_bytes_per_launch": top.bytes / max(1, top.launches), "peak_source": peaks["src"], "traffic": None,
+                 "algorithmic_bytes_per_launch": top.bytes / max(1, top.launches), "peak_source": peaks["src"], "traffic": traffic,
+                 "traffic_source": traffic_src,
                  "how": "CUDA events around every launch of one extra forward (same stream, same buffers, after the timed region)"})
     stage_ms = model.stage_times_ms(clips)
 
@@ -295,7 +322,7 @@ def main():
             "cuda_graph": not args.no_graph, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "arithmetic": "fp32 storage; GEMMs = 3-pass bf16 split (hi*hi+hi*lo+lo*hi) on tcgen05 with fp32 TMEM accumulation"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
