@@ -61,6 +61,30 @@ def test_gemm_tc(abi, m, n, k, variant):
     assert _rel(out, ref) < 3e-5, (m, n, k, variant)
 
 
+@pytest.mark.parametrize("m,k,kb,n2,with_res", [(1000, 64, 0, 64, True), (128, 64, 64, 64, False), (40000, 64, 0, 64, True),
+                                                 (5000, 64, 0, 128, True), (33333, 64, 64, 128, False), (300, 128, 0, 64, True),
+                                                 (50000, 64, 64, 64, False), (70001, 128, 0, 128, True)])
+def test_gemm_tc_fused2(abi, m, k, kb, n2, with_res):
+    """conv4 (+ residual / K-concatenated shortcut) chained with the next block's conv1 through the shared-memory panels"""
+    g = torch.Generator(device="cuda").manual_seed(m + k + kb + n2)
+    a = torch.randn(m, k, device="cuda", generator=g)
+    ab = torch.randn(m, kb, device="cuda", generator=g) if kb else None
+    w = torch.randn(256, k + kb, device="cuda", generator=g) / math.sqrt(k + kb)
+    scale, shift = torch.rand(256, device="cuda", generator=g) + 0.5, torch.randn(256, device="cuda", generator=g) * 0.1
+    res = torch.randn(m, 256, device="cuda", generator=g) if with_res else None
+    w2 = torch.randn(n2, 256, device="cuda", generator=g) / 16
+    scale2, shift2 = torch.rand(n2, device="cuda", generator=g) + 0.5, torch.randn(n2, device="cuda", generator=g) * 0.1
+    x, t1 = abi.gemm_tc_fused2(a, w, scale, shift, res, w2, scale2, shift2, ab)
+    acat = a.double() if ab is None else torch.cat([a, ab], 1).double()
+    ref_x = acat @ w.double().t() * scale.double() + shift.double()
+    if res is not None:
+        ref_x = ref_x + res.double()
+    ref_x = torch.relu(ref_x)
+    ref_t = torch.relu(ref_x @ w2.double().t() * scale2.double() + shift2.double())
+    assert _rel(x, ref_x) < 3e-5
+    assert _rel(t1, ref_t) < 3e-5
+
+
 @pytest.mark.parametrize("m,n,k,act", [(90, 3, 256, 0), (90, 4, 256, 2), (720, 80, 256, 0), (8, 2, 2048, 0), (333, 256, 64, 1)])
 def test_sgemm(abi, m, n, k, act):
     a = torch.randn(m, k, device="cuda")

@@ -7,7 +7,7 @@ import csv
 import json
 import sys
 
-FAMILY = [("gemm_bf16x3", "gemm_bf16x3_tcgen05"), ("stem_tc", "stem_conv"), ("dwconv", "dwconv3x3x3"), ("attn", "attention"),
+FAMILY = [("gemm_fused2", "gemm_fused2_tcgen05"), ("gemm_bf16x3", "gemm_bf16x3_tcgen05"), ("stem_tc", "stem_conv"), ("dwconv", "dwconv3x3x3"), ("attn", "attention"),
           ("layernorm", "layernorm"), ("gather_rows", "gather_rows"), ("sgemm", "sgemm_fp32"), ("maxpool", "maxpool"),
           ("tpool", "tpool"), ("posenc", "posenc"), ("mask_resize", "mask_resize"), ("to_split", "to_split")]
 

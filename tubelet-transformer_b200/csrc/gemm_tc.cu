@@ -440,6 +440,372 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// =============================================================================================================
+// Fused pair of pointwise convolutions for the 256-channel stage (layer1 of the CSN backbone, ir_CSN_152.py:70-90):
+//
+//   x'[m, 0:256] = relu(scale * ([A | Ab] W4^T) + shift + res)        conv4 (+ shortcut) of bottleneck i    -> split, HBM
+//   t1'[m, 0:N2] = relu(scale2 * (x' W1'^T) + shift2)                 conv1 of bottleneck i+1 (K2 = 256)    -> fp32,  HBM
+//
+// The second GEMM's A operand never leaves the SM: a finished 128 x 64 output panel of x' sits in shared memory in
+// exactly the layout a K-major SWIZZLE_128B UMMA operand needs (hi plane | mid plane, 128-byte rows), so while the
+// TMA store drains it the MMA warp multiplies it with k-block j of W1' into a second accumulator.  This removes the
+// separate conv1 launch and its read of x' (1.07 GB per bottleneck at 8 clips) -- the layer is HBM bound.
+// One CTA owns whole 128-row blocks (both 128-column halves of x'), W1' streams through the operand ring
+// (N2 x 256 x 4 B per row block, from L2).
+//   extra barriers: pready[slot]  epilogue -> MMA warp: panel is final and visible to the async proxy
+//                   pcons[slot]   tcgen05.commit: the second GEMM has consumed the panel (it may be recycled once
+//                                 the TMA store has drained too)
+//                   d2full / d2empty  second accumulator handshake
+// =============================================================================================================
+struct Params2 {
+  const float* scale2; const float* shift2;
+  int N2;
+};
+
+template <int N2>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
+                   const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmW2,
+                   const __grid_constant__ CUtensorMap tmC2, Params p, Params2 q) {
+  constexpr int BN = 128, STAGES = 2, PANELS = 3, STAGE_BYTES = 65536;
+  constexpr int NSUB = 2, P1 = 4, P2 = N2 / 64;             // x' = 2 sub-tiles of 128 columns = 4 panels; t1' = P2 panels
+  constexpr int W2_STAGES = N2 / 64;                        // ring stages holding W1' per row block (64 KB each)
+  constexpr int KBW = 4 / W2_STAGES;                        // k-blocks of the second GEMM per such stage
+  constexpr int W2_CHUNK = N2 * 256;                        // bytes of one k-block of W1' (hi + mid planes)
+  constexpr int D2_COL = 2 * BN;                            // TMEM: [0,256) two conv4 accumulators, [256, 256+N2) the second GEMM
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t panel_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = panel_base + PANELS * PANEL_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto pfree_bar = [&](int s) { return bar_base + 8u * (11 + s); };
+  auto pready_bar = [&](int s) { return bar_base + 8u * (14 + s); };
+  auto pcons_bar = [&](int s) { return bar_base + 8u * (17 + s); };
+  const uint32_t d2full_bar = bar_base + 8u * 20, d2empty_bar = bar_base + 8u * 21;
+  const uint32_t tmem_slot = bar_base + 8u * 22;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_base));
+  float* s_ss = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_base));   // [NSUB][scale | shift][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int kblocks = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_base & 1023u) __trap();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    if (p.kb1 < kblocks) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC2) : "memory");
+    if (p.res_mode == RES_TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < PANELS; ++s) {
+      mbar_init(pfull_bar(s), 1); mbar_init(pfree_bar(s), 1); mbar_init(pready_bar(s), 1); mbar_init(pcons_bar(s), 1);
+    }
+    mbar_init(d2full_bar, 1);
+    mbar_init(d2empty_bar, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // Ring order = the MMA warp's consumption order.  S(sub, t) = the k-blocks [A | W4 rows of sub] of row block t, W2(c, t) =
+  // chunk c of W1'.  After the first block's S(0), S(1):   per block t:  W2(0,t) S(0,t+1) [W2(1,t)] S(1,t+1)
+  // and the MMA warp issues                                              G2(t,0..1) G1(t+1,0) G2(t,2..3) G1(t+1,1)
+  // so the next block's first accumulator is ready before the epilogue has finished this block's panels.
+  if (warp == 0) {
+    // ================= operand producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_s = [&](int sub, int m_blk) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          if (kb < p.kb1) tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM, 0);
+          else tma_load_3d(sa, &tmA2, full_bar(stage), (kb - p.kb1) * BK, m_blk * BM, 0);
+          tma_load_3d(sa + 2 * A_PLANE_BYTES, &tmW, full_bar(stage), kb * BK, sub * BN, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      };
+      auto load_w2 = [&](int c) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        mbar_expect_tx(full_bar(stage), KBW * W2_CHUNK);
+        for (int e = 0; e < KBW; ++e) tma_load_3d(sa + e * W2_CHUNK, &tmW2, full_bar(stage), (c * KBW + e) * BK, 0, 0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      if ((int)blockIdx.x < m_tiles) { load_s(0, blockIdx.x); load_s(1, blockIdx.x); }
+      for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x) {
+        const int next = m_blk + gridDim.x;
+        const bool has_next = next < m_tiles;
+        if (W2_STAGES == 1) {
+          load_w2(0);
+          if (has_next) { load_s(0, next); load_s(1, next); }
+        } else {
+          load_w2(0);
+          if (has_next) load_s(0, next);
+          load_w2(1);
+          if (has_next) load_s(1, next);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc1 = make_idesc(BM, BN), idesc2 = make_idesc(BM, N2);
+    const uint64_t desc0 = make_smem_desc(smem_base);
+    const uint64_t pdesc0 = make_smem_desc(panel_base);
+    int stage = 0, pslot = 0;
+    uint32_t phase = 0, ready_ph = 0;                        // ready_ph bit s: parity of the next pready[s] completion
+    // conv4 accumulator `sub` of the n-th row block of this CTA
+    auto g1 = [&](int sub, int n) {
+      mbar_wait(tempty_bar(sub), (uint32_t)((n & 1) ^ 1));
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(sub * BN);
+#pragma unroll 1
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t a_hi = desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4)), a_mid = a_hi + (A_PLANE_BYTES >> 4);
+          const uint64_t w_hi = a_hi + ((2 * A_PLANE_BYTES) >> 4), w_mid = w_hi + ((BN * BK * 2) >> 4);
+          const uint32_t first = kb == 0 ? 0u : 1u;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, a_mid + 2 * k, w_hi + 2 * k, idesc1, k == 0 ? first : 1u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, a_hi + 2 * k, w_mid + 2 * k, idesc1, 1);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, a_hi + 2 * k, w_hi + 2 * k, idesc1, 1);
+          umma_commit(empty_bar(stage));
+          if (kb == kblocks - 1) umma_commit(tfull_bar(sub));
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    };
+    // k-block j of the second GEMM = output panel j of x', read from its panel buffer
+    int w2_stage = 0;                                       // ring slot of the W1' chunk in use (conv4 stages are consumed in between)
+    auto g2 = [&](int j) {
+      if (j % KBW == 0) {
+        mbar_wait(full_bar(stage), phase);
+        w2_stage = stage;
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      mbar_wait(pready_bar(pslot), (ready_ph >> pslot) & 1u);
+      ready_ph ^= 1u << pslot;
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t tmem_d2 = tmem_base + (uint32_t)D2_COL;
+        const uint64_t a_hi = pdesc0 + (uint64_t)(pslot * (PANEL_BYTES >> 4)), a_mid = a_hi + (SUB_BYTES >> 4);
+        const uint64_t w_hi = desc0 + (uint64_t)(w2_stage * (STAGE_BYTES >> 4)) + (uint64_t)((j % KBW) * (W2_CHUNK >> 4));
+        const uint64_t w_mid = w_hi + ((N2 * BK * 2) >> 4);
+        const uint32_t first = j == 0 ? 0u : 1u;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d2, a_mid + 2 * k, w_hi + 2 * k, idesc2, k == 0 ? first : 1u);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d2, a_hi + 2 * k, w_mid + 2 * k, idesc2, 1);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d2, a_hi + 2 * k, w_hi + 2 * k, idesc2, 1);
+        umma_commit(pcons_bar(pslot));
+        if (j % KBW == KBW - 1) umma_commit(empty_bar(w2_stage));
+        if (j == P1 - 1) umma_commit(d2full_bar);
+      }
+      __syncwarp();
+      if (++pslot == PANELS) pslot = 0;
+    };
+    int tl = 0;
+    if ((int)blockIdx.x < m_tiles) { g1(0, 0); g1(1, 0); }
+    for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x, ++tl) {
+      const bool has_next = m_blk + (int)gridDim.x < m_tiles;
+      mbar_wait(d2empty_bar, (uint32_t)((tl & 1) ^ 1));      // the epilogue has drained the previous block's second accumulator
+      tcgen05_fence_after();
+      // the next block's first accumulator is issued early only when the ring has room for its operands while a W1' chunk is
+      // still held (one conv4 stage per sub-tile, or W1' released in halves); otherwise after the last k-block of this block
+      const bool early = has_next && (kblocks == 1 || KBW == 2);
+      g2(0); g2(1);
+      if (early) g1(0, tl + 1);
+      g2(2); g2(3);
+      if (has_next && !early) g1(0, tl + 1);
+      if (has_next) g1(1, tl + 1);
+      for (int jp = 0; jp < P2; ++jp)                          // the t1' panels use ring slots too (not operands)
+        if (++pslot == PANELS) pslot = 0;
+    }
+  } else if (warp == 2) {
+    // ================= panel producer =================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x) {
+        for (int j = 0; j < P1 + P2; ++j) {
+          mbar_wait(pfree_bar(slot), phase ^ 1);
+          if (j < P1 && p.res_mode == RES_TMA) {
+            mbar_expect_tx(pfull_bar(slot), PANEL_BYTES);
+            tma_load_3d(panel_base + slot * PANEL_BYTES, &tmR, pfull_bar(slot), j * 64, m_blk * BM, 0);
+          } else {
+            mbar_arrive(pfull_bar(slot));
+          }
+          if (++slot == PANELS) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 3..6) =================
+    const int lg = warp & 3;
+    const int et = threadIdx.x - EPI_WARP0 * 32;
+    const int r = lg * 32 + lane;
+    for (int sub = 0; sub < NSUB; ++sub) {
+      s_ss[sub * 2 * BN + et] = p.scale ? __ldg(p.scale + sub * BN + et) : 1.f;
+      s_ss[sub * 2 * BN + BN + et] = p.shift ? __ldg(p.shift + sub * BN + et) : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    int tl = 0, slot = 0, prev_slot = -1;
+    bool prev_is_x = false;
+    uint32_t pphase = 0, cons_ph = 0;                        // cons_ph bit s: parity of the next pcons[s] completion
+    // et == 0: issue the store of panel `slot`, then recycle the previous panel once its store has drained (and, if it
+    // was an x' panel, the second GEMM has consumed it)
+    auto store_and_recycle = [&](bool is_x) {
+      bulk_commit();
+      bulk_wait_read<PANELS - 2>();
+      if (prev_slot >= 0) {
+        if (prev_is_x) {
+          mbar_wait(pcons_bar(prev_slot), (cons_ph >> prev_slot) & 1u);
+          cons_ph ^= 1u << prev_slot;
+        }
+        mbar_arrive(pfree_bar(prev_slot));
+      }
+      prev_slot = slot;
+      prev_is_x = is_x;
+    };
+    for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x, ++tl) {
+      for (int sub = 0; sub < NSUB; ++sub) {
+        const int as = sub;
+        const float* s_scale = s_ss + sub * 2 * BN;
+        const float* s_shift = s_scale + BN;
+        mbar_wait(tfull_bar(as), (uint32_t)(tl & 1));
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int jj = 0; jj < 2; ++jj) {
+          mbar_wait(pfull_bar(slot), pphase);
+          const uint32_t pb = panel_base + slot * PANEL_BYTES;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + jj * 64 + h * 32), acc);
+            const int cl = jj * 64 + h * 32;
+            float v[32];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              const float4 sc = *reinterpret_cast<const float4*>(s_scale + cl + 4 * c4);
+              const float4 sh = *reinterpret_cast<const float4*>(s_shift + cl + 4 * c4);
+              v[4 * c4] = fmaf(__uint_as_float(acc[4 * c4]), sc.x, sh.x);
+              v[4 * c4 + 1] = fmaf(__uint_as_float(acc[4 * c4 + 1]), sc.y, sh.y);
+              v[4 * c4 + 2] = fmaf(__uint_as_float(acc[4 * c4 + 2]), sc.z, sh.z);
+              v[4 * c4 + 3] = fmaf(__uint_as_float(acc[4 * c4 + 3]), sc.w, sh.w);
+            }
+            if (p.res_mode == RES_TMA) {
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) {
+                const uint4 a = lds128(swz(pb, r, 4 * h + c8));
+                const uint4 b = lds128(swz(pb + SUB_BYTES, r, 4 * h + c8));
+                v[8 * c8] += bf16_lo_to_f32(a.x) + bf16_lo_to_f32(b.x); v[8 * c8 + 1] += bf16_hi_to_f32(a.x) + bf16_hi_to_f32(b.x);
+                v[8 * c8 + 2] += bf16_lo_to_f32(a.y) + bf16_lo_to_f32(b.y); v[8 * c8 + 3] += bf16_hi_to_f32(a.y) + bf16_hi_to_f32(b.y);
+                v[8 * c8 + 4] += bf16_lo_to_f32(a.z) + bf16_lo_to_f32(b.z); v[8 * c8 + 5] += bf16_hi_to_f32(a.z) + bf16_hi_to_f32(b.z);
+                v[8 * c8 + 6] += bf16_lo_to_f32(a.w) + bf16_lo_to_f32(b.w); v[8 * c8 + 7] += bf16_hi_to_f32(a.w) + bf16_hi_to_f32(b.w);
+              }
+            }
+            if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+            }
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              uint4 hi, mid;
+              split_bf16x2(v[8 * c8], v[8 * c8 + 1], hi.x, mid.x);
+              split_bf16x2(v[8 * c8 + 2], v[8 * c8 + 3], hi.y, mid.y);
+              split_bf16x2(v[8 * c8 + 4], v[8 * c8 + 5], hi.z, mid.z);
+              split_bf16x2(v[8 * c8 + 6], v[8 * c8 + 7], hi.w, mid.w);
+              sts128(swz(pb, r, 4 * h + c8), hi);
+              sts128(swz(pb + SUB_BYTES, r, 4 * h + c8), mid);
+            }
+          }
+          if (jj == 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+          }
+          fence_proxy_async();                               // visible to the TMA store AND to the second GEMM's MMAs
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            mbar_arrive(pready_bar(slot));
+            tma_store_3d(&tmC, pb, sub * BN + jj * 64, m_blk * BM, 0);
+            store_and_recycle(true);
+          }
+          if (++slot == PANELS) { slot = 0; pphase ^= 1; }
+        }
+      }
+      // ---- second accumulator: t1' = relu(scale2 * D2 + shift2), fp32 panels ----
+      mbar_wait(d2full_bar, (uint32_t)(tl & 1));
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int jp = 0; jp < P2; ++jp) {
+        mbar_wait(pfull_bar(slot), pphase);
+        const uint32_t pb = panel_base + slot * PANEL_BYTES;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(D2_COL + jp * 64 + h * 32), acc);
+          const int c0 = jp * 64 + h * 32;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(q.scale2 + c0) + c4);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(q.shift2 + c0) + c4);
+            uint4 o;
+            o.x = __float_as_uint(fmaxf(fmaf(__uint_as_float(acc[4 * c4]), sc.x, sh.x), 0.f));
+            o.y = __float_as_uint(fmaxf(fmaf(__uint_as_float(acc[4 * c4 + 1]), sc.y, sh.y), 0.f));
+            o.z = __float_as_uint(fmaxf(fmaf(__uint_as_float(acc[4 * c4 + 2]), sc.z, sh.z), 0.f));
+            o.w = __float_as_uint(fmaxf(fmaf(__uint_as_float(acc[4 * c4 + 3]), sc.w, sh.w), 0.f));
+            sts128(swz(pb + h * SUB_BYTES, r, c4), o);
+          }
+        }
+        if (jp == P2 - 1) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d2empty_bar);
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          tma_store_3d(&tmC2, pb, 0, m_blk * BM, (jp * 64) >> 5);
+          store_and_recycle(false);
+        }
+        if (++slot == PANELS) { slot = 0; pphase ^= 1; }
+      }
+    }
+    if (et == 0) bulk_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -470,6 +836,10 @@ static cudaError_t init_once() {
   e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDeep::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgN64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgN64::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_fused2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_fused2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return cudaSuccess;
@@ -557,6 +927,49 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   if (bn == 64) return launch_cfg<CfgN64>(tmA, tmA2, tmW, tmC, tmR, p, st);
   if (KT >= 512) return launch_cfg<CfgDeep>(tmA, tmA2, tmW, tmC, tmR, p, st);
   return launch_cfg<CfgWide>(tmA, tmA2, tmW, tmC, tmR, p, st);
+}
+
+// conv4 (a: N must be 256, split output, TMA or no residual) fused with the next bottleneck's conv1 (W2p packed
+// [2][N2][256], N2 in {64, 128}; fp32 result C2 [M, ldc2])
+cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const float* scale2, const float* shift2, float* C2, int N2,
+                                  int ldc2, cudaStream_t st) {
+  using namespace tc;
+  cudaError_t e = init_once();
+  if (e != cudaSuccess) return e;
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const int KT = a.K + (a.Ab ? a.Kb : 0);
+  const bool res_ok = !a.res || (a.res_mod <= 0 && a.res_fmt == FMT_SPLIT && aligned16(a.res) && a.ldr % 8 == 0 && a.N <= a.ldr);
+  if (a.M <= 0 || a.N != 256 || a.K % 64 != 0 || a.lda % 8 != 0 || a.K > a.lda || a.a_fmt != FMT_SPLIT || a.Wp == nullptr ||
+      a.c_fmt != FMT_SPLIT || a.act == ACT_SIGMOID || !aligned16(a.A) || !aligned16(a.Wp) || !aligned16(a.C) || a.ldc % 8 != 0 ||
+      a.N > a.ldc || (a.Ab && (a.Kb % 64 != 0 || a.Kb <= 0 || a.ldb % 8 != 0 || a.Kb > a.ldb || !aligned16(a.Ab))) || !res_ok ||
+      (N2 != 64 && N2 != 128) || W2p == nullptr || !aligned16(W2p) || C2 == nullptr || !aligned16(C2) || ldc2 % 8 != 0 || N2 > ldc2) {
+    snprintf(g_err, sizeof g_err, "gemm_tc_fused2: unsupported problem M=%d N=%d K=%d N2=%d", a.M, a.N, KT, N2);
+    return cudaErrorInvalidValue;
+  }
+  Params p{};
+  p.scale = a.scale; p.shift = a.shift;
+  p.out_fmt = FMT_SPLIT;
+  p.M = a.M; p.N = a.N; p.K = KT; p.act = a.act;
+  p.kb1 = a.K / BK;
+  p.res_mode = a.res ? RES_TMA : RES_NONE;
+  Params2 q{scale2, shift2, N2};
+  CUtensorMap tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2;
+  if (!encode_split_map(&tmA, a.A, a.K, a.M, a.lda, BM)) return cudaErrorInvalidValue;
+  tmA2 = tmA;
+  if (a.Ab && !encode_split_map(&tmA2, a.Ab, a.Kb, a.M, a.ldb, BM)) return cudaErrorInvalidValue;
+  if (!encode3(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.Wp, KT, a.N, 2, (uint64_t)KT * 2, (uint64_t)a.N * KT * 2, 64, 128, 2))
+    return cudaErrorInvalidValue;
+  if (!encode_split_map(&tmC, a.C, a.N, a.M, a.ldc, BM)) return cudaErrorInvalidValue;
+  tmR = tmC;
+  if (a.res && !encode_split_map(&tmR, a.res, a.N, a.M, a.ldr, BM)) return cudaErrorInvalidValue;
+  if (!encode3(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, W2p, a.N, N2, 2, (uint64_t)a.N * 2, (uint64_t)N2 * a.N * 2, 64, N2, 2))
+    return cudaErrorInvalidValue;
+  if (!encode_f32_panel_map(&tmC2, C2, N2, a.M, ldc2)) return cudaErrorInvalidValue;
+  const int m_tiles = ceil_div(a.M, BM);
+  const int grid = m_tiles < g_num_sms ? m_tiles : g_num_sms;
+  if (N2 == 64) gemm_fused2_kernel<64><<<grid, NUM_THREADS, CfgWide::SMEM_BYTES, st>>>(tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
+  else gemm_fused2_kernel<128><<<grid, NUM_THREADS, CfgWide::SMEM_BYTES, st>>>(tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
+  return cudaGetLastError();
 }
 
 // fp32 [N,K] -> bf16 [2][N][K] (hi plane, mid plane)

@@ -133,7 +133,7 @@ struct TuberPlan {
   cudaStream_t copy_stream = nullptr, run_stream = nullptr;
   cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
   bool slot_busy[2] = {false, false};
-  bool force_simt = false;
+  bool force_simt = false, no_fuse2 = false;
   bool profiling = false, debug_keep = false, use_graph = false;
   cudaEvent_t ev[TUBER_NUM_STAGES + 1] = {};
   bool ev_valid = false;
@@ -699,21 +699,48 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
   cx.tap("stem", cur, FMT_SPLIT, (long long)B * t * h * w, 64);
 
   // ---- bottlenecks: 1x1x1 -> depthwise 3x3x3 (stride) -> 1x1x1 (+ shortcut) -> ReLU ----
+  bool t1_ready = false;                                     // conv1 of the coming block was already produced by the previous block's fused conv4
   for (int li = 0; li < 4; ++li) {
     cx.stage_mark(1 + li);
-    for (const Block& b : p->blocks[li]) {
+    for (size_t bi = 0; bi < p->blocks[li].size(); ++bi) {
+      const Block& b = p->blocks[li][bi];
+      const Block* nb = bi + 1 < p->blocks[li].size() ? &p->blocks[li][bi + 1] : (li + 1 < 4 ? &p->blocks[li + 1][0] : nullptr);
       const int to = (t - 1) / b.st_t + 1, ho = (h - 1) / b.st_s + 1, wo = (w - 1) / b.st_s + 1;
       const long long vin = (long long)B * t * h * w, vout = (long long)B * to * ho * wo;
-      cx.gemm(cur, FMT_SPLIT, b.cin, vin, b.conv1, nullptr, 0, 0, 0, t1, FMT_F32, b.planes, ACT_RELU);
+      if (!t1_ready) cx.gemm(cur, FMT_SPLIT, b.cin, vin, b.conv1, nullptr, 0, 0, 0, t1, FMT_F32, b.planes, ACT_RELU);
+      t1_ready = false;
       cx.launch("dwconv3x3x3", 4.0 * ((double)vin + vout) * b.planes, 54.0 * vout * b.planes,
                 [&] { return launch_dwconv(t1, b.dw.w, b.dw.scale, b.dw.shift, t2, B, t, h, w, b.planes, b.st_t, b.st_s, to, ho, wo, st); });
+      // 256-channel stage: conv4 of this block and conv1 of the next one run as one kernel (the next block's input tile is
+      // multiplied while it still sits in shared memory), see gemm_fused2_kernel
+      const bool fuse = !p->force_simt && !p->no_fuse2 && b.cout == 256 && nb && nb->cin == 256 && (nb->planes == 64 || nb->planes == 128) &&
+                        b.planes % 64 == 0 && b.cin % 64 == 0;
+      const void* xa = nullptr;                              // the shortcut's input rows (strided voxel gather when the block strides)
       if (b.has_ds) {
-        const void* xa = cur;                                // the shortcut's input rows (strided voxel gather when the block strides)
+        xa = cur;
         if (b.st_t != 1 || b.st_s != 1) {
           cx.launch("gather_rows", 8.0 * vout * b.cin, 0.0,
                     [&] { return launch_gather_rows(cur, xg, b.cin * 4, B, t, h, w, b.st_t, b.st_s, to, ho, wo, st); });
           xa = xg;
         }
+      }
+      if (fuse) {
+        GemmArgs a{};
+        const Lin& w4 = b.has_ds ? b.c4ds : b.conv4;
+        a.A = t2; a.a_fmt = FMT_SPLIT; a.lda = b.planes;
+        a.Ab = b.has_ds ? xa : nullptr; a.ldb = b.cin; a.Kb = b.has_ds ? b.cin : 0;
+        a.Wf = w4.wf; a.Wp = w4.wp; a.scale = w4.scale; a.shift = w4.shift;
+        a.res = b.has_ds ? nullptr : cur; a.res_fmt = FMT_SPLIT; a.ldr = b.cin; a.res_mod = 0;
+        a.C = nxt; a.c_fmt = FMT_SPLIT; a.ldc = b.cout;
+        a.M = (int)vout; a.N = b.cout; a.K = b.planes; a.act = ACT_RELU;
+        const Lin& c1 = nb->conv1;
+        if (p->kprof) snprintf(cx.tag, sizeof cx.tag, "M=%lld N=%d K=%d -> N2=%d", vout, b.cout, w4.K, c1.N);
+        const double mn = (double)vout * b.cout;
+        cx.launch("gemm_fused2_tcgen05", 4.0 * ((double)vout * w4.K + (double)w4.N * w4.K + mn * (b.has_ds ? 1 : 2) + (double)vout * c1.N + (double)c1.N * c1.K),
+                  2.0 * mn * w4.K + 2.0 * (double)vout * c1.N * c1.K,
+                  [&] { return launch_gemm_tc_fused2(a, c1.wp, c1.scale, c1.shift, t1, c1.N, c1.N, st); });
+        t1_ready = true;
+      } else if (b.has_ds) {
         cx.gemm(t2, FMT_SPLIT, b.planes, vout, b.c4ds, nullptr, 0, 0, 0, nxt, FMT_SPLIT, b.cout, ACT_RELU, xa, b.cin, b.cin);
       } else {
         cx.gemm(t2, FMT_SPLIT, b.planes, vout, b.conv4, cur, FMT_SPLIT, b.cin, 0, nxt, FMT_SPLIT, b.cout, ACT_RELU);
@@ -969,6 +996,8 @@ int tuber_plan_create(const TuberConfig* cfg, TuberPlan** out_plan) {
   p->device = dev;
   const char* fs = getenv("TUBER_FORCE_SIMT");
   p->force_simt = fs && fs[0] == '1';
+  const char* nf = getenv("TUBER_NO_FUSE2");
+  p->no_fuse2 = nf && nf[0] == '1';
   *out_plan = p;
   return TUBER_OK;
 }
@@ -1285,6 +1314,17 @@ int tuber_op_gemm_tc(const void* a_split, const void* w_packed, const float* sca
   a.res = res; a.res_fmt = res_fmt; a.ldr = N; a.res_mod = res_mod; a.C = c; a.c_fmt = c_fmt; a.ldc = N;
   a.M = M; a.N = N; a.K = K; a.act = relu ? ACT_RELU : ACT_NONE;
   CK(launch_gemm_tc(a, (cudaStream_t)stream));
+  return TUBER_OK;
+}
+int tuber_op_gemm_tc_fused2(const void* a_split, const void* ab_split, const void* w_packed, const float* scale, const float* shift,
+                            const void* res_split, void* c_split, int32_t M, int32_t K, int32_t Kb, const void* w2_packed,
+                            const float* scale2, const float* shift2, float* c2, int32_t N2, void* stream) {
+  GemmArgs a{};
+  a.A = a_split; a.a_fmt = FMT_SPLIT; a.lda = K; a.Ab = ab_split; a.ldb = Kb; a.Kb = ab_split ? Kb : 0;
+  a.Wp = w_packed; a.scale = scale; a.shift = shift;
+  a.res = res_split; a.res_fmt = FMT_SPLIT; a.ldr = 256; a.res_mod = 0; a.C = c_split; a.c_fmt = FMT_SPLIT; a.ldc = 256;
+  a.M = M; a.N = 256; a.K = K; a.act = ACT_RELU;
+  CK(launch_gemm_tc_fused2(a, w2_packed, scale2, shift2, c2, N2, N2, (cudaStream_t)stream));
   return TUBER_OK;
 }
 int tuber_op_sgemm(const float* A, const float* W, const float* bias, const float* res, float* C, int32_t M, int32_t N, int32_t K,
