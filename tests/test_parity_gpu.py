@@ -192,3 +192,21 @@ def test_full_size_properties(yaml, batch):
         assert el2 < 1e-5, (k, emax, el2)
     info = model.shape_info(batch, 32, 256, 256)
     assert (info.Tf, info.Hf, info.Wf, info.Tp) == (4, 16, 16, 1)
+
+
+def test_fused_and_folded_paths_match_the_plain_launch_sequence(monkeypatch):
+    """BASELINE.json configs[1] at full clip size: the fused conv4 -> conv1 kernel of the 256-channel stage and the folded
+    decode pool (key projection folded into the pooled query, frames mixed before the value projection, grouped GEMM)
+    against the plain one-kernel-per-layer sequence (TUBER_NO_FUSE2 / TUBER_POOL_UNFOLDED are read at plan creation)."""
+    import tuber_b200
+    from oracle import tuber_oracle as O
+    cfg = tuber_b200.load_cfg("TubeR_CSN50_AVA21.yaml")
+    sd = O.make_state_dict(cfg, seed=0, bn="random")
+    clips = O.make_clips(3, 32, 256, 256, seed=2).cuda()           # 3 clips: row blocks that straddle clips, M % 128 == 0 only per clip
+    fast = {k: v.clone() for k, v in _model(cfg, sd).forward_raw(clips).items()}
+    monkeypatch.setenv("TUBER_NO_FUSE2", "1")
+    monkeypatch.setenv("TUBER_POOL_UNFOLDED", "1")
+    plain = _model(cfg, sd).forward_raw(clips)
+    for k in fast:
+        emax, el2 = _rel(fast[k], plain[k])
+        assert emax < 1e-4 and el2 < 1e-4, (k, emax, el2)

@@ -60,6 +60,7 @@ struct Params {
   int out_fmt;
   int M, N, K, act;
   int kb1;                                              // k-blocks taken from the first A operand (the rest from the second)
+  int group_rows;                                       // > 0: grouped GEMM (GemmArgs::group_rows), a multiple of BM
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -232,7 +233,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
           if (kb < p.kb1) tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM, 0);
           else tma_load_3d(sa, &tmA2, full_bar(stage), (kb - p.kb1) * BK, m_blk * BM, 0);
-          tma_load_3d(sa + 2 * A_PLANE_BYTES, &tmW, full_bar(stage), kb * BK, n_blk * BN, 0);
+          const int wrow = p.group_rows > 0 ? (m_blk * BM / p.group_rows) * p.N : 0;   // grouped: this row block's W rows
+          tma_load_3d(sa + 2 * A_PLANE_BYTES, &tmW, full_bar(stage), kb * BK, wrow + n_blk * BN, 0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -307,9 +309,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t aphase = (it >> 1) & 1;
       float* s_scale = s_ss + as * 2 * BN;
       float* s_shift = s_scale + BN;
+      const int grp = p.group_rows > 0 ? m_blk * BM / p.group_rows : 0;
+      const int gcol = grp * p.N;                           // grouped: column / parameter offset of this row block's group
       if (et < BN) {
-        s_scale[et] = p.scale ? __ldg(p.scale + n_blk * BN + et) : 1.f;
-        s_shift[et] = p.shift ? __ldg(p.shift + n_blk * BN + et) : 0.f;
+        s_scale[et] = p.scale ? __ldg(p.scale + gcol + n_blk * BN + et) : 1.f;
+        s_shift[et] = p.shift ? __ldg(p.shift + gcol + n_blk * BN + et) : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
       mbar_wait(tfull_bar(as), aphase);
@@ -407,9 +411,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         fence_proxy_async();                              // generic-proxy writes -> visible to the TMA store
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) {
-          const int col = n_blk * BN + j * 64;
-          if (p.out_fmt == FMT_F32) tma_store_3d(&tmC, pb, 0, m_blk * BM, col >> 5);
-          else tma_store_3d(&tmC, pb, col, m_blk * BM, 0);
+          const int col = gcol + n_blk * BN + j * 64;
+          const int orow = m_blk * BM - grp * p.group_rows;
+          if (p.out_fmt == FMT_F32) tma_store_3d(&tmC, pb, 0, orow, col >> 5);
+          else tma_store_3d(&tmC, pb, col, orow, 0);
           bulk_commit();
           // keep at most PANELS-2 stores in flight, then recycle the buffer(s) whose store has drained
           if constexpr (C::PANELS == 1) {
@@ -906,6 +911,13 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   p.M = a.M; p.N = a.N; p.K = KT; p.act = a.act;
   p.kb1 = a.K / BK;
   p.res_mode = RES_NONE;
+  const int groups = a.group_rows > 0 ? a.M / a.group_rows : 1;
+  if (a.group_rows > 0 && (a.group_rows % BM != 0 || a.M % a.group_rows != 0 || a.res || a.Ab || (long long)groups * a.N > a.ldc)) {
+    snprintf(g_err, sizeof g_err, "gemm_tc: bad grouped problem M=%d group_rows=%d N=%d ldc=%d", a.M, a.group_rows, a.N, a.ldc);
+    return cudaErrorInvalidValue;
+  }
+  p.group_rows = a.group_rows > 0 ? a.group_rows : 0;
+  const int c_rows = a.group_rows > 0 ? (a.group_out_rows > 0 ? a.group_out_rows : a.group_rows) : a.M, c_cols = groups * a.N;
   if (a.res) {
     const bool tma_ok = a.res_mod <= 0 && a.res_fmt == a.c_fmt && aligned16(a.res) && a.ldr % 8 == 0 && a.N <= a.ldr;
     p.res_mode = tma_ok ? RES_TMA : RES_DIRECT;
@@ -915,9 +927,9 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   if (!encode_split_map(&tmA, a.A, a.K, a.M, a.lda, BM)) return cudaErrorInvalidValue;
   tmA2 = tmA;
   if (a.Ab && !encode_split_map(&tmA2, a.Ab, a.Kb, a.M, a.ldb, BM)) return cudaErrorInvalidValue;
-  if (!encode3(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.Wp, KT, a.N, 2, (uint64_t)KT * 2, (uint64_t)a.N * KT * 2, 64, bn, 2))
+  if (!encode3(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.Wp, KT, (uint64_t)groups * a.N, 2, (uint64_t)KT * 2, (uint64_t)groups * a.N * KT * 2, 64, bn, 2))
     return cudaErrorInvalidValue;
-  bool ok = a.c_fmt == FMT_F32 ? encode_f32_panel_map(&tmC, a.C, a.N, a.M, a.ldc) : encode_split_map(&tmC, a.C, a.N, a.M, a.ldc, BM);
+  bool ok = a.c_fmt == FMT_F32 ? encode_f32_panel_map(&tmC, a.C, c_cols, c_rows, a.ldc) : encode_split_map(&tmC, a.C, c_cols, c_rows, a.ldc, BM);
   if (!ok) return cudaErrorInvalidValue;
   tmR = tmC;
   if (p.res_mode == RES_TMA) {

@@ -37,6 +37,10 @@ cudaError_t launch_slice_frames(const void* in, void* out, int row_bytes, int B,
 // temporal pooling of split features [B,Tin,HW,C] -> split [B,Tout,HW,C], window k, stride k
 cudaError_t launch_tpool(const void* in_split, void* out_split, int B, int Tin, int HW, int C, int k,
                          int Tout, int is_max, cudaStream_t st);
+// decode pool: per pixel and head, scores u_h . x_t over the Tf frames, softmax, mixed token sum_t p x_t (see kernels_simt.cu)
+//   xt split [B*Tf*HW, 2048], U fp32 [8][2048], y split [8*group_stride, 2048] (row = h*group_stride + pixel); Tf <= 8
+cudaError_t launch_pool_mix(const void* xt_split, const float* U, void* y_split, int B, int Tf, int HW, long long group_stride,
+                            cudaStream_t st);
 // mean over N rows of a split tensor [B,N,C] -> fp32 [B,C]
 cudaError_t launch_global_avgpool(const void* in_split, float* out, int B, int N, int C, cudaStream_t st);
 
@@ -57,6 +61,10 @@ struct GemmArgs {
   void* C2; int ldc2;                        // optional second copy of C in the OTHER format
   int M, N, K;
   int act;                                   // ACT_NONE / ACT_RELU / ACT_SIGMOID (sigmoid: SIMT only)
+  // grouped form (tcgen05 kernel only; 0 = plain): rows [g*group_rows, (g+1)*group_rows) of A are multiplied with rows
+  // [g*N, (g+1)*N) of W (scale / shift likewise) and written to C[row - g*group_rows, g*N + n]; M = groups * group_rows
+  int group_rows;
+  int group_out_rows;                        // rows of C actually written per group (<= group_rows; 0 = group_rows): padding rows are clipped
 };
 cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st);
 

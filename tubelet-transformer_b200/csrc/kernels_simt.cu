@@ -259,7 +259,7 @@ constexpr int THREADS = TH * (TW / 8) * (CC / 4);         // 256
 
 __global__ void __launch_bounds__(dwr::THREADS, 1)
 dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __restrict__ wpk, const float* __restrict__ scale,
-                      const float* __restrict__ shift, void* __restrict__ out, int B, int T, int H, int W, int C, int TC, int nitems, int mode) {
+                      const float* __restrict__ shift, void* __restrict__ out, int B, int T, int H, int W, int C, int TC, int nitems) {
   using namespace dwr;
   extern __shared__ __align__(128) float4 dwr_smem[];
   const int tid = threadIdx.x;
@@ -341,7 +341,7 @@ dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __r
       }
       const int it = t0 - 1 + s;
       const ulonglong2* tsm = reinterpret_cast<const ulonglong2*>(dwr_smem) + (q % NSLOT) * PLANE_F4;
-      if (mode != 1 && it >= 0 && it < T) {                               // (frames outside the clip are all zero: nothing to add)
+      if (it >= 0 && it < T) {                               // (frames outside the clip are all zero: nothing to add)
         const bool do_p = it - 1 >= t0, do_c = it >= t0 && it < tend, do_n = it + 1 < tend;
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
@@ -354,7 +354,7 @@ dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __r
         }
       }
       const int ot = it - 1;
-      if (mode != 2 && ot >= t0 && ot < tend && oh < H) {
+      if (ot >= t0 && ot < tend && oh < H) {
         const long long orow0 = (((long long)b * T + ot) * H + oh) * W + ow0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -447,7 +447,7 @@ cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale,
       while (TC > 2 && cols * ceil_div(Ti, TC) < 2LL * g_num_sms) TC = (TC + 1) / 2;
       const long long items = cols * ceil_div(Ti, TC);
       const int grid = (int)(items < g_num_sms ? items : g_num_sms);
-      dwconv_s1_roll_kernel<<<grid, dwr::THREADS, dwr::SMEM_BYTES, st>>>(tmR, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, TC, (int)items, [] { const char* e = getenv("TUBER_DW_MODE"); return e ? atoi(e) : 0; }());
+      dwconv_s1_roll_kernel<<<grid, dwr::THREADS, dwr::SMEM_BYTES, st>>>(tmR, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, TC, (int)items);
       return cudaGetLastError();
     }
     const long long tiles = (long long)B * ceil_div(Ti, TT) * ceil_div(Hi, TH) * ceil_div(Wi, TW) * (C / CC);
@@ -539,6 +539,96 @@ cudaError_t launch_tpool(const void* in_split, void* out_split, int B, int Tin, 
                          int is_max, cudaStream_t st) {
   long long total = (long long)B * Tout * HW * (C / 4);
   tpool_kernel<<<ceil_div(total, 256), 256, 0, st>>>(in_split, out_split, B, Tin, HW, C, k, Tout, is_max);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// Decode pool (backbone_builder.py:75-78; transformer_layers.py:306-366): the cross-attention of the learned pooled
+// query over the Tf frame tokens of one pixel, with both projections moved out of the token loop.  The query is input
+// independent, so   q_h . (Wk_h x_t + bk_h) = u_h . x_t + const   with u_h = scale * Wk_h^T q_h (folded at finalize; the
+// constant cancels in the softmax over t), and   sum_t p_t (Wv_h x_t + bv_h) = Wv_h (sum_t p_t x_t) + bv_h.
+// This kernel computes, per pixel and head, the Tf scores, their softmax and the mixed token y_h = sum_t p[h][t] x_t
+// (d = 2048); the value projection then runs on B*HW*8 mixed rows instead of B*Tf*HW tokens x (K and V) -- 4.7x fewer
+// FLOPs than projecting every token to K and V.  One CTA per pixel, thread = 8 consecutive channels.
+//   xt: split [B*Tf*HW, 2048]; U: fp32 [8][2048]; y: split [8 * Mp, 2048], row = h * Mp + pixel (Mp >= B*HW: group stride)
+// =============================================================================================
+template <int MAXT>
+__global__ void __launch_bounds__(256)
+pool_mix_kernel(const void* __restrict__ xt, const float* __restrict__ U, void* __restrict__ y, int B, int Tf, int HW, long long Mp) {
+  constexpr int D = 2048, NH = 8;
+  __shared__ float red[8][NH * MAXT];
+  __shared__ float prob[NH * MAXT];
+  const int pix = blockIdx.x, b = pix / HW, hw = pix % HW;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, c0 = tid * 8;
+  float x[MAXT][8];
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t) {
+    if (t < Tf) {
+      const __nv_bfloat16* hp = split_hi(xt, ((long long)b * Tf + t) * HW + hw, D) + c0;
+      const float4 a = load_split4(hp, hp + D), c = load_split4(hp + 4, hp + D + 4);
+      x[t][0] = a.x; x[t][1] = a.y; x[t][2] = a.z; x[t][3] = a.w; x[t][4] = c.x; x[t][5] = c.y; x[t][6] = c.z; x[t][7] = c.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[t][e] = 0.f;
+    }
+  }
+  float part[NH][MAXT];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const float4 u0 = __ldg(reinterpret_cast<const float4*>(U + h * D + c0)), u1 = __ldg(reinterpret_cast<const float4*>(U + h * D + c0) + 1);
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) {
+      float d = x[t][0] * u0.x;
+      d = fmaf(x[t][1], u0.y, d); d = fmaf(x[t][2], u0.z, d); d = fmaf(x[t][3], u0.w, d);
+      d = fmaf(x[t][4], u1.x, d); d = fmaf(x[t][5], u1.y, d); d = fmaf(x[t][6], u1.z, d); d = fmaf(x[t][7], u1.w, d);
+      part[h][t] = warp_sum(d);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+#pragma unroll
+      for (int t = 0; t < MAXT; ++t) red[warp][h * MAXT + t] = part[h][t];
+  }
+  __syncthreads();
+  if (tid < NH) {                                            // softmax over the Tf frames of head tid
+    float sc[MAXT], m = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[w][tid * MAXT + t];
+      sc[t] = t < Tf ? v : -INFINITY;
+      m = fmaxf(m, sc[t]);
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) { sc[t] = expf(sc[t] - m); l += sc[t]; }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) prob[tid * MAXT + t] = sc[t] * inv;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) {
+      const float pr = prob[h * MAXT + t];                   // 0 for t >= Tf
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaf(pr, x[t][e], o[e]);
+    }
+    __nv_bfloat16* hp = split_hi(y, (long long)h * Mp + pix, D) + c0;
+    store_split4(hp, hp + D, make_float4(o[0], o[1], o[2], o[3]));
+    store_split4(hp + 4, hp + D + 4, make_float4(o[4], o[5], o[6], o[7]));
+  }
+}
+
+cudaError_t launch_pool_mix(const void* xt_split, const float* U, void* y_split, int B, int Tf, int HW, long long group_stride,
+                            cudaStream_t st) {
+  if (Tf < 1 || Tf > 8) return cudaErrorInvalidValue;
+  if (Tf <= 4) pool_mix_kernel<4><<<B * HW, 256, 0, st>>>(xt_split, U, y_split, B, Tf, HW, group_stride);
+  else pool_mix_kernel<8><<<B * HW, 256, 0, st>>>(xt_split, U, y_split, B, Tf, HW, group_stride);
   return cudaGetLastError();
 }
 

@@ -111,7 +111,8 @@ struct TuberPlan {
   // decode pool (input-independent parts folded at finalize)
   float* pool_tgt1 = nullptr;        // [2048] LN1(query_pool + self_attn(query_pool))
   float* pool_q = nullptr;           // [2048] Wq tgt1 + bq of the cross attention
-  Lin pool_kv, pool_out, pool_lin1, pool_lin2;
+  Lin pool_kv, pool_v, pool_out, pool_lin1, pool_lin2;
+  float* pool_u = nullptr;           // [8][2048]: scale * Wk_h^T q_h, the key projection folded into the pooled query
   LnP pool_n2, pool_n3, pool_nf;
   Lin input_proj, class_proj;
   std::vector<EncLayer> enc;
@@ -133,7 +134,7 @@ struct TuberPlan {
   cudaStream_t copy_stream = nullptr, run_stream = nullptr;
   cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
   bool slot_busy[2] = {false, false};
-  bool force_simt = false, no_fuse2 = false;
+  bool force_simt = false, no_fuse2 = false, pool_unfolded = false;
   bool profiling = false, debug_keep = false, use_graph = false;
   cudaEvent_t ev[TUBER_NUM_STAGES + 1] = {};
   bool ev_valid = false;
@@ -387,6 +388,21 @@ int do_finalize(TuberPlan* p) {
     p->pool_tgt1 = pk.upload(tgt1);
     p->pool_q = pk.upload(qcf);
     p->pool_kv = pk.linear_rows(L + ".multihead_attn.in_proj_weight", L + ".multihead_attn.in_proj_bias", 3 * D, D, D, 2 * D);
+    p->pool_v = pk.linear_rows(L + ".multihead_attn.in_proj_weight", L + ".multihead_attn.in_proj_bias", 3 * D, D, 2 * D, D);
+    {
+      // scores of head h: (q_h * scale) . (Wk_h x + bk_h) = u_h . x + const, u_h = scale * Wk_h^T q_h; the constant is the same for
+      // every frame of a pixel and cancels in the softmax over frames (transformer_layers.py:338-352)
+      const int NH = 8, HD = D / NH;
+      const double scale = 1.0 / sqrt((double)HD);
+      std::vector<float> u((size_t)NH * D);
+      for (int h = 0; h < NH; ++h)
+        for (int k = 0; k < D; ++k) {
+          double acc = 0;
+          for (int d2 = 0; d2 < HD; ++d2) acc += (double)ca_w->data[(size_t)(D + h * HD + d2) * D + k] * qc[h * HD + d2];
+          u[(size_t)h * D + k] = (float)(acc * scale);
+        }
+      p->pool_u = pk.upload(u);
+    }
     p->pool_out = pk.linear(L + ".multihead_attn.out_proj", D, D);
     p->pool_lin1 = pk.linear(L + ".linear1", 2048, D);
     p->pool_lin2 = pk.linear(L + ".linear2", D, 2048);
@@ -774,11 +790,28 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
   } else if (c.pool == TUBER_POOL_DECODE) {
     // per pixel: one learned query attends over the Tf frame tokens (d = 2048, 8 heads x 256)
     const long long Mp = (long long)B * HW;
-    float* kv = cx.f32(Mc, 2 * CB);
-    cx.gemm(xt, FMT_SPLIT, CB, Mc, p->pool_kv, nullptr, 0, 0, 0, kv, FMT_F32, 2 * CB, ACT_NONE);
     void* att = cx.split(Mp, CB);
-    cx.attention(p->pool_q, CB, seqmap(1, 0, 0, 0), kv, kv + CB, 2 * CB, seqmap(HW, (long long)Tf * HW, 1, HW), att, CB,
-                 seqmap(1, 1, 0, 1), nullptr, (int)Mp, 8, 1, Tf, CB / 8);
+    if (Tf <= 8 && !p->force_simt && !p->pool_unfolded) {
+      // folded form: scores from u_h . x_t, frames mixed per head BEFORE the value projection, which then runs as a grouped
+      // GEMM over the 8 heads (rows = (head, pixel), W rows = that head's slice of Wv): no K / V tensor of all tokens
+      const long long Mg = (Mp + 127) / 128 * 128;            // group stride: a multiple of the GEMM's row block (padding rows are never stored)
+      void* mix = cx.split(8 * Mg, CB);
+      cx.launch("pool_mix", 4.0 * ((double)Mc + 8.0 * Mp) * CB, 2.0 * (double)Mc * CB * 16,
+                [&] { return launch_pool_mix(xt, p->pool_u, mix, B, Tf, HW, Mg, st); });
+      GemmArgs a{};
+      a.A = mix; a.a_fmt = FMT_SPLIT; a.lda = CB;
+      a.Wf = p->pool_v.wf; a.Wp = p->pool_v.wp; a.scale = nullptr; a.shift = p->pool_v.shift;
+      a.C = att; a.c_fmt = FMT_SPLIT; a.ldc = CB;
+      a.M = (int)(8 * Mg); a.N = CB / 8; a.K = CB; a.act = ACT_NONE; a.group_rows = (int)Mg; a.group_out_rows = (int)Mp;
+      if (p->kprof) snprintf(cx.tag, sizeof cx.tag, "grouped 8 x (M=%lld N=%d K=%d)", Mp, CB / 8, CB);
+      cx.launch("gemm_bf16x3_tcgen05", 4.0 * (8.0 * Mp * CB + (double)CB * CB + (double)Mp * CB), 2.0 * 8.0 * Mp * (CB / 8) * CB,
+                [&] { return launch_gemm_tc(a, st); });
+    } else {
+      float* kv = cx.f32(Mc, 2 * CB);
+      cx.gemm(xt, FMT_SPLIT, CB, Mc, p->pool_kv, nullptr, 0, 0, 0, kv, FMT_F32, 2 * CB, ACT_NONE);
+      cx.attention(p->pool_q, CB, seqmap(1, 0, 0, 0), kv, kv + CB, 2 * CB, seqmap(HW, (long long)Tf * HW, 1, HW), att, CB,
+                   seqmap(1, 1, 0, 1), nullptr, (int)Mp, 8, 1, Tf, CB / 8);
+    }
     void* o1 = cx.split(Mp, CB);
     cx.gemm(att, FMT_SPLIT, CB, Mp, p->pool_out, nullptr, 0, 0, 0, o1, FMT_SPLIT, CB, ACT_NONE);
     void* t2s = cx.split(Mp, CB);
@@ -998,6 +1031,8 @@ int tuber_plan_create(const TuberConfig* cfg, TuberPlan** out_plan) {
   p->force_simt = fs && fs[0] == '1';
   const char* nf = getenv("TUBER_NO_FUSE2");
   p->no_fuse2 = nf && nf[0] == '1';
+  const char* pu = getenv("TUBER_POOL_UNFOLDED");
+  p->pool_unfolded = pu && pu[0] == '1';
   *out_plan = p;
   return TUBER_OK;
 }
