@@ -18,8 +18,7 @@ namespace attn_mma {
 constexpr int D = 32;            // head dim
 constexpr int KC = 64;           // keys per chunk
 constexpr int QW = 16;           // queries per warp
-constexpr int NW = 4;            // warps per CTA
-constexpr int QT = QW * NW;      // queries per CTA
+// warps per CTA = NW (template): 4 (64 queries) or 8 (128 queries: half the K/V staging per query for L > 64)
 constexpr int LDS_ROW = 40;      // bf16 per shared-memory row (32 + 8 pad: ldmatrix rows 80 B apart are conflict free)
 
 TB_DEVINL long long seq_row0(const SeqMap& m, int n) {
@@ -53,8 +52,12 @@ struct __align__(16) Smem {
   float msk[KC];                 // 0 or -inf per key of the chunk
 };
 
+template <int NW>
 __global__ void __launch_bounds__(NW * 32)
 attn_mma_kernel(AttnArgs p) {
+  constexpr int QT = QW * NW;      // queries per CTA
+  constexpr int TPK = NW / 2;      // staging threads per key (each converts 32 / TPK dims of K and of V)
+  constexpr int F4 = 8 / TPK;      // float4 per thread and tensor
   __shared__ Smem sm;
   const int n = blockIdx.z, h = blockIdx.y, l0 = blockIdx.x * QT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -75,9 +78,9 @@ attn_mma_kernel(AttnArgs p) {
       split2(v.x * p.scale, v.y * p.scale, q_hi[ks][e], q_mid[ks][e]);
     }
 
-  // chunk staging: thread -> (key = tid / 2 (+0), 16 dims = (tid & 1) * 16 ..): 4 float4 of K and 4 of V
-  const int skey = tid >> 1, sd0 = (tid & 1) * 16;
-  float4 pk[4], pv[4];
+  // chunk staging: thread -> (key = tid / TPK, dims (tid % TPK) * 4 * F4 ..): F4 float4 of K and of V
+  const int skey = tid / TPK, sd0 = (tid % TPK) * 4 * F4;
+  float4 pk[F4], pv[F4];
   auto fetch = [&](int c) {
     const int s = c * KC + skey;
     if (s < p.S) {
@@ -85,15 +88,15 @@ attn_mma_kernel(AttnArgs p) {
       const float4* kp = reinterpret_cast<const float4*>(p.k + krow * p.ldk + h * D + sd0);
       const float4* vp = reinterpret_cast<const float4*>(p.v + krow * p.ldv + h * D + sd0);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { pk[i] = __ldg(kp + i); pv[i] = __ldg(vp + i); }
+      for (int i = 0; i < F4; ++i) { pk[i] = __ldg(kp + i); pv[i] = __ldg(vp + i); }
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { pk[i] = make_float4(0.f, 0.f, 0.f, 0.f); pv[i] = pk[i]; }
+      for (int i = 0; i < F4; ++i) { pk[i] = make_float4(0.f, 0.f, 0.f, 0.f); pv[i] = pk[i]; }
     }
   };
   auto stage = [&](int c) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < F4; ++i) {
       store_split4(&sm.k_hi[skey][sd0 + 4 * i], &sm.k_mid[skey][sd0 + 4 * i], pk[i]);
       store_split4(&sm.v_hi[skey][sd0 + 4 * i], &sm.v_mid[skey][sd0 + 4 * i], pv[i]);
     }
@@ -313,7 +316,12 @@ cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
     return cudaGetLastError();
   }
   if (a.NB > 65535 || a.H > 65535) return cudaErrorNotSupported;
-  dim3 grid(ceil_div(a.L, QT), a.H, a.NB);
-  attn_mma_kernel<<<grid, NW * 32, 0, st>>>(a);
+  if (a.L > 64) {
+    dim3 grid(ceil_div(a.L, 8 * QW), a.H, a.NB);
+    attn_mma_kernel<8><<<grid, 8 * 32, 0, st>>>(a);
+  } else {
+    dim3 grid(ceil_div(a.L, 4 * QW), a.H, a.NB);
+    attn_mma_kernel<4><<<grid, 4 * 32, 0, st>>>(a);
+  }
   return cudaGetLastError();
 }

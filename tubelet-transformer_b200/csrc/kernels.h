@@ -77,6 +77,11 @@ struct LnArgs {
   float* out_f32; int ldo;                   // nullable; out row = (r / rpg) * group_stride + r % rpg + row_off
   int rpg; long long group_stride; long long row_off;
   void* out_split; int lds; int split_col_off;   // nullable; row r, columns split_col_off + [0,C)
+  // chained second norm (the decoder's shared final norm on every layer output, transformer.py:116-126; the decode pool's
+  // norm3 -> pool_decoder.norm): when gamma2 is set, the first result goes to out_split at row r (no remap), and
+  // LayerNorm(first result as stored, gamma2, beta2) goes to out2_split at the remapped row
+  const float* gamma2; const float* beta2;
+  void* out2_split; int lds2;
 };
 cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t st);
 

@@ -763,8 +763,15 @@ sgemm_kernel(GemmArgs p) {
   }
 }
 
+__global__ void head_gemm_kernel(GemmArgs p);
+
 cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st) {
   if (a.K % 16 != 0 || a.Kb % 16 != 0 || a.M <= 0 || a.N <= 0 || a.Wf == nullptr) return cudaErrorInvalidValue;
+  if (a.N <= 96 && !a.Ab && !a.res && !a.C2 && a.c_fmt == FMT_F32 && a.K <= 2048 && a.lda % 4 == 0) {
+    const long long total = (long long)a.M * a.N;
+    head_gemm_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a);
+    return cudaGetLastError();
+  }
   dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64));
   sgemm_kernel<<<grid, 256, 0, st>>>(a);
   return cudaGetLastError();
@@ -812,6 +819,8 @@ layernorm_kernel(LnArgs p) {
   }
   const float rstd = 1.f / sqrtf(warp_sum(q) / (float)p.C + p.eps);
   long long orow = p.rpg > 0 ? (r / p.rpg) * p.group_stride + (r % p.rpg) + p.row_off : r + p.row_off;
+  const bool chain = p.gamma2 != nullptr;
+  float s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     int c = i * 128 + lane * 4;
@@ -824,10 +833,74 @@ layernorm_kernel(LnArgs p) {
     o.w = (v[i].w - mean) * rstd * g.w + b.w;
     if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + c) = o;
     if (p.out_split) {
-      __nv_bfloat16* hi = split_hi(p.out_split, orow, p.lds) + p.split_col_off + c;
+      __nv_bfloat16* hi = split_hi(p.out_split, chain ? r : orow, p.lds) + p.split_col_off + c;
       store_split4(hi, hi + p.lds, o);
     }
+    if (chain) {                                            // the second norm sees the first result as stored (hi + mid)
+      uint32_t h0, m0, h1, m1;
+      split_bf16x2(o.x, o.y, h0, m0);
+      split_bf16x2(o.z, o.w, h1, m1);
+      v[i].x = bf16_lo_to_f32(h0) + bf16_lo_to_f32(m0); v[i].y = bf16_hi_to_f32(h0) + bf16_hi_to_f32(m0);
+      v[i].z = bf16_lo_to_f32(h1) + bf16_lo_to_f32(m1); v[i].w = bf16_hi_to_f32(h1) + bf16_hi_to_f32(m1);
+      s2 += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
   }
+  if (!chain) return;
+  const float mean2 = warp_sum(s2) / (float)p.C;
+  float q2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float a = v[i].x - mean2, b = v[i].y - mean2, c = v[i].z - mean2, d = v[i].w - mean2;
+    q2 += a * a + b * b + c * c + d * d;
+  }
+  const float rstd2 = 1.f / sqrtf(warp_sum(q2) / (float)p.C + p.eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int c = i * 128 + lane * 4;
+    float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma2 + c));
+    float4 b = __ldg(reinterpret_cast<const float4*>(p.beta2 + c));
+    float4 o;
+    o.x = (v[i].x - mean2) * rstd2 * g.x + b.x;
+    o.y = (v[i].y - mean2) * rstd2 * g.y + b.y;
+    o.z = (v[i].z - mean2) * rstd2 * g.z + b.z;
+    o.w = (v[i].w - mean2) * rstd2 * g.w + b.w;
+    __nv_bfloat16* hi = split_hi(p.out2_split, orow, p.lds2) + c;
+    store_split4(hi, hi + p.lds2, o);
+  }
+}
+
+// =============================================================================================
+// Tiny-N linear heads (class_embed_b N = 3 / 2, bbox_embed.layers.2 N = 4 + sigmoid, class_fc N = 80 / 22;
+// tuber_ava.py:64-73,121-125,141-142): one thread per output element, K <= 2048, A fp32 or split.  The tiled SIMT GEMM
+// above needs 64 x 64 tiles to be efficient and took ~20 us for these 0.1 - 30 MFLOP products.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+head_gemm_kernel(GemmArgs p) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)p.M * p.N) return;
+  const int n = (int)(idx % p.N);
+  const long long m = idx / p.N;
+  const float4* w = reinterpret_cast<const float4*>(p.Wf + (long long)n * p.K);
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  if (p.a_fmt == FMT_F32) {
+    const float4* a = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.A) + m * p.lda);
+    for (int k = 0; k < p.K / 4; ++k) {
+      const float4 x = __ldg(a + k), y = __ldg(w + k);
+      acc0 = fmaf(x.x, y.x, acc0); acc1 = fmaf(x.y, y.y, acc1); acc2 = fmaf(x.z, y.z, acc2); acc3 = fmaf(x.w, y.w, acc3);
+    }
+  } else {
+    const __nv_bfloat16* h = split_hi(p.A, m, p.lda);
+    for (int k = 0; k < p.K / 4; ++k) {
+      const float4 x = load_split4(h + 4 * k, h + p.lda + 4 * k), y = __ldg(w + k);
+      acc0 = fmaf(x.x, y.x, acc0); acc1 = fmaf(x.y, y.y, acc1); acc2 = fmaf(x.z, y.z, acc2); acc3 = fmaf(x.w, y.w, acc3);
+    }
+  }
+  float v = (acc0 + acc1) + (acc2 + acc3);
+  if (p.scale) v *= __ldg(p.scale + n);
+  if (p.shift) v += __ldg(p.shift + n);
+  if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
+  else if (p.act == ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+  reinterpret_cast<float*>(p.C)[m * p.ldc + n] = v;
 }
 
 cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t st) {

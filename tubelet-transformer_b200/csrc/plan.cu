@@ -118,6 +118,8 @@ struct TuberPlan {
   std::vector<EncLayer> enc;
   std::vector<DecLayer> dec;
   LnP dec_norm;
+  float* dec0_c1 = nullptr;          // [d]: decoder layer 0 after its (input independent) self-attention block: LN1(Wo bv + bo)
+  float* dec0_qc = nullptr;          // [Q, d]: its cross-attention query Wq (dec0_c1 + query_embed) + bq
   Lin pos_proj;                      // N = Le*3d + Ld*2d: per encoder layer [Wq;Wk;0], per decoder layer [Wk_cross;0]
   Lin mem_kv;                        // N = Ld*2d: per decoder layer [Wk_cross;Wv_cross]
   float* dim_t = nullptr; float* dim_s = nullptr;
@@ -470,6 +472,31 @@ int do_finalize(TuberPlan* p) {
     p->dec.push_back(l);
   }
   if (pk.status != TUBER_OK) return pk.status;
+  {
+    // decoder layer 0 sees tgt = 0: q = k = query_pos terms, v_j = bv for every j, so softmax(..) V = bv, the self-attention
+    // block returns Wo bv + bo for every query, and after norm1 the state is one constant row c1 (transformer.py:60,225-231)
+    const std::string P = "transformer.decoder.layers.0";
+    const HostTensor* sb = pk.get(P + ".self_attn.in_proj_bias", {3 * d});
+    const HostTensor* ow = pk.get(P + ".self_attn.out_proj.weight", {d, d});
+    const HostTensor* ob = pk.get(P + ".self_attn.out_proj.bias", {d});
+    const HostTensor* g1 = pk.get(P + ".norm1.weight", {d});
+    const HostTensor* b1 = pk.get(P + ".norm1.bias", {d});
+    const HostTensor* cw = pk.get(P + ".multihead_attn.in_proj_weight", {3 * d, d});
+    const HostTensor* cb = pk.get(P + ".multihead_attn.in_proj_bias", {3 * d});
+    if (pk.status != TUBER_OK) return pk.status;
+    std::vector<double> bv(sb->data.begin() + 2 * d, sb->data.begin() + 3 * d);
+    std::vector<double> c1 = host_matvec(*ow, ob, 0, d, d, bv);
+    host_layernorm(c1, g1->data, b1->data);
+    std::vector<float> c1f(c1.begin(), c1.end()), qcf((size_t)Q * d);
+    for (int q = 0; q < Q; ++q) {
+      std::vector<double> x(d);
+      for (int k = 0; k < d; ++k) x[k] = c1[k] + (double)qe->data[(size_t)q * d + k];
+      std::vector<double> y = host_matvec(*cw, cb, 0, d, d, x);
+      for (int n = 0; n < d; ++n) qcf[(size_t)q * d + n] = (float)y[n];
+    }
+    p->dec0_c1 = pk.upload(c1f);
+    p->dec0_qc = pk.upload(qcf);
+  }
   p->dec_norm = pk.ln("transformer.decoder.norm", d);
   p->pos_proj = pk.make_lin(posw, NP, d, nullptr, nullptr);
   p->mem_kv = pk.make_lin(memw, c.dec_layers * 2 * d, d, nullptr, &memb);
@@ -578,15 +605,16 @@ struct Ctx {
   // out = LayerNorm(x + res); x fp32 or split; fp32 and / or split outputs
   void layernorm(const void* x, int x_fmt, int ldx, const void* res, int res_fmt, int ldr, const LnP& ln, long long rows,
                  float* out_f32, int ldo, void* out_split, int lds, int split_col_off = 0, int rpg = 0,
-                 long long group_stride = 0, long long row_off = 0) {
+                 long long group_stride = 0, long long row_off = 0, const LnP* ln2 = nullptr, void* out2_split = nullptr, int lds2 = 0) {
     if (!ok()) return;
     LnArgs a{};
+    if (ln2) { a.gamma2 = ln2->g; a.beta2 = ln2->b; a.out2_split = out2_split; a.lds2 = lds2; }
     a.x = x; a.x_fmt = x_fmt; a.ldx = ldx; a.res = res; a.res_fmt = res_fmt; a.ldr = ldr;
     a.gamma = ln.g; a.beta = ln.b; a.eps = LN_EPS; a.rows = (int)rows; a.C = ln.C;
     a.out_f32 = out_f32; a.ldo = ldo; a.rpg = rpg; a.group_stride = group_stride; a.row_off = row_off;
     a.out_split = out_split; a.lds = lds; a.split_col_off = split_col_off;
     const double n = (double)rows * ln.C;
-    launch("layernorm", 4.0 * n * (1 + (res ? 1 : 0) + (out_f32 ? 1 : 0) + (out_split ? 1 : 0)), 8.0 * n,
+    launch("layernorm", 4.0 * n * (1 + (res ? 1 : 0) + (out_f32 ? 1 : 0) + (out_split ? 1 : 0) + (ln2 ? 1 : 0)), 8.0 * n * (ln2 ? 2 : 1),
            [&] { return launch_layernorm(a, st); });
   }
 
@@ -820,9 +848,8 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     cx.gemm(t2s, FMT_SPLIT, CB, Mp, p->pool_lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, 2048, ACT_RELU);
     cx.gemm(hdn, FMT_SPLIT, 2048, Mp, p->pool_lin2, t2s, FMT_SPLIT, CB, 0, o1, FMT_SPLIT, CB, ACT_NONE);
     void* t3 = cx.split(Mp, CB);
-    cx.layernorm(o1, FMT_SPLIT, CB, nullptr, 0, 0, p->pool_n3, Mp, nullptr, 0, t3, CB);
     void* o = cx.split(Mp, CB);
-    cx.layernorm(t3, FMT_SPLIT, CB, nullptr, 0, 0, p->pool_nf, Mp, nullptr, 0, o, CB);
+    cx.layernorm(o1, FMT_SPLIT, CB, nullptr, 0, 0, p->pool_n3, Mp, nullptr, 0, t3, CB, 0, 0, 0, 0, &p->pool_nf, o, CB);   // norm3, then the decoder's final norm
     xs = o;
   }
   cx.tap("xs", xs, FMT_SPLIT, Mtok, CB);
@@ -893,21 +920,26 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     void* hdn = cx.split(Mq, c.dim_ff);
     for (int i = 0; i < Ld; ++i) {
       const DecLayer& l = p->dec[i];
-      cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.sa_in, l.pq_sa, FMT_F32, 3 * d, Q, qkv, FMT_F32, 3 * d, ACT_NONE);
-      cx.attention(qkv, 3 * d, seqmap(1, Q, 0, 1), qkv + d, qkv + 2 * d, 3 * d, seqmap(1, Q, 0, 1), att, d, seqmap(1, Q, 0, 1),
-                   nullptr, B, nh, Q, Q, hd);
-      cx.gemm(att, FMT_SPLIT, d, Mq, l.sa_out, tgt_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
-      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, l.n1, Mq, nullptr, 0, tgt_s, d);
-      cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.ca_q, l.pq_ca, FMT_F32, d, Q, qc, FMT_F32, d, ACT_NONE);
-      cx.attention(qc, d, seqmap(1, Q, 0, 1), memkv + (size_t)i * 2 * d, memkv + (size_t)i * 2 * d + d, Ld * 2 * d,
-                   seqmap(1, Ntok, 0, 1), att, d, seqmap(1, Q, 0, 1), kpm, B, nh, Q, Ntok, hd);
-      cx.gemm(att, FMT_SPLIT, d, Mq, l.ca_out, tgt_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+      const bool folded0 = i == 0 && p->dec0_c1 != nullptr;
+      if (!folded0) {
+        cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.sa_in, l.pq_sa, FMT_F32, 3 * d, Q, qkv, FMT_F32, 3 * d, ACT_NONE);
+        cx.attention(qkv, 3 * d, seqmap(1, Q, 0, 1), qkv + d, qkv + 2 * d, 3 * d, seqmap(1, Q, 0, 1), att, d, seqmap(1, Q, 0, 1),
+                     nullptr, B, nh, Q, Q, hd);
+        cx.gemm(att, FMT_SPLIT, d, Mq, l.sa_out, tgt_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+        cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, l.n1, Mq, nullptr, 0, tgt_s, d);
+        cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.ca_q, l.pq_ca, FMT_F32, d, Q, qc, FMT_F32, d, ACT_NONE);
+      }
+      // layer 0 starts from tgt = 0 (transformer.py:60), so its self-attention block and cross-attention query are input
+      // independent and were folded at finalize: tgt after norm1 = dec0_c1 (one row for every query), query = dec0_qc [Q, d]
+      cx.attention(folded0 ? p->dec0_qc : qc, d, folded0 ? seqmap(1, 0, 0, 1) : seqmap(1, Q, 0, 1), memkv + (size_t)i * 2 * d,
+                   memkv + (size_t)i * 2 * d + d, Ld * 2 * d, seqmap(1, Ntok, 0, 1), att, d, seqmap(1, Q, 0, 1), kpm, B, nh, Q, Ntok, hd);
+      if (folded0) cx.gemm(att, FMT_SPLIT, d, Mq, l.ca_out, p->dec0_c1, FMT_F32, d, 1, o, FMT_SPLIT, d, ACT_NONE);
+      else cx.gemm(att, FMT_SPLIT, d, Mq, l.ca_out, tgt_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
       cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, l.n2, Mq, nullptr, 0, tgt_s, d);
       cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, c.dim_ff, ACT_RELU);
       cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mq, l.lin2, tgt_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
-      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, l.n3, Mq, nullptr, 0, tgt_s, d);
-      // shared final norm on every layer's output (transformer.py:116-126), row (b, q) -> (b, i, q)
-      cx.layernorm(tgt_s, FMT_SPLIT, d, nullptr, 0, 0, p->dec_norm, Mq, nullptr, 0, hs_s, d, 0, Q, (long long)Ld * Q, (long long)i * Q);
+      // norm3, then the shared final norm on every layer's output (transformer.py:116-126), row (b, q) -> (b, i, q)
+      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, l.n3, Mq, nullptr, 0, tgt_s, d, 0, Q, (long long)Ld * Q, (long long)i * Q, &p->dec_norm, hs_s, d);
     }
   }
   cx.tap("hs", hs_s, FMT_SPLIT, Mh, d);
