@@ -59,6 +59,8 @@ attn_mma_kernel(AttnArgs p) {
   constexpr int TPK = NW / 2;      // staging threads per key (each converts 32 / TPK dims of K and of V)
   constexpr int F4 = 8 / TPK;      // float4 per thread and tensor
   __shared__ Smem sm;
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.z, h = blockIdx.y, l0 = blockIdx.x * QT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const long long q0 = seq_row0(p.qm, n), k0 = seq_row0(p.km, n);
@@ -236,6 +238,8 @@ attn_mma_kernel(AttnArgs p) {
 template <int MAXT>
 __global__ void __launch_bounds__(128)
 attn_tiny_kernel(AttnArgs p) {
+  pdl_trigger();
+  pdl_wait();
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int hgroups = p.H / 8;                           // 8 heads per warp pass
@@ -312,16 +316,14 @@ cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
   if (a.ldq % 4 || a.ldk % 4 || a.ldv % 4 || a.ldo % 4) return cudaErrorNotSupported;
   if (a.L <= 8 && a.S <= 8 && a.H % 8 == 0) {
     const long long warps = (long long)a.NB * (a.H / 8);
-    attn_tiny_kernel<8><<<ceil_div(warps * 32, 128), 128, 0, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(attn_tiny_kernel<8>, dim3(ceil_div(warps * 32, 128)), dim3(128), 0, st, a);
   }
   if (a.NB > 65535 || a.H > 65535) return cudaErrorNotSupported;
   if (a.L > 64) {
     dim3 grid(ceil_div(a.L, 8 * QW), a.H, a.NB);
-    attn_mma_kernel<8><<<grid, 8 * 32, 0, st>>>(a);
+    return launch_pdl(attn_mma_kernel<8>, grid, dim3(8 * 32), 0, st, a);
   } else {
     dim3 grid(ceil_div(a.L, 4 * QW), a.H, a.NB);
-    attn_mma_kernel<4><<<grid, 4 * 32, 0, st>>>(a);
+    return launch_pdl(attn_mma_kernel<4>, grid, dim3(4 * 32), 0, st, a);
   }
-  return cudaGetLastError();
 }

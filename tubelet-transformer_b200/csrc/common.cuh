@@ -85,3 +85,30 @@ TB_DEVINL float warp_max(float v) {
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------
+// A forward is a chain of ~190 dependent launches, most of them a few microseconds long.  Kernels launched through
+// launch_pdl may be scheduled while their predecessor is still running: they set up (barriers, tensor memory, descriptor
+// prefetch) and then block in pdl_wait() until the predecessor grid has completed and its writes are visible.  Every
+// kernel launched this way calls pdl_wait() before its first global access; pdl_trigger() at its top lets ITS successor
+// start early.  (Captured into CUDA graphs as programmatic dependency edges.)
+TB_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+TB_DEVINL void pdl_trigger() {
+#ifdef TUBER_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+bool tuber_pdl_enabled();   // plan.cu: off by default (measured: no gain inside CUDA graphs), TUBER_PDL=1 turns it on
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tuber_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

@@ -61,6 +61,7 @@ struct Params {
   int M, N, K, act;
   int kb1;                                              // k-blocks taken from the first A operand (the rest from the second)
   int group_rows;                                       // > 0: grouped GEMM (GemmArgs::group_rows), a multiple of BM
+  int ksplit, part_rows;                                // split-K: work item = (tile, part); part s -> rows + s*part_rows of C
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -186,13 +187,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / BN;
-  const int num_tiles = m_tiles * n_tiles;
-  const int kblocks = p.K / BK;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int num_tiles = m_tiles * n_tiles * ksplit;         // work items: (output tile, K part); "tile" below = item index
+  const int kblocks = p.K / BK / ksplit;                    // k-blocks per item
+  const int kb_total = p.K / BK;
 
   if (warp == 0 && lane == 0) {
     if (smem_base & 1023u) __trap();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    if (p.kb1 < kblocks) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    if (p.kb1 < kb_total) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     if (p.res_mode == RES_TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
@@ -219,6 +222,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();                                               // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ================= operand producer =================
@@ -226,8 +231,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int part = tile % ksplit, ot = tile / ksplit;
+        const int m_blk = ot / n_tiles, n_blk = ot % n_tiles;
+        for (int kb = part * kblocks; kb < (part + 1) * kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
@@ -281,10 +287,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int part = tile % ksplit, ot = tile / ksplit;
+        const int m_blk = ot / n_tiles, n_blk = ot % n_tiles;
         for (int j = 0; j < C::PANELS_PER_TILE; ++j) {
           mbar_wait(pfree_bar(slot), phase ^ 1);         // the store that last read this buffer has drained
-          if (p.res_mode == RES_TMA) {
+          if (p.res_mode == RES_TMA && part == 0) {
             const int col = n_blk * BN + j * 64;
             mbar_expect_tx(pfull_bar(slot), PANEL_BYTES);
             if (p.out_fmt == FMT_F32) tma_load_3d(panel_base + slot * PANEL_BYTES, &tmR, pfull_bar(slot), 0, m_blk * BM, col >> 5);
@@ -304,16 +311,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     int it = 0, slot = 0, prev_slot = -1;
     uint32_t pphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int part = tile % ksplit, ot = tile / ksplit;
+      const int m_blk = ot / n_tiles, n_blk = ot % n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       float* s_scale = s_ss + as * 2 * BN;
       float* s_shift = s_scale + BN;
       const int grp = p.group_rows > 0 ? m_blk * BM / p.group_rows : 0;
       const int gcol = grp * p.N;                           // grouped: column / parameter offset of this row block's group
+      const int res_mode = part == 0 ? p.res_mode : RES_NONE;   // split-K: shift and residual go into part 0 only
       if (et < BN) {
         s_scale[et] = p.scale ? __ldg(p.scale + gcol + n_blk * BN + et) : 1.f;
-        s_shift[et] = p.shift ? __ldg(p.shift + gcol + n_blk * BN + et) : 0.f;
+        s_shift[et] = (p.shift && part == 0) ? __ldg(p.shift + gcol + n_blk * BN + et) : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
       mbar_wait(tfull_bar(as), aphase);
@@ -340,7 +349,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), sc.z, sh.z);
             v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), sc.w, sh.w);
           }
-          if (p.res_mode == RES_TMA) {
+          if (res_mode == RES_TMA) {
             if (p.out_fmt == FMT_F32) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
@@ -359,7 +368,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 v[8 * q + 6] += bf16_lo_to_f32(a.w) + bf16_lo_to_f32(b.w); v[8 * q + 7] += bf16_hi_to_f32(a.w) + bf16_hi_to_f32(b.w);
               }
             }
-          } else if (p.res_mode == RES_DIRECT && row_ok) {
+          } else if (res_mode == RES_DIRECT && row_ok) {
             const int n0 = n_blk * BN + cl;
             if (p.res_fmt == FMT_F32) {
               const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + rrow * p.ldr + n0);
@@ -412,7 +421,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) {
           const int col = gcol + n_blk * BN + j * 64;
-          const int orow = m_blk * BM - grp * p.group_rows;
+          const int orow = m_blk * BM - grp * p.group_rows + part * p.part_rows;
           if (p.out_fmt == FMT_F32) tma_store_3d(&tmC, pb, 0, orow, col >> 5);
           else tma_store_3d(&tmC, pb, col, orow, 0);
           bulk_commit();
@@ -526,6 +535,8 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();
 
   // Ring order = the MMA warp's consumption order.  S(sub, t) = the k-blocks [A | W4 rows of sub] of row block t, W2(c, t) =
   // chunk c of W1'.  After the first block's S(0), S(1):   per block t:  W2(0,t) S(0,t+1) [W2(1,t)] S(1,t+1)
@@ -879,10 +890,9 @@ static bool encode_f32_panel_map(CUtensorMap* map, const void* base, uint64_t co
 template <class C>
 static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
                               const Params& p, cudaStream_t st) {
-  const int tiles = ceil_div(p.M, BM) * (p.N / C::BN);
+  const int tiles = ceil_div(p.M, BM) * (p.N / C::BN) * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_bf16x3_kernel<C><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmA2, tmW, tmC, tmR, p);
-  return cudaGetLastError();
+  return launch_pdl(gemm_bf16x3_kernel<C>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
 }
 
 }  // namespace tc
@@ -904,7 +914,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   }
   // 128-wide tiles unless that leaves most of the machine idle (token-sized GEMMs): then 64-wide tiles double the CTA count
   int bn = (a.N % 128 == 0) ? 128 : 64;
-  if (bn == 128 && (long long)ceil_div(a.M, BM) * (a.N / 128) * 2 <= g_num_sms) bn = 64;
+  if (bn == 128 && (long long)ceil_div(a.M, BM) * (a.N / 128) * 2 * (a.ksplit > 1 ? a.ksplit : 1) <= g_num_sms) bn = 64;
   Params p{};
   p.scale = a.scale; p.shift = a.shift;
   p.out_fmt = a.c_fmt;
@@ -917,7 +927,17 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
     return cudaErrorInvalidValue;
   }
   p.group_rows = a.group_rows > 0 ? a.group_rows : 0;
-  const int c_rows = a.group_rows > 0 ? (a.group_out_rows > 0 ? a.group_out_rows : a.group_rows) : a.M, c_cols = groups * a.N;
+  int c_rows = a.group_rows > 0 ? (a.group_out_rows > 0 ? a.group_out_rows : a.group_rows) : a.M;
+  const int c_cols = groups * a.N;
+  p.ksplit = 1;
+  if (a.ksplit > 1) {
+    if (a.group_rows > 0 || a.Ab || a.act != ACT_NONE || a.c_fmt != FMT_F32 || (a.K / BK) % a.ksplit != 0 || a.part_rows < a.M || a.part_rows % BM != 0) {
+      snprintf(g_err, sizeof g_err, "gemm_tc: bad split-K problem K=%d ksplit=%d part_rows=%d M=%d", a.K, a.ksplit, a.part_rows, a.M);
+      return cudaErrorInvalidValue;
+    }
+    p.ksplit = a.ksplit; p.part_rows = a.part_rows;
+    c_rows = (a.ksplit - 1) * a.part_rows + a.M;
+  }
   if (a.res) {
     const bool tma_ok = a.res_mod <= 0 && a.res_fmt == a.c_fmt && aligned16(a.res) && a.ldr % 8 == 0 && a.N <= a.ldr;
     p.res_mode = tma_ok ? RES_TMA : RES_DIRECT;
@@ -979,9 +999,8 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
   if (!encode_f32_panel_map(&tmC2, C2, N2, a.M, ldc2)) return cudaErrorInvalidValue;
   const int m_tiles = ceil_div(a.M, BM);
   const int grid = m_tiles < g_num_sms ? m_tiles : g_num_sms;
-  if (N2 == 64) gemm_fused2_kernel<64><<<grid, NUM_THREADS, CfgWide::SMEM_BYTES, st>>>(tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
-  else gemm_fused2_kernel<128><<<grid, NUM_THREADS, CfgWide::SMEM_BYTES, st>>>(tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
-  return cudaGetLastError();
+  if (N2 == 64) return launch_pdl(gemm_fused2_kernel<64>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
+  return launch_pdl(gemm_fused2_kernel<128>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
 }
 
 // fp32 [N,K] -> bf16 [2][N][K] (hi plane, mid plane)

@@ -64,6 +64,10 @@ struct GemmArgs {
   // grouped form (tcgen05 kernel only; 0 = plain): rows [g*group_rows, (g+1)*group_rows) of A are multiplied with rows
   // [g*N, (g+1)*N) of W (scale / shift likewise) and written to C[row - g*group_rows, g*N + n]; M = groups * group_rows
   int group_rows;
+  // split-K (tcgen05 kernel only; 0/1 = off): the K range is cut into ksplit parts computed by different CTAs; part s is
+  // written (fp32, no activation; shift and residual only in part 0) to rows [s*part_rows, s*part_rows + M) of C, and the
+  // consumer (launch_layernorm with x_parts) adds the parts -- deterministic, unlike atomics
+  int ksplit; int part_rows;
   int group_out_rows;                        // rows of C actually written per group (<= group_rows; 0 = group_rows): padding rows are clipped
 };
 cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st);
@@ -71,6 +75,7 @@ cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st);
 // ---- LayerNorm over the last dim (C in {256, 2048}) of x (+ res) ---------------------------
 struct LnArgs {
   const void* x; int x_fmt; int ldx;         // fp32 or split
+  int x_parts; long long x_part_stride;      // > 1: x = sum of x_parts fp32 slabs, x_part_stride rows apart (split-K partial sums)
   const void* res; int res_fmt; int ldr;     // optional: normalise x + res (fp32 or split; ldr 0 = broadcast row)
   const float* gamma; const float* beta; float eps;
   int rows, C;

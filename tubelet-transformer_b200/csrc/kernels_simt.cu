@@ -293,6 +293,8 @@ dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __r
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();
   if (tid == 0)
     for (int q = 0; q < NSLOT - 1 && q < total; ++q) issue(q);
 
@@ -447,8 +449,7 @@ cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale,
       while (TC > 2 && cols * ceil_div(Ti, TC) < 2LL * g_num_sms) TC = (TC + 1) / 2;
       const long long items = cols * ceil_div(Ti, TC);
       const int grid = (int)(items < g_num_sms ? items : g_num_sms);
-      dwconv_s1_roll_kernel<<<grid, dwr::THREADS, dwr::SMEM_BYTES, st>>>(tmR, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, TC, (int)items);
-      return cudaGetLastError();
+      return launch_pdl(dwconv_s1_roll_kernel, dim3(grid), dim3(dwr::THREADS), dwr::SMEM_BYTES, st, tmR, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, TC, (int)items);
     }
     const long long tiles = (long long)B * ceil_div(Ti, TT) * ceil_div(Hi, TH) * ceil_div(Wi, TW) * (C / CC);
     const long long slots = (long long)g_num_sms * (NSTAGE == 1 ? 2 : 1);
@@ -558,6 +559,8 @@ pool_mix_kernel(const void* __restrict__ xt, const float* __restrict__ U, void* 
   constexpr int D = 2048, NH = 8;
   __shared__ float red[8][NH * MAXT];
   __shared__ float prob[NH * MAXT];
+  pdl_trigger();
+  pdl_wait();
   const int pix = blockIdx.x, b = pix / HW, hw = pix % HW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, c0 = tid * 8;
   float x[MAXT][8];
@@ -627,9 +630,8 @@ pool_mix_kernel(const void* __restrict__ xt, const float* __restrict__ U, void* 
 cudaError_t launch_pool_mix(const void* xt_split, const float* U, void* y_split, int B, int Tf, int HW, long long group_stride,
                             cudaStream_t st) {
   if (Tf < 1 || Tf > 8) return cudaErrorInvalidValue;
-  if (Tf <= 4) pool_mix_kernel<4><<<B * HW, 256, 0, st>>>(xt_split, U, y_split, B, Tf, HW, group_stride);
-  else pool_mix_kernel<8><<<B * HW, 256, 0, st>>>(xt_split, U, y_split, B, Tf, HW, group_stride);
-  return cudaGetLastError();
+  if (Tf <= 4) return launch_pdl(pool_mix_kernel<4>, dim3(B * HW), dim3(256), 0, st, xt_split, U, y_split, B, Tf, HW, group_stride);
+  return launch_pdl(pool_mix_kernel<8>, dim3(B * HW), dim3(256), 0, st, xt_split, U, y_split, B, Tf, HW, group_stride);
 }
 
 // AdaptiveAvgPool3d(1) over all positions (tuber_ava.py:48,124): split [B,N,C] -> fp32 [B,C]
@@ -769,8 +771,7 @@ cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st) {
   if (a.K % 16 != 0 || a.Kb % 16 != 0 || a.M <= 0 || a.N <= 0 || a.Wf == nullptr) return cudaErrorInvalidValue;
   if (a.N <= 96 && !a.Ab && !a.res && !a.C2 && a.c_fmt == FMT_F32 && a.K <= 2048 && a.lda % 4 == 0) {
     const long long total = (long long)a.M * a.N;
-    head_gemm_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(head_gemm_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, st, a);
   }
   dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64));
   sgemm_kernel<<<grid, 256, 0, st>>>(a);
@@ -784,6 +785,8 @@ cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st) {
 template <int NV>   // float4 chunks per lane: C = 128 * NV
 __global__ void __launch_bounds__(256)
 layernorm_kernel(LnArgs p) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= p.rows) return;
   const long long r = warp;
@@ -794,6 +797,10 @@ layernorm_kernel(LnArgs p) {
     int c = i * 128 + lane * 4;
     if (p.x_fmt == FMT_F32) {
       v[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + r * p.ldx + c));
+      for (int s = 1; s < p.x_parts; ++s) {                // split-K partial sums, added in a fixed order
+        const float4 u = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + (r + s * p.x_part_stride) * p.ldx + c));
+        v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+      }
     } else {
       const __nv_bfloat16* h = split_hi(p.x, r, p.ldx) + c;
       v[i] = load_split4(h, h + p.ldx);
@@ -876,6 +883,8 @@ layernorm_kernel(LnArgs p) {
 // =============================================================================================
 __global__ void __launch_bounds__(256)
 head_gemm_kernel(GemmArgs p) {
+  pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)p.M * p.N) return;
   const int n = (int)(idx % p.N);
@@ -906,9 +915,9 @@ head_gemm_kernel(GemmArgs p) {
 cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t st) {
   int grid = ceil_div((long long)a.rows * 32, 256);
   if (a.C == 256)
-    layernorm_kernel<2><<<grid, 256, 0, st>>>(a);
+    return launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, st, a);
   else if (a.C == 2048)
-    layernorm_kernel<16><<<grid, 256, 0, st>>>(a);
+    return launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(256), 0, st, a);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();

@@ -23,6 +23,13 @@
 #include "../../include/tuber_b200.h"
 #include "kernels.h"
 
+bool tuber_pdl_enabled() {
+  // measured on B200 inside the captured graph: no gain without an early trigger (1194 vs 1193 clips/s), 1.5 % slower with
+  // griddepcontrol.launch_dependents at kernel entry -> off unless TUBER_PDL=1
+  static const bool on = [] { const char* e = getenv("TUBER_PDL"); return e && e[0] == '1'; }();
+  return on;
+}
+
 namespace {
 
 thread_local char g_last_error[512] = "";
@@ -584,9 +591,10 @@ struct Ctx {
 
   // C = act(scale * A W^T + shift + res)
   void gemm(const void* A, int a_fmt, int lda, long long M, const Lin& w, const void* res, int res_fmt, int ldr, int res_mod,
-            void* C, int c_fmt, int ldc, int act, const void* Ab = nullptr, int ldb = 0, int Kb = 0) {
+            void* C, int c_fmt, int ldc, int act, const void* Ab = nullptr, int ldb = 0, int Kb = 0, int ksplit = 0, int part_rows = 0) {
     if (!ok()) return;
     GemmArgs a{};
+    a.ksplit = ksplit; a.part_rows = part_rows;
     a.A = A; a.a_fmt = a_fmt; a.lda = lda;
     a.Ab = Ab; a.ldb = ldb; a.Kb = Ab ? Kb : 0;
     a.Wf = w.wf; a.Wp = w.wp; a.scale = w.scale; a.shift = w.shift;
@@ -595,7 +603,8 @@ struct Ctx {
     a.M = (int)M; a.N = w.N; a.K = w.K - a.Kb; a.act = act;
     const bool tc_ok = a_fmt == FMT_SPLIT && w.N % 64 == 0 && w.K % 64 == 0 && act != ACT_SIGMOID && lda % 8 == 0 && ldc % 8 == 0;
     const bool tc = tc_ok && !p->force_simt;
-    if (p->kprof) snprintf(tag, sizeof tag, "M=%lld N=%d K=%d res=%d/%d out=%d act=%d", M, w.N, w.K, res ? 1 + res_fmt : 0, res_mod, c_fmt, act);
+    if (!tc && ksplit > 1) { status = fail(TUBER_ERR_STATE, "split-K GEMM needs the tensor-core path"); return; }
+    if (p->kprof) snprintf(tag, sizeof tag, "M=%lld N=%d K=%d res=%d/%d out=%d act=%d ksplit=%d", M, w.N, w.K, res ? 1 + res_fmt : 0, res_mod, c_fmt, act, ksplit);
     const double mn = (double)M * w.N;
     const double bytes = 4.0 * ((double)M * w.K + (double)w.N * w.K + mn + (res ? (res_mod > 0 ? (double)res_mod * w.N : mn) : 0.0));
     launch(tc ? "gemm_bf16x3_tcgen05" : "sgemm_fp32", bytes, 2.0 * mn * w.K,
@@ -605,9 +614,11 @@ struct Ctx {
   // out = LayerNorm(x + res); x fp32 or split; fp32 and / or split outputs
   void layernorm(const void* x, int x_fmt, int ldx, const void* res, int res_fmt, int ldr, const LnP& ln, long long rows,
                  float* out_f32, int ldo, void* out_split, int lds, int split_col_off = 0, int rpg = 0,
-                 long long group_stride = 0, long long row_off = 0, const LnP* ln2 = nullptr, void* out2_split = nullptr, int lds2 = 0) {
+                 long long group_stride = 0, long long row_off = 0, const LnP* ln2 = nullptr, void* out2_split = nullptr, int lds2 = 0,
+                 int x_parts = 0, long long x_part_stride = 0) {
     if (!ok()) return;
     LnArgs a{};
+    a.x_parts = x_parts; a.x_part_stride = x_part_stride;
     if (ln2) { a.gamma2 = ln2->g; a.beta2 = ln2->b; a.out2_split = out2_split; a.lds2 = lds2; }
     a.x = x; a.x_fmt = x_fmt; a.ldx = ldx; a.res = res; a.res_fmt = res_fmt; a.ldr = ldr;
     a.gamma = ln.g; a.beta = ln.b; a.eps = LN_EPS; a.rows = (int)rows; a.C = ln.C;
@@ -654,6 +665,15 @@ struct Ctx {
     cudaEventRecord(p->ev[i], st);
   }
 };
+
+// split-K factor for a token-sized GEMM with a long K (FFN second layer: N = 256, K = 2048): enough parts to put ~128 CTAs
+// to work, at least 4 k-blocks each
+inline int choose_ksplit(long long M, int N, int K) {
+  const long long tiles = ((M + 127) / 128) * (N / 64);
+  int s = 1;
+  while (s < 8 && tiles * s * 2 <= 160 && (K / 64) % (s * 2) == 0 && K / 64 / (s * 2) >= 4) s *= 2;
+  return s;
+}
 
 inline SeqMap seqmap(int inner, long long outer, long long inner_stride, long long step) {
   SeqMap m; m.inner = inner; m.outer = outer; m.inner_stride = inner_stride; m.step = step;
@@ -888,6 +908,9 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     void* att = cx.split(Mtok, d);
     void* o = cx.split(Mtok, d);
     void* hdn = cx.split(Mtok, c.dim_ff);
+    const int ks2 = p->force_simt ? 1 : choose_ksplit(Mtok, d, c.dim_ff);
+    const long long pr2 = (Mtok + 127) / 128 * 128;          // rows between partial-sum slabs (whole row blocks: a tile's padding rows stay inside its slab)
+    float* o2 = ks2 > 1 ? cx.f32((long long)ks2 * pr2, d) : nullptr;
     for (int i = 0; i < Le; ++i) {
       const EncLayer& e = p->enc[i];
       cx.gemm(src_s, FMT_SPLIT, d, Mtok, e.in, posp + (size_t)i * 3 * d, FMT_F32, NP, pos_mod, qkv, FMT_F32, 3 * d, ACT_NONE);
@@ -896,8 +919,13 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
       cx.gemm(att, FMT_SPLIT, d, Mtok, e.out, src_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
       cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, e.n1, Mtok, nullptr, 0, src_s, d);
       cx.gemm(src_s, FMT_SPLIT, d, Mtok, e.lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, c.dim_ff, ACT_RELU);
-      cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mtok, e.lin2, src_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
-      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, e.n2, Mtok, nullptr, 0, src_s, d);
+      if (ks2 > 1) {     // split-K partial sums (fp32 slabs of o2), added by the LayerNorm kernel
+        cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mtok, e.lin2, src_s, FMT_SPLIT, d, 0, o2, FMT_F32, d, ACT_NONE, nullptr, 0, 0, ks2, (int)pr2);
+        cx.layernorm(o2, FMT_F32, d, nullptr, 0, 0, e.n2, Mtok, nullptr, 0, src_s, d, 0, 0, 0, 0, nullptr, nullptr, 0, ks2, pr2);
+      } else {
+        cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mtok, e.lin2, src_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+        cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, e.n2, Mtok, nullptr, 0, src_s, d);
+      }
     }
   }
   cx.tap("memory", src_s, FMT_SPLIT, Mtok, d);
@@ -918,6 +946,9 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     void* att = cx.split(Mq, d);
     void* o = cx.split(Mq, d);
     void* hdn = cx.split(Mq, c.dim_ff);
+    const int ksd = p->force_simt ? 1 : choose_ksplit(Mq, d, c.dim_ff);
+    const long long prd = (Mq + 127) / 128 * 128;
+    float* od = ksd > 1 ? cx.f32((long long)ksd * prd, d) : nullptr;
     for (int i = 0; i < Ld; ++i) {
       const DecLayer& l = p->dec[i];
       const bool folded0 = i == 0 && p->dec0_c1 != nullptr;
@@ -937,9 +968,15 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
       else cx.gemm(att, FMT_SPLIT, d, Mq, l.ca_out, tgt_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
       cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, l.n2, Mq, nullptr, 0, tgt_s, d);
       cx.gemm(tgt_s, FMT_SPLIT, d, Mq, l.lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, c.dim_ff, ACT_RELU);
-      cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mq, l.lin2, tgt_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
       // norm3, then the shared final norm on every layer's output (transformer.py:116-126), row (b, q) -> (b, i, q)
-      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, l.n3, Mq, nullptr, 0, tgt_s, d, 0, Q, (long long)Ld * Q, (long long)i * Q, &p->dec_norm, hs_s, d);
+      if (ksd > 1) {
+        cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mq, l.lin2, tgt_s, FMT_SPLIT, d, 0, od, FMT_F32, d, ACT_NONE, nullptr, 0, 0, ksd, (int)prd);
+        cx.layernorm(od, FMT_F32, d, nullptr, 0, 0, l.n3, Mq, nullptr, 0, tgt_s, d, 0, Q, (long long)Ld * Q, (long long)i * Q, &p->dec_norm, hs_s, d,
+                     ksd, prd);
+      } else {
+        cx.gemm(hdn, FMT_SPLIT, c.dim_ff, Mq, l.lin2, tgt_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+        cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, l.n3, Mq, nullptr, 0, tgt_s, d, 0, Q, (long long)Ld * Q, (long long)i * Q, &p->dec_norm, hs_s, d);
+      }
     }
   }
   cx.tap("hs", hs_s, FMT_SPLIT, Mh, d);
