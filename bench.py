@@ -292,7 +292,7 @@ def main():
                         "tensor_frac": round(tfs / peaks["bf16_tflops"], 4)})
     top = max(stats, key=lambda s: s.ms)
     t_hbm = top.bytes / (peaks["hbm_gbs"] * 1e9)
-    t_tc = 3.0 * top.flops / (peaks["bf16_tflops"] * 1e12) if b"tcgen05" in top.name else 0.0   # bf16x3: 3 MMA passes
+    t_tc = 3.0 * top.flops / (peaks["bf16_tflops"] * 1e12) if (b"tcgen05" in top.name or b"gemm_bf16x3" in top.name or b"gemm2_bf16x3" in top.name) else 0.0   # bf16x3: 3 MMA passes
     if t_hbm >= t_tc:
         ach = top.bytes / (top.ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}

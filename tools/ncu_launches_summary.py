@@ -7,7 +7,8 @@ import csv
 import json
 import sys
 
-FAMILY = [("gemm_fused2", "gemm_fused2_tcgen05"), ("gemm_bf16x3", "gemm_bf16x3_tcgen05"), ("stem_tc", "stem_conv"), ("dwconv", "dwconv3x3x3"), ("attn", "attention"),
+FAMILY = [("gemm_fused2", "gemm_fused2_tcgen05"), ("gemm2_bf16x3", "gemm2_bf16x3_pair"), ("Cfg<128, 2, 3>", "gemm_bf16x3_wide"), ("Cfg<128, 3, 1>", "gemm_bf16x3_deep"),
+          ("Cfg<64, 3, 2>", "gemm_bf16x3_n64"), ("Cfg<256, 2, 1>", "gemm_bf16x3_big"), ("stem_tc", "stem_conv"), ("dwconv", "dwconv3x3x3"), ("attn", "attention"),
           ("layernorm", "layernorm"), ("gather_rows", "gather_rows"), ("sgemm", "sgemm_fp32"), ("maxpool", "maxpool"),
           ("tpool", "tpool"), ("posenc", "posenc"), ("mask_resize", "mask_resize"), ("to_split", "to_split")]
 

@@ -26,6 +26,7 @@
 // formats) use per-thread global loads (small token-sized GEMMs only).
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.h"
@@ -47,7 +48,8 @@ template <int BN_, int STAGES_, int PANELS_> struct Cfg {
   static constexpr int TMEM_COLS = 2 * BN;                      // power of two >= 32
   static constexpr int PANELS_PER_TILE = BN / 64;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SS_BYTES = 4 * BN * 4;                   // scale, shift x 2 accumulator stages
+  static constexpr int SS_STAGES = BN > 128 ? 1 : 2;            // BN = 256: one copy (the epilogue's panel barrier orders reuse), to fit 227 KB
+  static constexpr int SS_BYTES = SS_STAGES * 2 * BN * 4;       // scale, shift per accumulator stage
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PANELS * PANEL_BYTES + BAR_BYTES + SS_BYTES;
   static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared-memory limit");
   static_assert(2 * STAGES + 4 + 2 * PANELS + 1 <= BAR_BYTES / 8, "barrier area too small");
@@ -315,14 +317,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int m_blk = ot / n_tiles, n_blk = ot % n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      float* s_scale = s_ss + as * 2 * BN;
+      float* s_scale = s_ss + (C::SS_STAGES == 2 ? as : 0) * 2 * BN;
       float* s_shift = s_scale + BN;
       const int grp = p.group_rows > 0 ? m_blk * BM / p.group_rows : 0;
       const int gcol = grp * p.N;                           // grouped: column / parameter offset of this row block's group
       const int res_mode = part == 0 ? p.res_mode : RES_NONE;   // split-K: shift and residual go into part 0 only
-      if (et < BN) {
-        s_scale[et] = p.scale ? __ldg(p.scale + gcol + n_blk * BN + et) : 1.f;
-        s_shift[et] = (p.shift && part == 0) ? __ldg(p.shift + gcol + n_blk * BN + et) : 0.f;
+      for (int cidx = et; cidx < BN; cidx += 128) {
+        s_scale[cidx] = p.scale ? __ldg(p.scale + gcol + n_blk * BN + cidx) : 1.f;
+        s_shift[cidx] = (p.shift && part == 0) ? __ldg(p.shift + gcol + n_blk * BN + cidx) : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
       mbar_wait(tfull_bar(as), aphase);
@@ -822,6 +824,319 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// =============================================================================================================
+// CTA-pair variant for the deep-K shapes (K >= 512, N % 256 == 0): tcgen05.mma.cta_group::2, one 256 x 256 output tile
+// per pair.  The single-CTA kernel moves 64 KB from L2 into shared memory per k-block and 128 x 128 tile (operands
+// are 4 bytes per element for three bf16 passes), i.e. ~85 B/clk/SM at the tensor rate -- twice what L2 delivers per SM, and
+// these GEMMs ran at 50-60 % of the MMA rate.  In a pair each CTA loads its own 128 rows of A and its own 128 of the 256
+// W rows (64 KB per k-block as before) but the MMA covers 256 x 256: 4x the FLOPs per byte fetched.
+//   per CTA: 3 stages x (A 32 KB + W half 32 KB), one 32 KB panel buffer, 2 x 256 TMEM columns (double-buffered accumulator)
+//   barriers: full[s]   local TMA completion;  xfull[s] (leader) the peer's relay warp reports ITS stage s full
+//             empty[s]  tcgen05.commit multicast to both CTAs;  tfull[a] commit multicast;  tempty[a] (leader) 8 epilogue warps
+// =============================================================================================================
+TB_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+TB_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+TB_DEVINL uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+TB_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+TB_DEVINL void umma2_commit_mc(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+TB_DEVINL void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
+                    const __grid_constant__ CUtensorMap tmR, Params p) {
+  constexpr int BN2 = 256, BNH = 128, STAGES = 3, STAGE_BYTES = 65536, PPT = BN2 / 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t panel_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = panel_base + PANEL_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (3 + s); };
+  auto xfull_bar = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (9 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (11 + s); };
+  const uint32_t pfull_bar = bar_base + 8u * 13, pfree_bar = bar_base + 8u * 14;
+  const uint32_t tmem_slot = bar_base + 8u * 15;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_base));
+  float* s_ss = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_base));   // scale[256] | shift[256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = p.N / BN2;
+  const int num_tiles = m_tiles * n_tiles;
+  const int kblocks = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_base & 1023u) __trap();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    if (p.kb1 < kblocks) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    if (p.res_mode == RES_TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(xfull_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+    mbar_init(pfull_bar, 1);
+    mbar_init(pfree_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= operand producer: this CTA's 128 rows of A and 128 of the tile's 256 W rows =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int row0 = m_blk * 2 * BM + (int)rank * BM;
+        const int wrow = (p.group_rows > 0 ? (m_blk * 2 * BM / p.group_rows) * p.N : 0) + n_blk * BN2 + (int)rank * BNH;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          if (kb < p.kb1) tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, row0, 0);
+          else tma_load_3d(sa, &tmA2, full_bar(stage), (kb - p.kb1) * BK, row0, 0);
+          tma_load_3d(sa + 2 * A_PLANE_BYTES, &tmW, full_bar(stage), kb * BK, wrow, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank != 0) {
+      // ================= relay (peer CTA): report each locally completed stage to the leader =================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t remote[STAGES];
+        for (int s = 0; s < STAGES; ++s) remote[s] = mapa_rank(xfull_bar(s), 0);
+        for (int tile = pair; tile < num_tiles; tile += npairs)
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            mbar_arrive_cluster(remote[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+      }
+    } else {
+      // ================= MMA issuer (leader CTA) =================
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN2);
+      const uint64_t desc0 = make_smem_desc(smem_base);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+        const int as = it & 1;
+        mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN2);
+#pragma unroll 1
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          mbar_wait(xfull_bar(stage), phase);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t a_hi = desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4)), a_mid = a_hi + (A_PLANE_BYTES >> 4);
+            const uint64_t w_hi = a_hi + ((2 * A_PLANE_BYTES) >> 4), w_mid = w_hi + ((BNH * BK * 2) >> 4);
+            const uint32_t first = kb == 0 ? 0u : 1u;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_d, a_mid + 2 * k, w_hi + 2 * k, idesc, k == 0 ? first : 1u);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_d, a_hi + 2 * k, w_mid + 2 * k, idesc, 1);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_d, a_hi + 2 * k, w_hi + 2 * k, idesc, 1);
+            umma2_commit_mc(empty_bar(stage));
+            if (kb == kblocks - 1) umma2_commit_mc(tfull_bar(as));
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= panel producer =================
+    if (lane == 0) {
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int row0 = m_blk * 2 * BM + (int)rank * BM;
+        for (int j = 0; j < PPT; ++j) {
+          mbar_wait(pfree_bar, phase ^ 1);
+          if (p.res_mode == RES_TMA) {
+            const int col = n_blk * BN2 + j * 64;
+            mbar_expect_tx(pfull_bar, PANEL_BYTES);
+            if (p.out_fmt == FMT_F32) tma_load_3d(panel_base, &tmR, pfull_bar, 0, row0, col >> 5);
+            else tma_load_3d(panel_base, &tmR, pfull_bar, col, row0, 0);
+          } else {
+            mbar_arrive(pfull_bar);
+          }
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 3..6): this CTA's 128 rows x 256 columns =================
+    const int lg = warp & 3;
+    const int et = threadIdx.x - EPI_WARP0 * 32;
+    const int r = lg * 32 + lane;
+    const uint32_t tempty_remote0 = mapa_rank(tempty_bar(0), 0), tempty_remote1 = mapa_rank(tempty_bar(1), 0);
+    float* s_scale = s_ss;
+    float* s_shift = s_ss + BN2;
+    int it = 0;
+    uint32_t pphase = 0;
+    for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int as = it & 1;
+      const int grp = p.group_rows > 0 ? m_blk * 2 * BM / p.group_rows : 0;
+      const int gcol = grp * p.N;
+      for (int c = et; c < BN2; c += 128) {
+        s_scale[c] = p.scale ? __ldg(p.scale + gcol + n_blk * BN2 + c) : 1.f;
+        s_shift[c] = p.shift ? __ldg(p.shift + gcol + n_blk * BN2 + c) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull_bar(as), (it >> 1) & 1);
+      tcgen05_fence_after();
+      const int row0 = m_blk * 2 * BM + (int)rank * BM;
+      const long long row = (long long)row0 + r;
+      const bool row_ok = row < p.M;
+      const long long rrow = p.res_mod > 0 ? row % p.res_mod : row;
+#pragma unroll 1
+      for (int j = 0; j < PPT; ++j) {
+        mbar_wait(pfull_bar, pphase);
+        const uint32_t pb = panel_base;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN2 + j * 64 + h * 32), acc);
+          const int cl = j * 64 + h * 32;
+          float v[32];
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + cl + 4 * q4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + cl + 4 * q4);
+            v[4 * q4] = fmaf(__uint_as_float(acc[4 * q4]), sc.x, sh.x);
+            v[4 * q4 + 1] = fmaf(__uint_as_float(acc[4 * q4 + 1]), sc.y, sh.y);
+            v[4 * q4 + 2] = fmaf(__uint_as_float(acc[4 * q4 + 2]), sc.z, sh.z);
+            v[4 * q4 + 3] = fmaf(__uint_as_float(acc[4 * q4 + 3]), sc.w, sh.w);
+          }
+          if (p.res_mode == RES_TMA) {
+            if (p.out_fmt == FMT_F32) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const uint4 t = lds128(swz(pb + h * SUB_BYTES, r, q4));
+                v[4 * q4] += __uint_as_float(t.x); v[4 * q4 + 1] += __uint_as_float(t.y);
+                v[4 * q4 + 2] += __uint_as_float(t.z); v[4 * q4 + 3] += __uint_as_float(t.w);
+              }
+            } else {
+#pragma unroll
+              for (int q8 = 0; q8 < 4; ++q8) {
+                const uint4 a = lds128(swz(pb, r, 4 * h + q8));
+                const uint4 b = lds128(swz(pb + SUB_BYTES, r, 4 * h + q8));
+                v[8 * q8] += bf16_lo_to_f32(a.x) + bf16_lo_to_f32(b.x); v[8 * q8 + 1] += bf16_hi_to_f32(a.x) + bf16_hi_to_f32(b.x);
+                v[8 * q8 + 2] += bf16_lo_to_f32(a.y) + bf16_lo_to_f32(b.y); v[8 * q8 + 3] += bf16_hi_to_f32(a.y) + bf16_hi_to_f32(b.y);
+                v[8 * q8 + 4] += bf16_lo_to_f32(a.z) + bf16_lo_to_f32(b.z); v[8 * q8 + 5] += bf16_hi_to_f32(a.z) + bf16_hi_to_f32(b.z);
+                v[8 * q8 + 6] += bf16_lo_to_f32(a.w) + bf16_lo_to_f32(b.w); v[8 * q8 + 7] += bf16_hi_to_f32(a.w) + bf16_hi_to_f32(b.w);
+              }
+            }
+          } else if (p.res_mode == RES_DIRECT && row_ok) {
+            const int n0 = n_blk * BN2 + cl;
+            if (p.res_fmt == FMT_F32) {
+              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + rrow * p.ldr + n0);
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 t = __ldg(rp + q4);
+                v[4 * q4] += t.x; v[4 * q4 + 1] += t.y; v[4 * q4 + 2] += t.z; v[4 * q4 + 3] += t.w;
+              }
+            } else {
+              const __nv_bfloat16* hp = split_hi(p.res, rrow, p.ldr) + n0;
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 t = load_split4(hp + 4 * q4, hp + p.ldr + 4 * q4);
+                v[4 * q4] += t.x; v[4 * q4 + 1] += t.y; v[4 * q4 + 2] += t.z; v[4 * q4 + 3] += t.w;
+              }
+            }
+          }
+          if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+          }
+          if (p.out_fmt == FMT_F32) {
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4)
+              sts128(swz(pb + h * SUB_BYTES, r, q4), make_uint4(__float_as_uint(v[4 * q4]), __float_as_uint(v[4 * q4 + 1]),
+                                                                __float_as_uint(v[4 * q4 + 2]), __float_as_uint(v[4 * q4 + 3])));
+          } else {
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8) {
+              uint4 hi, mid;
+              split_bf16x2(v[8 * q8], v[8 * q8 + 1], hi.x, mid.x);
+              split_bf16x2(v[8 * q8 + 2], v[8 * q8 + 3], hi.y, mid.y);
+              split_bf16x2(v[8 * q8 + 4], v[8 * q8 + 5], hi.z, mid.z);
+              split_bf16x2(v[8 * q8 + 6], v[8 * q8 + 7], hi.w, mid.w);
+              sts128(swz(pb, r, 4 * h + q8), hi);
+              sts128(swz(pb + SUB_BYTES, r, 4 * h + q8), mid);
+            }
+          }
+        }
+        if (j == PPT - 1) {                                  // accumulator fully read: hand it back to the leader's MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(as ? tempty_remote1 : tempty_remote0);
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const int col = gcol + n_blk * BN2 + j * 64;
+          const int orow = row0 - grp * p.group_rows;
+          if (p.out_fmt == FMT_F32) tma_store_3d(&tmC, pb, 0, orow, col >> 5);
+          else tma_store_3d(&tmC, pb, col, orow, 0);
+          bulk_commit();
+          bulk_wait_read<0>();
+          mbar_arrive(pfree_bar);
+        }
+        pphase ^= 1;
+      }
+    }
+    if (et == 0) bulk_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                        // the leader's MMAs read this CTA's shared memory until its last commit
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -830,6 +1145,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 using CfgWide = Cfg<128, 2, 3>;   // memory-bound shapes: panels pipelined (load residual | compute | store)
 using CfgDeep = Cfg<128, 3, 1>;   // K >= 512: deeper operand ring, one panel buffer
 using CfgN64 = Cfg<64, 3, 2>;     // N == 64 (or N % 128 != 0)
+using CfgBig = Cfg<256, 2, 1>;    // K >= 512, N % 256 == 0 and enough row blocks: 128 x 256 tiles (A tile reused over 256 columns,
+                                  // 25 % less L2 -> shared-memory traffic per FLOP; these shapes are L2-bandwidth / tensor bound)
+
+constexpr int PAIR_SMEM_BYTES = 3 * 65536 + PANEL_BYTES + 256 + 2 * 256 * 4;   // gemm2_bf16x3_kernel
+static_assert(PAIR_SMEM_BYTES <= 232448, "over the 227 KB shared-memory limit");
 
 static char g_err[256] = "";
 static EncodeTiledFn g_encode = nullptr;
@@ -852,6 +1172,10 @@ static cudaError_t init_once() {
   e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDeep::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgN64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgN64::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgBig::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm2_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(gemm_fused2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
   if (e != cudaSuccess) return e;
@@ -887,6 +1211,25 @@ static bool encode_f32_panel_map(CUtensorMap* map, const void* base, uint64_t co
   return encode3(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, 32, rows, cols / 32, ld * 4, 128, 32, BM, 2);
 }
 
+// 128 x 256 tiles for the deep-K shapes when they still fill most of the machine
+static bool use_big_tiles(const GemmArgs& a, int KT) {
+  // measured: not faster than 128 x 128 (33-37 vs 31-33 us on M=16384 N=256 K=1024) -- the deep shapes are bound by L2 -> SM
+  // bandwidth per CTA, which only operand sharing across a CTA pair fixes (gemm2_bf16x3_kernel); kept behind TUBER_BIG_TILES=1
+  static const bool on = [] { const char* e = getenv("TUBER_BIG_TILES"); return e && e[0] == '1'; }();
+  if (!on || KT < 512 || a.N % 256 != 0 || a.ksplit > 1) return false;
+  const long long tiles = (long long)ceil_div(a.M, BM) * (a.N / 256);
+  return tiles >= 100;
+}
+
+// CTA pairs (cta_group::2, 256 x 256 tiles) for the deep-K shapes
+static bool use_pair_tiles(const GemmArgs& a, int KT) {
+  static const bool off = [] { const char* e = getenv("TUBER_NO_PAIR_GEMM"); return e && e[0] == '1'; }();
+  if (off || KT < 512 || a.N % 256 != 0 || a.ksplit > 1) return false;
+  if (a.group_rows > 0 && a.group_rows % (2 * BM) != 0) return false;
+  const long long tiles = (long long)ceil_div(a.M, 2 * BM) * (a.N / 256);
+  return tiles >= 48;                                       // at least ~2/3 of the 74 pairs busy
+}
+
 template <class C>
 static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
                               const Params& p, cudaStream_t st) {
@@ -915,6 +1258,9 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   // 128-wide tiles unless that leaves most of the machine idle (token-sized GEMMs): then 64-wide tiles double the CTA count
   int bn = (a.N % 128 == 0) ? 128 : 64;
   if (bn == 128 && (long long)ceil_div(a.M, BM) * (a.N / 128) * 2 * (a.ksplit > 1 ? a.ksplit : 1) <= g_num_sms) bn = 64;
+  if (use_big_tiles(a, KT)) bn = 256;
+  const bool pair_tiles = use_pair_tiles(a, KT);
+  if (pair_tiles) bn = 128;                                 // W box: each CTA of the pair loads 128 of the tile's 256 rows
   Params p{};
   p.scale = a.scale; p.shift = a.shift;
   p.out_fmt = a.c_fmt;
@@ -956,9 +1302,27 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
     ok = a.c_fmt == FMT_F32 ? encode_f32_panel_map(&tmR, a.res, a.N, a.M, a.ldr) : encode_split_map(&tmR, a.res, a.N, a.M, a.ldr, BM);
     if (!ok) return cudaErrorInvalidValue;
   }
+  if (pair_tiles) {
+    const int tiles = ceil_div(p.M, 2 * BM) * (p.N / 256);
+    const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
+    return launch_pdl(gemm2_bf16x3_kernel, dim3(2 * pairs), dim3(NUM_THREADS), PAIR_SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
+  }
+  if (bn == 256) return launch_cfg<CfgBig>(tmA, tmA2, tmW, tmC, tmR, p, st);
   if (bn == 64) return launch_cfg<CfgN64>(tmA, tmA2, tmW, tmC, tmR, p, st);
   if (KT >= 512) return launch_cfg<CfgDeep>(tmA, tmA2, tmW, tmC, tmR, p, st);
   return launch_cfg<CfgWide>(tmA, tmA2, tmW, tmC, tmR, p, st);
+}
+
+// which template configuration launch_gemm_tc picks (the per-launch profile reports them as separate kernels)
+const char* gemm_tc_config_name(const GemmArgs& a) {
+  if (tc::g_num_sms == 0) tc::init_once();
+  const int KT = a.K + (a.Ab ? a.Kb : 0);
+  int bn = (a.N % 128 == 0) ? 128 : 64;
+  if (bn == 128 && (long long)ceil_div(a.M, tc::BM) * (a.N / 128) * 2 * (a.ksplit > 1 ? a.ksplit : 1) <= tc::g_num_sms) bn = 64;
+  if (tc::use_pair_tiles(a, KT)) return "gemm2_bf16x3_pair";
+  if (tc::use_big_tiles(a, KT)) return "gemm_bf16x3_big";
+  if (bn == 64) return "gemm_bf16x3_n64";
+  return KT >= 512 ? "gemm_bf16x3_deep" : "gemm_bf16x3_wide";
 }
 
 // conv4 (a: N must be 256, split output, TMA or no residual) fused with the next bottleneck's conv1 (W2p packed

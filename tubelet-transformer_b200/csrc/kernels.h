@@ -124,6 +124,9 @@ cudaError_t launch_from_split(const void* in, int ldi, float* out, int ldo, long
 // ---- tcgen05 bf16x3 GEMM (gemm_tc.cu) -------------------------------------------------------
 cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st);
 const char* gemm_tc_last_error();
+// name of the template configuration launch_gemm_tc will use: gemm_bf16x3_wide (<128,2,3>, memory-bound shapes), _deep (<128,3,1>,
+// K >= 512), _n64 (<64,3,2>, N = 64 or token-sized)
+const char* gemm_tc_config_name(const GemmArgs& a);
 // conv4 (+ shortcut / residual) of one bottleneck fused with conv1 of the next (256-channel stage): a describes the first
 // GEMM (N = 256, split output), the second is C2[M, N2] = relu(scale2 * (C W2^T) + shift2) in fp32, N2 in {64, 128}
 cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const float* scale2, const float* shift2, float* C2, int N2,

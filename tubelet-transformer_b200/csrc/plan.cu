@@ -607,7 +607,7 @@ struct Ctx {
     if (p->kprof) snprintf(tag, sizeof tag, "M=%lld N=%d K=%d res=%d/%d out=%d act=%d ksplit=%d", M, w.N, w.K, res ? 1 + res_fmt : 0, res_mod, c_fmt, act, ksplit);
     const double mn = (double)M * w.N;
     const double bytes = 4.0 * ((double)M * w.K + (double)w.N * w.K + mn + (res ? (res_mod > 0 ? (double)res_mod * w.N : mn) : 0.0));
-    launch(tc ? "gemm_bf16x3_tcgen05" : "sgemm_fp32", bytes, 2.0 * mn * w.K,
+    launch(tc ? gemm_tc_config_name(a) : "sgemm_fp32", bytes, 2.0 * mn * w.K,
            [&] { return tc ? launch_gemm_tc(a, st) : launch_sgemm(a, st); });
   }
 
@@ -852,7 +852,7 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
       a.C = att; a.c_fmt = FMT_SPLIT; a.ldc = CB;
       a.M = (int)(8 * Mg); a.N = CB / 8; a.K = CB; a.act = ACT_NONE; a.group_rows = (int)Mg; a.group_out_rows = (int)Mp;
       if (p->kprof) snprintf(cx.tag, sizeof cx.tag, "grouped 8 x (M=%lld N=%d K=%d)", Mp, CB / 8, CB);
-      cx.launch("gemm_bf16x3_tcgen05", 4.0 * (8.0 * Mp * CB + (double)CB * CB + (double)Mp * CB), 2.0 * 8.0 * Mp * (CB / 8) * CB,
+      cx.launch("gemm_bf16x3_deep", 4.0 * (8.0 * Mp * CB + (double)CB * CB + (double)Mp * CB), 2.0 * 8.0 * Mp * (CB / 8) * CB,
                 [&] { return launch_gemm_tc(a, st); });
     } else {
       float* kv = cx.f32(Mc, 2 * CB);
