@@ -97,7 +97,8 @@ def test_sgemm(abi, m, n, k, act):
 
 @pytest.mark.parametrize("c,st_t,st_s,dims", [(64, 1, 1, (2, 4, 9, 10)), (128, 2, 2, (1, 8, 16, 16)), (512, 2, 1, (2, 3, 5, 7)),
                                               (256, 2, 2, (1, 5, 7, 9)), (64, 1, 1, (1, 8, 32, 32)), (128, 1, 1, (2, 5, 16, 17)),
-                                              (512, 1, 1, (1, 1, 3, 3)), (256, 1, 1, (1, 2, 8, 8))])
+                                              (512, 1, 1, (1, 1, 3, 3)), (256, 1, 1, (1, 2, 8, 8)), (128, 2, 2, (2, 32, 64, 64)),
+                                              (64, 2, 2, (1, 7, 19, 35))])
 def test_dwconv(abi, c, st_t, st_s, dims):
     from tuber_b200 import _lib
     b, t, h, w = dims

@@ -386,6 +386,155 @@ dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __r
   }
 }
 
+// Stride-(2,2,2) variant of the rolling-t kernel (first block of layer2 / layer3, ir_CSN_152.py:48-51 with stride 2): a work
+// item = (clip, TC output frames, 8 x 16 output tile, 32 channels); input frame it = 2*ot - 1 + kt feeds output frame ot, so an
+// odd input frame 2j-1 finishes output j-1 (kt = 2, emitted) and starts output j (kt = 0), an even frame 2j adds kt = 1 to
+// output j: two accumulator sets alternate.  A thread owns 4 output columns x 4 channels and reads the 3 x 9 input window of a
+// frame from the halo tile (17 x 33 x 32 ch, one 5-D TMA load per frame, 3-slot ring).
+namespace dws {
+constexpr int TH = 8, TW = 16, CC = 32, IH = 2 * TH + 1, IW = 2 * TW + 1, NSLOT = 3, TCMAX = 4;
+constexpr int PLANE_F4 = IH * IW * (CC / 4);
+constexpr int PLANE_BYTES = PLANE_F4 * 16;                // 71808
+constexpr int W_F4 = 27 * (CC / 4);
+constexpr int OFF_W = NSLOT * PLANE_BYTES;
+constexpr int OFF_BAR = OFF_W + 2 * W_F4 * 16;
+constexpr int SMEM_BYTES = OFF_BAR + NSLOT * 8;
+constexpr int THREADS = TH * (TW / 4) * (CC / 4);         // 256
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+}  // namespace dws
+
+__global__ void __launch_bounds__(dws::THREADS, 1)
+dwconv_s2_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __restrict__ wpk, const float* __restrict__ scale,
+                      const float* __restrict__ shift, void* __restrict__ out, int B, int Ti, int To, int Ho, int Wo, int C, int TC,
+                      int nitems) {
+  using namespace dws;
+  extern __shared__ __align__(128) float4 dws_smem[];
+  const int tid = threadIdx.x;
+  const int wt = (Wo + TW - 1) / TW, ht = (Ho + TH - 1) / TH, tcn = (To + TC - 1) / TC, nch = C / CC;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(dws_smem);
+  const uint32_t bar0 = sbase + OFF_BAR;
+  const int S = 2 * TC + 1;                                 // input frames per item: 2*t0 - 1 .. 2*(t0 + TC - 1) + 1
+
+  auto decode = [&](int item, int& b, int& t0, int& h0, int& w0, int& cb) {
+    cb = (item % nch) * CC; item /= nch;
+    w0 = (item % wt) * TW; item /= wt;
+    h0 = (item % ht) * TH; item /= ht;
+    t0 = (item % tcn) * TC;
+    b = item / tcn;
+  };
+  const int my_items = (int)blockIdx.x < nitems ? (nitems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total = my_items * S;
+  auto issue = [&](int q) {
+    const int k = q / S, s = q - k * S;
+    int b, t0, h0, w0, cb;
+    decode(blockIdx.x + k * gridDim.x, b, t0, h0, w0, cb);
+    const uint32_t dst = sbase + (q % NSLOT) * PLANE_BYTES, bar = bar0 + 8 * (q % NSLOT);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)PLANE_BYTES) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(&tmIn), "r"(bar), "r"(cb), "r"(2 * w0 - 1), "r"(2 * h0 - 1), "r"(2 * t0 - 1 + s), "r"(b) : "memory");
+  };
+  if (tid == 0) {
+    for (int i = 0; i < NSLOT; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int q = 0; q < NSLOT - 1 && q < total; ++q) issue(q);
+
+  const int c4 = tid & 7, wq = (tid >> 3) & 3, lh = tid >> 5;
+  typedef unsigned long long u64;
+  u64 accX[4][2], accY[4][2];
+  auto zero = [](u64 (&a)[4][2]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j][0] = a[j][1] = 0ull;
+  };
+  int q = 0;
+  for (int k = 0; k < my_items; ++k) {
+    int b, t0, h0, w0, cb;
+    decode(blockIdx.x + k * gridDim.x, b, t0, h0, w0, cb);
+    float4* wsm4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(dws_smem) + OFF_W) + (k & 1) * W_F4;
+    if (tid < W_F4) wsm4[tid] = __ldg(reinterpret_cast<const float4*>(wpk + (tid >> 3) * C + cb) + (tid & 7));
+    const ulonglong2* wsm = reinterpret_cast<const ulonglong2*>(wsm4);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cb) + c4);
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cb) + c4);
+    __syncthreads();
+    const int oh = h0 + lh, ow0 = w0 + wq * 4;
+    const int tend = min(t0 + TC, To);
+    zero(accX); zero(accY);
+    // one input frame: acc_fin (output frame jf, taps kt_fin) is finished and emitted, acc_add (taps kt_add) is added to
+    auto frame = [&](int it, u64 (*fin)[2], int jf, u64 (*add)[2], int kt_add, bool do_add) {
+      if (tid == 0 && q + NSLOT - 1 < total) issue(q + NSLOT - 1);
+      {
+        const uint32_t bar = bar0 + 8 * (q % NSLOT), par = (uint32_t)((q / NSLOT) & 1);
+        asm volatile(
+            "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n"
+            ::"r"(bar), "r"(par) : "memory");
+      }
+      const ulonglong2* tsm = reinterpret_cast<const ulonglong2*>(dws_smem) + (q % NSLOT) * PLANE_F4;
+      const bool do_fin = fin != nullptr && jf >= t0 && jf < tend;
+      if (it >= 0 && it < Ti && (do_fin || do_add)) {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          ulonglong2 x[9];
+#pragma unroll
+          for (int j = 0; j < 9; ++j) x[j] = tsm[((2 * lh + kh) * IW + wq * 8 + j) * (CC / 4) + c4];
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            if (do_fin) {
+              const ulonglong2 wv = wsm[((2 * 3 + kh) * 3 + kw) * (CC / 4) + c4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(fin[j][0]) : "l"(x[2 * j + kw].x), "l"(wv.x));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(fin[j][1]) : "l"(x[2 * j + kw].y), "l"(wv.y));
+              }
+            }
+            if (do_add) {
+              const ulonglong2 wv = wsm[((kt_add * 3 + kh) * 3 + kw) * (CC / 4) + c4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(add[j][0]) : "l"(x[2 * j + kw].x), "l"(wv.x));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(add[j][1]) : "l"(x[2 * j + kw].y), "l"(wv.y));
+              }
+            }
+          }
+        }
+      }
+      if (do_fin) {
+        if (oh < Ho) {
+          const long long orow0 = (((long long)b * To + jf) * Ho + oh) * Wo + ow0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (ow0 + j < Wo) {
+              float4 o;
+              o.x = fmaxf(fmaf(__uint_as_float((uint32_t)fin[j][0]), sc.x, sh.x), 0.f);
+              o.y = fmaxf(fmaf(__uint_as_float((uint32_t)(fin[j][0] >> 32)), sc.y, sh.y), 0.f);
+              o.z = fmaxf(fmaf(__uint_as_float((uint32_t)fin[j][1]), sc.z, sh.z), 0.f);
+              o.w = fmaxf(fmaf(__uint_as_float((uint32_t)(fin[j][1] >> 32)), sc.w, sh.w), 0.f);
+              __nv_bfloat16* hi = split_hi(out, orow0 + j, C) + cb + c4 * 4;
+              store_split4(hi, hi + C, o);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fin[j][0] = fin[j][1] = 0ull;
+      }
+      __syncthreads();
+      ++q;
+    };
+    // output frame j lives in accX for even (j - t0), accY for odd
+    for (int jj = 0; jj <= TC; jj += 2) {
+      const int j = t0 + jj;
+      frame(2 * j - 1, accY, j - 1, accX, 0, j < tend);                   // odd input frame: finish j-1 (kt = 2), start j (kt = 0)
+      if (jj < TC) frame(2 * j, nullptr, 0, accX, 1, j < tend);           // even input frame: kt = 1 of j
+      if (jj + 1 <= TC) {
+        frame(2 * j + 1, accX, j, accY, 0, j + 1 < tend);
+        if (jj + 1 < TC) frame(2 * j + 2, nullptr, 0, accY, 1, j + 1 < tend);
+      }
+    }
+  }
+}
+
 namespace dwt {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -404,6 +553,8 @@ static cudaError_t init_once() {
   e = cudaFuncSetAttribute(dwconv_s1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(dwconv_s1_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dwr::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(dwconv_s2_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dws::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return cudaSuccess;
@@ -455,6 +606,25 @@ cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale,
     const long long slots = (long long)g_num_sms * (NSTAGE == 1 ? 2 : 1);
     const int grid = (int)(tiles < slots ? tiles : slots);
     dwconv_s1_tiled_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmIn, tmW, scale, shift, out_split, B, Ti, Hi, Wi, C, (int)tiles);
+    return cudaGetLastError();
+  }
+  if (st_t == 2 && st_s == 2 && C % dws::CC == 0) {
+    using namespace dws;
+    cudaError_t e = dwt::init_once();
+    if (e != cudaSuccess) return e;
+    CUtensorMap tmS;
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Ti, (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)Wi * C * 4, (cuuint64_t)Hi * Wi * C * 4, (cuuint64_t)Ti * Hi * Wi * C * 4};
+    cuuint32_t box[5] = {CC, IW, IH, 1, 1}, es[5] = {1, 1, 1, 1, 1};
+    if (dwt::g_encode(&tmS, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+    const long long cols = (long long)B * ceil_div(Ho, TH) * ceil_div(Wo, TW) * (C / CC);
+    int TC = To < TCMAX ? To : TCMAX;
+    while (TC > 1 && cols * ceil_div(To, TC) < 2LL * dwt::g_num_sms) TC = (TC + 1) / 2;
+    const long long items = cols * ceil_div(To, TC);
+    const int grid = (int)(items < dwt::g_num_sms ? items : dwt::g_num_sms);
+    dwconv_s2_roll_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmS, wpk, scale, shift, out_split, B, Ti, To, Ho, Wo, C, TC, (int)items);
     return cudaGetLastError();
   }
   long long total = (long long)B * To * Ho * ((Wo + 3) / 4) * (C / 4);
@@ -770,7 +940,7 @@ __global__ void head_gemm_kernel(GemmArgs p);
 cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st) {
   if (a.K % 16 != 0 || a.Kb % 16 != 0 || a.M <= 0 || a.N <= 0 || a.Wf == nullptr) return cudaErrorInvalidValue;
   if (a.N <= 96 && !a.Ab && !a.res && !a.C2 && a.c_fmt == FMT_F32 && a.K <= 2048 && a.lda % 4 == 0) {
-    const long long total = (long long)a.M * a.N;
+    const long long total = (long long)a.M * a.N * 8;
     return launch_pdl(head_gemm_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, st, a);
   }
   dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64));
@@ -783,7 +953,7 @@ cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st) {
 // fp32 and/or split-bf16 outputs, optional output-row remap (stacks decoder layers, concat).
 // =============================================================================================
 template <int NV>   // float4 chunks per lane: C = 128 * NV
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)                  // (NV = 16 would otherwise take 196 registers: one CTA per SM, 2x slower)
 layernorm_kernel(LnArgs p) {
   pdl_trigger();
   pdl_wait();
@@ -885,26 +1055,33 @@ __global__ void __launch_bounds__(256)
 head_gemm_kernel(GemmArgs p) {
   pdl_trigger();
   pdl_wait();
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)p.M * p.N) return;
-  const int n = (int)(idx % p.N);
-  const long long m = idx / p.N;
+  // 8 lanes per output element: lane s takes the float4 chunks s, s+8, s+16, ... of the K axis, so the 8 lanes read 128
+  // contiguous bytes of the weight row and of the activation row per step; xor-shuffle reduction at the end
+  const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int s = threadIdx.x & 7;
+  const bool live = idx < (long long)p.M * p.N;
+  const int n = live ? (int)(idx % p.N) : 0;
+  const long long m = live ? idx / p.N : 0;
   const float4* w = reinterpret_cast<const float4*>(p.Wf + (long long)n * p.K);
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
   if (p.a_fmt == FMT_F32) {
     const float4* a = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.A) + m * p.lda);
-    for (int k = 0; k < p.K / 4; ++k) {
+    for (int k = s; k < p.K / 4; k += 8) {
       const float4 x = __ldg(a + k), y = __ldg(w + k);
       acc0 = fmaf(x.x, y.x, acc0); acc1 = fmaf(x.y, y.y, acc1); acc2 = fmaf(x.z, y.z, acc2); acc3 = fmaf(x.w, y.w, acc3);
     }
   } else {
     const __nv_bfloat16* h = split_hi(p.A, m, p.lda);
-    for (int k = 0; k < p.K / 4; ++k) {
+    for (int k = s; k < p.K / 4; k += 8) {
       const float4 x = load_split4(h + 4 * k, h + p.lda + 4 * k), y = __ldg(w + k);
       acc0 = fmaf(x.x, y.x, acc0); acc1 = fmaf(x.y, y.y, acc1); acc2 = fmaf(x.z, y.z, acc2); acc3 = fmaf(x.w, y.w, acc3);
     }
   }
   float v = (acc0 + acc1) + (acc2 + acc3);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  if (!live || s != 0) return;
   if (p.scale) v *= __ldg(p.scale + n);
   if (p.shift) v += __ldg(p.shift + n);
   if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
