@@ -159,14 +159,14 @@ int tuber_op_pack_weight(const float* w_dev /* [N,K] fp32 */, void* out_dev, int
 int tuber_op_gemm_tc(const void* a_split_dev, const void* w_packed_dev, const float* scale_dev,
                      const float* shift_dev, const void* res_dev, int32_t res_fmt, int32_t res_mod, void* c_dev,
                      int32_t c_fmt, int32_t M, int32_t N, int32_t K, int32_t relu, void* stream);
-/* Two chained pointwise convolutions of the 256-channel stage in one kernel (reference ir_CSN_152.py:84-90 of block i then
- * :73-75 of block i+1):  C[M,256] = relu(scale*([A | Ab] W^T) + shift + res) (split),  C2[M,N2] = relu(scale2*(C W2^T) + shift2)
- * (fp32).  A split [M,K], Ab split [M,Kb] or NULL, W packed [2][256][K+Kb], res split [M,256] or NULL, W2 packed [2][N2][256],
- * N2 in {64, 128}. */
+/* Two chained pointwise convolutions in one kernel (reference ir_CSN_152.py:84-90 of block i then :73-75 of block i+1):
+ * C[M,N1] = relu(scale*([A | Ab] W^T) + shift + res) (split),  C2[M,N2] = relu(scale2*(C W2^T) + shift2) (fp32).
+ * A split [M,K], Ab split [M,Kb] or NULL, W packed [2][N1][K+Kb], res split [M,N1] or NULL, W2 packed [2][N2][N1];
+ * (N1, N2) in {(256, 64), (256, 128), (512, 128)}. */
 int tuber_op_gemm_tc_fused2(const void* a_split_dev, const void* ab_split_dev, const void* w_packed_dev, const float* scale_dev,
                             const float* shift_dev, const void* res_split_dev, void* c_split_dev, int32_t M, int32_t K, int32_t Kb,
-                            const void* w2_packed_dev, const float* scale2_dev, const float* shift2_dev, float* c2_dev, int32_t N2,
-                            void* stream);
+                            const void* w2_packed_dev, const float* scale2_dev, const float* shift2_dev, float* c2_dev, int32_t N1,
+                            int32_t N2, void* stream);
 /* fp32 CUDA-core GEMM: C = act(A W^T + bias + res), act: 0 none, 1 relu, 2 sigmoid */
 int tuber_op_sgemm(const float* a_dev, const float* w_dev, const float* bias_dev, const float* res_dev, float* c_dev,
                    int32_t M, int32_t N, int32_t K, int32_t act, void* stream);

@@ -58,15 +58,15 @@ def sgemm(a, w, bias=None, res=None, act=0):
 
 
 def gemm_tc_fused2(a, w, scale, shift, res, w2, scale2, shift2, ab=None):
-    """x' = relu(scale * ([a | ab] w^T) + shift + res) (M,256);  t1' = relu(scale2 * (x' w2^T) + shift2) (M,N2) -- one kernel."""
+    """x' = relu(scale * ([a | ab] w^T) + shift + res) (M,N1);  t1' = relu(scale2 * (x' w2^T) + shift2) (M,N2) -- one kernel."""
     m, k = a.shape
     kb = ab.shape[1] if ab is not None else 0
-    n2 = w2.shape[0]
+    n1, n2 = w.shape[0], w2.shape[0]
     a_s, w_p, w2_p = to_split(a.contiguous()), pack_weight(w.contiguous()), pack_weight(w2.contiguous())
     ab_s = to_split(ab.contiguous()) if ab is not None else None
     r = to_split(res.contiguous()) if res is not None else None
-    c = torch.empty((m, 256), device="cuda", dtype=torch.float32)
+    c = torch.empty((m, n1), device="cuda", dtype=torch.float32)
     c2 = torch.empty((m, n2), device="cuda", dtype=torch.float32)
     _lib.check(_lib.load().tuber_op_gemm_tc_fused2(P(a_s), P(ab_s), P(w_p), P(scale), P(shift), P(r), P(c), m, k, kb, P(w2_p), P(scale2),
-                                                   P(shift2), P(c2), n2, stream()))
-    return from_split(c, m, 256), c2
+                                                   P(shift2), P(c2), n1, n2, stream()))
+    return from_split(c, m, n1), c2

@@ -61,18 +61,20 @@ def test_gemm_tc(abi, m, n, k, variant):
     assert _rel(out, ref) < 3e-5, (m, n, k, variant)
 
 
-@pytest.mark.parametrize("m,k,kb,n2,with_res", [(1000, 64, 0, 64, True), (128, 64, 64, 64, False), (40000, 64, 0, 64, True),
-                                                 (5000, 64, 0, 128, True), (33333, 64, 64, 128, False), (300, 128, 0, 64, True),
-                                                 (50000, 64, 64, 64, False), (70001, 128, 0, 128, True)])
-def test_gemm_tc_fused2(abi, m, k, kb, n2, with_res):
+@pytest.mark.parametrize("m,k,kb,n1,n2,with_res", [(1000, 64, 0, 256, 64, True), (128, 64, 64, 256, 64, False), (40000, 64, 0, 256, 64, True),
+                                                    (5000, 64, 0, 256, 128, True), (33333, 64, 64, 256, 128, False),
+                                                    (300, 128, 0, 256, 64, True), (50000, 64, 64, 256, 64, False),
+                                                    (70001, 128, 0, 256, 128, True), (700, 128, 0, 512, 128, True),
+                                                    (45000, 128, 0, 512, 128, True), (30001, 128, 256, 512, 128, False)])
+def test_gemm_tc_fused2(abi, m, k, kb, n1, n2, with_res):
     """conv4 (+ residual / K-concatenated shortcut) chained with the next block's conv1 through the shared-memory panels"""
     g = torch.Generator(device="cuda").manual_seed(m + k + kb + n2)
     a = torch.randn(m, k, device="cuda", generator=g)
     ab = torch.randn(m, kb, device="cuda", generator=g) if kb else None
-    w = torch.randn(256, k + kb, device="cuda", generator=g) / math.sqrt(k + kb)
-    scale, shift = torch.rand(256, device="cuda", generator=g) + 0.5, torch.randn(256, device="cuda", generator=g) * 0.1
-    res = torch.randn(m, 256, device="cuda", generator=g) if with_res else None
-    w2 = torch.randn(n2, 256, device="cuda", generator=g) / 16
+    w = torch.randn(n1, k + kb, device="cuda", generator=g) / math.sqrt(k + kb)
+    scale, shift = torch.rand(n1, device="cuda", generator=g) + 0.5, torch.randn(n1, device="cuda", generator=g) * 0.1
+    res = torch.randn(m, n1, device="cuda", generator=g) if with_res else None
+    w2 = torch.randn(n2, n1, device="cuda", generator=g) / math.sqrt(n1)
     scale2, shift2 = torch.rand(n2, device="cuda", generator=g) + 0.5, torch.randn(n2, device="cuda", generator=g) * 0.1
     x, t1 = abi.gemm_tc_fused2(a, w, scale, shift, res, w2, scale2, shift2, ab)
     acat = a.double() if ab is None else torch.cat([a, ab], 1).double()

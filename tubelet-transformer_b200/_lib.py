@@ -69,7 +69,7 @@ PROTOTYPES = {
     "tuber_op_from_split": (_I, [_P, _P, _L, _I, _P]),
     "tuber_op_pack_weight": (_I, [_P, _P, _I, _I, _P]),
     "tuber_op_gemm_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
-    "tuber_op_gemm_tc_fused2": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "tuber_op_gemm_tc_fused2": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P]),
     "tuber_op_sgemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "tuber_op_dwconv": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tuber_op_stem": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),

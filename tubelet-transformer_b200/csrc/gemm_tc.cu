@@ -478,18 +478,18 @@ struct Params2 {
   int N2;
 };
 
-template <int N2>
+template <int N1, int N2>   // N1 = channels of x' (256: layer1, 512: layer2), N2 = planes of the next bottleneck's conv1
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmW2,
                    const __grid_constant__ CUtensorMap tmC2, Params p, Params2 q) {
   constexpr int BN = 128, STAGES = 2, PANELS = 3, STAGE_BYTES = 65536;
-  constexpr int NSUB = 2, P1 = 4, P2 = N2 / 64;             // x' = 2 sub-tiles of 128 columns = 4 panels; t1' = P2 panels
-  constexpr int W2_STAGES = N2 / 64;                        // ring stages holding W1' per row block (64 KB each)
-  constexpr int KBW = 4 / W2_STAGES;                        // k-blocks of the second GEMM per such stage
+  constexpr int NSUB = N1 / BN, P1 = N1 / 64, P2 = N2 / 64;  // x' = NSUB sub-tiles of 128 columns = P1 panels; t1' = P2 panels
   constexpr int W2_CHUNK = N2 * 256;                        // bytes of one k-block of W1' (hi + mid planes)
+  constexpr int KBW = STAGE_BYTES / W2_CHUNK;               // k-blocks of the second GEMM per ring stage (4 or 2)
   constexpr int D2_COL = 2 * BN;                            // TMEM: [0,256) two conv4 accumulators, [256, 256+N2) the second GEMM
+  static_assert(KBW == 2 || KBW == 4, "W1' chunking");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t panel_base = smem_base + STAGES * STAGE_BYTES;
@@ -505,11 +505,15 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t d2full_bar = bar_base + 8u * 20, d2empty_bar = bar_base + 8u * 21;
   const uint32_t tmem_slot = bar_base + 8u * 22;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_base));
-  float* s_ss = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_base));   // [NSUB][scale | shift][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BM - 1) / BM;
   const int kblocks = p.K / BK;
+  // The k-th conv4 accumulator after the first two of a row block, g = sub + 2: sub-tile g of this block, or sub-tile g - NSUB
+  // of the CTA's next block.  It is issued right after the panels of sub-tile `sub` have been consumed by the second GEMM --
+  // unless a W1' chunk spans both sub-tiles' panels and a conv4 stage needs more than the one free ring slot (KBW = 4 and
+  // more than one k-block): then all of them follow the block's last panel.
+  const bool delay = KBW == 4 && kblocks > 1;
 
   if (warp == 0 && lane == 0) {
     if (smem_base & 1023u) __trap();
@@ -541,9 +545,9 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   pdl_wait();
 
   // Ring order = the MMA warp's consumption order.  S(sub, t) = the k-blocks [A | W4 rows of sub] of row block t, W2(c, t) =
-  // chunk c of W1'.  After the first block's S(0), S(1):   per block t:  W2(0,t) S(0,t+1) [W2(1,t)] S(1,t+1)
-  // and the MMA warp issues                                              G2(t,0..1) G1(t+1,0) G2(t,2..3) G1(t+1,1)
-  // so the next block's first accumulator is ready before the epilogue has finished this block's panels.
+  // chunk c (KBW k-blocks) of W1'.  After the first block's S(0), S(1), per block and sub-tile s:
+  //   producer   [W2(c) when panel 2s starts a chunk]  S(s + 2)            MMA warp   G2(2s) G2(2s+1)  G1(s + 2)
+  // so the next accumulator is ready before the epilogue has finished the current panels.
   if (warp == 0) {
     // ================= operand producer =================
     if (lane == 0) {
@@ -571,15 +575,16 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x) {
         const int next = m_blk + gridDim.x;
         const bool has_next = next < m_tiles;
-        if (W2_STAGES == 1) {
-          load_w2(0);
-          if (has_next) { load_s(0, next); load_s(1, next); }
-        } else {
-          load_w2(0);
-          if (has_next) load_s(0, next);
-          load_w2(1);
-          if (has_next) load_s(1, next);
+        auto load_g = [&](int g) {
+          if (g < NSUB) load_s(g, m_blk);
+          else if (has_next) load_s(g - NSUB, next);
+        };
+        for (int sub = 0; sub < NSUB; ++sub) {
+          if ((2 * sub) % KBW == 0) load_w2(2 * sub / KBW);
+          if (!delay) load_g(sub + 2);
         }
+        if (delay)
+          for (int sub = 0; sub < NSUB; ++sub) load_g(sub + 2);
       }
     }
   } else if (warp == 1) {
@@ -589,11 +594,14 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint64_t pdesc0 = make_smem_desc(panel_base);
     int stage = 0, pslot = 0;
     uint32_t phase = 0, ready_ph = 0;                        // ready_ph bit s: parity of the next pready[s] completion
-    // conv4 accumulator `sub` of the n-th row block of this CTA
-    auto g1 = [&](int sub, int n) {
-      mbar_wait(tempty_bar(sub), (uint32_t)((n & 1) ^ 1));
+    int acc_uses[2] = {0, 0};                                // how often each conv4 accumulator buffer has been issued
+    // conv4 sub-tile `sub` into accumulator buffer sub & 1
+    auto g1 = [&](int sub) {
+      const int buf = sub & 1;
+      mbar_wait(tempty_bar(buf), (uint32_t)((acc_uses[buf] & 1) ^ 1));
+      ++acc_uses[buf];
       tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(sub * BN);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
 #pragma unroll 1
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
@@ -609,14 +617,14 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, a_hi + 2 * k, w_hi + 2 * k, idesc1, 1);
           umma_commit(empty_bar(stage));
-          if (kb == kblocks - 1) umma_commit(tfull_bar(sub));
+          if (kb == kblocks - 1) umma_commit(tfull_bar(buf));
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     };
-    // k-block j of the second GEMM = output panel j of x', read from its panel buffer
     int w2_stage = 0;                                       // ring slot of the W1' chunk in use (conv4 stages are consumed in between)
+    // k-block j of the second GEMM = output panel j of x', read from its panel buffer
     auto g2 = [&](int j) {
       if (j % KBW == 0) {
         mbar_wait(full_bar(stage), phase);
@@ -646,19 +654,19 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (++pslot == PANELS) pslot = 0;
     };
     int tl = 0;
-    if ((int)blockIdx.x < m_tiles) { g1(0, 0); g1(1, 0); }
+    if ((int)blockIdx.x < m_tiles) { g1(0); g1(1); }
     for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x, ++tl) {
       const bool has_next = m_blk + (int)gridDim.x < m_tiles;
       mbar_wait(d2empty_bar, (uint32_t)((tl & 1) ^ 1));      // the epilogue has drained the previous block's second accumulator
       tcgen05_fence_after();
-      // the next block's first accumulator is issued early only when the ring has room for its operands while a W1' chunk is
-      // still held (one conv4 stage per sub-tile, or W1' released in halves); otherwise after the last k-block of this block
-      const bool early = has_next && (kblocks == 1 || KBW == 2);
-      g2(0); g2(1);
-      if (early) g1(0, tl + 1);
-      g2(2); g2(3);
-      if (has_next && !early) g1(0, tl + 1);
-      if (has_next) g1(1, tl + 1);
+      for (int sub = 0; sub < NSUB; ++sub) {
+        g2(2 * sub); g2(2 * sub + 1);
+        const int g = sub + 2;
+        if (!delay && (g < NSUB || has_next)) g1(g % NSUB);
+      }
+      if (delay)
+        for (int sub = 0; sub < NSUB; ++sub)
+          if (sub + 2 < NSUB || has_next) g1((sub + 2) % NSUB);
       for (int jp = 0; jp < P2; ++jp)                          // the t1' panels use ring slots too (not operands)
         if (++pslot == PANELS) pslot = 0;
     }
@@ -685,12 +693,8 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int lg = warp & 3;
     const int et = threadIdx.x - EPI_WARP0 * 32;
     const int r = lg * 32 + lane;
-    for (int sub = 0; sub < NSUB; ++sub) {
-      s_ss[sub * 2 * BN + et] = p.scale ? __ldg(p.scale + sub * BN + et) : 1.f;
-      s_ss[sub * 2 * BN + BN + et] = p.shift ? __ldg(p.shift + sub * BN + et) : 0.f;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     int tl = 0, slot = 0, prev_slot = -1;
+    int acc_seen[2] = {0, 0};
     bool prev_is_x = false;
     uint32_t pphase = 0, cons_ph = 0;                        // cons_ph bit s: parity of the next pcons[s] completion
     // et == 0: issue the store of panel `slot`, then recycle the previous panel once its store has drained (and, if it
@@ -710,10 +714,9 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     };
     for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x, ++tl) {
       for (int sub = 0; sub < NSUB; ++sub) {
-        const int as = sub;
-        const float* s_scale = s_ss + sub * 2 * BN;
-        const float* s_shift = s_scale + BN;
-        mbar_wait(tfull_bar(as), (uint32_t)(tl & 1));
+        const int as = sub & 1;
+        mbar_wait(tfull_bar(as), (uint32_t)(acc_seen[as] & 1));
+        ++acc_seen[as];
         tcgen05_fence_after();
 #pragma unroll 1
         for (int jj = 0; jj < 2; ++jj) {
@@ -723,12 +726,12 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int h = 0; h < 2; ++h) {
             uint32_t acc[32];
             tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + jj * 64 + h * 32), acc);
-            const int cl = jj * 64 + h * 32;
+            const int c0 = sub * BN + jj * 64 + h * 32;      // column of x'
             float v[32];
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
-              const float4 sc = *reinterpret_cast<const float4*>(s_scale + cl + 4 * c4);
-              const float4 sh = *reinterpret_cast<const float4*>(s_shift + cl + 4 * c4);
+              const float4 sc = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + c0) + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
+              const float4 sh = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift + c0) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
               v[4 * c4] = fmaf(__uint_as_float(acc[4 * c4]), sc.x, sh.x);
               v[4 * c4 + 1] = fmaf(__uint_as_float(acc[4 * c4 + 1]), sc.y, sh.y);
               v[4 * c4 + 2] = fmaf(__uint_as_float(acc[4 * c4 + 2]), sc.z, sh.z);
@@ -1177,9 +1180,11 @@ static cudaError_t init_once() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(gemm2_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_fused2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+  e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_fused2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+  e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_fused2_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return cudaSuccess;
@@ -1335,7 +1340,7 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const int KT = a.K + (a.Ab ? a.Kb : 0);
   const bool res_ok = !a.res || (a.res_mod <= 0 && a.res_fmt == FMT_SPLIT && aligned16(a.res) && a.ldr % 8 == 0 && a.N <= a.ldr);
-  if (a.M <= 0 || a.N != 256 || a.K % 64 != 0 || a.lda % 8 != 0 || a.K > a.lda || a.a_fmt != FMT_SPLIT || a.Wp == nullptr ||
+  if (a.M <= 0 || !(a.N == 256 || (a.N == 512 && N2 == 128)) || a.K % 64 != 0 || a.lda % 8 != 0 || a.K > a.lda || a.a_fmt != FMT_SPLIT || a.Wp == nullptr ||
       a.c_fmt != FMT_SPLIT || a.act == ACT_SIGMOID || !aligned16(a.A) || !aligned16(a.Wp) || !aligned16(a.C) || a.ldc % 8 != 0 ||
       a.N > a.ldc || (a.Ab && (a.Kb % 64 != 0 || a.Kb <= 0 || a.ldb % 8 != 0 || a.Kb > a.ldb || !aligned16(a.Ab))) || !res_ok ||
       (N2 != 64 && N2 != 128) || W2p == nullptr || !aligned16(W2p) || C2 == nullptr || !aligned16(C2) || ldc2 % 8 != 0 || N2 > ldc2) {
@@ -1363,8 +1368,9 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
   if (!encode_f32_panel_map(&tmC2, C2, N2, a.M, ldc2)) return cudaErrorInvalidValue;
   const int m_tiles = ceil_div(a.M, BM);
   const int grid = m_tiles < g_num_sms ? m_tiles : g_num_sms;
-  if (N2 == 64) return launch_pdl(gemm_fused2_kernel<64>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
-  return launch_pdl(gemm_fused2_kernel<128>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
+  if (a.N == 512) return launch_pdl(gemm_fused2_kernel<512, 128>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
+  if (N2 == 64) return launch_pdl(gemm_fused2_kernel<256, 64>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
+  return launch_pdl(gemm_fused2_kernel<256, 128>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
 }
 
 // fp32 [N,K] -> bf16 [2][N][K] (hi plane, mid plane)

@@ -777,8 +777,8 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
                 [&] { return launch_dwconv(t1, b.dw.w, b.dw.scale, b.dw.shift, t2, B, t, h, w, b.planes, b.st_t, b.st_s, to, ho, wo, st); });
       // 256-channel stage: conv4 of this block and conv1 of the next one run as one kernel (the next block's input tile is
       // multiplied while it still sits in shared memory), see gemm_fused2_kernel
-      const bool fuse = !p->force_simt && !p->no_fuse2 && b.cout == 256 && nb && nb->cin == 256 && (nb->planes == 64 || nb->planes == 128) &&
-                        b.planes % 64 == 0 && b.cin % 64 == 0;
+      const bool fuse = !p->force_simt && !p->no_fuse2 && nb && nb->cin == b.cout && b.planes % 64 == 0 && b.cin % 64 == 0 &&
+                        ((b.cout == 256 && (nb->planes == 64 || nb->planes == 128)) || (b.cout == 512 && nb->planes == 128));
       const void* xa = nullptr;                              // the shortcut's input rows (strided voxel gather when the block strides)
       if (b.has_ds) {
         xa = cur;
@@ -1422,12 +1422,12 @@ int tuber_op_gemm_tc(const void* a_split, const void* w_packed, const float* sca
 }
 int tuber_op_gemm_tc_fused2(const void* a_split, const void* ab_split, const void* w_packed, const float* scale, const float* shift,
                             const void* res_split, void* c_split, int32_t M, int32_t K, int32_t Kb, const void* w2_packed,
-                            const float* scale2, const float* shift2, float* c2, int32_t N2, void* stream) {
+                            const float* scale2, const float* shift2, float* c2, int32_t N1, int32_t N2, void* stream) {
   GemmArgs a{};
   a.A = a_split; a.a_fmt = FMT_SPLIT; a.lda = K; a.Ab = ab_split; a.ldb = Kb; a.Kb = ab_split ? Kb : 0;
   a.Wp = w_packed; a.scale = scale; a.shift = shift;
-  a.res = res_split; a.res_fmt = FMT_SPLIT; a.ldr = 256; a.res_mod = 0; a.C = c_split; a.c_fmt = FMT_SPLIT; a.ldc = 256;
-  a.M = M; a.N = 256; a.K = K; a.act = ACT_RELU;
+  a.res = res_split; a.res_fmt = FMT_SPLIT; a.ldr = N1; a.res_mod = 0; a.C = c_split; a.c_fmt = FMT_SPLIT; a.ldc = N1;
+  a.M = M; a.N = N1; a.K = K; a.act = ACT_RELU;
   CK(launch_gemm_tc_fused2(a, w2_packed, scale2, shift2, c2, N2, N2, (cudaStream_t)stream));
   return TUBER_OK;
 }
