@@ -682,9 +682,12 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
       s_sh[et] = __ldg(p.shift + et);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    const int pw = et >> 1, hq = et & 1;                           // pooled column, which 32 of the 64 channels
+    const int pw = et >> 1, hq = et & 1;                           // pooled column; hq: the even / odd 4-channel chunks (32 channels)
     const uint32_t rowb = sb + OFF_ROW2;
-    auto rswz = [&](int pos, int chunk) { return rowb + (uint32_t)pos * 256u + (uint32_t)(((chunk ^ (pos >> 1)) & 15) << 4); };
+    // 16-byte chunk `chunk` (4 channels) of position `pos`: rows are 256 B apart (bank-aligned), so the low 3 chunk bits are XORed
+    // with pos & 7 -- conflict-free both for the row write (8 consecutive positions, same chunk, per 128-bit phase) and for the
+    // pool read (4 consecutive pooled columns = positions 2 apart, x the thread pair hq = 0/1 that owns even / odd chunks)
+    auto rswz = [&](int pos, int chunk) { return rowb + (uint32_t)pos * 256u + (uint32_t)((((chunk ^ pos) & 7) | (chunk & 8)) << 4); };
     const uint32_t tempty_remote0 = mapa_rank(tempty_bar(0), 0), tempty_remote1 = mapa_rank(tempty_bar(1), 0);
     int it = 0;
     for (int i = pair; i < steps; i += npairs) {
@@ -734,7 +737,7 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
             if (cc < 0 || cc >= p.W1) continue;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const uint4 v = lds128(rswz(cc, hq * 8 + e));
+              const uint4 v = lds128(rswz(cc, 2 * e + hq));
               hm[e].x = fmaxf(hm[e].x, __uint_as_float(v.x)); hm[e].y = fmaxf(hm[e].y, __uint_as_float(v.y));
               hm[e].z = fmaxf(hm[e].z, __uint_as_float(v.z)); hm[e].w = fmaxf(hm[e].w, __uint_as_float(v.w));
             }
@@ -753,9 +756,9 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
         if (emit && pw < p.W2) {
           const int ph = oh >> 1;
           const long long vox = ((long long)bt * p.H2 + ph) * p.W2 + pw;
-          __nv_bfloat16* hi = split_hi(p.pooled, vox, 64) + hq * 32;
+          __nv_bfloat16* hi = split_hi(p.pooled, vox, 64) + hq * 4;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) store_split4(hi + 4 * e, hi + 64 + 4 * e, run[e]);
+          for (int e = 0; e < 8; ++e) store_split4(hi + 8 * e, hi + 64 + 8 * e, run[e]);
         }
         if (odd) {                                                 // this row is row 2(ph+1)-1 of the next pooled row
 #pragma unroll
