@@ -1229,7 +1229,8 @@ static bool use_big_tiles(const GemmArgs& a, int KT) {
 // CTA pairs (cta_group::2, 256 x 256 tiles) for the deep-K shapes
 static bool use_pair_tiles(const GemmArgs& a, int KT) {
   static const bool off = [] { const char* e = getenv("TUBER_NO_PAIR_GEMM"); return e && e[0] == '1'; }();
-  if (off || KT < 512 || a.N % 256 != 0 || a.ksplit > 1) return false;
+  static const int min_k = [] { const char* e = getenv("TUBER_PAIR_MINK"); return e ? atoi(e) : 512; }();
+  if (off || KT < min_k || a.N % 256 != 0 || a.ksplit > 1) return false;
   if (a.group_rows > 0 && a.group_rows % (2 * BM) != 0) return false;
   const long long tiles = (long long)ceil_div(a.M, 2 * BM) * (a.N / 256);
   return tiles >= 48;                                       // at least ~2/3 of the 74 pairs busy

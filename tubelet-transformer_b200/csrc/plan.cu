@@ -140,8 +140,8 @@ struct TuberPlan {
   // forward_host staging: two slots so that the host copies of step i+1 overlap the kernels of step i
   char* stage_in[2] = {nullptr, nullptr}; size_t stage_in_cap[2] = {0, 0};
   char* stage_out[2] = {nullptr, nullptr}; size_t stage_out_cap[2] = {0, 0};
-  cudaStream_t copy_stream = nullptr, run_stream = nullptr;
-  cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr, run_stream = nullptr, out_stream = nullptr;
+  cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr}, fwd_done[2] = {nullptr, nullptr};
   bool slot_busy[2] = {false, false};
   bool force_simt = false, no_fuse2 = false, pool_unfolded = false;
   bool profiling = false, debug_keep = false, use_graph = false;
@@ -1118,9 +1118,11 @@ void tuber_plan_destroy(TuberPlan* p) {
     if (p->stage_out[i]) cudaFree(p->stage_out[i]);
     if (p->h2d_done[i]) cudaEventDestroy(p->h2d_done[i]);
     if (p->slot_done[i]) cudaEventDestroy(p->slot_done[i]);
+    if (p->fwd_done[i]) cudaEventDestroy(p->fwd_done[i]);
   }
   if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   if (p->run_stream) cudaStreamDestroy(p->run_stream);
+  if (p->out_stream) cudaStreamDestroy(p->out_stream);
   if (p->ev_valid) for (auto& e : p->ev) cudaEventDestroy(e);
   for (auto& r : p->kp) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   delete p;
@@ -1230,7 +1232,8 @@ namespace {
 // H2D (+mask) -> forward -> D2H of one batch through staging slot `slot`.  `in_st` carries the input copies,
 // `st` the kernels and the output copies; the caller decides whether they are the same stream.
 int host_step(TuberPlan* p, int slot, const float* clips_host, const uint8_t* mask_host, int B, int T, int H, int W,
-              float* logits_host, float* boxes_host, float* logits_b_host, cudaStream_t in_st, cudaStream_t st) {
+              float* logits_host, float* boxes_host, float* logits_b_host, cudaStream_t in_st, cudaStream_t st,
+              cudaStream_t out_st = nullptr) {
   const TuberConfig& c = p->cfg;
   const size_t clip_bytes = (size_t)B * 3 * T * H * W * 4, mask_bytes = mask_host ? (size_t)B * H * W : 0;
   const size_t in_need = clip_bytes + ((mask_bytes + 255) & ~(size_t)255) + 256;
@@ -1265,9 +1268,16 @@ int host_step(TuberPlan* p, int slot, const float* clips_host, const uint8_t* ma
     CK(cudaStreamWaitEvent(st, p->h2d_done[slot], 0));
   }
   TRY(tuber_forward(p, d_clips, d_mask, B, T, H, W, d_logits, d_boxes, d_lb, st));
-  CK(cudaMemcpyAsync(logits_host, d_logits, n_logits * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(boxes_host, d_boxes, n_boxes * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(logits_b_host, d_lb, n_lb * 4, cudaMemcpyDeviceToHost, st));
+  // pipelined form: the result copies run on their own stream so that the next slot's kernels are not held up by them
+  cudaStream_t ost = st;
+  if (out_st && out_st != st) {
+    CK(cudaEventRecord(p->fwd_done[slot], st));
+    CK(cudaStreamWaitEvent(out_st, p->fwd_done[slot], 0));
+    ost = out_st;
+  }
+  CK(cudaMemcpyAsync(logits_host, d_logits, n_logits * 4, cudaMemcpyDeviceToHost, ost));
+  CK(cudaMemcpyAsync(boxes_host, d_boxes, n_boxes * 4, cudaMemcpyDeviceToHost, ost));
+  CK(cudaMemcpyAsync(logits_b_host, d_lb, n_lb * 4, cudaMemcpyDeviceToHost, ost));
   return TUBER_OK;
 }
 
@@ -1275,9 +1285,11 @@ int ensure_host_pipeline(TuberPlan* p) {
   if (p->copy_stream) return TUBER_OK;
   CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&p->run_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&p->out_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     CK(cudaEventCreateWithFlags(&p->h2d_done[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&p->slot_done[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&p->fwd_done[i], cudaEventDisableTiming));
   }
   return TUBER_OK;
 }
@@ -1303,8 +1315,9 @@ int tuber_forward_host_submit(TuberPlan* p, int32_t slot, const float* clips_hos
   if (!clips_host || !logits_host || !boxes_host || !logits_b_host) return fail(TUBER_ERR_INVALID, "null host pointer");
   if (p->slot_busy[slot]) return fail(TUBER_ERR_STATE, "slot %d still in flight: call tuber_forward_host_wait first", slot);
   TRY(ensure_host_pipeline(p));
-  TRY(host_step(p, slot, clips_host, mask_host, B, T, H, W, logits_host, boxes_host, logits_b_host, p->copy_stream, p->run_stream));
-  CK(cudaEventRecord(p->slot_done[slot], p->run_stream));
+  TRY(host_step(p, slot, clips_host, mask_host, B, T, H, W, logits_host, boxes_host, logits_b_host, p->copy_stream, p->run_stream,
+                p->out_stream));
+  CK(cudaEventRecord(p->slot_done[slot], p->out_stream));
   p->slot_busy[slot] = true;
   return TUBER_OK;
 }
