@@ -64,6 +64,8 @@ struct Params {
   int kb1;                                              // k-blocks taken from the first A operand (the rest from the second)
   int group_rows;                                       // > 0: grouped GEMM (GemmArgs::group_rows), a multiple of BM
   int ksplit, part_rows;                                // split-K: work item = (tile, part); part s -> rows + s*part_rows of C
+  int a2_wo;                                            // > 0: A2 is a strided 5-D map; output rows per (b,t) frame = a2_wo * a2_ho
+  int a2_ho, a2_st, a2_ss;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -100,6 +102,25 @@ TB_DEVINL void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, i
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+TB_DEVINL void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+// second A operand: plain rows, or the strided voxel gather of a striding bottleneck's shortcut (128 consecutive output voxels
+// = a box {Wo, bh, bbt} of the output grid = the same box with element strides in the input tensor)
+struct Params;
+TB_DEVINL void load_a2(uint32_t dst, const CUtensorMap* map, uint32_t bar, int k0, int row0, int a2_wo, int a2_ho, int a2_st, int a2_ss) {
+  if (a2_wo <= 0) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(k0), "r"(row0), "r"(0) : "memory");
+  } else {
+    const int per_bt = a2_wo * a2_ho;
+    const int bt = row0 / per_bt, ho = (row0 - bt * per_bt) / a2_wo;
+    tma_load_5d(dst, map, bar, k0, 0, ho * a2_ss, bt * a2_st, 0);
+  }
 }
 TB_DEVINL void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -240,7 +261,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
           if (kb < p.kb1) tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM, 0);
-          else tma_load_3d(sa, &tmA2, full_bar(stage), (kb - p.kb1) * BK, m_blk * BM, 0);
+          else load_a2(sa, &tmA2, full_bar(stage), (kb - p.kb1) * BK, m_blk * BM, p.a2_wo, p.a2_ho, p.a2_st, p.a2_ss);
           const int wrow = p.group_rows > 0 ? (m_blk * BM / p.group_rows) * p.N : 0;   // grouped: this row block's W rows
           tma_load_3d(sa + 2 * A_PLANE_BYTES, &tmW, full_bar(stage), kb * BK, wrow + n_blk * BN, 0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -559,7 +580,7 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           if (kb < p.kb1) tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM, 0);
-          else tma_load_3d(sa, &tmA2, full_bar(stage), (kb - p.kb1) * BK, m_blk * BM, 0);
+          else load_a2(sa, &tmA2, full_bar(stage), (kb - p.kb1) * BK, m_blk * BM, p.a2_wo, p.a2_ho, p.a2_st, p.a2_ss);
           tma_load_3d(sa + 2 * A_PLANE_BYTES, &tmW, full_bar(stage), kb * BK, sub * BN, 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -929,7 +950,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           if (kb < p.kb1) tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, row0, 0);
-          else tma_load_3d(sa, &tmA2, full_bar(stage), (kb - p.kb1) * BK, row0, 0);
+          else load_a2(sa, &tmA2, full_bar(stage), (kb - p.kb1) * BK, row0, p.a2_wo, p.a2_ho, p.a2_st, p.a2_ss);
           tma_load_3d(sa + 2 * A_PLANE_BYTES, &tmW, full_bar(stage), kb * BK, wrow, 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -1236,6 +1257,29 @@ static bool use_pair_tiles(const GemmArgs& a, int KT) {
   return tiles >= 48;                                       // at least ~2/3 of the 74 pairs busy
 }
 
+// A2 as a strided gather: dims {K, Wi, Hi, BTi, 2 planes}, element strides {1, ss, ss, st, 1}, box = 128 output voxels
+static bool encode_a2(CUtensorMap* map, const GemmArgs& a, Params& p) {
+  p.a2_wo = 0;
+  if (!a.Ab) return true;
+  if (a.ab_Wo <= 0) return encode_split_map(map, a.Ab, a.Kb, a.M, a.ldb, BM);
+  if (!gemm_tc_strided_ab_ok(a.M, a.ab_Wo, a.ab_Ho, a.ab_Wi, a.ab_Hi, a.ab_BTi, a.ab_st_t, a.ab_st_s)) return false;
+  const int per_bt = a.ab_Wo * a.ab_Ho;
+  const int bh = per_bt >= BM ? BM / a.ab_Wo : a.ab_Ho, bbt = per_bt >= BM ? 1 : BM / per_bt;
+  cuuint64_t dims[5] = {(cuuint64_t)a.Kb, (cuuint64_t)a.ab_Wi, (cuuint64_t)a.ab_Hi, (cuuint64_t)a.ab_BTi, 2};
+  cuuint64_t strides[4] = {(cuuint64_t)a.ldb * 4, (cuuint64_t)a.ab_Wi * a.ldb * 4, (cuuint64_t)a.ab_Hi * a.ab_Wi * a.ldb * 4, (cuuint64_t)a.ldb * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)(a.ab_Wo * a.ab_st_s), (cuuint32_t)(bh * a.ab_st_s), (cuuint32_t)(bbt * a.ab_st_t), 2};
+  cuuint32_t es[5] = {1, (cuuint32_t)a.ab_st_s, (cuuint32_t)a.ab_st_s, (cuuint32_t)a.ab_st_t, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a.Ab), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled (strided A2) failed (%d): Wo=%d Ho=%d Wi=%d Hi=%d BTi=%d st=%d/%d", (int)r, a.ab_Wo, a.ab_Ho,
+             a.ab_Wi, a.ab_Hi, a.ab_BTi, a.ab_st_t, a.ab_st_s);
+    return false;
+  }
+  p.a2_wo = a.ab_Wo; p.a2_ho = a.ab_Ho; p.a2_st = a.ab_st_t; p.a2_ss = a.ab_st_s;
+  return true;
+}
+
 template <class C>
 static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
                               const Params& p, cudaStream_t st) {
@@ -1298,7 +1342,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   CUtensorMap tmA, tmA2, tmW, tmC, tmR;
   if (!encode_split_map(&tmA, a.A, a.K, a.M, a.lda, BM)) return cudaErrorInvalidValue;
   tmA2 = tmA;
-  if (a.Ab && !encode_split_map(&tmA2, a.Ab, a.Kb, a.M, a.ldb, BM)) return cudaErrorInvalidValue;
+  if (!encode_a2(&tmA2, a, p)) return cudaErrorInvalidValue;
   if (!encode3(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.Wp, KT, (uint64_t)groups * a.N, 2, (uint64_t)KT * 2, (uint64_t)groups * a.N * KT * 2, 64, bn, 2))
     return cudaErrorInvalidValue;
   bool ok = a.c_fmt == FMT_F32 ? encode_f32_panel_map(&tmC, a.C, c_cols, c_rows, a.ldc) : encode_split_map(&tmC, a.C, c_cols, c_rows, a.ldc, BM);
@@ -1317,6 +1361,18 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   if (bn == 64) return launch_cfg<CfgN64>(tmA, tmA2, tmW, tmC, tmR, p, st);
   if (KT >= 512) return launch_cfg<CfgDeep>(tmA, tmA2, tmW, tmC, tmR, p, st);
   return launch_cfg<CfgWide>(tmA, tmA2, tmW, tmC, tmR, p, st);
+}
+
+bool gemm_tc_strided_ab_ok(int M, int Wo, int Ho, int Wi, int Hi, int BTi, int st_t, int st_s) {
+  if (Wo <= 0 || Ho <= 0 || st_t < 1 || st_s < 1 || tc::BM % Wo != 0) return false;
+  const int per_bt = Wo * Ho;
+  if (per_bt >= tc::BM ? per_bt % tc::BM != 0 : tc::BM % per_bt != 0) return false;
+  if (M % per_bt != 0) return false;
+  const int BTo = M / per_bt;
+  // output frame bt must sit at input frame bt * st_t for every clip, and the strided box must stay inside the TMA limits
+  if (BTi != BTo * st_t || (Wo - 1) * st_s >= Wi || (Ho - 1) * st_s >= Hi) return false;
+  const int bh = per_bt >= tc::BM ? tc::BM / Wo : Ho, bbt = per_bt >= tc::BM ? 1 : tc::BM / per_bt;
+  return Wo * st_s <= 256 && bh * st_s <= 256 && bbt * st_t <= 256;
 }
 
 // which template configuration launch_gemm_tc picks (the per-launch profile reports them as separate kernels)
@@ -1358,7 +1414,7 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
   CUtensorMap tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2;
   if (!encode_split_map(&tmA, a.A, a.K, a.M, a.lda, BM)) return cudaErrorInvalidValue;
   tmA2 = tmA;
-  if (a.Ab && !encode_split_map(&tmA2, a.Ab, a.Kb, a.M, a.ldb, BM)) return cudaErrorInvalidValue;
+  if (!encode_a2(&tmA2, a, p)) return cudaErrorInvalidValue;
   if (!encode3(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.Wp, KT, a.N, 2, (uint64_t)KT * 2, (uint64_t)a.N * KT * 2, 64, 128, 2))
     return cudaErrorInvalidValue;
   if (!encode_split_map(&tmC, a.C, a.N, a.M, a.ldc, BM)) return cudaErrorInvalidValue;

@@ -53,6 +53,10 @@ cudaError_t launch_global_avgpool(const void* in_split, float* out, int B, int N
 struct GemmArgs {
   const void* A; int a_fmt; int lda;         // [M, lda] fp32 or split
   const void* Ab; int ldb; int Kb;           // optional second operand concatenated along K (same format as A): W is [N, K+Kb]
+  // Ab as a strided voxel gather (the shortcut of a striding bottleneck, ir_CSN_152.py:155-161): row m = output voxel (bt, ho, wo)
+  // reads row (bt*st_t, ho*st_s, wo*st_s) of the split tensor Ab [BTi, Hi, Wi, ldb]; Wo = 0: plain rows.  Only the tcgen05
+  // kernels (5-D TMA with element strides); see gemm_tc_strided_ab_ok
+  int ab_Wo, ab_Ho, ab_Wi, ab_Hi, ab_BTi, ab_st_t, ab_st_s;
   const float* Wf;                           // fp32 [N, K+Kb] row-major
   const void* Wp;                            // packed split weights: bf16 [2][N][K+Kb]
   const float* scale; const float* shift;    // [N] each, nullable (1 / 0)
@@ -127,6 +131,8 @@ const char* gemm_tc_last_error();
 // name of the template configuration launch_gemm_tc will use: gemm_bf16x3_wide (<128,2,3>, memory-bound shapes), _deep (<128,3,1>,
 // K >= 512), _n64 (<64,3,2>, N = 64 or token-sized)
 const char* gemm_tc_config_name(const GemmArgs& a);
+// can the tcgen05 kernels read Ab through the strided tensor map for this geometry (128-row tiles must be boxes of the output grid)?
+bool gemm_tc_strided_ab_ok(int M, int Wo, int Ho, int Wi, int Hi, int BTi, int st_t, int st_s);
 // conv4 (+ shortcut / residual) of one bottleneck fused with conv1 of the next (256-channel stage): a describes the first
 // GEMM (N = 256, split output), the second is C2[M, N2] = relu(scale2 * (C W2^T) + shift2) in fp32, N2 in {64, 128}
 cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const float* scale2, const float* shift2, float* C2, int N2,

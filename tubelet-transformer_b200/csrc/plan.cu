@@ -143,7 +143,7 @@ struct TuberPlan {
   cudaStream_t copy_stream = nullptr, run_stream = nullptr, out_stream = nullptr;
   cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr}, fwd_done[2] = {nullptr, nullptr};
   bool slot_busy[2] = {false, false};
-  bool force_simt = false, no_fuse2 = false, pool_unfolded = false;
+  bool force_simt = false, no_fuse2 = false, pool_unfolded = false, no_strided_tma = false;
   bool profiling = false, debug_keep = false, use_graph = false;
   cudaEvent_t ev[TUBER_NUM_STAGES + 1] = {};
   bool ev_valid = false;
@@ -591,10 +591,12 @@ struct Ctx {
 
   // C = act(scale * A W^T + shift + res)
   void gemm(const void* A, int a_fmt, int lda, long long M, const Lin& w, const void* res, int res_fmt, int ldr, int res_mod,
-            void* C, int c_fmt, int ldc, int act, const void* Ab = nullptr, int ldb = 0, int Kb = 0, int ksplit = 0, int part_rows = 0) {
+            void* C, int c_fmt, int ldc, int act, const void* Ab = nullptr, int ldb = 0, int Kb = 0, int ksplit = 0, int part_rows = 0,
+            const int* ab_geo = nullptr) {
     if (!ok()) return;
     GemmArgs a{};
     a.ksplit = ksplit; a.part_rows = part_rows;
+    if (ab_geo) { a.ab_Wo = ab_geo[0]; a.ab_Ho = ab_geo[1]; a.ab_Wi = ab_geo[2]; a.ab_Hi = ab_geo[3]; a.ab_BTi = ab_geo[4]; a.ab_st_t = ab_geo[5]; a.ab_st_s = ab_geo[6]; }
     a.A = A; a.a_fmt = a_fmt; a.lda = lda;
     a.Ab = Ab; a.ldb = ldb; a.Kb = Ab ? Kb : 0;
     a.Wf = w.wf; a.Wp = w.wp; a.scale = w.scale; a.shift = w.shift;
@@ -780,12 +782,19 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
       const bool fuse = !p->force_simt && !p->no_fuse2 && nb && nb->cin == b.cout && b.planes % 64 == 0 && b.cin % 64 == 0 &&
                         ((b.cout == 256 && (nb->planes == 64 || nb->planes == 128)) || (b.cout == 512 && nb->planes == 128));
       const void* xa = nullptr;                              // the shortcut's input rows (strided voxel gather when the block strides)
+      const int geo[7] = {wo, ho, w, h, B * t, b.st_t, b.st_s};
+      const int* ab_geo = nullptr;                           // set: the GEMM reads the strided rows itself (5-D TMA with element strides)
       if (b.has_ds) {
         xa = cur;
         if (b.st_t != 1 || b.st_s != 1) {
-          cx.launch("gather_rows", 8.0 * vout * b.cin, 0.0,
-                    [&] { return launch_gather_rows(cur, xg, b.cin * 4, B, t, h, w, b.st_t, b.st_s, to, ho, wo, st); });
-          xa = xg;
+          if (!p->force_simt && !p->no_strided_tma && b.cin % 64 == 0 &&
+              gemm_tc_strided_ab_ok((int)vout, wo, ho, w, h, B * t, b.st_t, b.st_s)) {
+            ab_geo = geo;
+          } else {
+            cx.launch("gather_rows", 8.0 * vout * b.cin, 0.0,
+                      [&] { return launch_gather_rows(cur, xg, b.cin * 4, B, t, h, w, b.st_t, b.st_s, to, ho, wo, st); });
+            xa = xg;
+          }
         }
       }
       if (fuse) {
@@ -793,6 +802,7 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
         const Lin& w4 = b.has_ds ? b.c4ds : b.conv4;
         a.A = t2; a.a_fmt = FMT_SPLIT; a.lda = b.planes;
         a.Ab = b.has_ds ? xa : nullptr; a.ldb = b.cin; a.Kb = b.has_ds ? b.cin : 0;
+        if (ab_geo) { a.ab_Wo = geo[0]; a.ab_Ho = geo[1]; a.ab_Wi = geo[2]; a.ab_Hi = geo[3]; a.ab_BTi = geo[4]; a.ab_st_t = geo[5]; a.ab_st_s = geo[6]; }
         a.Wf = w4.wf; a.Wp = w4.wp; a.scale = w4.scale; a.shift = w4.shift;
         a.res = b.has_ds ? nullptr : cur; a.res_fmt = FMT_SPLIT; a.ldr = b.cin; a.res_mod = 0;
         a.C = nxt; a.c_fmt = FMT_SPLIT; a.ldc = b.cout;
@@ -805,7 +815,7 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
                   [&] { return launch_gemm_tc_fused2(a, c1.wp, c1.scale, c1.shift, t1, c1.N, c1.N, st); });
         t1_ready = true;
       } else if (b.has_ds) {
-        cx.gemm(t2, FMT_SPLIT, b.planes, vout, b.c4ds, nullptr, 0, 0, 0, nxt, FMT_SPLIT, b.cout, ACT_RELU, xa, b.cin, b.cin);
+        cx.gemm(t2, FMT_SPLIT, b.planes, vout, b.c4ds, nullptr, 0, 0, 0, nxt, FMT_SPLIT, b.cout, ACT_RELU, xa, b.cin, b.cin, 0, 0, ab_geo);
       } else {
         cx.gemm(t2, FMT_SPLIT, b.planes, vout, b.conv4, cur, FMT_SPLIT, b.cin, 0, nxt, FMT_SPLIT, b.cout, ACT_RELU);
       }
@@ -1102,6 +1112,8 @@ int tuber_plan_create(const TuberConfig* cfg, TuberPlan** out_plan) {
   p->no_fuse2 = nf && nf[0] == '1';
   const char* pu = getenv("TUBER_POOL_UNFOLDED");
   p->pool_unfolded = pu && pu[0] == '1';
+  const char* ns = getenv("TUBER_NO_STRIDED_TMA");
+  p->no_strided_tma = ns && ns[0] == '1';
   *out_plan = p;
   return TUBER_OK;
 }
