@@ -133,7 +133,7 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="TubeR_CSN50_AVA21.yaml")
@@ -250,7 +250,7 @@ def main():
 
     e2e_run(3)
     sync_all()
-    e2e_steps = max(4, args.steps)
+    e2e_steps = max(4, min(args.steps, 50))
     t0 = time.perf_counter()
     e2e_run(e2e_steps)                              # returns after the last step's D2H copies have completed
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
