@@ -150,6 +150,14 @@ int tuber_get_kernel_profile(TuberPlan* plan, TuberKernelStat* out, int32_t capa
  * "layer1".."layer4" (B,T,H,W,C) channels-last.  Returns element count through *n_out; dst_dev may be NULL to query. */
 int tuber_debug_fetch(TuberPlan* plan, const char* what, float* dst_dev, int64_t* n_out, void* stream);
 
+/* Post-processing of one decoder layer's outputs fused with the packing of the detection rows the reference's evaluation loop
+ * writes (models/criterion.py:413-482 PostProcess / PostProcessAVA; utils/video_action_recognition.py:311-346,411-415):
+ * out_dev [B*Q, 4 + C + 1] = boxes (x1,y1,x2,y2) scaled to sizes_dev [B,2] = (H,W) | class scores | foreground probability.
+ * logits_dev / boxes_dev / logits_b_dev are the (B,L,Q,.) tensors of tuber_forward ((B,2) actor-ness logits outside AVA);
+ * `layer` selects the decoder layer (L-1 = the model's prediction). */
+int tuber_postprocess(TuberPlan* plan, const float* logits_dev, const float* boxes_dev, const float* logits_b_dev,
+                      const float* sizes_dev, int32_t B, int32_t layer, float* out_dev, void* stream);
+
 /* ---- single operators (unit tests / microbenchmarks; same kernels the plan launches) ------- */
 int tuber_op_to_split(const float* in_dev, void* out_dev, int64_t rows, int32_t cols, void* stream);
 int tuber_op_from_split(const void* in_dev, float* out_dev, int64_t rows, int32_t cols, void* stream);

@@ -59,3 +59,25 @@ def test_postprocess_ava_gate():
     assert scores[0, 1].abs().max() == 0            # p_actor = 1/3 < 0.8 -> gated to zero
     assert torch.allclose(scores[0, 0], 0.5 * pb[0, 0])
     assert torch.allclose(xyxy[0, 0], torch.tensor([80.0, 30.0, 120.0, 70.0]))
+
+
+def test_postprocess_oracle_matches_reference_golden():
+    """oracle.postprocess_ava against the reference's own PostProcessAVA (tests/golden/postprocess.npz, oracle/make_golden_post.py)."""
+    g = np.load(os.path.join(GOLD, "postprocess.npz"))
+    scores, xyxy, pb = O.postprocess_ava(torch.from_numpy(g["logits"]), torch.from_numpy(g["boxes"]), torch.from_numpy(g["logits_b"]),
+                                         torch.from_numpy(g["sizes"]))
+    assert np.abs(scores.numpy() - g["scores_ava"]).max() < 1e-6
+    assert np.abs(xyxy.numpy() - g["boxes_ava"]).max() < 1e-4
+    assert np.abs(pb.numpy() - g["p_ava"]).max() < 1e-6
+
+
+def test_detection_line_format_is_the_reference_file_format():
+    """format_detection_lines reproduces the loop's text lines (video_action_recognition.py:411-415) byte for byte and they
+    parse back the way evaluates/evaluate_ava.py:108-112 reads them."""
+    import tuber_b200
+    g = np.load(os.path.join(GOLD, "postprocess.npz"))
+    rows = np.concatenate([g["boxes_ava"], g["scores_ava"], g["p_ava"]], axis=-1)          # (B, Q, 4 + C + 1)
+    lines = tuber_b200.format_detection_lines([str(i) for i in g["ids"]], rows)
+    assert lines == [str(l) for l in g["lines"]]
+    parsed = [[float(x) for x in line.split(' [')[1].split(']')[0].split(',')] for line in lines]
+    assert np.array_equal(np.array(parsed), g["parsed"])

@@ -211,3 +211,51 @@ def test_fused_and_folded_paths_match_the_plain_launch_sequence(monkeypatch):
     for k in fast:
         emax, el2 = _rel(fast[k], plain[k])
         assert emax < 1e-4 and el2 < 1e-4, (k, emax, el2)
+
+
+def test_detection_rows_match_reference_postprocessors():
+    """tuber_postprocess (fused post-processing + row packing) against the reference's PostProcessAVA / PostProcess outputs
+    (tests/golden/postprocess.npz) and through the PostProcess* modules of build_model."""
+    import tuber_b200
+    from oracle import tuber_oracle as O
+    g = np.load(os.path.join(GOLD, "postprocess.npz"))
+    sizes = torch.from_numpy(g["sizes"])
+
+    def model_for(yaml, over):
+        cfg = tuber_b200.load_cfg(yaml, over)
+        model, _, post = tuber_b200.build_model(cfg)
+        model.load_state_dict(O.make_state_dict(cfg, seed=0), strict=True)
+        return model.cuda().eval(), post
+
+    # ---- AVA: sigmoid scores gated by the actor probability (criterion.py:447-482) ----
+    B, Q, C = g["logits"].shape
+    model, post = model_for("TubeR_CSN50_AVA21.yaml", ["CONFIG.MODEL.ENC_LAYERS", 1, "CONFIG.MODEL.DEC_LAYERS", 2, "CONFIG.MODEL.QUERY_NUM", Q])
+    L = model.dec_layers
+    raw = {"pred_logits": torch.zeros(B, L, Q, C, device="cuda"), "pred_boxes": torch.zeros(B, L, Q, 4, device="cuda"),
+           "pred_logits_b": torch.zeros(B, L, Q, 3, device="cuda")}
+    raw["pred_logits"][:, -1] = torch.from_numpy(g["logits"]).cuda()
+    raw["pred_boxes"][:, -1] = torch.from_numpy(g["boxes"]).cuda()
+    raw["pred_logits_b"][:, -1] = torch.from_numpy(g["logits_b"]).cuda()
+    rows = model.detection_rows(raw, sizes).cpu().numpy()
+    assert np.abs(rows[..., :4] - g["boxes_ava"]).max() < 1e-3
+    assert np.abs(rows[..., 4:4 + C] - g["scores_ava"]).max() < 2e-6
+    assert np.abs(rows[..., 4 + C:] - g["p_ava"]).max() < 2e-6
+    gate = g["p_ava"][..., 0] > 0.8
+    assert (rows[..., 4:4 + C][~gate] == 0).all() and gate.any()
+    # the module returned by build_model (reference signature: three numpy arrays)
+    s, b, p = post["bbox"]({"pred_logits": raw["pred_logits"][:, -1], "pred_boxes": raw["pred_boxes"][:, -1],
+                            "pred_logits_b": raw["pred_logits_b"][:, -1]}, sizes.cuda())
+    assert np.abs(s - g["scores_ava"]).max() < 2e-6 and np.abs(b - g["boxes_ava"]).max() < 1e-3 and np.abs(p - g["p_ava"]).max() < 2e-6
+
+    # ---- JHMDB-style: softmax scores, per-clip 2-way foreground logits (criterion.py:413-445) ----
+    Bj, Qj, Cj = g["logits_j"].shape
+    model, _ = model_for("Tuber_CSN152_JHMDB.yaml", ["CONFIG.MODEL.ENC_LAYERS", 1, "CONFIG.MODEL.DEC_LAYERS", 1, "CONFIG.MODEL.QUERY_NUM", 5,
+                                                    "CONFIG.MODEL.TEMP_LEN", 8])
+    assert model.num_queries == Qj and model.num_class_out == Cj
+    raw = {"pred_logits": torch.from_numpy(g["logits_j"]).cuda().reshape(Bj, 1, Qj, Cj).contiguous(),
+           "pred_boxes": torch.from_numpy(g["boxes_j"]).cuda().reshape(Bj, 1, Qj, 4).contiguous(),
+           "pred_logits_b": torch.from_numpy(g["logits_bj"]).cuda().contiguous()}
+    rows = model.detection_rows(raw, sizes).cpu().numpy()
+    assert np.abs(rows[..., :4] - g["boxes_jo"]).max() < 1e-3
+    assert np.abs(rows[..., 4:4 + Cj] - g["scores_j"]).max() < 2e-6
+    assert np.abs(rows[..., 4 + Cj] - np.broadcast_to(g["p_j"], (Bj, Qj))).max() < 2e-6

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "tuber_set_kernel_profiling": (_I, [_P, _I]),
     "tuber_get_kernel_profile": (_I, [_P, C.POINTER(TuberKernelStat), _I, C.POINTER(_I)]),
     "tuber_debug_fetch": (_I, [_P, C.c_char_p, _P, C.POINTER(_L), _P]),
+    "tuber_postprocess": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "tuber_op_to_split": (_I, [_P, _P, _L, _I, _P]),
     "tuber_op_from_split": (_I, [_P, _P, _L, _I, _P]),
     "tuber_op_pack_weight": (_I, [_P, _P, _I, _I, _P]),

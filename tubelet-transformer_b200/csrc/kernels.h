@@ -113,6 +113,12 @@ cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t st);
 // attn_mma.cu; cudaErrorNotSupported when the shape is outside what it covers
 cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);
 
+// ---- post-processing + detection rows (criterion.py:413-482; video_action_recognition.py:411-415) -------------
+// logits [B, Q, C] (clip stride l_sb floats), boxes [B, Q, 4] (b_sb), logits_b [B, Q, 3] (AVA) or [B, 2] (lb_sb), sizes [B, 2] = (H, W);
+// out [B*Q, 4 + C + 1] = xyxy scaled | scores | foreground probability
+cudaError_t launch_postprocess(const float* logits, long long l_sb, const float* boxes, long long b_sb, const float* logits_b,
+                               long long lb_sb, const float* sizes, float* out, int B, int Q, int C, int ava, cudaStream_t st);
+
 // ---- masks and position code (backbone_builder.py:85-86, position_encoding.py:32-72) ------
 cudaError_t launch_mask_resize(const uint8_t* mask, uint8_t* fmask, int B, int H, int W, int T, int Hf,
                                int Wf, cudaStream_t st);

@@ -1326,6 +1326,60 @@ cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t st) {
 }
 
 // =============================================================================================
+// Post-processing fused with the packing of the detection rows the evaluation loop writes
+// (reference models/criterion.py:413-482 PostProcess / PostProcessAVA; utils/video_action_recognition.py:311-346,411-415:
+// one text line per (clip, query) = boxes xyxy scaled | class scores | foreground probability):
+//   AVA   : p = softmax(logits_b)[1]; scores = sigmoid(logits) * (p > 0.8 ? p : 0)
+//   other : scores = softmax(logits); p = softmax(logits_b[clip])[1]   (logits_b is per clip, 2 values)
+//   boxes : (cx,cy,w,h) in [0,1] -> (x1,y1,x2,y2) * (W,H,W,H) with (H,W) = sizes[clip]
+// One warp per (clip, query); out row = [4 | C | 1] floats.
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+postprocess_kernel(const float* __restrict__ logits, long long l_sb, const float* __restrict__ boxes, long long b_sb,
+                   const float* __restrict__ logits_b, long long lb_sb, const float* __restrict__ sizes, float* __restrict__ out,
+                   int B, int Q, int C, int ava) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B * Q) return;
+  const int b = w / Q, q = w % Q;
+  const float* lg = logits + b * l_sb + (long long)q * C;
+  const float* bx = boxes + b * b_sb + (long long)q * 4;
+  float* o = out + (long long)w * (C + 5);
+  float p;
+  if (ava) {
+    const float* lb = logits_b + b * lb_sb + (long long)q * 3;
+    const float a0 = lb[0], a1 = lb[1], a2 = lb[2], m = fmaxf(a0, fmaxf(a1, a2));
+    const float e0 = expf(a0 - m), e1 = expf(a1 - m), e2 = expf(a2 - m);
+    p = e1 / (e0 + e1 + e2);
+    const float gate = p > 0.8f ? p : 0.f;
+    for (int c = lane; c < C; c += 32) o[4 + c] = gate / (1.f + expf(-lg[c]));
+  } else {
+    const float* lb = logits_b + b * lb_sb;
+    const float m2 = fmaxf(lb[0], lb[1]), e0 = expf(lb[0] - m2), e1 = expf(lb[1] - m2);
+    p = e1 / (e0 + e1);
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, lg[c]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += expf(lg[c] - m);
+    sum = warp_sum(sum);
+    for (int c = lane; c < C; c += 32) o[4 + c] = expf(lg[c] - m) / sum;
+  }
+  if (lane == 0) {
+    const float H = sizes[2 * b], W = sizes[2 * b + 1];
+    const float cx = bx[0], cy = bx[1], bw = bx[2], bh = bx[3];
+    o[0] = (cx - 0.5f * bw) * W; o[1] = (cy - 0.5f * bh) * H; o[2] = (cx + 0.5f * bw) * W; o[3] = (cy + 0.5f * bh) * H;
+    o[4 + C] = p;
+  }
+}
+
+cudaError_t launch_postprocess(const float* logits, long long l_sb, const float* boxes, long long b_sb, const float* logits_b,
+                               long long lb_sb, const float* sizes, float* out, int B, int Q, int C, int ava, cudaStream_t st) {
+  if (B <= 0 || Q <= 0 || C <= 0) return cudaErrorInvalidValue;
+  postprocess_kernel<<<ceil_div((long long)B * Q * 32, 128), 128, 0, st>>>(logits, l_sb, boxes, b_sb, logits_b, lb_sb, sizes, out, B, Q, C, ava);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
 // Padding mask at feature resolution and the 3-D sine position code
 // =============================================================================================
 // nearest-neighbour resize (B,H,W) -> (B,T,Hf,Wf), repeated over T  (backbone_builder.py:85-86)

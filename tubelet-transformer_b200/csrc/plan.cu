@@ -1422,6 +1422,20 @@ int tuber_debug_fetch(TuberPlan* p, const char* what, float* dst_dev, int64_t* n
   return TUBER_OK;
 }
 
+int tuber_postprocess(TuberPlan* p, const float* logits_dev, const float* boxes_dev, const float* logits_b_dev, const float* sizes_dev,
+                      int32_t B, int32_t layer, float* out_dev, void* stream) {
+  if (!p || !logits_dev || !boxes_dev || !logits_b_dev || !sizes_dev || !out_dev) return fail(TUBER_ERR_INVALID, "null argument");
+  const TuberConfig& c = p->cfg;
+  if (B < 1 || layer < 0 || layer >= c.dec_layers) return fail(TUBER_ERR_INVALID, "bad batch %d / layer %d", B, layer);
+  const long long L = c.dec_layers, Q = c.num_queries, C = c.num_classes;
+  const float* lg = logits_dev + (long long)layer * Q * C;
+  const float* bx = boxes_dev + (long long)layer * Q * 4;
+  const float* lb = c.ava_mode ? logits_b_dev + (long long)layer * Q * 3 : logits_b_dev;
+  CK(launch_postprocess(lg, L * Q * C, bx, L * Q * 4, lb, c.ava_mode ? L * Q * 3 : 2, sizes_dev, out_dev, B, (int)Q, (int)C, c.ava_mode,
+                        (cudaStream_t)stream));
+  return TUBER_OK;
+}
+
 // ---- single operators ------------------------------------------------------------------------
 int tuber_op_to_split(const float* in, void* out, int64_t rows, int32_t cols, void* stream) {
   CK(launch_to_split(in, cols, out, cols, rows, cols, (cudaStream_t)stream));

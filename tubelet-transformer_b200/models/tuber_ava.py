@@ -332,6 +332,28 @@ class DETR(nn.Module):
                                   for i in range(self.dec_layers - 1)]
         return res
 
+    # -- detection hand-off -------------------------------------------
+    @torch.no_grad()
+    def detection_rows(self, raw: Dict[str, Tensor], target_sizes: Tensor, layer: int = -1) -> Tensor:
+        """Post-processing fused with the packing of the rows the reference's evaluation loop writes
+        (criterion.py:413-482; utils/video_action_recognition.py:311-346,411-415).  `raw` = the all-layer outputs of
+        `forward_raw` (on the GPU), `target_sizes` (B,2) = (height, width) per clip.  Returns a CUDA tensor
+        (B, Q, 4 + C + 1): boxes xyxy in pixels | class scores | foreground probability -- one text line per row."""
+        dev = self._device()
+        logits, boxes, logits_b = raw["pred_logits"], raw["pred_boxes"], raw["pred_logits_b"]
+        B = logits.shape[0]
+        layer = layer % self.dec_layers
+        sizes = target_sizes.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(sizes.shape) != (B, 2):
+            raise ValueError("target_sizes must be (B, 2) = (height, width)")
+        out = torch.empty((B, self.num_queries, 4 + self.num_class_out + 1), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().tuber_postprocess(self.plan(), C.c_void_p(logits.data_ptr()), C.c_void_p(boxes.data_ptr()),
+                                                     C.c_void_p(logits_b.data_ptr()), C.c_void_p(sizes.data_ptr()), B, layer,
+                                                     C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+        return out
+
     # -- instrumentation ----------------------------------------------------------------------
     def stage_times_ms(self, clips: Tensor, mask: Optional[Tensor] = None) -> Dict[str, float]:
         lib = _lib.load()
@@ -392,6 +414,21 @@ class PostProcess(nn.Module):
         assert len(logits) == len(target_sizes) and target_sizes.shape[1] == 2
         xyxy = _cxcywh_to_xyxy_scaled(boxes, target_sizes)
         return logits.softmax(-1).cpu().numpy(), xyxy.cpu().numpy(), logits_b.softmax(-1).cpu().numpy()[..., 1:]
+
+
+def format_detection_lines(frame_ids, rows) -> List[str]:
+    """The reference's per-rank result file (utils/video_action_recognition.py:411-415, parsed by evaluates/evaluate_ava.py:101-130):
+    one line "{frame_id} [x1, y1, x2, y2, s_0, ..., s_{C-1}, p]" per (clip, query).  `rows` = `detection_rows(...)` moved to the
+    host (B, Q, 4+C+1) or flattened (N, 4+C+1); `frame_ids` one id per clip (repeated for its queries) or one per row."""
+    import numpy as np
+    rows = np.asarray(rows, dtype=np.float32)
+    flat = rows.reshape(-1, rows.shape[-1])
+    ids = list(frame_ids)
+    if rows.ndim == 3 and len(ids) == rows.shape[0]:
+        ids = [i for i in ids for _ in range(rows.shape[1])]
+    if len(ids) != flat.shape[0]:
+        raise ValueError("one frame id per clip or per row")
+    return ["{} {}\n".format(i, r.tolist()) for i, r in zip(ids, flat)]
 
 
 class _TrainingOnlyCriterion(nn.Module):
