@@ -446,6 +446,10 @@ class _TrainingOnlyCriterion(nn.Module):
 def build_model(cfg):
     """-> (model, criterion, postprocessors), the reference's build_model signature (tuber_ava.py:160-221)."""
     model = DETR(cfg)
+    m = cfg.CONFIG.MODEL
+    if bool(getattr(m, "PRETRAINED", False)):                                  # build_CSN(load_pretrain=cfg.CONFIG.MODEL.PRETRAINED), ir_CSN_152.py:321-333
+        from ..utils.checkpoint import load_csn_mat
+        load_csn_mat(model, m.PRETRAIN_BACKBONE_DIR)
     ava = cfg.CONFIG.DATA.DATASET_NAME == "ava"
     postprocessors = {"bbox": PostProcessAVA() if ava else PostProcess()}
     return model, _TrainingOnlyCriterion(), postprocessors
