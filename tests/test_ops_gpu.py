@@ -27,7 +27,7 @@ def test_split_roundtrip(abi):
 
 
 @pytest.mark.parametrize("m,n,k", [(300, 64, 64), (128, 128, 256), (1000, 256, 2048), (4096, 512, 128), (77, 192, 512),
-                                   (20000, 256, 64), (16384, 256, 1024), (13000, 512, 512)])
+                                   (20000, 256, 64), (16384, 256, 1024), (13000, 512, 512), (16484, 256, 1024)])
 @pytest.mark.parametrize("variant", ["plain", "bn_relu_res", "split_out_split_res", "res_mod", "mixed_res_f32_out_split", "split_out"])
 def test_gemm_tc(abi, m, n, k, variant):
     g = torch.Generator(device="cuda").manual_seed(m * 7 + n + k)
