@@ -247,7 +247,7 @@ dwconv_s1_tiled_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_co
 // LDS.128 for the input + 3.4 for the broadcast weights, against 108 FMAs), which moves the kernel from shared-memory bound
 // to HBM / FMA bound; items, steps and ring slots run as one flat software pipeline (prefetch distance 3) across items.
 namespace dwr {
-constexpr int TH = 16, TW = 16, CC = 32, IH = TH + 2, IW = TW + 2, NSLOT = 4, TCMAX = 8;
+constexpr int TH = 16, TW = 16, CC = 32, IH = TH + 2, IW = TW + 2, NSLOT = 4, TCMAX = 16;
 constexpr int PLANE_F4 = IH * IW * (CC / 4);              // float4 slots of one input frame of the halo tile
 constexpr int PLANE_BYTES = PLANE_F4 * 16;                // 41472
 constexpr int W_F4 = 27 * (CC / 4);
@@ -392,7 +392,7 @@ dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __r
 // output j: two accumulator sets alternate.  A thread owns 4 output columns x 4 channels and reads the 3 x 9 input window of a
 // frame from the halo tile (17 x 33 x 32 ch, one 5-D TMA load per frame, 3-slot ring).
 namespace dws {
-constexpr int TH = 8, TW = 16, CC = 32, IH = 2 * TH + 1, IW = 2 * TW + 1, NSLOT = 3, TCMAX = 4;
+constexpr int TH = 8, TW = 16, CC = 32, IH = 2 * TH + 1, IW = 2 * TW + 1, NSLOT = 3, TCMAX = 64;
 constexpr int PLANE_F4 = IH * IW * (CC / 4);
 constexpr int PLANE_BYTES = PLANE_F4 * 16;                // 71808
 constexpr int W_F4 = 27 * (CC / 4);
@@ -596,8 +596,15 @@ cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale,
         return cudaErrorInvalidValue;
       // frames per item: as many as possible (fewer halo frames) while the grid still fills the machine about twice
       const long long cols = (long long)B * ceil_div(Hi, dwr::TH) * ceil_div(Wi, dwr::TW) * (C / dwr::CC);
-      int TC = Ti < dwr::TCMAX ? Ti : dwr::TCMAX;
-      while (TC > 2 && cols * ceil_div(Ti, TC) < 2LL * g_num_sms) TC = (TC + 1) / 2;
+      // frames per item: minimise (rounds over the SMs) x (steps per item = TC + 2 halo frames); ties go to the longer item
+      int TC = 1;
+      long long best = -1;
+      for (int k = 1; k <= Ti; ++k) {
+        const int tc = ceil_div(Ti, k);
+        if (tc > dwr::TCMAX) continue;
+        const long long cost = (long long)ceil_div(cols * ceil_div(Ti, tc), g_num_sms) * (tc + 2);
+        if (best < 0 || cost < best) { best = cost; TC = tc; }
+      }
       const long long items = cols * ceil_div(Ti, TC);
       const int grid = (int)(items < g_num_sms ? items : g_num_sms);
       return launch_pdl(dwconv_s1_roll_kernel, dim3(grid), dim3(dwr::THREADS), dwr::SMEM_BYTES, st, tmR, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, TC, (int)items);
@@ -620,8 +627,14 @@ cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
     const long long cols = (long long)B * ceil_div(Ho, TH) * ceil_div(Wo, TW) * (C / CC);
-    int TC = To < TCMAX ? To : TCMAX;
-    while (TC > 1 && cols * ceil_div(To, TC) < 2LL * dwt::g_num_sms) TC = (TC + 1) / 2;
+    int TC = 1;
+    long long best = -1;
+    for (int k = 1; k <= To; ++k) {                          // minimise rounds x (2 TC + 1) input frames per item
+      const int tc = ceil_div(To, k);
+      if (tc > TCMAX) continue;
+      const long long cost = (long long)ceil_div(cols * ceil_div(To, tc), dwt::g_num_sms) * (2 * tc + 1);
+      if (best < 0 || cost < best) { best = cost; TC = tc; }
+    }
     const long long items = cols * ceil_div(To, TC);
     const int grid = (int)(items < dwt::g_num_sms ? items : dwt::g_num_sms);
     dwconv_s2_roll_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmS, wpk, scale, shift, out_split, B, Ti, To, Ho, Wo, C, TC, (int)items);
