@@ -52,83 +52,13 @@ struct __align__(16) Smem {
   float msk[KC];                 // 0 or -inf per key of the chunk
 };
 
-template <int NW>
-__global__ void __launch_bounds__(NW * 32)
-attn_mma_kernel(AttnArgs p) {
-  constexpr int QT = QW * NW;      // queries per CTA
-  constexpr int TPK = NW / 2;      // staging threads per key (each converts 32 / TPK dims of K and of V)
-  constexpr int F4 = 8 / TPK;      // float4 per thread and tensor
-  __shared__ Smem sm;
-  pdl_trigger();
-  pdl_wait();
-  const int n = blockIdx.z, h = blockIdx.y, l0 = blockIdx.x * QT;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const long long q0 = seq_row0(p.qm, n), k0 = seq_row0(p.km, n);
-  const uint8_t* mrow = p.kpm ? p.kpm + (long long)(n / p.kpm_div) * p.S : nullptr;
-  const int lw = l0 + warp * QW;                         // first query of this warp
-  const bool warp_active = lw < p.L;
-
-  // ---- Q fragments (A operand, rows g and g+8, k = 2t,2t+1 (+8) of each 16-wide k step), pre-scaled ----
-  uint32_t q_hi[2][4], q_mid[2][4];
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int row = lw + g + (e & 1) * 8, col = ks * 16 + (e >> 1) * 8 + 2 * t;
-      float2 v = make_float2(0.f, 0.f);
-      if (row < p.L) v = __ldg(reinterpret_cast<const float2*>(p.q + (q0 + (long long)row * p.qm.step) * p.ldq + h * D + col));
-      split2(v.x * p.scale, v.y * p.scale, q_hi[ks][e], q_mid[ks][e]);
-    }
-
-  // chunk staging: thread -> (key = tid / TPK, dims (tid % TPK) * 4 * F4 ..): F4 float4 of K and of V
-  const int skey = tid / TPK, sd0 = (tid % TPK) * 4 * F4;
-  float4 pk[F4], pv[F4];
-  auto fetch = [&](int c) {
-    const int s = c * KC + skey;
-    if (s < p.S) {
-      const long long krow = k0 + (long long)s * p.km.step;
-      const float4* kp = reinterpret_cast<const float4*>(p.k + krow * p.ldk + h * D + sd0);
-      const float4* vp = reinterpret_cast<const float4*>(p.v + krow * p.ldv + h * D + sd0);
-#pragma unroll
-      for (int i = 0; i < F4; ++i) { pk[i] = __ldg(kp + i); pv[i] = __ldg(vp + i); }
-    } else {
-#pragma unroll
-      for (int i = 0; i < F4; ++i) { pk[i] = make_float4(0.f, 0.f, 0.f, 0.f); pv[i] = pk[i]; }
-    }
-  };
-  auto stage = [&](int c) {
-#pragma unroll
-    for (int i = 0; i < F4; ++i) {
-      store_split4(&sm.k_hi[skey][sd0 + 4 * i], &sm.k_mid[skey][sd0 + 4 * i], pk[i]);
-      store_split4(&sm.v_hi[skey][sd0 + 4 * i], &sm.v_mid[skey][sd0 + 4 * i], pv[i]);
-    }
-    if (tid < KC) {
-      const int s = c * KC + tid;
-      sm.msk[tid] = (s >= p.S || (mrow && mrow[s])) ? -INFINITY : 0.f;
-    }
-  };
-
-  float o[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) o[i][e] = 0.f;
-  float mx[2] = {-INFINITY, -INFINITY}, ls[2] = {0.f, 0.f};
-
-  const int nchunks = (p.S + KC - 1) / KC;
-  // ldmatrix lane addressing: matrix mi = lane / 8, row r = lane % 8
-  const int mi = lane >> 3, mr = lane & 7;
+// one chunk of up to 64 keys (staged in `sm` as bf16 hi | mid) for the 16 queries of a warp: scores, online softmax, O += P V
+TB_DEVINL void process_chunk(const Smem& sm, int valid, const uint32_t (&q_hi)[2][4], const uint32_t (&q_mid)[2][4], float (&o)[4][4],
+                              float (&mx)[2], float (&ls)[2], int lane) {
+  const int t = lane & 3;
+  const int mi = lane >> 3, mr = lane & 7;                 // ldmatrix lane addressing: matrix mi = lane / 8, row r = lane % 8
   const uint32_t k_hi_b = smem_u32(&sm.k_hi[mr][mi * 8]), k_mid_b = smem_u32(&sm.k_mid[mr][mi * 8]);
   const uint32_t v_hi_b = smem_u32(&sm.v_hi[(mi & 1) * 8 + mr][(mi >> 1) * 8]), v_mid_b = smem_u32(&sm.v_mid[(mi & 1) * 8 + mr][(mi >> 1) * 8]);
-
-  fetch(0);
-  for (int c = 0; c < nchunks; ++c) {
-    __syncthreads();                                     // the previous chunk's readers are done
-    stage(c);
-    __syncthreads();
-    if (c + 1 < nchunks) fetch(c + 1);                   // in flight while this chunk is computed
-    if (!warp_active) continue;
-    const int valid = min(KC, p.S - c * KC);
     const int ntiles = (valid + 7) >> 3;                 // 8-key score tiles that hold at least one real key
 
     // ---- scores: s[j] = Q K^T for keys 8j .. 8j+7 of the chunk ----
@@ -203,6 +133,80 @@ attn_mma_kernel(AttnArgs p) {
       }
     }
   }
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32)
+attn_mma_kernel(AttnArgs p) {
+  constexpr int QT = QW * NW;      // queries per CTA
+  constexpr int TPK = NW / 2;      // staging threads per key (each converts 32 / TPK dims of K and of V)
+  constexpr int F4 = 8 / TPK;      // float4 per thread and tensor
+  __shared__ Smem sm;
+  pdl_trigger();
+  pdl_wait();
+  const int n = blockIdx.z, h = blockIdx.y, l0 = blockIdx.x * QT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const long long q0 = seq_row0(p.qm, n), k0 = seq_row0(p.km, n);
+  const uint8_t* mrow = p.kpm ? p.kpm + (long long)(n / p.kpm_div) * p.S : nullptr;
+  const int lw = l0 + warp * QW;                         // first query of this warp
+  const bool warp_active = lw < p.L;
+
+  // ---- Q fragments (A operand, rows g and g+8, k = 2t,2t+1 (+8) of each 16-wide k step), pre-scaled ----
+  uint32_t q_hi[2][4], q_mid[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int row = lw + g + (e & 1) * 8, col = ks * 16 + (e >> 1) * 8 + 2 * t;
+      float2 v = make_float2(0.f, 0.f);
+      if (row < p.L) v = __ldg(reinterpret_cast<const float2*>(p.q + (q0 + (long long)row * p.qm.step) * p.ldq + h * D + col));
+      split2(v.x * p.scale, v.y * p.scale, q_hi[ks][e], q_mid[ks][e]);
+    }
+
+  // chunk staging: thread -> (key = tid / TPK, dims (tid % TPK) * 4 * F4 ..): F4 float4 of K and of V
+  const int skey = tid / TPK, sd0 = (tid % TPK) * 4 * F4;
+  float4 pk[F4], pv[F4];
+  auto fetch = [&](int c) {
+    const int s = c * KC + skey;
+    if (s < p.S) {
+      const long long krow = k0 + (long long)s * p.km.step;
+      const float4* kp = reinterpret_cast<const float4*>(p.k + krow * p.ldk + h * D + sd0);
+      const float4* vp = reinterpret_cast<const float4*>(p.v + krow * p.ldv + h * D + sd0);
+#pragma unroll
+      for (int i = 0; i < F4; ++i) { pk[i] = __ldg(kp + i); pv[i] = __ldg(vp + i); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < F4; ++i) { pk[i] = make_float4(0.f, 0.f, 0.f, 0.f); pv[i] = pk[i]; }
+    }
+  };
+  auto stage = [&](int c) {
+#pragma unroll
+    for (int i = 0; i < F4; ++i) {
+      store_split4(&sm.k_hi[skey][sd0 + 4 * i], &sm.k_mid[skey][sd0 + 4 * i], pk[i]);
+      store_split4(&sm.v_hi[skey][sd0 + 4 * i], &sm.v_mid[skey][sd0 + 4 * i], pv[i]);
+    }
+    if (tid < KC) {
+      const int s = c * KC + tid;
+      sm.msk[tid] = (s >= p.S || (mrow && mrow[s])) ? -INFINITY : 0.f;
+    }
+  };
+
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[i][e] = 0.f;
+  float mx[2] = {-INFINITY, -INFINITY}, ls[2] = {0.f, 0.f};
+
+  const int nchunks = (p.S + KC - 1) / KC;
+  fetch(0);
+  for (int c = 0; c < nchunks; ++c) {
+    __syncthreads();                                     // the previous chunk's readers are done
+    stage(c);
+    __syncthreads();
+    if (c + 1 < nchunks) fetch(c + 1);                   // in flight while this chunk is computed
+    if (!warp_active) continue;
+    process_chunk(sm, min(KC, p.S - c * KC), q_hi, q_mid, o, mx, ls, lane);
+  }
   if (!warp_active) return;
   // ---- normalise and store (fp32 and / or split) ----
   const long long o0 = seq_row0(p.om, n);
@@ -228,6 +232,109 @@ attn_mma_kernel(AttnArgs p) {
         *reinterpret_cast<uint32_t*>(hp + p.ldo + col) = mid;
       }
     }
+  }
+}
+
+// L <= 16 (the DETR decoder's cross-attention: 15 tubelet queries over the T'H'W' memory tokens, transformer.py:232-241): one query
+// tile per (sequence, head), so instead of one warp walking all key chunks in turn while three warps only help staging, every
+// warp takes its own chunks (warp w: chunks w, w+4, ...) with a private staging area and no CTA-wide barriers; the partial
+// (max, sum, O) triples are merged through shared memory at the end.  S = 256: one chunk latency instead of four.
+constexpr int SPLIT_NW = 4;
+__global__ void __launch_bounds__(SPLIT_NW * 32)
+attn_mma_split_kernel(AttnArgs p) {
+  extern __shared__ __align__(16) uint8_t split_smem[];
+  Smem* sms = reinterpret_cast<Smem*>(split_smem);
+  pdl_trigger();
+  pdl_wait();
+  const int n = blockIdx.z, h = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const long long q0 = seq_row0(p.qm, n), k0 = seq_row0(p.km, n);
+  const uint8_t* mrow = p.kpm ? p.kpm + (long long)(n / p.kpm_div) * p.S : nullptr;
+  Smem& sm = sms[warp];
+
+  uint32_t q_hi[2][4], q_mid[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int row = g + (e & 1) * 8, col = ks * 16 + (e >> 1) * 8 + 2 * t;
+      float2 v = make_float2(0.f, 0.f);
+      if (row < p.L) v = __ldg(reinterpret_cast<const float2*>(p.q + (q0 + (long long)row * p.qm.step) * p.ldq + h * D + col));
+      split2(v.x * p.scale, v.y * p.scale, q_hi[ks][e], q_mid[ks][e]);
+    }
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[i][e] = 0.f;
+  float mx[2] = {-INFINITY, -INFINITY}, ls[2] = {0.f, 0.f};
+
+  const int nchunks = (p.S + KC - 1) / KC;
+  for (int c = warp; c < nchunks; c += SPLIT_NW) {
+    __syncwarp();
+    // this warp stages its chunk: lane -> keys lane and lane + 32, all 32 dims of K and V
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int key = lane + 32 * half, sidx = c * KC + key;
+      if (sidx < p.S) {
+        const long long krow = k0 + (long long)sidx * p.km.step;
+        const float4* kp = reinterpret_cast<const float4*>(p.k + krow * p.ldk + h * D);
+        const float4* vp = reinterpret_cast<const float4*>(p.v + krow * p.ldv + h * D);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          store_split4(&sm.k_hi[key][4 * i], &sm.k_mid[key][4 * i], __ldg(kp + i));
+          store_split4(&sm.v_hi[key][4 * i], &sm.v_mid[key][4 * i], __ldg(vp + i));
+        }
+      } else {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          store_split4(&sm.k_hi[key][4 * i], &sm.k_mid[key][4 * i], z);
+          store_split4(&sm.v_hi[key][4 * i], &sm.v_mid[key][4 * i], z);
+        }
+      }
+      sm.msk[key] = (sidx >= p.S || (mrow && mrow[sidx])) ? -INFINITY : 0.f;
+    }
+    __syncwarp();
+    process_chunk(sm, min(KC, p.S - c * KC), q_hi, q_mid, o, mx, ls, lane);
+  }
+  // ---- merge the warps' partial results (rows g and g + 8 of each warp's quad lanes) ----
+  __syncthreads();                                           // staging areas are free: reuse them as float scratch
+  float* scratch = reinterpret_cast<float*>(split_smem);      // [warp][row 16][m, l, o[32]] = 34 floats per row
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float l = ls[r];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    float* row = scratch + ((warp * 16) + g + 8 * r) * 36;
+    if (t == 0) { row[0] = mx[r]; row[1] = l; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { row[2 + i * 8 + 2 * t] = o[i][2 * r]; row[2 + i * 8 + 2 * t + 1] = o[i][2 * r + 1]; }
+  }
+  __syncthreads();
+  // thread -> (query row = tid / 8, 4 output dims = (tid % 8) * 4)
+  const int row = tid >> 3, d0 = (tid & 7) * 4;
+  if (row >= p.L) return;
+  float m = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < SPLIT_NW; ++w) m = fmaxf(m, scratch[(w * 16 + row) * 36]);
+  float l = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int w = 0; w < SPLIT_NW; ++w) {
+    const float* pr = scratch + (w * 16 + row) * 36;
+    const float f = (pr[0] == -INFINITY) ? 0.f : expf(pr[0] - m);   // a warp without chunks / fully masked chunks contributes nothing
+    l += pr[1] * f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] += pr[2 + d0 + e] * f;
+  }
+  const float inv = 1.f / l;                                 // every key masked: NaN, as the reference's softmax
+  const long long orow = seq_row0(p.om, n) + (long long)row * p.om.step;
+  const int col = h * D + d0;
+  const float4 res = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+  if (p.o_f32) *reinterpret_cast<float4*>(p.o_f32 + orow * p.ldo + col) = res;
+  if (p.o_split) {
+    __nv_bfloat16* hp = split_hi(p.o_split, orow, p.ldo);
+    store_split4(hp + col, hp + p.ldo + col, res);
   }
 }
 
@@ -319,6 +426,16 @@ cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
     return launch_pdl(attn_tiny_kernel<8>, dim3(ceil_div(warps * 32, 128)), dim3(128), 0, st, a);
   }
   if (a.NB > 65535 || a.H > 65535) return cudaErrorNotSupported;
+  if (a.L <= QW && a.S > KC) {                               // one query tile, several key chunks: split the keys over the warps
+    static bool attr_set = false;
+    const size_t smem = SPLIT_NW * sizeof(Smem);
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_mma_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    return launch_pdl(attn_mma_split_kernel, dim3(1, a.H, a.NB), dim3(SPLIT_NW * 32), smem, st, a);
+  }
   if (a.L > 64) {
     dim3 grid(ceil_div(a.L, 8 * QW), a.H, a.NB);
     return launch_pdl(attn_mma_kernel<8>, grid, dim3(8 * 32), 0, st, a);
