@@ -949,8 +949,10 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     cx.gemm(src_s, FMT_SPLIT, d, Mtok, p->mem_kv, posp + (size_t)Le * 3 * d, FMT_F32, NP, pos_mod, memkv, FMT_F32, Ld * 2 * d,
             ACT_NONE);
     void* tgt_s = cx.split(Mq, d);
-    // tgt = zeros_like(query_embed), transformer.py:60 (all-zero bits are zero in split format too)
-    cx.launch("memset", 4.0 * Mq * d, 0.0, [&] { return cudaMemsetAsync(tgt_s, 0, (size_t)Mq * d * 4, st); });
+    // tgt = zeros_like(query_embed), transformer.py:60 (all-zero bits are zero in split format too); with layer 0 folded at
+    // finalize the zero state is never read
+    if (p->dec0_c1 == nullptr)
+      cx.launch("memset", 4.0 * Mq * d, 0.0, [&] { return cudaMemsetAsync(tgt_s, 0, (size_t)Mq * d * 4, st); });
     float* qkv = cx.f32(Mq, 3 * d);
     float* qc = cx.f32(Mq, d);
     void* att = cx.split(Mq, d);
