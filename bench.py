@@ -64,6 +64,25 @@ def _ncu_traffic(kernel: str):
     return None, None
 
 
+def _bind_to_gpu_cpus(index: int):
+    """Multi-GPU e2e is bound by host -> device copies (8 x 25 MB/clip streams): keep each rank's threads, and therefore its
+    first-touched pinned buffers, on the CPUs NVML reports as local to its GPU.  Returns the CPU count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -185,6 +204,7 @@ def main():
     # ---------------------------------------------------------------- this repo's arm (B200)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the tuber_b200 path has no CPU fallback")
+    numa = _bind_to_gpu_cpus(local) if world > 1 else None   # pinned staging buffers land on the GPU's own NUMA node
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -317,7 +337,7 @@ def main():
             "data": "synthetic", "config": workload, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "forward_host_submit/_wait (double-buffered: H2D of step i+1 overlaps step i)",
-                    "synchronous_per_call_rank0": e2e_sync_val},
+                    "synchronous_per_call_rank0": e2e_sync_val, "rank0_cpus_bound": numa},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "cuda_graph": not args.no_graph, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
