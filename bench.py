@@ -286,6 +286,25 @@ def main():
     for _ in range(e2e_steps):
         model.forward_host(h_clips[0], None, h_out[0])
     e2e_sync_val = B * e2e_steps / (time.perf_counter() - t0)
+    # the same pipeline fed with decoded uint8 frames (B,T,H,W,3): 3 bytes per pixel cross the bus and the reference's ToTensor +
+    # Normalize run on the device (tuber_forward_host_u8_submit) -- reported beside e2e, not instead of it
+    h_frames = [O.make_frames_u8(B, T, H, W, seed=20 + rank + 100 * i).pin_memory() for i in range(2)]
+
+    def e2e_u8_run(n):
+        model.forward_host_u8_submit(0, h_frames[0], None, h_out[0])
+        for i in range(1, n):
+            model.forward_host_u8_submit(i & 1, h_frames[i & 1], None, h_out[i & 1])
+            model.forward_host_wait((i - 1) & 1)
+        model.forward_host_wait((n - 1) & 1)
+
+    e2e_u8_run(3)
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_u8_run(e2e_steps)
+    e2e_u8_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_u8_s, op=dist.ReduceOp.MAX)
+    e2e_u8_val = B * world * e2e_steps / float(e2e_u8_s.item())
 
     if rank != 0:
         if world > 1:
@@ -327,8 +346,8 @@ def main():
     stage_ms = model.stage_times_ms(clips)
 
     cpu = None
-    if not args.no_cpu_baseline:
-        v, cores, sample = _cpu_reference(cfg, sd, T, H, W, budget_s=12.0, max_clips=8)
+    if not args.no_cpu_baseline and world == 1:                 # rank 0 at N = 1 only
+        v, cores, sample = _cpu_reference(cfg, sd, T, H, W, budget_s=15.0, max_clips=32)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     value = B * world * args.steps / (ms_total * 1e-3)
@@ -338,6 +357,9 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "forward_host_submit/_wait (double-buffered: H2D of step i+1 overlaps step i)",
                     "synchronous_per_call_rank0": e2e_sync_val, "rank0_cpus_bound": numa},
+            "e2e_u8": {"value": e2e_u8_val, "unit": UNIT, "h2d_bytes_per_step": h_frames[0].numel(), "d2h_bytes_per_step": d2h,
+                       "steps": e2e_steps, "api": "forward_host_u8_submit/_wait: uint8 (B,T,H,W,3) frames in pinned host memory, "
+                                                  "ToTensor + Normalize on the device (+1 launch per step)"},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "cuda_graph": not args.no_graph, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},

@@ -101,6 +101,24 @@ int tuber_forward_host_submit(TuberPlan* plan, int32_t slot, const float* clips_
                               int32_t T, int32_t H, int32_t W, float* logits_host, float* boxes_host, float* logits_b_host);
 int tuber_forward_host_wait(TuberPlan* plan, int32_t slot);
 
+/* ---- uint8 frames in (replaces the tail of the reference's input pipeline) ----------------------
+ * The reference decodes JPEG frames to uint8 RGB and then runs, on the host, ToTensor (uint8 HWC -> float32 CHW, / 255) and
+ * Normalize ((x - mean) / std) per frame, stacks and permutes to (3,T,H,W) (datasets/video_transforms.py:294-296,308-314;
+ * datasets/ava_frame.py:71-72,158-162) -- 12 bytes per pixel then cross the bus.  These entry points take the decoded frames
+ * themselves, uint8 (B,T,H,W,3) RGB, and apply that transform on the device (3 bytes per pixel cross the bus); the values fed
+ * to the stem are bit-identical to the reference transform's (a 3 x 256 value table evaluated in fp32 the way torch does).
+ * tuber_set_input_norm sets mean / std (3 floats each; default = the reference's ImageNet constants, ava_frame.py:159-162);
+ * it synchronises the device.  tuber_input_lut is the host-only table builder (no device needed), lut_out = float[3*256].
+ * tuber_forward_host_u8_submit shares its slots and tuber_forward_host_wait with tuber_forward_host_submit. */
+int tuber_input_lut(const float* mean, const float* std, float* lut_out);
+int tuber_set_input_norm(TuberPlan* plan, const float* mean, const float* std);
+int tuber_forward_u8(TuberPlan* plan, const uint8_t* frames_dev, const uint8_t* mask_dev, int32_t B, int32_t T, int32_t H,
+                     int32_t W, float* logits_dev, float* boxes_dev, float* logits_b_dev, void* stream);
+int tuber_forward_host_u8(TuberPlan* plan, const uint8_t* frames_host, const uint8_t* mask_host, int32_t B, int32_t T,
+                          int32_t H, int32_t W, float* logits_host, float* boxes_host, float* logits_b_host, void* stream);
+int tuber_forward_host_u8_submit(TuberPlan* plan, int32_t slot, const uint8_t* frames_host, const uint8_t* mask_host, int32_t B,
+                                 int32_t T, int32_t H, int32_t W, float* logits_host, float* boxes_host, float* logits_b_host);
+
 /* Output geometry for an input shape: feature-map size after the backbone (T',H',W'), tokens seen
  * by the DETR encoder, number of kernel launches one forward issues. */
 typedef struct TuberShapeInfo {
@@ -193,6 +211,9 @@ int tuber_op_layernorm(const float* x_dev, const float* res_dev, const float* ga
 int tuber_op_attention(const float* q_dev, const float* k_dev, const float* v_dev, const uint8_t* kpm_dev,
                        float* out_dev, int32_t NB, int32_t H, int32_t L, int32_t S, int32_t D, float scale,
                        void* stream);
+/* uint8 frames (B, pixels_per_clip, 3) -> fp32 (B, 3, pixels_per_clip) = ((u / 255) - mean[c]) / std[c].  Synchronises the stream. */
+int tuber_op_normalize_u8(const uint8_t* frames_dev, const float* mean, const float* std, float* out_dev, int32_t B,
+                          int64_t pixels_per_clip, void* stream);
 /* 3-D sine position code from a feature-resolution mask (B,T,H,W) -> (B, T*H*W, d_model) */
 int tuber_op_posenc(const uint8_t* fmask_dev, float* pos_dev, int32_t B, int32_t T, int32_t H, int32_t W,
                     int32_t d_model, void* stream);

@@ -201,6 +201,28 @@ def make_clips(batch: int, t: int, h: int, w: int, seed: int = 2) -> torch.Tenso
     return torch.from_numpy(rng.standard_normal(size=(batch, 3, t, h, w), dtype=np.float32))
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)      # datasets/ava_frame.py:159-162
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def make_frames_u8(batch: int, t: int, h: int, w: int, seed: int = 3) -> torch.Tensor:
+    """Synthetic decoded RGB frames, uint8 (B,T,H,W,3), PCG64-seeded."""
+    rng = np.random.default_rng(seed)
+    return torch.from_numpy(rng.integers(0, 256, size=(batch, t, h, w, 3), dtype=np.uint8))
+
+
+def frames_to_clips(frames_u8: torch.Tensor, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> torch.Tensor:
+    """uint8 frames (B,T,H,W,3) -> the (B,3,T,H,W) fp32 clips the reference's input pipeline feeds the model:
+    per frame ``to_tensor`` (HWC uint8 -> CHW float32, ``.div(255)``; datasets/video_transforms.py:294-296) and
+    ``normalize`` (``.sub_(mean).div_(std)`` with fp32 mean / std; :308-314), then ``stack`` + ``permute(1,0,2,3)``
+    (datasets/ava_frame.py:71-72).  Same torch ops, batched."""
+    x = frames_u8.permute(0, 1, 4, 2, 3).to(torch.float32).div(255)            # (B,T,3,H,W)
+    m = torch.as_tensor(mean, dtype=torch.float32).view(1, 1, 3, 1, 1)
+    s = torch.as_tensor(std, dtype=torch.float32).view(1, 1, 3, 1, 1)
+    x = x.sub_(m).div_(s)
+    return x.permute(0, 2, 1, 3, 4).contiguous()
+
+
 def pad_clips(clips: List[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
     """Zero-pad a ragged list of (3,T,H,W) clips to the batch maximum and build the
     (B,H,W) bool mask, True on padding -- utils/misc.py:385-399."""

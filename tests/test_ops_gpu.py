@@ -191,3 +191,34 @@ def test_posenc(abi):
     _lib.check(_lib.load().tuber_op_posenc(abi.P(m8), abi.P(out), b, t, h, w, 256, abi.stream()))
     torch.cuda.synchronize()
     assert float((out.cpu() - ref).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 12, 20), (1, 3, 7, 9), (3, 8, 64, 64)])
+@pytest.mark.parametrize("norm", ["imagenet", "other"])
+def test_normalize_u8(abi, shape, norm):
+    """uint8 frames -> normalised fp32 clip: bit-identical to the reference's ToTensor + Normalize (restated by oracle.frames_to_clips,
+    pinned by tests/golden/input_u8.npz); T*H*W % 4 != 0 exercises the scalar path."""
+    from oracle import tuber_oracle as O
+    from tuber_b200 import _lib
+    mean, std = (O.IMAGENET_MEAN, O.IMAGENET_STD) if norm == "imagenet" else ((0.45, 0.5, 0.375), (0.225, 0.3, 0.25))
+    fr = O.make_frames_u8(*shape, seed=11)
+    ref = O.frames_to_clips(fr, mean, std)
+    B, T, H, W = shape
+    out = torch.empty((B, 3, T, H, W), device="cuda", dtype=torch.float32)
+    m, s = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    _lib.check(_lib.load().tuber_op_normalize_u8(abi.P(fr.cuda()), m, s, abi.P(out), B, T * H * W, abi.stream()))
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_normalize_u8_golden(abi):
+    import os
+    import numpy as np
+    from tuber_b200 import _lib
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "input_u8.npz"))
+    for name in ("a", "b", "table"):
+        fr, ref = torch.from_numpy(g[f"frames_{name}"]), torch.from_numpy(g[f"clips2_{name}"])
+        B, T, H, W, _ = fr.shape
+        out = torch.empty((B, 3, T, H, W), device="cuda", dtype=torch.float32)
+        m, s = (C.c_float * 3)(*[float(v) for v in g["mean2"]]), (C.c_float * 3)(*[float(v) for v in g["std2"]])
+        _lib.check(_lib.load().tuber_op_normalize_u8(abi.P(fr.cuda()), m, s, abi.P(out), B, T * H * W, abi.stream()))
+        assert torch.equal(out.cpu(), ref), name

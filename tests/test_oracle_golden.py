@@ -81,3 +81,23 @@ def test_detection_line_format_is_the_reference_file_format():
     assert lines == [str(l) for l in g["lines"]]
     parsed = [[float(x) for x in line.split(' [')[1].split(']')[0].split(',')] for line in lines]
     assert np.array_equal(np.array(parsed), g["parsed"])
+
+
+# ---- uint8 input transform ---------------------------------------------------------
+def test_input_transform_oracle_and_value_table_match_reference_golden():
+    """oracle.frames_to_clips and the library's host-side value table (tuber_input_lut, no device needed) against the
+    reference's own ToTensor + Normalize + stack + permute (tests/golden/input_u8.npz, oracle/make_golden_input.py): bit-exact."""
+    from tuber_b200 import _lib
+    g = np.load(os.path.join(GOLD, "input_u8.npz"))
+    for mk, sk, ck in (("mean", "std", "clips"), ("mean2", "std2", "clips2")):
+        mean, std = [float(v) for v in g[mk]], [float(v) for v in g[sk]]
+        lut = np.asarray(_lib.input_lut(mean, std), dtype=np.float32).reshape(3, 256)
+        for name in ("a", "b", "table"):
+            fr, ref = g[f"frames_{name}"], g[f"{ck}_{name}"]
+            got = O.frames_to_clips(torch.from_numpy(fr), mean, std).numpy()
+            assert got.shape == ref.shape
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (ck, name)
+            via_lut = np.stack([lut[c][fr[..., c]] for c in range(3)], axis=1)            # (B,3,T,H,W)
+            assert np.array_equal(via_lut.view(np.uint32), ref.view(np.uint32)), (ck, name, "lut")
+    with pytest.raises(_lib.TuberError):
+        _lib.input_lut((0.5, 0.5, 0.5), (0.2, 0.0, 0.2))                                   # zero std is refused

@@ -160,6 +160,54 @@ def test_host_entry_points_match_device_path():
         model.forward_host_wait(0)                            # nothing in flight
 
 
+def test_uint8_frames_path_is_bit_identical_to_the_float_path():
+    """tuber_forward_u8 / tuber_forward_host_u8 / ..._u8_submit on decoded uint8 frames give, bit for bit, what the fp32 entry
+    points give on the clip the reference's host transform (oracle.frames_to_clips, pinned by tests/golden/input_u8.npz) makes of
+    those frames -- and therefore the reference's outputs within the same tolerance."""
+    from oracle import tuber_oracle as O
+    cfg, sd, clips, _ = build_case("A_csn50_avg_bnrand")
+    B, _, T, H, W = clips.shape
+    model = _model(cfg, sd)
+    frames = O.make_frames_u8(B, T, H, W, seed=5)
+    as_float = O.frames_to_clips(frames)
+    ref = {k: v.cpu() for k, v in model.forward_raw(as_float.cuda()).items()}
+    got = model.forward_raw_u8(frames.cuda())
+    for k in ref:
+        assert torch.equal(got[k].cpu(), ref[k]), k
+    oracle = O.forward(cfg, sd, as_float, None)
+    for k in ("pred_logits", "pred_boxes", "pred_logits_b"):
+        emax, el2 = _rel(_layers_first(got, k), oracle[k])
+        assert emax <= TOL and el2 <= TOL, (k, emax, el2)
+    model.use_cuda_graph(True)
+    pinned = frames.pin_memory()
+    for _ in range(2):                                        # second call replays the captured graph
+        out = model.forward_host_u8(pinned)
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+    other = O.make_frames_u8(B, T, H, W, seed=6).pin_memory()
+    ref2 = {k: v.cpu() for k, v in model.forward_raw(O.frames_to_clips(other).cuda()).items()}
+    o0 = model.forward_host_u8_submit(0, pinned)
+    o1 = model.forward_host_u8_submit(1, other)
+    model.forward_host_wait(0)
+    o0b = {k: v.clone() for k, v in o0.items()}
+    o0 = model.forward_host_submit(0, O.frames_to_clips(other).pin_memory(), None, o0)      # fp32 and uint8 submissions share the slots
+    model.forward_host_wait(1)
+    model.forward_host_wait(0)
+    for k in ref:
+        assert torch.equal(o0b[k], ref[k]) and torch.equal(o1[k], ref2[k]) and torch.equal(o0[k], ref2[k]), k
+    # another mean / std: the table is replaced, results follow the oracle's transform with those constants
+    mean, std = (0.45, 0.5, 0.375), (0.225, 0.3, 0.25)
+    model.set_input_norm(mean, std)
+    ref3 = {k: v.cpu() for k, v in model.forward_raw(O.frames_to_clips(frames, mean, std).cuda()).items()}
+    got3 = model.forward_raw_u8(frames.cuda())
+    for k in ref3:
+        assert torch.equal(got3[k].cpu(), ref3[k]), k
+    with pytest.raises(ValueError):
+        model.forward_raw_u8(frames.cuda().float())           # not uint8
+    with pytest.raises(RuntimeError):
+        model.set_input_norm(mean, (0.2, 0.0, 0.2))           # zero std
+
+
 def test_no_fallback_off_device():
     import tuber_b200
     cfg, sd, clips, _ = build_case("A_csn50")

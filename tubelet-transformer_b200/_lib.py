@@ -54,6 +54,11 @@ PROTOTYPES = {
     "tuber_forward_host": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "tuber_forward_host_submit": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "tuber_forward_host_wait": (_I, [_P, _I]),
+    "tuber_input_lut": (_I, [C.POINTER(_F), C.POINTER(_F), C.POINTER(_F)]),
+    "tuber_set_input_norm": (_I, [_P, C.POINTER(_F), C.POINTER(_F)]),
+    "tuber_forward_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "tuber_forward_host_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "tuber_forward_host_u8_submit": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "tuber_query_shapes": (_I, [_P, _I, _I, _I, _I, C.POINTER(TuberShapeInfo)]),
     "tuber_set_graph": (_I, [_P, _I]),
     "tuber_set_force_simt": (_I, [_P, _I]),
@@ -76,6 +81,7 @@ PROTOTYPES = {
     "tuber_op_stem": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "tuber_op_layernorm": (_I, [_P, _P, _P, _P, _P, _L, _I, _P]),
     "tuber_op_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "tuber_op_normalize_u8": (_I, [_P, C.POINTER(_F), C.POINTER(_F), _P, _I, _L, _P]),
     "tuber_op_posenc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
 }
 
@@ -99,6 +105,13 @@ def load() -> C.CDLL:
         raise ImportError("libtuber_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+def input_lut(mean, std):
+    """The 3 x 256 value table of the reference's ToTensor + Normalize (host-only; tuber_input_lut) as a list of 768 floats."""
+    m, s, out = (_F * 3)(*mean), (_F * 3)(*std), (_F * 768)()
+    check(load().tuber_input_lut(m, s, out))
+    return list(out)
 
 
 def check(status: int) -> None:

@@ -119,6 +119,10 @@ cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);
 cudaError_t launch_postprocess(const float* logits, long long l_sb, const float* boxes, long long b_sb, const float* logits_b,
                                long long lb_sb, const float* sizes, float* out, int B, int Q, int C, int ava, cudaStream_t st);
 
+// ---- uint8 frames -> normalised fp32 clip (video_transforms.py:294-296,308-314; ava_frame.py:71-72) ------------
+// frames [B][pixels_per_clip = T*H*W][3] uint8 (RGB, HWC), lut [3][256] fp32 (see tuber_set_input_norm), out [B][3][pixels_per_clip] fp32
+cudaError_t launch_normalize_u8(const uint8_t* frames, const float* lut, float* out, int B, long long pixels_per_clip, cudaStream_t st);
+
 // ---- masks and position code (backbone_builder.py:85-86, position_encoding.py:32-72) ------
 cudaError_t launch_mask_resize(const uint8_t* mask, uint8_t* fmask, int B, int H, int W, int T, int Hf,
                                int Wf, cudaStream_t st);

@@ -1393,6 +1393,61 @@ cudaError_t launch_postprocess(const float* logits, long long l_sb, const float*
 }
 
 // =============================================================================================
+// uint8 frames -> normalised fp32 clip: the reference's ToTensor + Normalize + stack + permute
+// (datasets/video_transforms.py:294-296,308-314; datasets/ava_frame.py:71-72) on the device, so that the host ships 3 bytes per
+// pixel instead of 12.  in [B][T*H*W pixels][3] (decoded RGB frames, HWC), out [B][3][T*H*W] = NestedTensor.tensors.
+// lut[c][u] = ((float)u / 255 - mean[c]) / std[c], evaluated on the host in fp32 exactly as torch evaluates it: bit-identical
+// to the reference transform.  HBM bound: 3 B read + 12 B written per pixel.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+normalize_u8_kernel(const uint8_t* __restrict__ in, const float* __restrict__ lut, float* __restrict__ out, long long P, int B, int vec) {
+  __shared__ float s_lut[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = __ldg(lut + i);
+  __syncthreads();
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+  if (vec) {                                                         // P % 4 == 0, aligned bases: 4 pixels = 12 bytes = three words per thread step
+    const long long G = P >> 2, total = G * B;
+    for (long long g = tid; g < total; g += nthr) {
+      const long long b = g / G, p4 = g - b * G;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (b * P + 4 * p4) * 3);
+      const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);   // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+      float* o = out + b * 3 * P + 4 * p4;
+      const float4 r = make_float4(s_lut[w0 & 255u], s_lut[w0 >> 24], s_lut[(w1 >> 16) & 255u], s_lut[(w2 >> 8) & 255u]);
+      const float4 gg = make_float4(s_lut[256 + ((w0 >> 8) & 255u)], s_lut[256 + (w1 & 255u)], s_lut[256 + (w1 >> 24)],
+                                    s_lut[256 + ((w2 >> 16) & 255u)]);
+      const float4 bb = make_float4(s_lut[512 + ((w0 >> 16) & 255u)], s_lut[512 + ((w1 >> 8) & 255u)], s_lut[512 + (w2 & 255u)],
+                                    s_lut[512 + (w2 >> 24)]);
+      *reinterpret_cast<float4*>(o) = r;
+      *reinterpret_cast<float4*>(o + P) = gg;
+      *reinterpret_cast<float4*>(o + 2 * P) = bb;
+    }
+  } else {
+    const long long total = P * B;
+    for (long long i = tid; i < total; i += nthr) {
+      const long long b = i / P, px = i - b * P;
+      const uint8_t* src = in + i * 3;
+      float* o = out + b * 3 * P + px;
+      o[0] = s_lut[src[0]];
+      o[P] = s_lut[256 + src[1]];
+      o[2 * P] = s_lut[512 + src[2]];
+    }
+  }
+}
+
+cudaError_t launch_normalize_u8(const uint8_t* frames, const float* lut, float* out, int B, long long pixels_per_clip, cudaStream_t st) {
+  if (B <= 0 || pixels_per_clip <= 0) return cudaErrorInvalidValue;
+  const int vec = (pixels_per_clip & 3) == 0 && (reinterpret_cast<uintptr_t>(frames) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const long long work = vec ? (pixels_per_clip >> 2) * B : pixels_per_clip * B;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long want = ceil_div(work, 256);
+  const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);   // 8 resident CTAs per SM, grid-stride
+  normalize_u8_kernel<<<grid, 256, 0, st>>>(frames, lut, out, pixels_per_clip, B, vec);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
 // Padding mask at feature resolution and the 3-D sine position code
 // =============================================================================================
 // nearest-neighbour resize (B,H,W) -> (B,T,Hf,Wf), repeated over T  (backbone_builder.py:85-86)

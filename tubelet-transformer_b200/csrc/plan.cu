@@ -143,6 +143,9 @@ struct TuberPlan {
   cudaStream_t copy_stream = nullptr, run_stream = nullptr, out_stream = nullptr;
   cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr}, fwd_done[2] = {nullptr, nullptr};
   bool slot_busy[2] = {false, false};
+  // uint8 input path (tuber_forward_u8*): value table of the reference's ToTensor + Normalize and the fp32 clip it expands into
+  float* in_lut = nullptr;           // [3][256] on the device
+  float* u8_clip = nullptr; size_t u8_clip_cap = 0;
   bool force_simt = false, no_fuse2 = false, pool_unfolded = false, no_strided_tma = false;
   bool profiling = false, debug_keep = false, use_graph = false;
   cudaEvent_t ev[TUBER_NUM_STAGES + 1] = {};
@@ -1127,6 +1130,8 @@ void tuber_plan_destroy(TuberPlan* p) {
   for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   if (p->ws) cudaFree(p->ws);
+  if (p->in_lut) cudaFree(p->in_lut);
+  if (p->u8_clip) cudaFree(p->u8_clip);
   for (int i = 0; i < 2; ++i) {
     if (p->stage_in[i]) cudaFree(p->stage_in[i]);
     if (p->stage_out[i]) cudaFree(p->stage_out[i]);
@@ -1243,14 +1248,51 @@ int tuber_forward(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev,
 
 namespace {
 
+// The value table of the reference's input transform: to_tensor (uint8 -> float32, / 255) followed by Normalize
+// ((x - mean) / std), datasets/video_transforms.py:294-296,308-314, evaluated per channel and byte value in fp32 the way torch does
+// (volatile: no contraction, no double-precision intermediates).
+void build_input_lut(const float mean[3], const float stdv[3], float* lut) {
+  for (int c = 0; c < 3; ++c)
+    for (int u = 0; u < 256; ++u) {
+      volatile float v = (float)u;
+      v = v / 255.0f;
+      v = v - mean[c];
+      v = v / stdv[c];
+      lut[c * 256 + u] = v;
+    }
+}
+
+int upload_input_lut(TuberPlan* p, const float mean[3], const float stdv[3]) {
+  float lut[768];
+  build_input_lut(mean, stdv, lut);
+  CK(cudaSetDevice(p->device));
+  CK(cudaDeviceSynchronize());                                      // forwards in flight may still read the old table
+  if (!p->in_lut) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, sizeof(lut)));
+    p->in_lut = (float*)q;
+  }
+  CK(cudaMemcpy(p->in_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+  return TUBER_OK;
+}
+
+const float kImageNetMean[3] = {0.485f, 0.456f, 0.406f}, kImageNetStd[3] = {0.229f, 0.224f, 0.225f};   // ava_frame.py:159-162
+
+int ensure_input_lut(TuberPlan* p) { return p->in_lut ? TUBER_OK : upload_input_lut(p, kImageNetMean, kImageNetStd); }
+
 // H2D (+mask) -> forward -> D2H of one batch through staging slot `slot`.  `in_st` carries the input copies,
 // `st` the kernels and the output copies; the caller decides whether they are the same stream.
-int host_step(TuberPlan* p, int slot, const float* clips_host, const uint8_t* mask_host, int B, int T, int H, int W,
-              float* logits_host, float* boxes_host, float* logits_b_host, cudaStream_t in_st, cudaStream_t st,
+// `frames_host` (uint8 [B,T,H,W,3]) replaces `clips_host` on the uint8 path: 3 bytes per pixel cross the bus and
+// normalize_u8_kernel expands them into the slot's fp32 clip buffer on `st` before the forward.
+int host_step(TuberPlan* p, int slot, const float* clips_host, const uint8_t* frames_host, const uint8_t* mask_host, int B, int T, int H,
+              int W, float* logits_host, float* boxes_host, float* logits_b_host, cudaStream_t in_st, cudaStream_t st,
               cudaStream_t out_st = nullptr) {
   const TuberConfig& c = p->cfg;
   const size_t clip_bytes = (size_t)B * 3 * T * H * W * 4, mask_bytes = mask_host ? (size_t)B * H * W : 0;
-  const size_t in_need = clip_bytes + ((mask_bytes + 255) & ~(size_t)255) + 256;
+  const size_t mask_room = ((mask_bytes + 255) & ~(size_t)255) + 256;
+  const size_t u8_bytes = frames_host ? (size_t)B * 3 * T * H * W : 0;
+  const size_t in_need = clip_bytes + mask_room + u8_bytes;
+  if (frames_host) TRY(ensure_input_lut(p));
   const size_t n_logits = (size_t)B * c.dec_layers * c.num_queries * c.num_classes, n_boxes = (size_t)B * c.dec_layers * c.num_queries * 4;
   const size_t n_lb = c.ava_mode ? (size_t)B * c.dec_layers * c.num_queries * 3 : (size_t)B * 2;
   const size_t out_need = (n_logits + n_boxes + n_lb) * 4 + 1024;
@@ -1275,12 +1317,15 @@ int host_step(TuberPlan* p, int slot, const float* clips_host, const uint8_t* ma
   float* d_logits = (float*)p->stage_out[slot];
   float* d_boxes = d_logits + ((n_logits + 63) & ~(size_t)63);
   float* d_lb = d_boxes + ((n_boxes + 63) & ~(size_t)63);
-  CK(cudaMemcpyAsync(d_clips, clips_host, clip_bytes, cudaMemcpyHostToDevice, in_st));
+  uint8_t* d_frames = reinterpret_cast<uint8_t*>(p->stage_in[slot] + clip_bytes + mask_room);
+  if (frames_host) CK(cudaMemcpyAsync(d_frames, frames_host, u8_bytes, cudaMemcpyHostToDevice, in_st));
+  else CK(cudaMemcpyAsync(d_clips, clips_host, clip_bytes, cudaMemcpyHostToDevice, in_st));
   if (mask_host) CK(cudaMemcpyAsync(d_mask, mask_host, mask_bytes, cudaMemcpyHostToDevice, in_st));
   if (in_st != st) {
     CK(cudaEventRecord(p->h2d_done[slot], in_st));
     CK(cudaStreamWaitEvent(st, p->h2d_done[slot], 0));
   }
+  if (frames_host) CK(launch_normalize_u8(d_frames, p->in_lut, d_clips, B, (long long)T * H * W, st));
   TRY(tuber_forward(p, d_clips, d_mask, B, T, H, W, d_logits, d_boxes, d_lb, st));
   // pipelined form: the result copies run on their own stream so that the next slot's kernels are not held up by them
   cudaStream_t ost = st;
@@ -1317,7 +1362,7 @@ int tuber_forward_host(TuberPlan* p, const float* clips_host, const uint8_t* mas
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   for (int i = 0; i < 2; ++i)
     if (p->slot_busy[i]) return fail(TUBER_ERR_STATE, "tuber_forward_host while an asynchronous submission is in flight");
-  TRY(host_step(p, 0, clips_host, mask_host, B, T, H, W, logits_host, boxes_host, logits_b_host, st, st));
+  TRY(host_step(p, 0, clips_host, nullptr, mask_host, B, T, H, W, logits_host, boxes_host, logits_b_host, st, st));
   CK(cudaStreamSynchronize(st));
   return TUBER_OK;
 }
@@ -1329,7 +1374,7 @@ int tuber_forward_host_submit(TuberPlan* p, int32_t slot, const float* clips_hos
   if (!clips_host || !logits_host || !boxes_host || !logits_b_host) return fail(TUBER_ERR_INVALID, "null host pointer");
   if (p->slot_busy[slot]) return fail(TUBER_ERR_STATE, "slot %d still in flight: call tuber_forward_host_wait first", slot);
   TRY(ensure_host_pipeline(p));
-  TRY(host_step(p, slot, clips_host, mask_host, B, T, H, W, logits_host, boxes_host, logits_b_host, p->copy_stream, p->run_stream,
+  TRY(host_step(p, slot, clips_host, nullptr, mask_host, B, T, H, W, logits_host, boxes_host, logits_b_host, p->copy_stream, p->run_stream,
                 p->out_stream));
   CK(cudaEventRecord(p->slot_done[slot], p->out_stream));
   p->slot_busy[slot] = true;
@@ -1342,6 +1387,69 @@ int tuber_forward_host_wait(TuberPlan* p, int32_t slot) {
   if (!p->slot_busy[slot]) return fail(TUBER_ERR_STATE, "slot %d has no submission in flight", slot);
   CK(cudaEventSynchronize(p->slot_done[slot]));
   p->slot_busy[slot] = false;
+  return TUBER_OK;
+}
+
+// ---- uint8 input path -------------------------------------------------------------------------
+int tuber_input_lut(const float* mean, const float* stdv, float* lut_out) {
+  if (!mean || !stdv || !lut_out) return fail(TUBER_ERR_INVALID, "null argument");
+  for (int c = 0; c < 3; ++c)
+    if (!(stdv[c] != 0.f)) return fail(TUBER_ERR_INVALID, "std[%d] is zero or NaN", c);
+  build_input_lut(mean, stdv, lut_out);
+  return TUBER_OK;
+}
+
+int tuber_set_input_norm(TuberPlan* p, const float* mean, const float* stdv) {
+  if (!p || !mean || !stdv) return fail(TUBER_ERR_INVALID, "null argument");
+  for (int c = 0; c < 3; ++c)
+    if (!(stdv[c] != 0.f)) return fail(TUBER_ERR_INVALID, "std[%d] is zero or NaN", c);
+  for (int i = 0; i < 2; ++i)
+    if (p->slot_busy[i]) return fail(TUBER_ERR_STATE, "tuber_set_input_norm while an asynchronous submission is in flight");
+  return upload_input_lut(p, mean, stdv);
+}
+
+int tuber_forward_u8(TuberPlan* p, const uint8_t* frames_dev, const uint8_t* mask_dev, int32_t B, int32_t T, int32_t H, int32_t W,
+                     float* logits_dev, float* boxes_dev, float* logits_b_dev, void* stream) {
+  TRY(check_forward_args(p, B, T, H, W));
+  if (!frames_dev || !logits_dev || !boxes_dev || !logits_b_dev) return fail(TUBER_ERR_INVALID, "null device pointer");
+  TRY(ensure_input_lut(p));
+  const size_t need = (size_t)B * 3 * T * H * W * 4;
+  if (need > p->u8_clip_cap) {
+    CK(cudaDeviceSynchronize());
+    if (p->u8_clip) cudaFree(p->u8_clip);
+    p->u8_clip = nullptr; p->u8_clip_cap = 0;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, need);
+    if (e != cudaSuccess) return fail(TUBER_ERR_CUDA, "clip buffer of %zu bytes: %s", need, cudaGetErrorString(e));
+    p->u8_clip = (float*)q; p->u8_clip_cap = need;
+  }
+  CK(launch_normalize_u8(frames_dev, p->in_lut, p->u8_clip, B, (long long)T * H * W, reinterpret_cast<cudaStream_t>(stream)));
+  return tuber_forward(p, p->u8_clip, mask_dev, B, T, H, W, logits_dev, boxes_dev, logits_b_dev, stream);
+}
+
+int tuber_forward_host_u8(TuberPlan* p, const uint8_t* frames_host, const uint8_t* mask_host, int32_t B, int32_t T, int32_t H,
+                          int32_t W, float* logits_host, float* boxes_host, float* logits_b_host, void* stream) {
+  TRY(check_forward_args(p, B, T, H, W));
+  if (!frames_host || !logits_host || !boxes_host || !logits_b_host) return fail(TUBER_ERR_INVALID, "null host pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int i = 0; i < 2; ++i)
+    if (p->slot_busy[i]) return fail(TUBER_ERR_STATE, "tuber_forward_host_u8 while an asynchronous submission is in flight");
+  TRY(host_step(p, 0, nullptr, frames_host, mask_host, B, T, H, W, logits_host, boxes_host, logits_b_host, st, st));
+  CK(cudaStreamSynchronize(st));
+  return TUBER_OK;
+}
+
+int tuber_forward_host_u8_submit(TuberPlan* p, int32_t slot, const uint8_t* frames_host, const uint8_t* mask_host, int32_t B, int32_t T,
+                                 int32_t H, int32_t W, float* logits_host, float* boxes_host, float* logits_b_host) {
+  TRY(check_forward_args(p, B, T, H, W));
+  if (slot < 0 || slot > 1) return fail(TUBER_ERR_INVALID, "slot must be 0 or 1");
+  if (!frames_host || !logits_host || !boxes_host || !logits_b_host) return fail(TUBER_ERR_INVALID, "null host pointer");
+  if (p->slot_busy[slot]) return fail(TUBER_ERR_STATE, "slot %d still in flight: call tuber_forward_host_wait first", slot);
+  TRY(ensure_host_pipeline(p));
+  TRY(host_step(p, slot, nullptr, frames_host, mask_host, B, T, H, W, logits_host, boxes_host, logits_b_host, p->copy_stream,
+                p->run_stream, p->out_stream));
+  CK(cudaEventRecord(p->slot_done[slot], p->out_stream));
+  p->slot_busy[slot] = true;
   return TUBER_OK;
 }
 
@@ -1523,6 +1631,22 @@ int tuber_op_attention(const float* q, const float* k, const float* v, const uin
   CK(launch_attention(a, (cudaStream_t)stream));
   return TUBER_OK;
 }
+int tuber_op_normalize_u8(const uint8_t* frames, const float* mean, const float* stdv, float* out, int32_t B, int64_t pixels_per_clip,
+                          void* stream) {
+  if (!frames || !mean || !stdv || !out || B <= 0 || pixels_per_clip <= 0) return fail(TUBER_ERR_INVALID, "bad argument");
+  float lut[768];
+  TRY(tuber_input_lut(mean, stdv, lut));
+  void* d = nullptr;
+  CK(cudaMalloc(&d, sizeof(lut)));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(d, lut, sizeof(lut), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = launch_normalize_u8(frames, (const float*)d, out, B, pixels_per_clip, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(TUBER_ERR_CUDA, "normalize_u8: %s", cudaGetErrorString(e));
+  return TUBER_OK;
+}
+
 int tuber_op_posenc(const uint8_t* fmask, float* pos, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d_model, void* stream) {
   const int nt = d_model / 8 * 2, ns = d_model / 8 * 3;
   std::vector<float> dt(nt), ds(ns);

@@ -315,6 +315,83 @@ class DETR(nn.Module):
     def forward_host_wait(self, slot: int) -> None:
         _lib.check(_lib.load().tuber_forward_host_wait(self.plan(), slot))
 
+    # -- uint8 frames in (tuber_forward_u8*, include/tuber_b200.h) -------
+    IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      # datasets/ava_frame.py:159-162
+
+    def set_input_norm(self, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> None:
+        """mean / std of the on-device ToTensor + Normalize applied to uint8 frames (video_transforms.py:294-296,308-314)."""
+        m, s = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+        with torch.cuda.device(self._device()):
+            _lib.check(_lib.load().tuber_set_input_norm(self.plan(), m, s))
+
+    @staticmethod
+    def _u8_shape(frames: Tensor):
+        if frames.dtype != torch.uint8 or frames.dim() != 5 or frames.shape[-1] != 3 or not frames.is_contiguous():
+            raise ValueError("frames must be a contiguous uint8 (B,T,H,W,3) tensor (decoded RGB frames)")
+        B, T, H, W, _ = frames.shape
+        return B, T, H, W
+
+    @torch.no_grad()
+    def forward_raw_u8(self, frames: Tensor, mask: Optional[Tensor] = None,
+                       out: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+        """`forward_raw` on decoded frames: uint8 (B,T,H,W,3) RGB on the model's device; normalisation + layout change run on the
+        GPU and feed the stem with exactly the values the reference's host transform would."""
+        if self.training:
+            raise RuntimeError("tuber_b200 implements the inference forward only; call model.eval()")
+        dev = self._device()
+        plan = self.plan()
+        frames = frames.to(device=dev)
+        B, T, H, W = self._u8_shape(frames)
+        mptr = None
+        if mask is not None:
+            if tuple(mask.shape) != (B, H, W):
+                raise ValueError("mask must be (B,H,W)")
+            mask = mask.to(device=dev).to(torch.uint8).contiguous()
+            mptr = C.c_void_p(mask.data_ptr())
+        L, Q = self.dec_layers, self.num_queries
+        if out is None:
+            out = {"pred_logits": torch.empty((B, L, Q, self.num_class_out), device=dev, dtype=torch.float32),
+                   "pred_boxes": torch.empty((B, L, Q, 4), device=dev, dtype=torch.float32),
+                   "pred_logits_b": torch.empty((B, L, Q, 3) if self.dataset_mode == "ava" else (B, 2),
+                                                device=dev, dtype=torch.float32)}
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().tuber_forward_u8(plan, C.c_void_p(frames.data_ptr()), mptr, B, T, H, W,
+                                                    C.c_void_p(out["pred_logits"].data_ptr()),
+                                                    C.c_void_p(out["pred_boxes"].data_ptr()),
+                                                    C.c_void_p(out["pred_logits_b"].data_ptr()), C.c_void_p(stream)))
+        return out
+
+    def _host_args_u8(self, frames: Tensor, mask: Optional[Tensor], out: Dict[str, Tensor]):
+        if frames.device.type != "cpu":
+            raise ValueError("frames must live in (pinned) host memory")
+        B, T, H, W = self._u8_shape(frames)
+        mptr = None
+        if mask is not None:
+            if mask.device.type != "cpu" or mask.dtype != torch.uint8 or not mask.is_contiguous() or tuple(mask.shape) != (B, H, W):
+                raise ValueError("mask must be a contiguous uint8 (B,H,W) host tensor")
+            mptr = C.c_void_p(mask.data_ptr())
+        return (C.c_void_p(frames.data_ptr()), mptr, B, T, H, W, C.c_void_p(out["pred_logits"].data_ptr()),
+                C.c_void_p(out["pred_boxes"].data_ptr()), C.c_void_p(out["pred_logits_b"].data_ptr()))
+
+    @torch.no_grad()
+    def forward_host_u8(self, frames: Tensor, mask: Optional[Tensor] = None, out: Optional[Dict[str, Tensor]] = None):
+        """Host uint8 frames -> H2D (3 bytes per pixel) -> normalise -> forward -> D2H, synchronous."""
+        out = out if out is not None else self._host_out(frames.shape[0])
+        with torch.cuda.device(self._device()):
+            stream = C.c_void_p(torch.cuda.current_stream(self._device()).cuda_stream)
+            _lib.check(_lib.load().tuber_forward_host_u8(self.plan(), *self._host_args_u8(frames, mask, out), stream))
+        return out
+
+    @torch.no_grad()
+    def forward_host_u8_submit(self, slot: int, frames: Tensor, mask: Optional[Tensor] = None,
+                               out: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+        """Pipelined form of `forward_host_u8` (same slots and `forward_host_wait` as `forward_host_submit`)."""
+        out = out if out is not None else self._host_out(frames.shape[0])
+        with torch.cuda.device(self._device()):
+            _lib.check(_lib.load().tuber_forward_host_u8_submit(self.plan(), slot, *self._host_args_u8(frames, mask, out)))
+        return out
+
     def forward(self, samples: Union[NestedTensor, List[Tensor], Tensor]):
         if isinstance(samples, (list, tuple)):
             samples = nested_tensor_from_tensor_list(list(samples))            # tuber_ava.py:112-113
