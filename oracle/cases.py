@@ -35,6 +35,14 @@ CASES = {
     "C_mid": dict(yaml="TubeR_CSN152_AVA21.yaml", over=[], clips=[(32, 128, 128)], wseed=0, cseed=2, bn="identity"),
     "D_small": dict(yaml="TubeR_CSN152_AVA22.yaml", over=[], clips=[(32, 64, 64)], wseed=6, cseed=7, bn="random"),
     "E_small": dict(yaml="Tuber_CSN152_JHMDB.yaml", over=[], clips=[(16, 64, 64)] * 2, wseed=8, cseed=9, bn="random"),
+    # the sizes the reference's evaluation transform really produces are not multiples of anything: Resize_Custom keeps the aspect
+    # ratio (datasets/video_transforms.py:213-228: 256 x int(256 * w / h) = 256x341 for 4:3, 256x455 for 16:9; JHMDB 224x298),
+    # and a batch mixes videos of different widths.  Scaled down by 4 here; the full sizes run against the live oracle on the GPU box
+    "B_odd": dict(yaml="TubeR_CSN50_AVA21.yaml", over=[], clips=[(32, 64, 85), (32, 64, 113)], wseed=12, cseed=13, bn="random"),
+    "C_odd": dict(yaml="TubeR_CSN152_AVA21.yaml", over=[], clips=[(32, 64, 113), (32, 75, 100)], wseed=14, cseed=15, bn="random"),
+    "E_odd": dict(yaml="Tuber_CSN152_JHMDB.yaml", over=[], clips=[(16, 56, 75)], wseed=16, cseed=17, bn="random"),
+    # conv rows wider than 128 outputs (W > 256): the stem takes its single-CTA kernel + separate max pool
+    "B_wide": dict(yaml="TubeR_CSN50_AVA21.yaml", over=[], clips=[(8, 40, 341)], wseed=18, cseed=19, bn="random"),
     "C_long": dict(yaml="TubeR_CSN152_AVA21.yaml", over=[], clips=[(64, 64, 64)], wseed=10, cseed=11, bn="random"),
 }
 

@@ -208,6 +208,35 @@ def test_uint8_frames_path_is_bit_identical_to_the_float_path():
         model.set_input_norm(mean, (0.2, 0.0, 0.2))           # zero std
 
 
+@pytest.mark.parametrize("yaml,shapes", [("TubeR_CSN50_AVA21.yaml", [(32, 256, 341)]),
+                                         ("TubeR_CSN50_AVA21.yaml", [(32, 256, 455), (32, 256, 341)]),
+                                         ("Tuber_CSN152_JHMDB.yaml", [(16, 224, 298)])])
+def test_real_evaluation_sizes_match_oracle(yaml, shapes):
+    """The clip sizes the reference's evaluation transform actually produces (Resize_Custom keeps the aspect ratio,
+    datasets/video_transforms.py:213-228: 256x341 / 256x455 on AVA, 224x298 on JHMDB; a batch mixes widths and is zero-padded with a
+    mask, utils/misc.py:367-402) at FULL size against the CPU oracle run here on the same seeded inputs."""
+    import tuber_b200
+    from oracle import tuber_oracle as O
+    cfg = tuber_b200.load_cfg(yaml)
+    sd = O.make_state_dict(cfg, seed=21, bn="random")
+    clips = [O.make_clips(1, t, h, w, seed=30 + i)[0] for i, (t, h, w) in enumerate(shapes)]
+    if len(clips) > 1:
+        batch, mask = O.pad_clips(clips)
+    else:
+        batch, mask = clips[0][None], None
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = O.forward(cfg, sd, batch, mask)
+    model = _model(cfg, sd)
+    model.use_cuda_graph(True)
+    for _ in range(2):                                        # eager + recorded, then graph replay
+        got = model.forward_raw(batch.cuda(), None if mask is None else mask.cuda())
+        torch.cuda.synchronize()
+        for k in ("pred_logits", "pred_boxes", "pred_logits_b"):
+            r = ref[k][-1] if got[k].dim() == 2 else ref[k]
+            emax, el2 = _rel(_layers_first(got, k), r)
+            assert emax <= TOL and el2 <= TOL, (yaml, shapes, k, emax, el2)
+
+
 def test_no_fallback_off_device():
     import tuber_b200
     cfg, sd, clips, _ = build_case("A_csn50")
