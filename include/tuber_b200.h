@@ -119,6 +119,23 @@ int tuber_forward_host_u8(TuberPlan* plan, const uint8_t* frames_host, const uin
 int tuber_forward_host_u8_submit(TuberPlan* plan, int32_t slot, const uint8_t* frames_host, const uint8_t* mask_host, int32_t B,
                                  int32_t T, int32_t H, int32_t W, float* logits_host, float* boxes_host, float* logits_b_host);
 
+/* ---- long-term context bank (BASELINE.json configs[3]) ------------------------------------------
+ * NOT IN THE REFERENCE: its README (README.md:16-18,86) announces the long-term context variant but the code was never
+ * released, so this layer is defined here, after the paper's description, and has no reference parity (its oracle is
+ * oracle/tuber_oracle.py::forward(bank=...)).  Definition:
+ *   bank entry of a clip   e = mean over the T' feature frames of class_proj(xt)             -> (H'W' tokens, d) fp32
+ *   context layer          mem_c <- LayerNorm(mem_c + MHA_8heads(q = mem_c, k = v = bank))   (weights ltc_attn.*, ltc_norm.*)
+ * applied to the class-branch tokens between the class encoder (tuber_ava.py:133-135) and the class cross-attention (:137-139).
+ * bank_dev: fp32 (bank_clips, bank_tokens, d), bank_clips = 1 (one window shared by the batch) or B (one window per clip),
+ * typically the entries of the 64 clips around the current one (16 384 tokens); NULL = no context layer (fill pass).
+ * bank_new_dev: fp32 (B, H'W', d), receives this batch's entries; NULL = not wanted.  Everything else as tuber_forward.
+ * The layer exists when the state_dict streamed through tuber_plan_set_weight held ltc_attn.in_proj_weight / in_proj_bias /
+ * out_proj.weight / out_proj.bias and ltc_norm.weight / bias (tuber_has_ltc). */
+int tuber_has_ltc(TuberPlan* plan);
+int tuber_forward_ltc(TuberPlan* plan, const float* clips_dev, const uint8_t* mask_dev, int32_t B, int32_t T, int32_t H, int32_t W,
+                      const float* bank_dev, int32_t bank_clips, int32_t bank_tokens, float* bank_new_dev, float* logits_dev,
+                      float* boxes_dev, float* logits_b_dev, void* stream);
+
 /* Output geometry for an input shape: feature-map size after the backbone (T',H',W'), tokens seen
  * by the DETR encoder, number of kernel launches one forward issues. */
 typedef struct TuberShapeInfo {
@@ -164,7 +181,7 @@ int tuber_set_kernel_profiling(TuberPlan* plan, int32_t enabled);
 int tuber_get_kernel_profile(TuberPlan* plan, TuberKernelStat* out, int32_t capacity, int32_t* n_out);
 /* Copy an intermediate of the last forward to fp32 device memory, for tests:
  * "xt" (B,T',H',W',2048) channels-last, "xs" (B,tokens,2048), "src" / "memory" (B,tokens,d),
- * "hs" (B,L,Q,d), "mem_c" (B,T'H'W',d), "pos" (B or 1,tokens,d); with debug-keep also "stem",
+ * "hs" (B,L,Q,d), "mem_c" (B,T'H'W',d), "mem_ltc" (same, after the context layer), "pos" (B or 1,tokens,d); with debug-keep also "stem",
  * "layer1".."layer4" (B,T,H,W,C) channels-last.  Returns element count through *n_out; dst_dev may be NULL to query. */
 int tuber_debug_fetch(TuberPlan* plan, const char* what, float* dst_dev, int64_t* n_out, void* stream);
 

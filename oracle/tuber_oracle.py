@@ -195,6 +195,31 @@ def make_state_dict(cfg, seed: int = 0, bn: str = "identity") -> Dict[str, torch
     return sd
 
 
+def ltc_param_spec(cfg) -> List[Tuple[str, tuple, str]]:
+    """Parameters of the long-term context layer.  NOT IN THE REFERENCE (announced in its README.md:16-18,86,
+    never released): defined in this repository, see ``forward(bank=...)``; kept out of ``param_spec`` so that the reference-pinned
+    state_dict and every golden fixture stay what they are."""
+    d = _m(cfg).D_MODEL
+    return _mha_spec("ltc_attn", d) + _ln_spec("ltc_norm", d)
+
+
+def make_ltc_state_dict(cfg, seed: int = 100) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic weights of the long-term context layer (same distributions as ``make_state_dict``)."""
+    rng = np.random.default_rng(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for name, shape, kind in ltc_param_spec(cfg):
+        if kind == "linear":
+            a = rng.uniform(-math.sqrt(3.0 / shape[1]), math.sqrt(3.0 / shape[1]), size=shape)
+        elif kind == "bias":
+            a = rng.uniform(-0.1, 0.1, size=shape)
+        elif kind == "ln_weight":
+            a = rng.uniform(0.8, 1.2, size=shape)
+        else:
+            a = 0.05 * rng.standard_normal(size=shape)
+        sd[name] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return sd
+
+
 def make_clips(batch: int, t: int, h: int, w: int, seed: int = 2) -> torch.Tensor:
     """Synthetic ImageNet-normalised clips (B,3,T,H,W), N(0,1), PCG64-seeded."""
     rng = np.random.default_rng(seed)
@@ -456,13 +481,18 @@ def class_encoder(sd, src_c: torch.Tensor, nhead: int = 8) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------
 @torch.no_grad()
 def forward(cfg, sd: Dict[str, torch.Tensor], clips: torch.Tensor, mask: Optional[torch.Tensor] = None,
-            taps: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+            taps: Optional[dict] = None, bank: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """DETR.forward (tuber_ava.py:97-148) in eval mode.
 
     clips (B,3,T,H,W) fp32, mask (B,H,W) bool (True = padding; None = no padding).
     Returns 'pred_logits' (L,B,Q,C), 'pred_boxes' (L,B,Q,4), 'pred_logits_b' (L,B,Q,3)
     [ava] or (L,B,2) [otherwise] for ALL decoder layers L (the reference's dict holds index
     -1 and, under AUX_LOSS, the first L-1 as 'aux_outputs', :144-157).
+
+    ``bank`` (Bb, Nb, d) with Bb in {1, B}: long-term context window -- NO REFERENCE COUNTERPART ("parity unpinned"): the
+    reference's README announces TubeR with long-term context but the code was never released.  Defined here after the paper:
+    a clip's bank entry is class_proj(xt) averaged over the T' feature frames (returned as taps['bank_new'], (B, H'W', d)); the
+    class-branch tokens attend over the window, post-norm: mem_c <- LN(mem_c + MHA(mem_c, bank, bank)) with ``ltc_attn`` / ``ltc_norm``.
     """
     m = _m(cfg)
     if m.NORMALIZE_BEFORE:
@@ -500,6 +530,12 @@ def forward(cfg, sd: Dict[str, torch.Tensor], clips: torch.Tensor, mask: Optiona
     mem_c = class_encoder(sd, src_c)                               # (B, T'H'W', d)
     if taps is not None:
         taps["mem_c"] = mem_c
+        taps["bank_new"] = src_c.mean(dim=2).flatten(2).transpose(1, 2).contiguous()        # (B, H'W', d)
+    if bank is not None:                                           # long-term context layer (in-repo definition, see docstring)
+        kb = bank.expand(bs, -1, -1)
+        mem_c = _ln(sd, "ltc_norm", mem_c + mha(sd, "ltc_attn", mem_c, kb, kb, 8))
+        if taps is not None:
+            taps["mem_ltc"] = mem_c
     q = hs.permute(1, 0, 2, 3).reshape(bs, nl * nq, d)             # every layer's queries of a clip
     q_class = mha(sd, "cross_attn", q, mem_c, mem_c, 8)
     q_class = q_class.view(bs, nl, nq, d).permute(1, 0, 2, 3)

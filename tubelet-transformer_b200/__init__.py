@@ -12,8 +12,9 @@ sm_100a kernels of ``csrc/`` behind the C-ABI declared in ``include/tuber_b200.h
 from .config import CfgNode, get_cfg_defaults, load_cfg  # noqa: F401
 from .models.tuber_ava import DETR, PostProcess, PostProcessAVA, build_model, format_detection_lines  # noqa: F401
 from .utils.misc import NestedTensor, nested_tensor_from_tensor_list  # noqa: F401
+from .utils.context_bank import ContextBank  # noqa: F401
 from .distributed import gather_detections, pack_detections, shard_range, unpack_detections  # noqa: F401
 
 __all__ = ["CfgNode", "get_cfg_defaults", "load_cfg", "DETR", "build_model", "PostProcess", "PostProcessAVA",
            "NestedTensor", "nested_tensor_from_tensor_list", "shard_range", "pack_detections",
-           "unpack_detections", "gather_detections", "format_detection_lines"]
+           "unpack_detections", "gather_detections", "format_detection_lines", "ContextBank"]

@@ -59,6 +59,8 @@ PROTOTYPES = {
     "tuber_forward_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "tuber_forward_host_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "tuber_forward_host_u8_submit": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "tuber_has_ltc": (_I, [_P]),
+    "tuber_forward_ltc": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P]),
     "tuber_query_shapes": (_I, [_P, _I, _I, _I, _I, C.POINTER(TuberShapeInfo)]),
     "tuber_set_graph": (_I, [_P, _I]),
     "tuber_set_force_simt": (_I, [_P, _I]),

@@ -134,6 +134,14 @@ struct TuberPlan {
   Lin ct_in, ct_out, cs_in, cs_out, c_lin1, c_lin2, x_q, x_kv, x_out;
   LnP c_n1t, c_n1s, c_n2;
   Lin head_b, bbox0, bbox1, bbox2, class_fc;
+  // long-term context layer (defined in this repo, the reference never released it): packed when the
+  // state_dict holds ltc_attn.* / ltc_norm.*
+  bool has_ltc = false;
+  Lin ltc_q, ltc_kv, ltc_out;
+  LnP ltc_n;
+  // arguments of the tuber_forward_ltc call in progress (read by run_forward and by the graph key)
+  const float* ltc_bank = nullptr; int ltc_bank_clips = 0, ltc_bank_tokens = 0;
+  float* ltc_new = nullptr;
 
   // run-time state
   char* ws = nullptr; size_t ws_cap = 0;
@@ -536,6 +544,14 @@ int do_finalize(TuberPlan* p) {
     p->x_kv = pk.linear_rows("cross_attn.in_proj_weight", "cross_attn.in_proj_bias", 3 * d, d, d, 2 * d);
     p->x_out = pk.linear("cross_attn.out_proj", d, d);
   }
+  // ---- long-term context layer (optional) ----
+  if (p->host.count("ltc_attn.in_proj_weight")) {
+    p->ltc_q = pk.linear_rows("ltc_attn.in_proj_weight", "ltc_attn.in_proj_bias", 3 * d, d, 0, d);
+    p->ltc_kv = pk.linear_rows("ltc_attn.in_proj_weight", "ltc_attn.in_proj_bias", 3 * d, d, d, 2 * d);
+    p->ltc_out = pk.linear("ltc_attn.out_proj", d, d);
+    p->ltc_n = pk.ln("ltc_norm", d);
+    p->has_ltc = true;
+  }
   // ---- heads (tuber_ava.py:64-73; criterion.py:485-492) ----
   p->head_b = c.ava_mode ? pk.linear("class_embed_b", 3, d) : pk.linear("class_embed_b", 2, POOL_DIM);
   p->bbox0 = pk.linear("bbox_embed.layers.0", d, d);
@@ -913,6 +929,13 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
   void* srcc_s = cx.split(Mc, d);
   cx.gemm(xt, FMT_SPLIT, CB, Mc, p->class_proj, nullptr, 0, 0, 0, srcc_s, FMT_SPLIT, d, ACT_NONE);
   cx.tap("src", src_s, FMT_SPLIT, Mtok, d);
+  // long-term context: this batch's bank entries = class_proj features averaged over the Tf feature frames, [B, HW, d] fp32
+  if (p->ltc_new) {
+    void* e_s = cx.split((long long)B * HW, d);
+    cx.launch("tpool", 4.0 * ((double)Mc + (double)B * HW) * d, (double)Mc * d,
+              [&] { return launch_tpool(srcc_s, e_s, B, Tf, HW, d, Tf, 1, 0, st); });
+    cx.launch("from_split", 8.0 * B * HW * d, 0.0, [&] { return launch_from_split(e_s, d, p->ltc_new, d, (long long)B * HW, d, st); });
+  }
 
   // ---- DETR encoder (transformer.py:153-168): post-norm, q = k = src + pos, v = src ----
   cx.stage_mark(7);
@@ -1041,6 +1064,27 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->c_n2, Mc, nullptr, 0, memc_s, d);
   }
   cx.tap("mem_c", memc_s, FMT_SPLIT, Mc, d);
+  // long-term context layer: every class-branch token of a clip attends over the bank window (bank_clips = 1: one window shared
+  // by the batch; = B: one per clip), post-norm like every other layer of the model:  mem_c <- LN(mem_c + MHA(mem_c, bank, bank))
+  if (p->ltc_bank && p->ltc_bank_tokens > 0) {
+    const int Nb = p->ltc_bank_tokens, Bb = p->ltc_bank_clips, Nc = Tf * HW;
+    const long long Mb = (long long)Bb * Nb;
+    void* bank_s = cx.split(Mb, d);
+    float* kvb = cx.f32(Mb, 2 * d);
+    float* ql = cx.f32(Mc, d);
+    void* att = cx.split(Mc, d);
+    void* o = cx.split(Mc, d);
+    void* memc2 = cx.split(Mc, d);
+    cx.launch("to_split", 8.0 * Mb * d, 0.0, [&] { return launch_to_split(p->ltc_bank, d, bank_s, d, Mb, d, st); });
+    cx.gemm(bank_s, FMT_SPLIT, d, Mb, p->ltc_kv, nullptr, 0, 0, 0, kvb, FMT_F32, 2 * d, ACT_NONE);
+    cx.gemm(memc_s, FMT_SPLIT, d, Mc, p->ltc_q, nullptr, 0, 0, 0, ql, FMT_F32, d, ACT_NONE);
+    cx.attention(ql, d, seqmap(1, Nc, 0, 1), kvb, kvb + d, 2 * d, seqmap(1, Bb == 1 ? 0 : Nb, 0, 1), att, d, seqmap(1, Nc, 0, 1), nullptr,
+                 B, CLS_HEADS, Nc, Nb, d / CLS_HEADS);
+    cx.gemm(att, FMT_SPLIT, d, Mc, p->ltc_out, memc_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+    cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->ltc_n, Mc, nullptr, 0, memc2, d);
+    memc_s = memc2;
+    cx.tap("mem_ltc", memc_s, FMT_SPLIT, Mc, d);
+  }
   // class cross-attention (tuber_ava.py:137-139) + class_fc (:141; Dropout(0.5) is the identity in eval)
   {
     const int Nc = Tf * HW, LQ = Ld * Q;
@@ -1213,7 +1257,8 @@ int tuber_forward(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev,
     return s;
   }
   std::vector<uintptr_t> key = {(uintptr_t)clips_dev, (uintptr_t)mask_dev, (uintptr_t)B, (uintptr_t)T, (uintptr_t)H, (uintptr_t)W,
-                                (uintptr_t)logits_dev, (uintptr_t)boxes_dev, (uintptr_t)logits_b_dev};
+                                (uintptr_t)logits_dev, (uintptr_t)boxes_dev, (uintptr_t)logits_b_dev, (uintptr_t)p->ltc_bank,
+                                (uintptr_t)p->ltc_bank_clips, (uintptr_t)p->ltc_bank_tokens, (uintptr_t)p->ltc_new};
   for (auto& g : p->graphs)
     if (g.key == key) { CK(cudaGraphLaunch(g.exec, st)); return TUBER_OK; }
   // first call for this (shape, buffers): run eagerly (this call's result; also performs the one-time
@@ -1425,6 +1470,25 @@ int tuber_forward_u8(TuberPlan* p, const uint8_t* frames_dev, const uint8_t* mas
   }
   CK(launch_normalize_u8(frames_dev, p->in_lut, p->u8_clip, B, (long long)T * H * W, reinterpret_cast<cudaStream_t>(stream)));
   return tuber_forward(p, p->u8_clip, mask_dev, B, T, H, W, logits_dev, boxes_dev, logits_b_dev, stream);
+}
+
+// ---- long-term context bank ------------------------------------------------------------------
+int tuber_has_ltc(TuberPlan* p) { return (p && p->has_ltc) ? 1 : 0; }
+
+int tuber_forward_ltc(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev, int32_t B, int32_t T, int32_t H, int32_t W,
+                      const float* bank_dev, int32_t bank_clips, int32_t bank_tokens, float* bank_new_dev, float* logits_dev,
+                      float* boxes_dev, float* logits_b_dev, void* stream) {
+  TRY(check_forward_args(p, B, T, H, W));
+  if (bank_dev) {
+    if (!p->has_ltc) return fail(TUBER_ERR_MISSING, "the plan holds no long-term context layer (ltc_attn.* / ltc_norm.* were never set)");
+    if (bank_tokens < 1 || (bank_clips != 1 && bank_clips != B))
+      return fail(TUBER_ERR_SHAPE, "bank of %d clips x %d tokens: clips must be 1 (shared window) or the batch size %d", bank_clips, bank_tokens, B);
+  }
+  p->ltc_bank = bank_dev; p->ltc_bank_clips = bank_dev ? bank_clips : 0; p->ltc_bank_tokens = bank_dev ? bank_tokens : 0;
+  p->ltc_new = bank_new_dev;
+  const int s = tuber_forward(p, clips_dev, mask_dev, B, T, H, W, logits_dev, boxes_dev, logits_b_dev, stream);
+  p->ltc_bank = nullptr; p->ltc_bank_clips = 0; p->ltc_bank_tokens = 0; p->ltc_new = nullptr;
+  return s;
 }
 
 int tuber_forward_host_u8(TuberPlan* p, const uint8_t* frames_host, const uint8_t* mask_host, int32_t B, int32_t T, int32_t H,

@@ -171,6 +171,15 @@ class DETR(nn.Module):
         self.class_embed_b = nn.Linear(d, 3) if ava else nn.Linear(2048, 2)
         self.bbox_embed = _MLP(d, d, 4, 3)
         self.class_fc = nn.Linear(d, self.num_class_out)
+        # long-term context (BASELINE.json configs[3]).  The reference keeps the switches -- CONFIG.USE_LFB
+        # (the loop then calls model(samples, lfb_features), utils/video_action_recognition.py:109-137) and MODEL.GENERATE_LFB
+        # (tuber_ava.py:80,178; tuber_jhmdb.py:111-112 returns the features instead of detections) -- but never released the
+        # layer itself (README.md:16-18,86): it is defined in this repository, see include/tuber_b200.h (tuber_forward_ltc)
+        self.use_lfb = bool(getattr(cfg.CONFIG, "USE_LFB", False))
+        self.generate_lfb = bool(getattr(m, "GENERATE_LFB", False))
+        if self.use_lfb:
+            self.ltc_attn = _MHA(d)
+            self.ltc_norm = nn.LayerNorm(d)
 
         blocks = _STAGE_BLOCKS["CSN-152" if m.BACKBONE_NAME == "CSN-152" else "CSN-50"]
         self._tcfg = _lib.TuberConfig(
@@ -242,10 +251,12 @@ class DETR(nn.Module):
 
     # -- forward ----------------------------------------------------------------------------
     @torch.no_grad()
-    def forward_raw(self, clips: Tensor, mask: Optional[Tensor] = None,
-                    out: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+    def forward_raw(self, clips: Tensor, mask: Optional[Tensor] = None, out: Optional[Dict[str, Tensor]] = None,
+                    bank: Optional[Tensor] = None, bank_out: Optional[Tensor] = None) -> Dict[str, Tensor]:
         """clips (B,3,T,H,W) fp32 on the model's device, mask (B,H,W) bool/uint8 or None ->
-        all-layer outputs 'pred_logits' (B,L,Q,C), 'pred_boxes' (B,L,Q,4), 'pred_logits_b' (B,L,Q,3) | (B,2)."""
+        all-layer outputs 'pred_logits' (B,L,Q,C), 'pred_boxes' (B,L,Q,4), 'pred_logits_b' (B,L,Q,3) | (B,2).
+        Long-term context (tuber_forward_ltc): `bank` (1 | B, tokens, d) fp32 = the window the class-branch tokens attend over;
+        `bank_out` (B, H'W', d) fp32 receives this batch's bank entries."""
         if self.training:
             raise RuntimeError("tuber_b200 implements the inference forward only; call model.eval()")
         if clips.dim() != 5 or clips.shape[1] != 3:
@@ -268,11 +279,32 @@ class DETR(nn.Module):
                                                 device=dev, dtype=torch.float32)}
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(_lib.load().tuber_forward(plan, C.c_void_p(clips.data_ptr()), mptr, B, T, H, W,
-                                                 C.c_void_p(out["pred_logits"].data_ptr()),
-                                                 C.c_void_p(out["pred_boxes"].data_ptr()),
-                                                 C.c_void_p(out["pred_logits_b"].data_ptr()), C.c_void_p(stream)))
+            outs = (C.c_void_p(out["pred_logits"].data_ptr()), C.c_void_p(out["pred_boxes"].data_ptr()),
+                    C.c_void_p(out["pred_logits_b"].data_ptr()), C.c_void_p(stream))
+            if bank is None and bank_out is None:
+                _lib.check(_lib.load().tuber_forward(plan, C.c_void_p(clips.data_ptr()), mptr, B, T, H, W, *outs))
+            else:
+                bptr, bclips, btok = None, 0, 0
+                if bank is not None:
+                    if (bank.dim() != 3 or bank.shape[2] != self.hidden_dim or bank.dtype != torch.float32 or bank.device != dev
+                            or not bank.is_contiguous()):
+                        raise ValueError("bank must be a contiguous fp32 (1 | B, tokens, d_model) tensor on the model's device")
+                    bptr, bclips, btok = C.c_void_p(bank.data_ptr()), int(bank.shape[0]), int(bank.shape[1])
+                nptr = None
+                if bank_out is not None:
+                    info = self.shape_info(B, T, H, W)
+                    if (tuple(bank_out.shape) != (B, info.Hf * info.Wf, self.hidden_dim) or bank_out.dtype != torch.float32
+                            or bank_out.device != dev or not bank_out.is_contiguous()):
+                        raise ValueError(f"bank_out must be a contiguous fp32 ({B}, {info.Hf * info.Wf}, {self.hidden_dim}) tensor on the model's device")
+                    nptr = C.c_void_p(bank_out.data_ptr())
+                _lib.check(_lib.load().tuber_forward_ltc(plan, C.c_void_p(clips.data_ptr()), mptr, B, T, H, W, bptr, bclips, btok, nptr,
+                                                         *outs))
         return out
+
+    def bank_entry_shape(self, B: int, T: int, H: int, W: int):
+        """(B, H'W', d): the bank entries one batch of clips of this size produces."""
+        info = self.shape_info(B, T, H, W)
+        return (B, info.Hf * info.Wf, self.hidden_dim)
 
     # -- host-memory entry points (tuber_forward_host*, include/tuber_b200.h) ----------------
     def _host_out(self, B: int) -> Dict[str, Tensor]:
@@ -392,14 +424,24 @@ class DETR(nn.Module):
             _lib.check(_lib.load().tuber_forward_host_u8_submit(self.plan(), slot, *self._host_args_u8(frames, mask, out)))
         return out
 
-    def forward(self, samples: Union[NestedTensor, List[Tensor], Tensor]):
+    def forward(self, samples: Union[NestedTensor, List[Tensor], Tensor], lfb_features: Optional[Tensor] = None):
+        """`model(samples)` (tuber_ava.py:97) or, under CONFIG.USE_LFB, `model(samples, lfb_features)` as the reference's loop calls
+        it (utils/video_action_recognition.py:133-137): lfb_features (1 | B, tokens, d) = the long-term context window.  With
+        MODEL.GENERATE_LFB the call returns this batch's bank entries (B, H'W', d) instead of detections (tuber_jhmdb.py:111-112)."""
         if isinstance(samples, (list, tuple)):
             samples = nested_tensor_from_tensor_list(list(samples))            # tuber_ava.py:112-113
         if isinstance(samples, Tensor):
             clips, mask = samples, None
         else:
             clips, mask = samples.tensors, samples.mask
-        raw = self.forward_raw(clips, mask)
+        if lfb_features is not None and not self.use_lfb:
+            raise RuntimeError("lfb_features given but the model was built without CONFIG.USE_LFB")
+        if self.generate_lfb:
+            B, _, T, H, W = clips.shape
+            entries = torch.empty(self.bank_entry_shape(B, T, H, W), device=self._device(), dtype=torch.float32)
+            self.forward_raw(clips, mask, bank_out=entries)
+            return entries
+        raw = self.forward_raw(clips, mask, bank=lfb_features)
         logits, boxes, logits_b = raw["pred_logits"], raw["pred_boxes"], raw["pred_logits_b"]
         ava = self.dataset_mode == "ava"
         pick_b = (lambda i: logits_b[:, i]) if ava else (lambda i: logits_b)   # tuber_ava.py:121-125
