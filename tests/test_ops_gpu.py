@@ -155,7 +155,11 @@ def test_layernorm(abi, c):
                                                (5, 8, 1, 4, 256, False), (2, 8, 90, 1024, 32, False), (4, 8, 4, 4, 32, False),
                                                (2, 8, 40, 33, 32, True), (1, 8, 320, 320, 32, False), (3, 8, 7, 17, 32, True),
                                                (2, 8, 64, 64, 32, False), (2, 8, 130, 70, 32, True), (3, 8, 8, 8, 32, True),
-                                               (2, 16, 2, 2, 32, False), (2, 8, 16, 129, 32, False)])
+                                               (2, 16, 2, 2, 32, False), (2, 8, 16, 129, 32, False),
+                                               # long sequences, no mask: the tcgen05 flash-attention kernel (attn_tc.cu) -- exact tiles,
+                                               # query / key tails, one chunk pair, many chunks
+                                               (1, 8, 128, 1024, 32, False), (2, 4, 300, 2500, 32, False), (1, 2, 129, 1025, 32, False),
+                                               (1, 8, 256, 16384, 32, False)])
 def test_attention(abi, nb, h, l, s, d, masked):
     from tuber_b200 import _lib
     e = h * d

@@ -1,0 +1,353 @@
+// Long-sequence attention core on tcgen05 (sm_100a): O = softmax(scale * Q K^T) V for head_dim 32 when a (sequence, head) has
+// at least one full 128-query tile and thousands of keys -- the long-term context layer (tuber_forward_ltc: 1024 class-branch
+// tokens of a clip over a 64-clip bank window = 16 384 keys).  The short attention sites of the forward
+// stay on the warp-level kernels of attn_mma.cu (their tiles are mostly padding at UMMA sizes).
+//
+// One CTA = one (sequence n, head h, tile of 128 queries); it walks the keys in chunks of 128, flash-attention style, with the
+// library's usual precision (common.cuh): every fp32 operand is split into bf16 hi + mid and a product is evaluated as
+// a_hi*b_hi + a_hi*b_mid + a_mid*b_hi with fp32 accumulation in tensor memory.
+//
+//   warps 5-8  loaders: Q tile once, then per chunk K (row = key: hi[32] | mid[32] bf16 = one 128-byte swizzled row, K-major)
+//              and V TRANSPOSED (row = head dim, 128 keys per row as two 64-key swizzle atoms; hi and mid planes) into a
+//              2-stage shared-memory ring, converted from the fp32 projections on the fly.
+//   warp 0     MMA issuer.  S = Q K^T: 6 tcgen05.mma (M=128, N=128, K=16; 2 dim halves x 3 passes) into TMEM columns [0,128).
+//              O_c = P V: 24 tcgen05.mma (M=128, N=32, K=16; 8 key steps x 3 passes) with P read FROM TENSOR MEMORY (A operand)
+//              and V^T from shared memory, into TMEM columns [192,224) -- a fresh accumulator per chunk.
+//   warps 1-4  softmax, thread = query row (its TMEM lane): pass 1 reads the 128 scores for the row maximum, pass 2 reads
+//              them again, exponentiates, splits into bf16 hi | mid and writes P back to tensor memory (hi over the score
+//              columns already consumed, mid to columns [128,192)); then adds the chunk's O_c to the running output in
+//              registers with the usual rescaling  o = o * exp(m_old - m_new) + O_c  -- no TMEM accumulator to rescale.
+// Two CTAs share an SM (80 KB of shared memory and 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
+#include <cuda.h>
+
+#include "kernels.h"
+
+namespace attn_tc {
+
+constexpr int D = 32, QT = 128, KC = 128;
+constexpr int Q_BYTES = QT * 128;                 // 128 rows x (hi 64 B | mid 64 B)
+constexpr int K_BYTES = KC * 128;
+constexpr int VT_PLANE = 2 * 32 * 128;            // [2 key atoms][32 dims][64 keys] bf16 = 8 KB
+constexpr int STAGE_BYTES = K_BYTES + 2 * VT_PLANE;   // 32 KB
+constexpr int OFF_Q = 0, OFF_STAGE = Q_BYTES, OFF_BAR = OFF_STAGE + 2 * STAGE_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int THREADS = 288;                      // warp 0 MMA, warps 1-4 softmax, warps 5-8 loaders
+constexpr int TMEM_COLS = 256;
+constexpr int COL_S = 0, COL_PMID = 128, COL_O = 192;
+
+TB_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+TB_DEVINL long long seq_row0(const SeqMap& m, int n) {
+  return (long long)(n / m.inner) * m.outer + (long long)(n % m.inner) * m.inner_stride;
+}
+TB_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+TB_DEVINL void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+TB_DEVINL void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+TB_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+TB_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+TB_DEVINL void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+TB_DEVINL void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+TB_DEVINL void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+TB_DEVINL void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes (rows) x 8 columns per K = 16 step, two bf16 per 32-bit column
+TB_DEVINL void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+TB_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+TB_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+TB_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+TB_DEVINL void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+TB_DEVINL void sts16(uint32_t addr, uint16_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+TB_DEVINL float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// K-major, 128B-swizzle shared-memory matrix descriptor (8-row groups 1024 B apart; same encoding as gemm_tc.cu / stem_tc.cu)
+TB_DEVINL uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {      // bf16 x bf16 -> fp32, both operands K-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// 16-byte chunk j of row r of a 128-byte-row swizzled tile
+TB_DEVINL uint32_t swz(uint32_t base, int r, int j) { return base + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4); }
+
+// 32 fp32 values of a row (8 x float4) times `mul` -> one swizzled operand row: chunks 0-3 = hi, 4-7 = mid
+TB_DEVINL void stage_row(uint32_t tile, int r, const float* __restrict__ src, float mul, bool valid) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 hi = make_uint4(0u, 0u, 0u, 0u), mid = hi;
+    if (valid) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * j), b = __ldg(reinterpret_cast<const float4*>(src) + 2 * j + 1);
+      split_bf16x2(a.x * mul, a.y * mul, hi.x, mid.x);
+      split_bf16x2(a.z * mul, a.w * mul, hi.y, mid.y);
+      split_bf16x2(b.x * mul, b.y * mul, hi.z, mid.z);
+      split_bf16x2(b.z * mul, b.w * mul, hi.w, mid.w);
+    }
+    sts128(swz(tile, r, j), hi);
+    sts128(swz(tile, r, 4 + j), mid);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+attn_tc_kernel(AttnArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bar = sb + OFF_BAR;
+  auto kv_full = [&](int s) { return bar + 8u * s; };          // loaders (128 arrivals) -> MMA
+  auto kv_empty = [&](int s) { return bar + 8u * (2 + s); };   // tcgen05.commit after P V -> loaders
+  const uint32_t s_full = bar + 32, p_full = bar + 40, o_full = bar + 48, tmem_slot = bar + 56;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 56);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.z, h = blockIdx.y, l0 = blockIdx.x * QT;
+  const int nchunks = (p.S + KC - 1) / KC;
+
+  if (threadIdx.x == 0) {
+    if (sb & 1023u) __trap();
+    mbar_init(kv_full(0), 128); mbar_init(kv_full(1), 128);
+    mbar_init(kv_empty(0), 1); mbar_init(kv_empty(1), 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc_s = make_idesc(128, KC), idesc_o = make_idesc(128, D);
+    const uint64_t q_desc = make_smem_desc(sb + OFF_Q);
+    for (int c = 0; c < nchunks; ++c) {
+      const int stage = c & 1;
+      const uint32_t st_base = sb + OFF_STAGE + stage * STAGE_BYTES;
+      mbar_wait(kv_full(stage), (uint32_t)((c >> 1) & 1));
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint64_t k_desc = make_smem_desc(st_base);
+        // 32 bytes (16 bf16) per K step: row bytes [0,64) = hi dims, [64,128) = mid dims; descriptor address unit = 16 B
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh) {
+          umma_ss(tmem_base + COL_S, q_desc + 4 + 2 * dh, k_desc + 2 * dh, idesc_s, dh);        // Q_mid K_hi
+          umma_ss(tmem_base + COL_S, q_desc + 2 * dh, k_desc + 4 + 2 * dh, idesc_s, 1u);        // Q_hi  K_mid
+          umma_ss(tmem_base + COL_S, q_desc + 2 * dh, k_desc + 2 * dh, idesc_s, 1u);            // Q_hi  K_hi
+        }
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_full, (uint32_t)(c & 1));
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint64_t vh_desc = make_smem_desc(st_base + K_BYTES), vm_desc = make_smem_desc(st_base + K_BYTES + VT_PLANE);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {                         // 16 keys per step; 64-key atoms are 4 KB apart
+          const uint64_t off = (uint64_t)((ks >> 2) * (4096 >> 4) + 2 * (ks & 3));
+          const uint32_t p_hi = tmem_base + COL_S + 8 * ks, p_mid = tmem_base + COL_PMID + 8 * ks;
+          umma_ts(tmem_base + COL_O, p_mid, vh_desc + off, idesc_o, ks == 0 ? 0u : 1u);
+          umma_ts(tmem_base + COL_O, p_hi, vm_desc + off, idesc_o, 1u);
+          umma_ts(tmem_base + COL_O, p_hi, vh_desc + off, idesc_o, 1u);
+        }
+        umma_commit(o_full);
+        umma_commit(kv_empty(stage));
+      }
+      __syncwarp();
+    }
+  } else if (warp <= 4) {
+    // ================= softmax + output accumulation: thread = query row =================
+    const int lg = warp & 3, row = lg * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(lg * 32) << 16);
+    float o[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int nvalid = min(KC, p.S - c * KC);
+      mbar_wait(s_full, (uint32_t)(c & 1));
+      tcgen05_fence_after();
+      float cm = -INFINITY;
+#pragma unroll 1
+      for (int b = 0; b < 4; ++b) {
+        uint32_t v[32];
+        tmem_ld32(t_lane + COL_S + 32 * b, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cm = fmaxf(cm, (32 * b + j < nvalid) ? __uint_as_float(v[j]) : -INFINITY);
+      }
+      const float m_new = fmaxf(m, cm);                          // finite: every chunk holds at least one key
+      const float corr = ex2(m - m_new);                         // first chunk: 2^-inf = 0
+      float psum = 0.f;
+#pragma unroll 1
+      for (int b = 0; b < 4; ++b) {
+        uint32_t v[32];
+        tmem_ld32(t_lane + COL_S + 32 * b, v);
+        uint32_t hi[16], mid[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float p0 = (32 * b + 2 * j < nvalid) ? ex2(__uint_as_float(v[2 * j]) - m_new) : 0.f;
+          const float p1 = (32 * b + 2 * j + 1 < nvalid) ? ex2(__uint_as_float(v[2 * j + 1]) - m_new) : 0.f;
+          psum += p0 + p1;
+          split_bf16x2(p0, p1, hi[j], mid[j]);
+        }
+        tmem_st16(t_lane + COL_S + 16 * b, hi);                  // over score columns this thread has already consumed
+        tmem_st16(t_lane + COL_PMID + 16 * b, mid);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive(p_full);
+      l = l * corr + psum;
+      m = m_new;
+      mbar_wait(o_full, (uint32_t)(c & 1));
+      tcgen05_fence_after();
+      {
+        uint32_t oc[32];
+        tmem_ld32(t_lane + COL_O, oc);
+#pragma unroll
+        for (int i = 0; i < D; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(oc[i]));
+      }
+      tcgen05_fence_before();
+    }
+    if (l0 + row < p.L) {
+      const float inv = 1.f / l;
+      const long long orow = seq_row0(p.om, n) + (long long)(l0 + row) * p.om.step;
+      const int col = h * D;
+      if (p.o_f32) {
+        float4* dst = reinterpret_cast<float4*>(p.o_f32 + orow * p.ldo + col);
+#pragma unroll
+        for (int i = 0; i < D / 4; ++i) dst[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
+      }
+      if (p.o_split) {
+        __nv_bfloat16* hp = split_hi(p.o_split, orow, p.ldo) + col;
+#pragma unroll
+        for (int i = 0; i < D / 4; ++i)
+          store_split4(hp + 4 * i, hp + p.ldo + 4 * i, make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv));
+      }
+    }
+  } else {
+    // ================= loaders: thread = query row (once), then = key of the chunk =================
+    const int t = threadIdx.x - 160;                             // 0..127
+    {
+      const int qrow = l0 + t;
+      const long long grow = seq_row0(p.qm, n) + (long long)qrow * p.qm.step;
+      // scores in the log2 domain: softmax(x) = 2^(x log2 e - max)
+      stage_row(sb + OFF_Q, t, p.q + grow * p.ldq + h * D, p.scale * 1.4426950408889634f, qrow < p.L);
+    }
+    const long long k0 = seq_row0(p.km, n);
+    for (int c = 0; c < nchunks; ++c) {
+      const int stage = c & 1;
+      const uint32_t st_base = sb + OFF_STAGE + stage * STAGE_BYTES;
+      if (c >= 2) mbar_wait(kv_empty(stage), (uint32_t)(((c >> 1) - 1) & 1));
+      const int key = c * KC + t;
+      const bool valid = key < p.S;
+      const long long krow = k0 + (long long)key * p.km.step;
+      stage_row(st_base, t, p.k + krow * p.ldk + h * D, 1.f, valid);
+      // V^T: value (key t, dim d) -> row d of key atom t / 64, 2-byte column t % 64
+      const uint32_t vt = st_base + K_BYTES + (uint32_t)((t >> 6) * 4096), kc = (uint32_t)(t & 63);
+      const float* vp = p.v + krow * p.ldv + h * D;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) a = __ldg(reinterpret_cast<const float4*>(vp) + j);
+        const float vals[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int d = 4 * j + e;
+          __nv_bfloat16 hi, mid;
+          split_bf16(vals[e], hi, mid);
+          const uint32_t off = (uint32_t)d * 128u + ((((kc >> 3) ^ (uint32_t)(d & 7)) << 4) | ((kc & 7u) << 1));
+          sts16(vt + off, __bfloat16_as_ushort(hi));
+          sts16(vt + VT_PLANE + off, __bfloat16_as_ushort(mid));
+        }
+      }
+      fence_proxy_async();                                       // generic-proxy writes -> visible to the tensor core's reads
+      mbar_arrive(kv_full(stage));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace attn_tc
+
+bool attention_tc_supported(const AttnArgs& a) {
+  return a.D == attn_tc::D && a.kpm == nullptr && a.L >= attn_tc::QT && a.S >= 1024 && a.NB > 0 && a.NB <= 65535 && a.H <= 65535 &&
+         a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0 && a.ldo % 4 == 0;
+}
+
+cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
+  using namespace attn_tc;
+  if (!attention_tc_supported(a)) return cudaErrorNotSupported;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(a.L, QT), a.H, a.NB);
+  return launch_pdl(attn_tc_kernel, grid, dim3(THREADS), SMEM_BYTES, st, a);
+}

@@ -112,6 +112,10 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st);
 cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t st);
 // attn_mma.cu; cudaErrorNotSupported when the shape is outside what it covers
 cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);
+// attn_tc.cu: tcgen05 flash attention for long sequences (head dim 32, no key mask, L >= 128, S >= 1024: the long-term context layer);
+// TUBER_ATTN_NO_TC=1 in the environment keeps those shapes on the mma.sync kernel (the tests' cross-check)
+bool attention_tc_supported(const AttnArgs& a);
+cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t st);
 
 // ---- post-processing + detection rows (criterion.py:413-482; video_action_recognition.py:411-415) -------------
 // logits [B, Q, C] (clip stride l_sb floats), boxes [B, Q, 4] (b_sb), logits_b [B, Q, 3] (AVA) or [B, 2] (lb_sb), sizes [B, 2] = (H, W);

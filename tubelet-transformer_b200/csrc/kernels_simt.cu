@@ -1312,6 +1312,8 @@ attn_tile_kernel(AttnArgs p) {
 
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st) {
   static const bool force_simt = [] { const char* e = getenv("TUBER_ATTN_SIMT"); return e && e[0] == '1'; }();
+  static const bool no_tc = [] { const char* e = getenv("TUBER_ATTN_NO_TC"); return e && e[0] == '1'; }();
+  if (!force_simt && !no_tc && attention_tc_supported(a)) return launch_attention_tc(a, st);
   if (!force_simt && a.D == 32) {
     cudaError_t e = launch_attention_mma(a, st);
     if (e != cudaErrorNotSupported) return e;
