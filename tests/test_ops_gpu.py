@@ -182,6 +182,25 @@ def test_attention(abi, nb, h, l, s, d, masked):
     assert _rel(out, ref) < 3e-5          # bf16x3 operand splitting (2^-16 per operand); the path's bar is 1e-3
 
 
+@pytest.mark.parametrize("nb,h,l,s", [(2, 4, 300, 2500), (1, 8, 128, 1024), (3, 2, 129, 1153)])
+def test_attention_tc_preconverted_keys(abi, nb, h, l, s, monkeypatch):
+    """The tcgen05 attention with K / V converted once into per-chunk tile images (the form the plan uses, attn_tc.cu PREP) gives
+    bit for bit what the same kernel gives when every CTA converts its own chunks."""
+    from tuber_b200 import _lib
+    d, e = 32, h * 32
+    g = torch.Generator(device="cuda").manual_seed(s)
+    q, k, v = (torch.randn(nb, n, e, device="cuda", generator=g) for n in (l, s, s))
+    outs = []
+    for prep in ("0", "1"):
+        monkeypatch.setenv("TUBER_OP_ATTN_PREP", prep)
+        out = torch.empty(nb, l, e, device="cuda")
+        _lib.check(_lib.load().tuber_op_attention(abi.P(q), abi.P(k), abi.P(v), None, abi.P(out), nb, h, l, s, d, C.c_float(d ** -0.5),
+                                                  abi.stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_posenc(abi):
     from oracle import tuber_oracle as O
     from tuber_b200 import _lib

@@ -18,6 +18,11 @@
 //              columns already consumed, mid to columns [128,192)); then adds the chunk's O_c to the running output in
 //              registers with the usual rescaling  o = o * exp(m_old - m_new) + O_c  -- no TMEM accumulator to rescale.
 // Two CTAs share an SM (80 KB of shared memory and 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
+//
+// PREP variant (used by the plan, which has workspace to give): every (key sequence, head) is read by all the query tiles of all
+// the clips that share it, so attn_tc_prep_kernel converts K / V ONCE into the exact 32 KB shared-memory image of each chunk
+// (swizzled K rows + transposed V planes) in global memory, and the attention CTAs fetch a chunk with one cp.async.bulk
+// (completion on the stage's mbarrier) -- the per-CTA conversion (a quarter of all issued instructions) disappears.
 #include <cuda.h>
 
 #include "kernels.h"
@@ -144,15 +149,58 @@ TB_DEVINL void stage_row(uint32_t tile, int r, const float* __restrict__ src, fl
   }
 }
 
+// thread t (0..127) = key t of chunk c: K row (hi | mid) and the key's column of the transposed V planes -> the stage image at
+// shared address st_base (K_BYTES of K, then V^T hi plane, then V^T mid plane)
+TB_DEVINL void stage_chunk(uint32_t st_base, int t, const AttnArgs& p, int h, long long k0, int c) {
+  const int key = c * KC + t;
+  const bool valid = key < p.S;
+  const long long krow = k0 + (long long)key * p.km.step;
+  stage_row(st_base, t, p.k + krow * p.ldk + h * D, 1.f, valid);
+  // V^T: value (key t, dim d) -> row d of key atom t / 64, 2-byte column t % 64
+  const uint32_t vt = st_base + K_BYTES + (uint32_t)((t >> 6) * 4096), kc = (uint32_t)(t & 63);
+  const float* vp = p.v + krow * p.ldv + h * D;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) a = __ldg(reinterpret_cast<const float4*>(vp) + j);
+    const float vals[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = 4 * j + e;
+      __nv_bfloat16 hi, mid;
+      split_bf16(vals[e], hi, mid);
+      const uint32_t off = (uint32_t)d * 128u + ((((kc >> 3) ^ (uint32_t)(d & 7)) << 4) | ((kc & 7u) << 1));
+      sts16(vt + off, __bfloat16_as_ushort(hi));
+      sts16(vt + VT_PLANE + off, __bfloat16_as_ushort(mid));
+    }
+  }
+}
+
+// K / V of one (key sequence, head, chunk) -> the chunk's shared-memory image, stored in global memory (see PREP above)
+__global__ void __launch_bounds__(128)
+attn_tc_prep_kernel(AttnArgs p, uint8_t* __restrict__ img) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem);
+  const int c = blockIdx.x, h = blockIdx.y, nkv = blockIdx.z, nchunks = gridDim.x;
+  pdl_trigger();
+  pdl_wait();
+  stage_chunk(sb, threadIdx.x, p, h, seq_row0(p.km, nkv), c);
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(img + ((size_t)(nkv * p.H + h) * nchunks + c) * STAGE_BYTES);
+  const uint4* src = reinterpret_cast<const uint4*>(smem);
+  for (int i = threadIdx.x; i < STAGE_BYTES / 16; i += 128) dst[i] = src[i];
+}
+
+template <bool PREP>
 __global__ void __launch_bounds__(THREADS, 2)
-attn_tc_kernel(AttnArgs p) {
+attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
   const uint32_t bar = sb + OFF_BAR;
   auto kv_full = [&](int s) { return bar + 8u * s; };          // loaders (128 arrivals) -> MMA
   auto kv_empty = [&](int s) { return bar + 8u * (2 + s); };   // tcgen05.commit after P V -> loaders
-  const uint32_t s_full = bar + 32, p_full = bar + 40, o_full = bar + 48, tmem_slot = bar + 56;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 56);
+  const uint32_t s_full = bar + 32, p_full = bar + 40, o_full = bar + 48, q_full = bar + 56, tmem_slot = bar + 64;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.z, h = blockIdx.y, l0 = blockIdx.x * QT;
@@ -160,7 +208,8 @@ attn_tc_kernel(AttnArgs p) {
 
   if (threadIdx.x == 0) {
     if (sb & 1023u) __trap();
-    mbar_init(kv_full(0), 128); mbar_init(kv_full(1), 128);
+    mbar_init(kv_full(0), PREP ? 1 : 128); mbar_init(kv_full(1), PREP ? 1 : 128);
+    mbar_init(q_full, 128);
     mbar_init(kv_empty(0), 1); mbar_init(kv_empty(1), 1);
     mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -180,6 +229,7 @@ attn_tc_kernel(AttnArgs p) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc_s = make_idesc(128, KC), idesc_o = make_idesc(128, D);
     const uint64_t q_desc = make_smem_desc(sb + OFF_Q);
+    mbar_wait(q_full, 0);
     for (int c = 0; c < nchunks; ++c) {
       const int stage = c & 1;
       const uint32_t st_base = sb + OFF_STAGE + stage * STAGE_BYTES;
@@ -227,12 +277,27 @@ attn_tc_kernel(AttnArgs p) {
       mbar_wait(s_full, (uint32_t)(c & 1));
       tcgen05_fence_after();
       float cm = -INFINITY;
+      if (nvalid == KC) {                                        // full chunk (all but possibly the last): no key predicates
 #pragma unroll 1
-      for (int b = 0; b < 4; ++b) {
-        uint32_t v[32];
-        tmem_ld32(t_lane + COL_S + 32 * b, v);
+        for (int b = 0; b < 4; ++b) {
+          uint32_t v[32];
+          tmem_ld32(t_lane + COL_S + 32 * b, v);
+          float c0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), c1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
 #pragma unroll
-        for (int j = 0; j < 32; ++j) cm = fmaxf(cm, (32 * b + j < nvalid) ? __uint_as_float(v[j]) : -INFINITY);
+          for (int j = 4; j < 32; j += 4) {
+            c0 = fmaxf(c0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+            c1 = fmaxf(c1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+          }
+          cm = fmaxf(cm, fmaxf(c0, c1));
+        }
+      } else {
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+          uint32_t v[32];
+          tmem_ld32(t_lane + COL_S + 32 * b, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cm = fmaxf(cm, (32 * b + j < nvalid) ? __uint_as_float(v[j]) : -INFINITY);
+        }
       }
       const float m_new = fmaxf(m, cm);                          // finite: every chunk holds at least one key
       const float corr = ex2(m - m_new);                         // first chunk: 2^-inf = 0
@@ -242,12 +307,24 @@ attn_tc_kernel(AttnArgs p) {
         uint32_t v[32];
         tmem_ld32(t_lane + COL_S + 32 * b, v);
         uint32_t hi[16], mid[16];
+        if (nvalid == KC) {
+          float ps1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float p0 = (32 * b + 2 * j < nvalid) ? ex2(__uint_as_float(v[2 * j]) - m_new) : 0.f;
-          const float p1 = (32 * b + 2 * j + 1 < nvalid) ? ex2(__uint_as_float(v[2 * j + 1]) - m_new) : 0.f;
-          psum += p0 + p1;
-          split_bf16x2(p0, p1, hi[j], mid[j]);
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = ex2(__uint_as_float(v[2 * j]) - m_new), p1 = ex2(__uint_as_float(v[2 * j + 1]) - m_new);
+            psum += p0;
+            ps1 += p1;
+            split_bf16x2(p0, p1, hi[j], mid[j]);
+          }
+          psum += ps1;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = (32 * b + 2 * j < nvalid) ? ex2(__uint_as_float(v[2 * j]) - m_new) : 0.f;
+            const float p1 = (32 * b + 2 * j + 1 < nvalid) ? ex2(__uint_as_float(v[2 * j + 1]) - m_new) : 0.f;
+            psum += p0 + p1;
+            split_bf16x2(p0, p1, hi[j], mid[j]);
+          }
         }
         tmem_st16(t_lane + COL_S + 16 * b, hi);                  // over score columns this thread has already consumed
         tmem_st16(t_lane + COL_PMID + 16 * b, mid);
@@ -292,35 +369,32 @@ attn_tc_kernel(AttnArgs p) {
       // scores in the log2 domain: softmax(x) = 2^(x log2 e - max)
       stage_row(sb + OFF_Q, t, p.q + grow * p.ldq + h * D, p.scale * 1.4426950408889634f, qrow < p.L);
     }
-    const long long k0 = seq_row0(p.km, n);
-    for (int c = 0; c < nchunks; ++c) {
-      const int stage = c & 1;
-      const uint32_t st_base = sb + OFF_STAGE + stage * STAGE_BYTES;
-      if (c >= 2) mbar_wait(kv_empty(stage), (uint32_t)(((c >> 1) - 1) & 1));
-      const int key = c * KC + t;
-      const bool valid = key < p.S;
-      const long long krow = k0 + (long long)key * p.km.step;
-      stage_row(st_base, t, p.k + krow * p.ldk + h * D, 1.f, valid);
-      // V^T: value (key t, dim d) -> row d of key atom t / 64, 2-byte column t % 64
-      const uint32_t vt = st_base + K_BYTES + (uint32_t)((t >> 6) * 4096), kc = (uint32_t)(t & 63);
-      const float* vp = p.v + krow * p.ldv + h * D;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) a = __ldg(reinterpret_cast<const float4*>(vp) + j);
-        const float vals[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int d = 4 * j + e;
-          __nv_bfloat16 hi, mid;
-          split_bf16(vals[e], hi, mid);
-          const uint32_t off = (uint32_t)d * 128u + ((((kc >> 3) ^ (uint32_t)(d & 7)) << 4) | ((kc & 7u) << 1));
-          sts16(vt + off, __bfloat16_as_ushort(hi));
-          sts16(vt + VT_PLANE + off, __bfloat16_as_ushort(mid));
+    fence_proxy_async();
+    mbar_arrive(q_full);
+    if (PREP) {
+      // one thread fetches the pre-converted 32 KB image of each chunk with a bulk copy that completes on the stage's barrier
+      if (t == 0) {
+        const int nkv = p.tc_shared_kv ? 0 : n;
+        const uint8_t* src = img + (size_t)(nkv * p.H + h) * nchunks * STAGE_BYTES;
+        for (int c = 0; c < nchunks; ++c) {
+          const int stage = c & 1;
+          const uint32_t st_base = sb + OFF_STAGE + stage * STAGE_BYTES;
+          if (c >= 2) mbar_wait(kv_empty(stage), (uint32_t)(((c >> 1) - 1) & 1));
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(kv_full(stage)), "r"((uint32_t)STAGE_BYTES) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(st_base), "l"(src + (size_t)c * STAGE_BYTES), "r"((uint32_t)STAGE_BYTES), "r"(kv_full(stage)) : "memory");
         }
       }
-      fence_proxy_async();                                       // generic-proxy writes -> visible to the tensor core's reads
-      mbar_arrive(kv_full(stage));
+    } else {
+      const long long k0 = seq_row0(p.km, n);
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c & 1;
+        const uint32_t st_base = sb + OFF_STAGE + stage * STAGE_BYTES;
+        if (c >= 2) mbar_wait(kv_empty(stage), (uint32_t)(((c >> 1) - 1) & 1));
+        stage_chunk(st_base, t, p, h, k0, c);
+        fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core's reads
+        mbar_arrive(kv_full(stage));
+      }
     }
   }
 
@@ -339,15 +413,29 @@ bool attention_tc_supported(const AttnArgs& a) {
          a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0 && a.ldo % 4 == 0;
 }
 
-cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
+size_t attention_tc_scratch_bytes(const AttnArgs& a) {
+  const bool shared = a.km.outer == 0 && a.km.inner_stride == 0;
+  return (size_t)(shared ? 1 : a.NB) * a.H * ceil_div(a.S, attn_tc::KC) * attn_tc::STAGE_BYTES;
+}
+
+// a.tc_scratch (attention_tc_scratch_bytes, 16-byte aligned): K / V are converted once by attn_tc_prep_kernel (second launch of this
+// call); without scratch every CTA converts its own chunks
+cudaError_t launch_attention_tc(const AttnArgs& a0, cudaStream_t st) {
   using namespace attn_tc;
-  if (!attention_tc_supported(a)) return cudaErrorNotSupported;
+  if (!attention_tc_supported(a0)) return cudaErrorNotSupported;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  AttnArgs a = a0;
+  a.tc_shared_kv = (a.km.outer == 0 && a.km.inner_stride == 0) ? 1 : 0;
   dim3 grid(ceil_div(a.L, QT), a.H, a.NB);
-  return launch_pdl(attn_tc_kernel, grid, dim3(THREADS), SMEM_BYTES, st, a);
+  if (a.tc_scratch == nullptr) return launch_pdl(attn_tc_kernel<false>, grid, dim3(THREADS), SMEM_BYTES, st, a, (const uint8_t*)nullptr);
+  dim3 pgrid(ceil_div(a.S, KC), a.H, a.tc_shared_kv ? 1 : a.NB);
+  cudaError_t e = launch_pdl(attn_tc_prep_kernel, pgrid, dim3(128), STAGE_BYTES, st, a, (uint8_t*)a.tc_scratch);
+  if (e != cudaSuccess) return e;
+  return launch_pdl(attn_tc_kernel<true>, grid, dim3(THREADS), SMEM_BYTES, st, a, (const uint8_t*)a.tc_scratch);
 }

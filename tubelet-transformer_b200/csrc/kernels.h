@@ -105,6 +105,7 @@ struct AttnArgs {
   const uint8_t* kpm; int kpm_div;           // key padding mask [NB / kpm_div, S] (1 = ignore key) or null
   int NB, H, L, S, D;                        // D = head dim (32, or any multiple of 32 for the warp kernel)
   float scale;
+  void* tc_scratch; int tc_shared_kv;        // attn_tc.cu only: optional workspace (attention_tc_scratch_bytes) / set by its launcher
 };
 // dispatcher: head_dim 32 -> the mma.sync kernels of attn_mma.cu (TUBER_ATTN_SIMT=1 in the environment forces the
 // CUDA-core kernels, the cross-check of the tests); other head dims -> the CUDA-core warp kernel
@@ -115,6 +116,7 @@ cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);
 // attn_tc.cu: tcgen05 flash attention for long sequences (head dim 32, no key mask, L >= 128, S >= 1024: the long-term context layer);
 // TUBER_ATTN_NO_TC=1 in the environment keeps those shapes on the mma.sync kernel (the tests' cross-check)
 bool attention_tc_supported(const AttnArgs& a);
+size_t attention_tc_scratch_bytes(const AttnArgs& a);
 cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t st);
 
 // ---- post-processing + detection rows (criterion.py:413-482; video_action_recognition.py:411-415) -------------

@@ -658,6 +658,13 @@ struct Ctx {
     a.o_f32 = nullptr; a.o_split = o_split; a.ldo = ldo; a.om = om;
     a.kpm = kpm; a.kpm_div = 1; a.NB = NB; a.H = H; a.L = L; a.S = S; a.D = D;
     a.scale = 1.f / sqrtf((float)D);
+    // long sequences run on the tcgen05 kernel, which wants K / V pre-converted once into per-chunk tile images (attn_tc.cu)
+    static const bool no_tc = [] { const char* e = getenv("TUBER_ATTN_NO_TC"); return e && e[0] == '1'; }();
+    static const bool no_prep = [] { const char* e = getenv("TUBER_ATTN_NO_PREP"); return e && e[0] == '1'; }();
+    if (!no_tc && !no_prep && attention_tc_supported(a)) {
+      a.tc_scratch = ws.alloc(attention_tc_scratch_bytes(a));
+      ++launches;                                              // the conversion launch (part of launch_attention_tc)
+    }
     if (p->kprof) snprintf(tag, sizeof tag, "NB=%d H=%d L=%d S=%d D=%d", NB, H, L, S, D);
     const double e = (double)H * D;
     launch("attention", 4.0 * e * ((double)NB * L * 2 + (double)NB * S * 2), 4.0 * (double)NB * H * L * S * D,
@@ -1692,6 +1699,18 @@ int tuber_op_attention(const float* q, const float* k, const float* v, const uin
   a.k = k; a.v = v; a.ldk = E; a.ldv = E; a.km = seqmap(1, S, 0, 1);
   a.o_f32 = out; a.ldo = E; a.om = seqmap(1, L, 0, 1);
   a.kpm = kpm; a.kpm_div = 1; a.NB = NB; a.H = H; a.L = L; a.S = S; a.D = D; a.scale = scale;
+  // long sequences (tcgen05 kernel): with TUBER_OP_ATTN_PREP=1 give it the conversion workspace the plan would (synchronises)
+  const char* prep = getenv("TUBER_OP_ATTN_PREP");
+  if (prep && prep[0] == '1' && attention_tc_supported(a)) {
+    void* scratch = nullptr;
+    CK(cudaMalloc(&scratch, attention_tc_scratch_bytes(a)));
+    a.tc_scratch = scratch;
+    cudaError_t e = launch_attention(a, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(scratch);
+    if (e != cudaSuccess) return fail(TUBER_ERR_CUDA, "attention: %s", cudaGetErrorString(e));
+    return TUBER_OK;
+  }
   CK(launch_attention(a, (cudaStream_t)stream));
   return TUBER_OK;
 }
