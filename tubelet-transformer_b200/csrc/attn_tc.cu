@@ -37,6 +37,7 @@ constexpr int STAGE_BYTES = K_BYTES + 2 * VT_PLANE;   // 32 KB
 constexpr int OFF_Q = 0, OFF_STAGE = Q_BYTES, OFF_BAR = OFF_STAGE + 2 * STAGE_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 constexpr int THREADS = 288;                      // warp 0 MMA, warps 1-4 softmax, warps 5-8 loaders
+constexpr int THREADS_PREP = 192;                 // PREP: warp 5 = one thread issuing bulk copies; the softmax warps stage Q
 constexpr int TMEM_COLS = 256;
 constexpr int COL_S = 0, COL_PMID = 128, COL_O = 192;
 
@@ -116,6 +117,24 @@ TB_DEVINL float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32 pairs (one issue slot per two operations: the softmax warps are issue bound)
+typedef unsigned long long u64;
+TB_DEVINL u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+TB_DEVINL void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+TB_DEVINL u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+TB_DEVINL u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 // K-major, 128B-swizzle shared-memory matrix descriptor (8-row groups 1024 B apart; same encoding as gemm_tc.cu / stem_tc.cu)
 TB_DEVINL uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -192,7 +211,7 @@ attn_tc_prep_kernel(AttnArgs p, uint8_t* __restrict__ img) {
 }
 
 template <bool PREP>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(PREP ? THREADS_PREP : THREADS, 2)
 attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
@@ -272,6 +291,13 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
 #pragma unroll
     for (int i = 0; i < D; ++i) o[i] = 0.f;
     float m = -INFINITY, l = 0.f;
+    if (PREP) {                                                  // no loader warps: this thread stages its own query row
+      const int qrow = l0 + row;
+      const long long grow = seq_row0(p.qm, n) + (long long)qrow * p.qm.step;
+      stage_row(sb + OFF_Q, row, p.q + grow * p.ldq + h * D, p.scale * 1.4426950408889634f, qrow < p.L);
+      fence_proxy_async();
+      mbar_arrive(q_full);
+    }
     for (int c = 0; c < nchunks; ++c) {
       const int nvalid = min(KC, p.S - c * KC);
       mbar_wait(s_full, (uint32_t)(c & 1));
@@ -308,15 +334,26 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
         tmem_ld32(t_lane + COL_S + 32 * b, v);
         uint32_t hi[16], mid[16];
         if (nvalid == KC) {
-          float ps1 = 0.f;
+          const u64 negm = pack2(-m_new, -m_new), neg1 = pack2(-1.f, -1.f);
+          u64 ps2 = pack2(0.f, 0.f);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float p0 = ex2(__uint_as_float(v[2 * j]) - m_new), p1 = ex2(__uint_as_float(v[2 * j + 1]) - m_new);
-            psum += p0;
-            ps1 += p1;
-            split_bf16x2(p0, p1, hi[j], mid[j]);
+            float x0, x1;
+            unpack2(add2(pack2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), negm), x0, x1);
+            const u64 pp = pack2(ex2(x0), ex2(x1));
+            ps2 = add2(ps2, pp);
+            float p0, p1;
+            unpack2(pp, p0, p1);
+            const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+            hi[j] = *reinterpret_cast<const uint32_t*>(&hb);
+            float d0, d1;                                        // p - float(hi), exactly
+            unpack2(fma2(pack2(__uint_as_float(hi[j] << 16), __uint_as_float(hi[j] & 0xffff0000u)), neg1, pp), d0, d1);
+            const __nv_bfloat162 mb = __floats2bfloat162_rn(d0, d1);
+            mid[j] = *reinterpret_cast<const uint32_t*>(&mb);
           }
-          psum += ps1;
+          float s0, s1;
+          unpack2(ps2, s0, s1);
+          psum += s0 + s1;
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -362,15 +399,15 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
     }
   } else {
     // ================= loaders: thread = query row (once), then = key of the chunk =================
-    const int t = threadIdx.x - 160;                             // 0..127
-    {
+    const int t = threadIdx.x - 160;                             // 0..127 (PREP: 0..31, only thread 0 works)
+    if (!PREP) {
       const int qrow = l0 + t;
       const long long grow = seq_row0(p.qm, n) + (long long)qrow * p.qm.step;
       // scores in the log2 domain: softmax(x) = 2^(x log2 e - max)
       stage_row(sb + OFF_Q, t, p.q + grow * p.ldq + h * D, p.scale * 1.4426950408889634f, qrow < p.L);
+      fence_proxy_async();
+      mbar_arrive(q_full);
     }
-    fence_proxy_async();
-    mbar_arrive(q_full);
     if (PREP) {
       // one thread fetches the pre-converted 32 KB image of each chunk with a bulk copy that completes on the stage's barrier
       if (t == 0) {
@@ -437,5 +474,5 @@ cudaError_t launch_attention_tc(const AttnArgs& a0, cudaStream_t st) {
   dim3 pgrid(ceil_div(a.S, KC), a.H, a.tc_shared_kv ? 1 : a.NB);
   cudaError_t e = launch_pdl(attn_tc_prep_kernel, pgrid, dim3(128), STAGE_BYTES, st, a, (uint8_t*)a.tc_scratch);
   if (e != cudaSuccess) return e;
-  return launch_pdl(attn_tc_kernel<true>, grid, dim3(THREADS), SMEM_BYTES, st, a, (const uint8_t*)a.tc_scratch);
+  return launch_pdl(attn_tc_kernel<true>, grid, dim3(THREADS_PREP), SMEM_BYTES, st, a, (const uint8_t*)a.tc_scratch);
 }
