@@ -7,13 +7,14 @@
 // library's usual precision (common.cuh): every fp32 operand is split into bf16 hi + mid and a product is evaluated as
 // a_hi*b_hi + a_hi*b_mid + a_mid*b_hi with fp32 accumulation in tensor memory.
 //
-//   warps 5-8  loaders: Q tile once, then per chunk K (row = key: hi[32] | mid[32] bf16 = one 128-byte swizzled row, K-major)
+//   warps 9-12 loaders: Q tile once, then per chunk K (row = key: hi[32] | mid[32] bf16 = one 128-byte swizzled row, K-major)
 //              and V TRANSPOSED (row = head dim, 128 keys per row as two 64-key swizzle atoms; hi and mid planes) into a
 //              2-stage shared-memory ring, converted from the fp32 projections on the fly.
 //   warp 0     MMA issuer.  S = Q K^T: 6 tcgen05.mma (M=128, N=128, K=16; 2 dim halves x 3 passes) into TMEM columns [0,128).
 //              O_c = P V: 24 tcgen05.mma (M=128, N=32, K=16; 8 key steps x 3 passes) with P read FROM TENSOR MEMORY (A operand)
 //              and V^T from shared memory, into TMEM columns [192,224) -- a fresh accumulator per chunk.
-//   warps 1-4  softmax, thread = query row (its TMEM lane): pass 1 reads the 128 scores for the row maximum, pass 2 reads
+//   warps 1-8  softmax, two threads per query row (its TMEM lane), each owning 64 of the chunk's keys and 16 output dims (the halves
+//              swap their maxima through shared memory): pass 1 reads the scores for the row maximum, pass 2 reads
 //              them again, exponentiates, splits into bf16 hi | mid and writes P back to tensor memory (hi over the score
 //              columns already consumed, mid to columns [128,192)); then adds the chunk's O_c to the running output in
 //              registers with the usual rescaling  o = o * exp(m_old - m_new) + O_c  -- no TMEM accumulator to rescale.
@@ -35,9 +36,10 @@ constexpr int K_BYTES = KC * 128;
 constexpr int VT_PLANE = 2 * 32 * 128;            // [2 key atoms][32 dims][64 keys] bf16 = 8 KB
 constexpr int STAGE_BYTES = K_BYTES + 2 * VT_PLANE;   // 32 KB
 constexpr int OFF_Q = 0, OFF_STAGE = Q_BYTES, OFF_BAR = OFF_STAGE + 2 * STAGE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 128;
-constexpr int THREADS = 288;                      // warp 0 MMA, warps 1-4 softmax, warps 5-8 loaders
-constexpr int THREADS_PREP = 192;                 // PREP: warp 5 = one thread issuing bulk copies; the softmax warps stage Q
+constexpr int OFF_XCH = OFF_BAR + 128;              // [2][128] floats
+constexpr int SMEM_BYTES = OFF_XCH + 1024;
+constexpr int THREADS = 416;                      // warp 0 MMA, warps 1-8 softmax (two per query row), warps 9-12 loaders
+constexpr int THREADS_PREP = 320;                 // PREP: warp 9 = one thread issuing bulk copies; softmax group 0 stages Q
 constexpr int TMEM_COLS = 256;
 constexpr int COL_S = 0, COL_PMID = 128, COL_O = 192;
 
@@ -105,6 +107,16 @@ TB_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+TB_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
@@ -230,7 +242,7 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
     mbar_init(kv_full(0), PREP ? 1 : 128); mbar_init(kv_full(1), PREP ? 1 : 128);
     mbar_init(q_full, 128);
     mbar_init(kv_empty(0), 1); mbar_init(kv_empty(1), 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 256); mbar_init(o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -273,7 +285,7 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {                         // 16 keys per step; 64-key atoms are 4 KB apart
           const uint64_t off = (uint64_t)((ks >> 2) * (4096 >> 4) + 2 * (ks & 3));
-          const uint32_t p_hi = tmem_base + COL_S + 8 * ks, p_mid = tmem_base + COL_PMID + 8 * ks;
+          const uint32_t p_hi = tmem_base + COL_S + 64 * (ks >> 2) + 8 * (ks & 3), p_mid = tmem_base + COL_PMID + 8 * ks;   // hi: per key half, see softmax
           umma_ts(tmem_base + COL_O, p_mid, vh_desc + off, idesc_o, ks == 0 ? 0u : 1u);
           umma_ts(tmem_base + COL_O, p_hi, vm_desc + off, idesc_o, 1u);
           umma_ts(tmem_base + COL_O, p_hi, vh_desc + off, idesc_o, 1u);
@@ -283,15 +295,18 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
       }
       __syncwarp();
     }
-  } else if (warp <= 4) {
-    // ================= softmax + output accumulation: thread = query row =================
-    const int lg = warp & 3, row = lg * 32 + lane;
+  } else if (warp <= 8) {
+    // ================= softmax + output accumulation: two threads per query row, each owns 64 of the chunk's 128 keys and 16 of
+    // the 32 output dims (group g = 0: warps 1-4, g = 1: warps 5-8; a warp reaches the TMEM lanes 32 (warp % 4) ..) =================
+    const int g = (warp - 1) >> 2, lg = warp & 3, row = lg * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(lg * 32) << 16);
-    float o[D];
+    const uint32_t col_s = COL_S + 64 * g, col_pm = COL_PMID + 32 * g;
+    float* xch = reinterpret_cast<float*>(smem + OFF_XCH);        // [2][128]: the two halves of a row exchange their maxima / sums
+    float o[D / 2];
 #pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    for (int i = 0; i < D / 2; ++i) o[i] = 0.f;
     float m = -INFINITY, l = 0.f;
-    if (PREP) {                                                  // no loader warps: this thread stages its own query row
+    if (PREP && g == 0) {                                        // no loader warps: group 0 stages the query rows
       const int qrow = l0 + row;
       const long long grow = seq_row0(p.qm, n) + (long long)qrow * p.qm.step;
       stage_row(sb + OFF_Q, row, p.q + grow * p.ldq + h * D, p.scale * 1.4426950408889634f, qrow < p.L);
@@ -299,15 +314,15 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
       mbar_arrive(q_full);
     }
     for (int c = 0; c < nchunks; ++c) {
-      const int nvalid = min(KC, p.S - c * KC);
+      const int nvalid = min(KC, p.S - c * KC) - 64 * g;           // valid keys among this thread's 64 (may be <= 0 in the last chunk)
       mbar_wait(s_full, (uint32_t)(c & 1));
       tcgen05_fence_after();
       float cm = -INFINITY;
-      if (nvalid == KC) {                                        // full chunk (all but possibly the last): no key predicates
+      if (nvalid >= 64) {                                        // full half chunk: no key predicates
 #pragma unroll 1
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < 2; ++b) {
           uint32_t v[32];
-          tmem_ld32(t_lane + COL_S + 32 * b, v);
+          tmem_ld32(t_lane + col_s + 32 * b, v);
           float c0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), c1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
 #pragma unroll
           for (int j = 4; j < 32; j += 4) {
@@ -318,22 +333,25 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
         }
       } else {
 #pragma unroll 1
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < 2; ++b) {
           uint32_t v[32];
-          tmem_ld32(t_lane + COL_S + 32 * b, v);
+          tmem_ld32(t_lane + col_s + 32 * b, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) cm = fmaxf(cm, (32 * b + j < nvalid) ? __uint_as_float(v[j]) : -INFINITY);
         }
       }
+      xch[g * 128 + row] = cm;
+      asm volatile("bar.sync 1, 256;" ::: "memory");             // (the slot is rewritten only after every thread has passed p_full of this chunk)
+      cm = fmaxf(cm, xch[(g ^ 1) * 128 + row]);
       const float m_new = fmaxf(m, cm);                          // finite: every chunk holds at least one key
       const float corr = ex2(m - m_new);                         // first chunk: 2^-inf = 0
       float psum = 0.f;
 #pragma unroll 1
-      for (int b = 0; b < 4; ++b) {
+      for (int b = 0; b < 2; ++b) {
         uint32_t v[32];
-        tmem_ld32(t_lane + COL_S + 32 * b, v);
+        tmem_ld32(t_lane + col_s + 32 * b, v);
         uint32_t hi[16], mid[16];
-        if (nvalid == KC) {
+        if (nvalid >= 64) {
           const u64 negm = pack2(-m_new, -m_new), neg1 = pack2(-1.f, -1.f);
           u64 ps2 = pack2(0.f, 0.f);
 #pragma unroll
@@ -363,8 +381,8 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
             split_bf16x2(p0, p1, hi[j], mid[j]);
           }
         }
-        tmem_st16(t_lane + COL_S + 16 * b, hi);                  // over score columns this thread has already consumed
-        tmem_st16(t_lane + COL_PMID + 16 * b, mid);
+        tmem_st16(t_lane + col_s + 16 * b, hi);                  // over score columns this thread has already consumed
+        tmem_st16(t_lane + col_pm + 16 * b, mid);
       }
       tmem_st_wait();
       tcgen05_fence_before();
@@ -374,32 +392,37 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
       mbar_wait(o_full, (uint32_t)(c & 1));
       tcgen05_fence_after();
       {
-        uint32_t oc[32];
-        tmem_ld32(t_lane + COL_O, oc);
+        uint32_t oc[16];
+        tmem_ld16(t_lane + COL_O + 16 * g, oc);
 #pragma unroll
-        for (int i = 0; i < D; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(oc[i]));
+        for (int i = 0; i < D / 2; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(oc[i]));
       }
       tcgen05_fence_before();
     }
+    // the row's normaliser = the sum of both halves
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    xch[g * 128 + row] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += xch[(g ^ 1) * 128 + row];
     if (l0 + row < p.L) {
       const float inv = 1.f / l;
       const long long orow = seq_row0(p.om, n) + (long long)(l0 + row) * p.om.step;
-      const int col = h * D;
+      const int col = h * D + 16 * g;
       if (p.o_f32) {
         float4* dst = reinterpret_cast<float4*>(p.o_f32 + orow * p.ldo + col);
 #pragma unroll
-        for (int i = 0; i < D / 4; ++i) dst[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
+        for (int i = 0; i < D / 8; ++i) dst[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
       }
       if (p.o_split) {
         __nv_bfloat16* hp = split_hi(p.o_split, orow, p.ldo) + col;
 #pragma unroll
-        for (int i = 0; i < D / 4; ++i)
+        for (int i = 0; i < D / 8; ++i)
           store_split4(hp + 4 * i, hp + p.ldo + 4 * i, make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv));
       }
     }
   } else {
     // ================= loaders: thread = query row (once), then = key of the chunk =================
-    const int t = threadIdx.x - 160;                             // 0..127 (PREP: 0..31, only thread 0 works)
+    const int t = threadIdx.x - 288;                             // 0..127 (PREP: 0..31, only thread 0 works)
     if (!PREP) {
       const int qrow = l0 + t;
       const long long grow = seq_row0(p.qm, n) + (long long)qrow * p.qm.step;
