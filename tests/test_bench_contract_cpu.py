@@ -1,0 +1,42 @@
+"""CPU: the bench.py contract that can be checked without a GPU -- the reference arm prints exactly one JSON line with the keys the
+driver reads, and the B200 arm refuses to run (no CPU fallback) when there is no CUDA device."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=600, cwd=ROOT)
+
+
+def test_reference_arm_prints_one_json_line():
+    r = _run("--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "1", "--batch", "1", "--clip", "8", "64", "64")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "clips/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert k in d, k
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_b200_arm_has_no_cpu_fallback():
+    if torch.cuda.is_available():
+        return
+    r = _run("--steps", "1")
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
