@@ -47,15 +47,28 @@ CASES = {
 }
 
 
+# Configuration branches no shipped YAML selects (max pool, LAST_STRIDE, SINGLE_FRAME: False): the oracle is pinned on them too
+# (tests/test_oracle_golden.py); they are not part of the GPU parity parametrisation above.
+CPU_ONLY_CASES = {
+    "X_max": dict(yaml="TubeR_CSN50_AVA21.yaml", over=_A + ["CONFIG.MODEL.TEMPORAL_DS_STRATEGY", "max", "CONFIG.MODEL.TEMP_LEN", 32],
+                  clips=[(32, 64, 64)], wseed=20, cseed=21, bn="random"),
+    "X_last_stride": dict(yaml="TubeR_CSN50_AVA21.yaml", over=_A + ["CONFIG.MODEL.LAST_STRIDE", True], clips=[(8, 128, 96)],
+                          wseed=22, cseed=23, bn="random"),
+    "X_all_frames": dict(yaml="TubeR_CSN50_AVA21.yaml", over=_A + ["CONFIG.MODEL.SINGLE_FRAME", False], clips=[(16, 64, 64)] * 2,
+                         wseed=24, cseed=25, bn="random"),
+}
+CASES_ALL = dict(CASES, **CPU_ONLY_CASES)
+
+
 def load_case_cfg(name: str):
     import tuber_b200  # config loader only (plain YAML plumbing)
-    c = CASES[name]
+    c = CASES_ALL[name]
     return tuber_b200.load_cfg(c["yaml"], c["over"])
 
 
 def build_case(name: str) -> Tuple[object, dict, torch.Tensor, Optional[torch.Tensor]]:
     """-> (cfg, state_dict, clips (B,3,T,H,W), mask (B,H,W) or None)."""
-    c = CASES[name]
+    c = CASES_ALL[name]
     cfg = load_case_cfg(name)
     sd = O.make_state_dict(cfg, seed=c["wseed"], bn=c["bn"])
     shapes = c["clips"]

@@ -31,7 +31,7 @@ REF = os.environ.get("TUBER_REFERENCE", "/root/reference")
 sys.path.insert(0, ROOT)
 
 from oracle import tuber_oracle as O          # noqa: E402
-from oracle.cases import CASES, build_case   # noqa: E402
+from oracle.cases import CASES, CASES_ALL, build_case   # noqa: E402
 
 
 def _reference_model(cfg):
@@ -45,7 +45,7 @@ def _reference_model(cfg):
 
 
 def run_case(name: str) -> None:
-    case = CASES[name]
+    case = CASES_ALL[name]
     cfg, sd, clips, mask = build_case(name)
     model = _reference_model(cfg)
     ref_sd = model.state_dict()
@@ -103,7 +103,7 @@ def run_case(name: str) -> None:
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or list(CASES_ALL)
     torch.set_num_threads(os.cpu_count() or 1)
     for n in names:
         run_case(n)

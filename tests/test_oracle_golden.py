@@ -10,13 +10,13 @@ import pytest
 import torch
 
 from oracle import tuber_oracle as O
-from oracle.cases import CASES, build_case
+from oracle.cases import CASES_ALL, build_case
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = 2e-5   # fp32 CPU vs fp32 CPU, different op grouping only
 
 
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", list(CASES_ALL))
 def test_oracle_matches_reference_golden(name):
     cfg, sd, clips, mask = build_case(name)
     g = np.load(os.path.join(GOLD, name + ".npz"))
