@@ -237,6 +237,20 @@ def test_real_evaluation_sizes_match_oracle(yaml, shapes):
             assert emax <= TOL and el2 <= TOL, (yaml, shapes, k, emax, el2)
 
 
+@pytest.mark.parametrize("name", ["X_max", "X_last_stride", "X_all_frames"])
+def test_unshipped_config_branches_match_reference_golden(name):
+    """TEMPORAL_DS_STRATEGY: max, LAST_STRIDE: True, SINGLE_FRAME: False -- branches of the reference no shipped YAML selects
+    (oracle/cases.py::CPU_ONLY_CASES, fixtures from the reference): the three output tensors of every decoder layer."""
+    cfg, sd, clips, mask = build_case(name)
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    model = _model(cfg, sd)
+    out = model.forward_raw(clips.cuda(), None if mask is None else mask.cuda())
+    torch.cuda.synchronize()
+    for key in ("pred_logits", "pred_boxes", "pred_logits_b"):
+        emax, el2 = _rel(_layers_first(out, key), torch.from_numpy(g[key]))
+        assert emax <= TOL and el2 <= TOL, (name, key, emax, el2)
+
+
 def test_no_fallback_off_device():
     import tuber_b200
     cfg, sd, clips, _ = build_case("A_csn50")
