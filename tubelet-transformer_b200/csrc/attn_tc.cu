@@ -15,10 +15,10 @@
 //              and V^T from shared memory, into TMEM columns [192,224) -- a fresh accumulator per chunk.
 //   warps 1-8  softmax, two threads per query row (its TMEM lane), each owning 64 of the chunk's keys and 16 output dims (the halves
 //              swap their maxima through shared memory): pass 1 reads the scores for the row maximum, pass 2 reads
-//              them again, exponentiates, splits into bf16 hi | mid and writes P back to tensor memory (hi over the score
-//              columns already consumed, mid to columns [128,192)); then adds the chunk's O_c to the running output in
+//              them again, exponentiates, splits into bf16 hi | mid and writes P back to tensor memory (hi of key half g over the
+//              score columns [64g, 64g+32) that thread has already consumed, mid to columns [128,192)); then adds its half of O_c to the running output in
 //              registers with the usual rescaling  o = o * exp(m_old - m_new) + O_c  -- no TMEM accumulator to rescale.
-// Two CTAs share an SM (80 KB of shared memory and 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
+// Two CTAs share an SM (81 KB of shared memory and 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
 //
 // PREP variant (used by the plan, which has workspace to give): every (key sequence, head) is read by all the query tiles of all
 // the clips that share it, so attn_tc_prep_kernel converts K / V ONCE into the exact 32 KB shared-memory image of each chunk
