@@ -210,7 +210,11 @@ def test_uint8_frames_path_is_bit_identical_to_the_float_path():
 
 @pytest.mark.parametrize("yaml,shapes", [("TubeR_CSN50_AVA21.yaml", [(32, 256, 341)]),
                                          ("TubeR_CSN50_AVA21.yaml", [(32, 256, 455), (32, 256, 341)]),
-                                         ("Tuber_CSN152_JHMDB.yaml", [(16, 224, 298)])])
+                                         ("Tuber_CSN152_JHMDB.yaml", [(16, 224, 298)]),
+                                         # the metric's own configuration (BASELINE.json configs[2]: CSN-152, avg pool -- SURVEY 8d's worst
+                                         # precision case) and configs[4] at their full sizes, two clips, randomised BatchNorm
+                                         ("TubeR_CSN152_AVA21.yaml", [(32, 256, 256)] * 2),
+                                         ("Tuber_CSN152_JHMDB.yaml", [(16, 256, 256)] * 2)])
 def test_real_evaluation_sizes_match_oracle(yaml, shapes):
     """The clip sizes the reference's evaluation transform actually produces (Resize_Custom keeps the aspect ratio,
     datasets/video_transforms.py:213-228: 256x341 / 256x455 on AVA, 224x298 on JHMDB; a batch mixes widths and is zero-padded with a
@@ -220,10 +224,10 @@ def test_real_evaluation_sizes_match_oracle(yaml, shapes):
     cfg = tuber_b200.load_cfg(yaml)
     sd = O.make_state_dict(cfg, seed=21, bn="random")
     clips = [O.make_clips(1, t, h, w, seed=30 + i)[0] for i, (t, h, w) in enumerate(shapes)]
-    if len(clips) > 1:
+    if len(set(shapes)) > 1:
         batch, mask = O.pad_clips(clips)
     else:
-        batch, mask = clips[0][None], None
+        batch, mask = torch.stack(clips), None
     torch.set_num_threads(os.cpu_count() or 1)
     ref = O.forward(cfg, sd, batch, mask)
     model = _model(cfg, sd)

@@ -550,18 +550,6 @@ def format_detection_lines(frame_ids, rows) -> List[str]:
     return ["{} {}\n".format(i, r.tolist()) for i, r in zip(ids, flat)]
 
 
-class _TrainingOnlyCriterion(nn.Module):
-    """The loss (reference SetCriterionAVA / SetCriterion, criterion.py:11-410) is training code and is
-    outside this package's scope; the object exists so ``build_model`` keeps its 3-tuple signature."""
-
-    def __init__(self):
-        super().__init__()
-        self.weight_dict: Dict[str, float] = {}
-
-    def forward(self, outputs, targets):
-        raise NotImplementedError("tuber_b200 covers the inference forward; use the reference criterion for losses")
-
-
 def build_model(cfg):
     """-> (model, criterion, postprocessors), the reference's build_model signature (tuber_ava.py:160-221)."""
     model = DETR(cfg)
@@ -571,4 +559,5 @@ def build_model(cfg):
         load_csn_mat(model, m.PRETRAIN_BACKBONE_DIR)
     ava = cfg.CONFIG.DATA.DATASET_NAME == "ava"
     postprocessors = {"bbox": PostProcessAVA() if ava else PostProcess()}
-    return model, _TrainingOnlyCriterion(), postprocessors
+    from .criterion import build_criterion
+    return model, build_criterion(cfg), postprocessors
