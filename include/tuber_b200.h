@@ -157,6 +157,8 @@ int tuber_set_force_simt(TuberPlan* plan, int32_t enabled);
 int tuber_set_debug_keep(TuberPlan* plan, int32_t enabled);
 /* Kernel launches (+ memsets / copies) issued by the last eager forward. */
 int tuber_last_launches(TuberPlan* plan);
+/* Recorded CUDA graphs the plan currently holds (one per (shape, buffer addresses); tuber_set_graph). */
+int tuber_graph_count(TuberPlan* plan);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* When enabled, tuber_forward brackets each stage with CUDA events (adds event records only). */

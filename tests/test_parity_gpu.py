@@ -354,3 +354,88 @@ def test_detection_rows_match_reference_postprocessors():
     assert np.abs(rows[..., :4] - g["boxes_jo"]).max() < 1e-3
     assert np.abs(rows[..., 4:4 + Cj] - g["scores_j"]).max() < 2e-6
     assert np.abs(rows[..., 4 + Cj] - np.broadcast_to(g["p_j"], (Bj, Qj))).max() < 2e-6
+
+
+def test_force_simt_switch_drops_recorded_graphs():
+    """tuber_set_force_simt after a shape has been recorded: the replayed graph must hold the CUDA-core kernels, not the recorded
+    tensor-core ones (the cross-check would otherwise compare the tensor-core path with itself)."""
+    from tuber_b200 import _lib
+    cfg, sd, clips, _ = build_case("A_csn50_avg_bnrand")
+    model = _model(cfg, sd)
+    model.use_cuda_graph(True)
+    x = clips.cuda()
+    out = {k: torch.empty_like(v) for k, v in model.forward_raw(x).items()}
+    for _ in range(2):
+        model.forward_raw(x, None, out)
+    tc = {k: v.clone() for k, v in out.items()}
+    _lib.check(_lib.load().tuber_set_force_simt(model.plan(), 1))
+    for _ in range(2):
+        model.forward_raw(x, None, out)
+    torch.cuda.synchronize()
+    assert any(not torch.equal(out[k], tc[k]) for k in tc)              # different arithmetic -> different low bits
+    for k in tc:
+        assert _rel(out[k], tc[k])[1] < 1e-4, k
+
+
+def test_graph_mode_replays_through_the_drop_in_call():
+    """model(samples) allocates its outputs: in graph mode the module stages clips / outputs per shape so that step 2.. replay."""
+    import tuber_b200
+    from tuber_b200 import _lib
+    cfg, sd, clips, _ = build_case("A_csn50")
+    model = _model(cfg, sd)
+    x = clips.cuda()
+    eager = model(x)
+    model.use_cuda_graph(True)
+    lib = _lib.load()
+    outs = [model(x) for _ in range(3)]
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o["pred_logits"], eager["pred_logits"]) and torch.equal(o["pred_boxes"], eager["pred_boxes"])
+    assert outs[0]["pred_logits"].data_ptr() != outs[1]["pred_logits"].data_ptr()       # the caller owns what it gets
+    assert lib.tuber_graph_count(model.plan()) == 1                                     # one recorded graph, replayed
+
+
+def test_weight_with_the_wrong_layout_is_rejected():
+    """tuber_plan_finalize: a (K, N)-transposed tensor has the right element count but not the right shape."""
+    import ctypes as C
+    import tuber_b200
+    from tuber_b200 import _lib
+    cfg, sd, _, _ = build_case("A_csn50")
+    model, _, _ = tuber_b200.build_model(cfg)
+    sd = dict(sd)
+    name = "transformer.encoder.layers.0.linear1.weight"                 # (2048, 256)
+    sd[name] = sd[name].t().contiguous()
+    lib = _lib.load()
+    plan = C.c_void_p()
+    with torch.cuda.device(0):
+        _lib.check(lib.tuber_plan_create(C.byref(model._tcfg), C.byref(plan)))
+        try:
+            for k, t in sd.items():
+                if not t.is_floating_point():
+                    continue
+                h = t.float().contiguous()
+                shape = (C.c_int64 * max(1, h.dim()))(*h.shape)
+                _lib.check(lib.tuber_plan_set_weight(plan, k.encode(), C.c_void_p(h.data_ptr()), shape, h.dim()))
+            assert lib.tuber_plan_finalize(plan) == _lib.TUBER_ERR_SHAPE
+            assert b"does not flatten" in lib.tuber_last_error()
+            bad = (C.c_int64 * 2)(-4, 4)
+            assert lib.tuber_plan_set_weight(plan, b"x", C.c_void_p(h.data_ptr()), bad, 2) == _lib.TUBER_ERR_SHAPE
+        finally:
+            lib.tuber_plan_destroy(plan)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """One plan per device in the same process: the kernels' shared-memory opt-in and the SM count are per device."""
+    cfg, sd, clips, _ = build_case("A_csn50_avg_bnrand")
+    g = np.load(os.path.join(GOLD, "A_csn50_avg_bnrand.npz"))
+    import tuber_b200
+    for dev in (1, 0):                                                    # the second device first: nothing was set up on it yet
+        model, _, _ = tuber_b200.build_model(cfg)
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda(dev).eval()
+        out = model.forward_raw(clips.cuda(dev))
+        torch.cuda.synchronize(dev)
+        for key in ("pred_logits", "pred_boxes", "pred_logits_b"):
+            emax, el2 = _rel(_layers_first(out, key), torch.from_numpy(g[key]))
+            assert emax <= TOL and el2 <= TOL, (dev, key, emax, el2)

@@ -15,6 +15,7 @@ TUBER_ABI_VERSION = 1
 NUM_STAGES = 10
 POOL = {"avg": 0, "max": 1, "decode": 2, "center": 3, "none": 4}
 FMT_F32, FMT_SPLIT = 0, 1
+TUBER_OK, TUBER_ERR_INVALID, TUBER_ERR_MISSING, TUBER_ERR_SHAPE, TUBER_ERR_CUDA, TUBER_ERR_STATE = 0, -1, -2, -3, -4, -5
 
 
 class TuberConfig(C.Structure):
@@ -66,6 +67,7 @@ PROTOTYPES = {
     "tuber_set_force_simt": (_I, [_P, _I]),
     "tuber_set_debug_keep": (_I, [_P, _I]),
     "tuber_last_launches": (_I, [_P]),
+    "tuber_graph_count": (_I, [_P]),
     "tuber_set_profiling": (_I, [_P, _I]),
     "tuber_get_stage_ms": (_I, [_P, C.POINTER(_F)]),
     "tuber_stage_name": (C.c_char_p, [_I]),

@@ -113,10 +113,10 @@ _DEFAULTS = {
         "AUTO_RANK_MATCH": True, "DIST_BACKEND": "nccl", "GPU": 0, "DISTRIBUTED": True,
     },
     "CONFIG": {
-        "EVAL_ONLY": False, "USE_LFB": False,
+        "EVAL_ONLY": False, "USE_LFB": False, "USE_LOCATION": False, "TWO_STREAM": False,
         "TRAIN": {"AUX_LOSS": True, "LR_BACKBONE": 1e-5, "BATCH_SIZE": 2},
         "VAL": {"BATCH_SIZE": 1, "FREQ": 1},
-        "DATA": {"DATASET_NAME": "ava", "NUM_CLASSES": 80, "IMG_SIZE": 256, "TEMP_LEN": 32},
+        "DATA": {"DATASET_NAME": "ava", "NUM_CLASSES": 80, "IMG_SIZE": 256, "TEMP_LEN": 32, "LABEL_PATH": "", "ANNO_PATH": "", "DATA_PATH": ""},
         "MODEL": {
             "SINGLE_FRAME": True, "BACKBONE_NAME": "CSN-152", "TEMPORAL_DS_STRATEGY": "avg",
             "LAST_STRIDE": False, "GENERATE_LFB": False,

@@ -427,13 +427,10 @@ cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
   }
   if (a.NB > 65535 || a.H > 65535) return cudaErrorNotSupported;
   if (a.L <= QW && a.S > KC) {                               // one query tile, several key chunks: split the keys over the warps
-    static bool attr_set = false;
+    static DeviceOnce once;
     const size_t smem = SPLIT_NW * sizeof(Smem);
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_mma_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
+    cudaError_t e = once.run([smem]() { return cudaFuncSetAttribute(attn_mma_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    if (e != cudaSuccess) return e;
     return launch_pdl(attn_mma_split_kernel, dim3(1, a.H, a.NB), dim3(SPLIT_NW * 32), smem, st, a);
   }
   if (a.L > 64) {

@@ -483,12 +483,14 @@ size_t attention_tc_scratch_bytes(const AttnArgs& a) {
 cudaError_t launch_attention_tc(const AttnArgs& a0, cudaStream_t st) {
   using namespace attn_tc;
   if (!attention_tc_supported(a0)) return cudaErrorNotSupported;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  static DeviceOnce once;
+  {
+    cudaError_t e = once.run([]() {
+      cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      return e;
+    });
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   AttnArgs a = a0;
   a.tc_shared_kv = (a.km.outer == 0 && a.km.inner_stride == 0) ? 1 : 0;

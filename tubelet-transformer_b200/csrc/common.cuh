@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 enum TuberFmt { FMT_F32 = 0, FMT_SPLIT = 1 };
 enum TuberAct { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
 
@@ -85,6 +87,40 @@ TB_DEVINL float warp_max(float v) {
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- per-device one-time set-up ----------------------------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to a DEVICE, not to the process: a second plan on
+// another GPU of the same process needs its own opt-in (include/tuber_b200.h: "one plan per (device, config), different plans are
+// independent").  DeviceOnce::run executes `setup` once per device, under a mutex (concurrent first calls from two host threads).
+struct DeviceOnce {
+  static constexpr int MAX_DEVICES = 64;
+  std::mutex mu;
+  bool done[MAX_DEVICES] = {};
+  template <class F>
+  cudaError_t run(F&& setup) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= MAX_DEVICES) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev]) return cudaSuccess;
+    e = setup();
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
+  }
+};
+// SM count of the CURRENT device (cached per device)
+static inline int device_num_sms() {
+  static int cache[DeviceOnce::MAX_DEVICES] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= DeviceOnce::MAX_DEVICES) return 1;
+  int n = cache[dev];
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n;                                  // benign race: every writer stores the same value
+  }
+  return n > 0 ? n : 1;
+}
 
 // ---- programmatic dependent launch (PDL) --------------------------------------------------------------------
 // A forward is a chain of ~190 dependent launches, most of them a few microseconds long.  Kernels launched through

@@ -1177,38 +1177,27 @@ static_assert(PAIR_SMEM_BYTES <= 232448, "over the 227 KB shared-memory limit");
 
 static char g_err[256] = "";
 static EncodeTiledFn g_encode = nullptr;
-static int g_num_sms = 0;
-
+static DeviceOnce g_dev_once;
 static cudaError_t init_once() {
-  if (g_encode) return cudaSuccess;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
-    snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled entry point not available");
-    return e != cudaSuccess ? e : cudaErrorNotSupported;
-  }
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDeep::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgN64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgN64::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgBig::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm2_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_fused2_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  return cudaSuccess;
+  return g_dev_once.run([]() -> cudaError_t {
+    if (!g_encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+      if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) return e != cudaSuccess ? e : cudaErrorNotSupported;
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDeep::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgN64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgN64::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgBig::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+    return e;
+  });
 }
 
 static bool encode3(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
@@ -1284,7 +1273,7 @@ template <class C>
 static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
                               const Params& p, cudaStream_t st) {
   const int tiles = ceil_div(p.M, BM) * (p.N / C::BN) * (p.ksplit > 1 ? p.ksplit : 1);
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  const int grid = tiles < device_num_sms() ? tiles : device_num_sms();
   return launch_pdl(gemm_bf16x3_kernel<C>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
 }
 
@@ -1307,7 +1296,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   }
   // 128-wide tiles unless that leaves most of the machine idle (token-sized GEMMs): then 64-wide tiles double the CTA count
   int bn = (a.N % 128 == 0) ? 128 : 64;
-  if (bn == 128 && (long long)ceil_div(a.M, BM) * (a.N / 128) * 2 * (a.ksplit > 1 ? a.ksplit : 1) <= g_num_sms) bn = 64;
+  if (bn == 128 && (long long)ceil_div(a.M, BM) * (a.N / 128) * 2 * (a.ksplit > 1 ? a.ksplit : 1) <= device_num_sms()) bn = 64;
   if (use_big_tiles(a, KT)) bn = 256;
   const bool pair_tiles = use_pair_tiles(a, KT);
   if (pair_tiles) bn = 128;                                 // W box: each CTA of the pair loads 128 of the tile's 256 rows
@@ -1354,7 +1343,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   }
   if (pair_tiles) {
     const int tiles = ceil_div(p.M, 2 * BM) * (p.N / 256);
-    const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
+    const int pairs = tiles < device_num_sms() / 2 ? tiles : device_num_sms() / 2;
     return launch_pdl(gemm2_bf16x3_kernel, dim3(2 * pairs), dim3(NUM_THREADS), PAIR_SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
   }
   if (bn == 256) return launch_cfg<CfgBig>(tmA, tmA2, tmW, tmC, tmR, p, st);
@@ -1377,10 +1366,9 @@ bool gemm_tc_strided_ab_ok(int M, int Wo, int Ho, int Wi, int Hi, int BTi, int s
 
 // which template configuration launch_gemm_tc picks (the per-launch profile reports them as separate kernels)
 const char* gemm_tc_config_name(const GemmArgs& a) {
-  if (tc::g_num_sms == 0) tc::init_once();
   const int KT = a.K + (a.Ab ? a.Kb : 0);
   int bn = (a.N % 128 == 0) ? 128 : 64;
-  if (bn == 128 && (long long)ceil_div(a.M, tc::BM) * (a.N / 128) * 2 * (a.ksplit > 1 ? a.ksplit : 1) <= tc::g_num_sms) bn = 64;
+  if (bn == 128 && (long long)ceil_div(a.M, tc::BM) * (a.N / 128) * 2 * (a.ksplit > 1 ? a.ksplit : 1) <= device_num_sms()) bn = 64;
   if (tc::use_pair_tiles(a, KT)) return "gemm2_bf16x3_pair";
   if (tc::use_big_tiles(a, KT)) return "gemm_bf16x3_big";
   if (bn == 64) return "gemm_bf16x3_n64";
@@ -1424,7 +1412,7 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
     return cudaErrorInvalidValue;
   if (!encode_f32_panel_map(&tmC2, C2, N2, a.M, ldc2)) return cudaErrorInvalidValue;
   const int m_tiles = ceil_div(a.M, BM);
-  const int grid = m_tiles < g_num_sms ? m_tiles : g_num_sms;
+  const int grid = m_tiles < device_num_sms() ? m_tiles : device_num_sms();
   if (a.N == 512) return launch_pdl(gemm_fused2_kernel<512, 128>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   if (N2 == 64) return launch_pdl(gemm_fused2_kernel<256, 64>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   return launch_pdl(gemm_fused2_kernel<256, 128>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);

@@ -540,24 +540,22 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
-static int g_num_sms = 0;
+static DeviceOnce g_dev_once;
 static cudaError_t init_once() {
-  if (g_encode) return cudaSuccess;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) return e != cudaSuccess ? e : cudaErrorNotSupported;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaFuncSetAttribute(dwconv_s1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(dwconv_s1_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dwr::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(dwconv_s2_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dws::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  return cudaSuccess;
+  return g_dev_once.run([]() -> cudaError_t {
+    if (!g_encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+      if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) return e != cudaSuccess ? e : cudaErrorNotSupported;
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_s1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_s1_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dwr::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_s2_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dws::SMEM_BYTES);
+    return e;
+  });
 }
 }  // namespace dwt
 
@@ -602,15 +600,15 @@ cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale,
       for (int k = 1; k <= Ti; ++k) {
         const int tc = ceil_div(Ti, k);
         if (tc > dwr::TCMAX) continue;
-        const long long cost = (long long)ceil_div(cols * ceil_div(Ti, tc), g_num_sms) * (tc + 2);
+        const long long cost = (long long)ceil_div(cols * ceil_div(Ti, tc), device_num_sms()) * (tc + 2);
         if (best < 0 || cost < best) { best = cost; TC = tc; }
       }
       const long long items = cols * ceil_div(Ti, TC);
-      const int grid = (int)(items < g_num_sms ? items : g_num_sms);
+      const int grid = (int)(items < device_num_sms() ? items : device_num_sms());
       return launch_pdl(dwconv_s1_roll_kernel, dim3(grid), dim3(dwr::THREADS), dwr::SMEM_BYTES, st, tmR, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, TC, (int)items);
     }
     const long long tiles = (long long)B * ceil_div(Ti, TT) * ceil_div(Hi, TH) * ceil_div(Wi, TW) * (C / CC);
-    const long long slots = (long long)g_num_sms * (NSTAGE == 1 ? 2 : 1);
+    const long long slots = (long long)device_num_sms() * (NSTAGE == 1 ? 2 : 1);
     const int grid = (int)(tiles < slots ? tiles : slots);
     dwconv_s1_tiled_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmIn, tmW, scale, shift, out_split, B, Ti, Hi, Wi, C, (int)tiles);
     return cudaGetLastError();
@@ -632,11 +630,11 @@ cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale,
     for (int k = 1; k <= To; ++k) {                          // minimise rounds x (2 TC + 1) input frames per item
       const int tc = ceil_div(To, k);
       if (tc > TCMAX) continue;
-      const long long cost = (long long)ceil_div(cols * ceil_div(To, tc), dwt::g_num_sms) * (2 * tc + 1);
+      const long long cost = (long long)ceil_div(cols * ceil_div(To, tc), device_num_sms()) * (2 * tc + 1);
       if (best < 0 || cost < best) { best = cost; TC = tc; }
     }
     const long long items = cols * ceil_div(To, TC);
-    const int grid = (int)(items < dwt::g_num_sms ? items : dwt::g_num_sms);
+    const int grid = (int)(items < device_num_sms() ? items : device_num_sms());
     dwconv_s2_roll_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmS, wpk, scale, shift, out_split, B, Ti, To, Ho, Wo, C, TC, (int)items);
     return cudaGetLastError();
   }

@@ -191,6 +191,24 @@ struct Packer {
         if (status == TUBER_OK) status = fail(TUBER_ERR_SHAPE, "weight '%s' has %lld elements, expected %lld", name.c_str(), (long long)have, (long long)want);
         return nullptr;
       }
+      // the expected shape is the logical (rows, cols) view: the tensor's own dimensions must flatten onto it in order
+      // ((64,3,3,7,7) -> {64,441}, (256,2048,1,1,1) -> {256,2048}); a transposed or re-laid-out tensor of the same size does not
+      auto dim = it->second.shape.begin();
+      const auto end = it->second.shape.end();
+      bool ok = true;
+      for (auto s : shape) {
+        int64_t acc = 1;
+        while (acc < s && dim != end) acc *= *dim++;
+        if (acc != s) { ok = false; break; }
+      }
+      for (; ok && dim != end; ++dim) ok = (*dim == 1);
+      if (!ok) {
+        std::string have_s, want_s;
+        for (auto s : it->second.shape) have_s += (have_s.empty() ? "" : ",") + std::to_string(s);
+        for (auto s : shape) want_s += (want_s.empty() ? "" : ",") + std::to_string(s);
+        if (status == TUBER_OK) status = fail(TUBER_ERR_SHAPE, "weight '%s' has shape (%s), which does not flatten to (%s)", name.c_str(), have_s.c_str(), want_s.c_str());
+        return nullptr;
+      }
     }
     return &it->second;
   }
@@ -203,7 +221,10 @@ struct Packer {
       return nullptr;
     }
     p->owned.push_back(d);
-    cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+      if (status == TUBER_OK) status = fail(TUBER_ERR_CUDA, "host -> device copy of %zu bytes failed", v.size() * sizeof(T));
+      return nullptr;
+    }
     return reinterpret_cast<T*>(d);
   }
 
@@ -1203,7 +1224,11 @@ int tuber_plan_set_weight(TuberPlan* p, const char* name, const float* host_data
   if (p->finalized) return fail(TUBER_ERR_STATE, "plan already finalized");
   HostTensor t;
   int64_t n = 1;
-  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= shape[i]; }
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] < 0 || (shape[i] > 0 && n > (int64_t(1) << 40) / shape[i])) return fail(TUBER_ERR_SHAPE, "weight '%s': bad dimension %lld", name, (long long)shape[i]);
+    t.shape.push_back(shape[i]);
+    n *= shape[i];
+  }
   t.data.assign(host_data, host_data + n);
   p->host[name] = std::move(t);
   return TUBER_OK;
@@ -1541,10 +1566,15 @@ int tuber_set_graph(TuberPlan* p, int32_t enabled) {
 }
 int tuber_set_force_simt(TuberPlan* p, int32_t enabled) {
   if (!p) return fail(TUBER_ERR_INVALID, "null plan");
+  if (p->force_simt != (enabled != 0)) {                               // recorded graphs hold the other kernel choice
+    for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);
+    p->graphs.clear();
+  }
   p->force_simt = enabled != 0;
   return TUBER_OK;
 }
 int tuber_last_launches(TuberPlan* p) { return p ? p->launches : 0; }
+int tuber_graph_count(TuberPlan* p) { return p ? (int)p->graphs.size() : 0; }
 
 int tuber_set_kernel_profiling(TuberPlan* p, int32_t enabled) {
   if (!p) return fail(TUBER_ERR_INVALID, "null plan");

@@ -907,23 +907,21 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
-static int g_num_sms = 0;
-
+static DeviceOnce g_dev_once;
 static cudaError_t init_once() {
-  if (g_encode) return cudaSuccess;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) return e != cudaSuccess ? e : cudaErrorNotSupported;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(stem_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p2::SMEM2_BYTES);
-  if (e != cudaSuccess) return e;
-  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  return cudaSuccess;
+  return g_dev_once.run([]() -> cudaError_t {
+    if (!g_encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+      if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) return e != cudaSuccess ? e : cudaErrorNotSupported;
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p2::SMEM2_BYTES);
+    return e;
+  });
 }
 
 }  // namespace stemtc
@@ -955,7 +953,7 @@ cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale
   if (fuse) {                                                      // CTA pairs (cta_group::2), pool fused
     Params p{x, scale, shift, pooled, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, (W1 - 1) / 2 + 1, 1};
     const int units = B * T * ((H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT);
-    int pairs = g_num_sms / 2;
+    int pairs = device_num_sms() / 2;
     if (pairs > (units + 1) / 2) pairs = (units + 1) / 2;
     if (pairs < 1) pairs = 1;
     stem_tc2_kernel<<<2 * pairs, NUM_THREADS, p2::SMEM2_BYTES, st>>>(tmW, p);
@@ -973,7 +971,7 @@ cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale
   }
   Params p{x, scale, shift, fuse ? pooled : nullptr, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, (W1 - 1) / 2 + 1, fuse ? 1 : 0};
   const int units = B * T * ((W1 + 127) / 128) * ((H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT);
-  int pairs = g_num_sms / 2;
+  int pairs = device_num_sms() / 2;
   if (pairs > units) pairs = units;
   if (pairs < 1) pairs = 1;
   stem_tc_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(tmW, tmOut, p);
