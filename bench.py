@@ -5,17 +5,22 @@
     python bench.py --impl reference [...]                         # the reference algorithm on the host CPU
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
 
-A step = one forward over one batch of synthetic clips.  Workload at every N: BASELINE.json configs[1]
-(TubeR_CSN50_AVA21.yaml shapes, random-init weights, 8 synthetic 32x256x256 clips per GPU); clips shard
-over ranks with no data-path collective inside the forward and one all-gather of packed detections per
-step ("weak" scaling: per-GPU batch fixed).
+A step = one forward over one batch of synthetic clips.  Workload at every N: the configuration BASELINE.json's metric is quoted
+on -- TubeR_CSN152_AVA21.yaml shapes (CSN-152 backbone, 6+6 layers, 15 tubelet queries), random-init weights, 8 synthetic 32x256x256
+clips per GPU per step (= BASELINE configs[2]'s 16-clip batch on two GPUs); clips shard over ranks with no data-path collective
+inside the forward and one all-gather of packed detections per step ("weak" scaling: per-GPU batch fixed).
   value    whole-job clips/s, inputs resident in HBM, CUDA-graph replay of the launch sequence
   e2e      the same through the host entry points (tuber_forward_host_submit/_wait): pinned host clips -> H2D ->
            forward -> D2H of the detections, every step; two slots, so step i+1's copy overlaps step i's kernels
   roofline the kernel with the largest share of device time, from a per-launch CUDA-event profile of
            one extra forward (algorithmic bytes / flops per launch over the summed event time)
-  cpu_baseline  the CPU oracle (a restatement of the reference on the same torch CPU ops) on a bounded
-           sample of the same workload, on this box's host cores
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref, placed by tools/install_reference.py: its own build_model(cfg) and
+           model.eval()(NestedTensor) on the host cores, kind "reference"), else the CPU oracle port (kind "port"), on a bounded
+           sample of the same workload
+  also     the other BASELINE.json configs, same timing rules, fewer steps: configs[1] (CSN-50), configs[2] as STRONG scaling (16 clips
+           in total: 16/N per GPU), configs[3] (long-term context bank, 64-clip window per clip), configs[4] (JHMDB, 16x256x256), and the
+           headline model on the clip size the reference's evaluation transform really produces (32x256x341)
+  same_box_baseline  the reference algorithm as stock PyTorch eager ops (cuDNN / cuBLAS) on the same B200, fp32 with TF32 off and on
 """
 from __future__ import annotations
 
@@ -35,7 +40,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-METRIC = "clips/sec (32x256x256 synthetic clips, TubeR forward)"
+METRIC = "clips/sec (32x256x256, CSN-152)"
 UNIT = "clips/s"
 
 
@@ -49,10 +54,16 @@ def _peaks():
 
 
 def _ncu_traffic(kernel: str):
-    """DRAM bytes per launch of `kernel` from the newest committed ncu launch-list summary (profiles/*_summary.json,
-    written by tools/ncu_launches_summary.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`)."""
+    """DRAM bytes per launch of `kernel` from the committed ncu launch-list summary of the current round's build
+    (profiles/r<round>_*_summary.json, newest round first; written by tools/ncu_launches_summary.py from
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over this very command)."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_summary.json")), key=os.path.getmtime)
+    import re
+
+    def round_of(path):
+        m = re.match(r"r(\d+)_", os.path.basename(path))
+        return (int(m.group(1)) if m else 0, os.path.basename(path))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_summary.json")), key=round_of)
     for f in reversed(files):
         try:
             with open(f) as fh:
@@ -125,19 +136,88 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _cpu_forward(cfg, sd):
+    """-> (fn(clips) running one CPU forward, kind).  kind "reference": the unmodified reference's own model (baseline/_ref);
+    "port": the CPU oracle restatement (used when the reference copy did not travel)."""
+    import contextlib
+    import io
+    from oracle import tuber_oracle as O
+    if os.path.isdir(os.path.join(REF_DIR, "models")):
+        try:
+            if REF_DIR not in sys.path:
+                sys.path.insert(0, REF_DIR)
+            with contextlib.redirect_stdout(io.StringIO()):
+                from models.tuber_ava import build_model as ref_build_model     # the reference's module, untouched
+                from utils.misc import NestedTensor as RefNestedTensor
+                model, _, _ = ref_build_model(cfg)
+            model.load_state_dict(sd, strict=True)
+            model.eval()
+
+            def run(clips):
+                mask = torch.zeros((clips.shape[0],) + tuple(clips.shape[3:]), dtype=torch.bool)
+                with torch.no_grad():
+                    return model(RefNestedTensor(clips, mask))
+            return run, "reference"
+        except Exception as exc:  # noqa: BLE001 -- fall back to the port, and say so on stderr
+            print(f"bench.py: reference under baseline/_ref not usable ({exc!r}); timing the oracle port", file=sys.stderr)
+    return (lambda clips: O.forward(cfg, sd, clips, None)), "port"
+
+
 def _cpu_reference(cfg, sd, T, H, W, budget_s: float, max_clips: int):
-    """Time the CPU oracle on a bounded sample: one clip per forward, all host threads."""
+    """Time the reference on the host CPU on a bounded sample: one clip per forward, all host threads."""
     from oracle import tuber_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    run, kind = _cpu_forward(cfg, sd)
     clip = O.make_clips(1, T, H, W, seed=2)
-    O.forward(cfg, sd, clip, None)                    # warm-up
+    run(clip)                    # warm-up
     n, t0 = 0, time.perf_counter()
     while n < max_clips and (n == 0 or time.perf_counter() - t0 < budget_s):
-        O.forward(cfg, sd, clip, None)
+        run(clip)
         n += 1
     dt = time.perf_counter() - t0
-    return n / dt, cores, f"{n} forwards of 1 clip {T}x{H}x{W} after 1 warm-up, {dt:.1f} s"
+    return n / dt, cores, kind, f"{n} forwards of 1 clip {T}x{H}x{W} after 1 warm-up, {dt:.1f} s"
+
+
+def _same_box_baseline(cfg, sd, clips, steps=5):
+    """SURVEY 8d's "same box" bar: the reference algorithm as stock PyTorch eager ops (conv3d / batch_norm / linear / softmax /
+    layer_norm through cuDNN + cuBLAS) on this B200, fp32 with TF32 off and on, same clips.  The oracle's functional restatement on
+    CUDA tensors -- a measurement, not a code path of the product."""
+    from oracle import tuber_oracle as O
+    res = {"what": "oracle restatement as PyTorch eager CUDA ops (cuDNN / cuBLAS), same weights and clips", "torch": torch.__version__,
+           "batch": int(clips.shape[0])}
+    sd_d = {k: v.cuda() for k, v in sd.items()}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.set_default_device("cuda")
+    try:
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cudnn.benchmark = True
+            try:
+                with torch.no_grad():
+                    for _ in range(2):
+                        O.forward(cfg, sd_d, clips, None)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(steps):
+                        O.forward(cfg, sd_d, clips, None)
+                    e1.record()
+                    torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                res[name] = {"value": clips.shape[0] * 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "steps": steps}
+            except Exception as exc:  # noqa: BLE001
+                res[name] = {"error": repr(exc)[:200]}
+    finally:
+        torch.set_default_device("cpu")
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = old
+        del sd_d
+        torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -152,15 +232,15 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=150)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="TubeR_CSN50_AVA21.yaml")
+    ap.add_argument("--config", default="TubeR_CSN152_AVA21.yaml")
     ap.add_argument("--batch", type=int, default=8, help="clips per GPU per step")
     ap.add_argument("--clip", type=int, nargs=3, default=[32, 256, 256], metavar=("T", "H", "W"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-also", action="store_true", help="skip the secondary CSN-152 measurement")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads (other BASELINE configs, same-box baseline)")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -173,8 +253,9 @@ def main():
     from oracle import tuber_oracle as O          # weights / clip generator + the CPU baseline (checker only)
     cfg = tuber_b200.load_cfg(args.config)
     sd = O.make_state_dict(cfg, seed=0, bn="random")
-    workload = {"workload": f"{args.config} shapes, random-init weights, {args.batch} synthetic {T}x{H}x{W} clips per GPU per step "
-                            f"(BASELINE.json configs[1])", "global_batch": args.batch * world, "per_gpu_batch": args.batch,
+    workload = {"workload": f"{args.config} shapes (the configuration BASELINE.json's metric is quoted on; configs[2]'s backbone and heads), "
+                            f"random-init weights, {args.batch} synthetic {T}x{H}x{W} clips per GPU per step",
+                "global_batch": args.batch * world, "per_gpu_batch": args.batch,
                 "parallelism": f"clip-sharded x{world}, one all-gather of packed detections per step",
                 "l2": "inputs (201 MB of clips per step) and activations (GBs) exceed the 126 MB L2; no flush needed"}
 
@@ -185,20 +266,23 @@ def main():
         per_step = max(1, min(args.batch, 2))
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
+        run, kind = _cpu_forward(cfg, sd)
         clips = O.make_clips(per_step, T, H, W, seed=2)
         for _ in range(max(1, min(args.warmup, 1))):
-            O.forward(cfg, sd, clips, None)
+            run(clips)
         steps = max(1, min(args.steps, 5))
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.forward(cfg, sd, clips, None)
+            run(clips)
         dt = time.perf_counter() - t0
         v = per_step * steps / dt
-        sample = f"{steps} steps of {per_step} clips {T}x{H}x{W} (bounded sample of the {args.batch}-clip step), {dt:.1f} s"
+        sample = (f"{steps} steps of {per_step} clips {T}x{H}x{W} (bounded sample of the {args.batch}-clip step), {dt:.1f} s; "
+                  + ("the unmodified reference's build_model(cfg) / model.eval()(NestedTensor) from baseline/_ref" if kind == "reference"
+                     else "oracle port (baseline/_ref absent); it evaluates the class branch once instead of DEC_LAYERS times"))
         emit({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
                           "warmup": 1, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload,
-                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
@@ -211,22 +295,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from tuber_b200 import _lib
     lib = _lib.load()
-    model, _, _ = tuber_b200.build_model(cfg)
-    model.load_state_dict(sd, strict=True)
-    model = model.cuda().eval()
-    B = args.batch
-    lo, _ = tuber_b200.shard_range(B * world, rank, world)
-    clips = O.make_clips(B, T, H, W, seed=2 + rank).cuda()
-    L, Q, NC = model.dec_layers, model.num_queries, model.num_class_out
-    out = {"pred_logits": torch.empty((B, L, Q, NC), device="cuda"), "pred_boxes": torch.empty((B, L, Q, 4), device="cuda"),
-           "pred_logits_b": torch.empty((B, L, Q, 3) if model.dataset_mode == "ava" else (B, 2), device="cuda")}
-    model.use_cuda_graph(not args.no_graph)
-
-    def step():
-        model.forward_raw(clips, None, out)
-        if world > 1:
-            last = {k: (v[:, -1] if v.dim() == 4 else v) for k, v in out.items()}
-            tuber_b200.gather_detections(tuber_b200.pack_detections(last), B * world)
+    use_graph = not args.no_graph
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -234,23 +304,54 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def build(config_name, overrides=(), extra_sd=None, state=None):
+        c = tuber_b200.load_cfg(config_name, list(overrides))
+        w = state if state is not None else O.make_state_dict(c, seed=0, bn="random")
+        if extra_sd is not None:
+            w = dict(w, **extra_sd(c))
+        m, _, _ = tuber_b200.build_model(c)
+        m.load_state_dict(w, strict=True)
+        m = m.cuda().eval()
+        m.use_cuda_graph(use_graph)
+        return c, w, m
+
+    def out_buffers(m, b):
+        L, Q, NC = m.dec_layers, m.num_queries, m.num_class_out
+        return {"pred_logits": torch.empty((b, L, Q, NC), device="cuda"), "pred_boxes": torch.empty((b, L, Q, 4), device="cuda"),
+                "pred_logits_b": torch.empty((b, L, Q, 3) if m.dataset_mode == "ava" else (b, 2), device="cuda")}
+
+    def timed(m, x, out, steps, n_global, **kw):
+        """W warm-up steps, then `steps` steps between barrier + synchronize, CUDA events, max over ranks -> ms in total.
+        Every step ends with the all-gather of the packed last-layer detections when there is more than one rank."""
+        def step():
+            m.forward_raw(x, None, out, **kw)
+            if world > 1:
+                last = {k: (v[:, -1] if v.dim() == 4 else v) for k, v in out.items()}
+                tuber_b200.gather_detections(tuber_b200.pack_detections(last), n_global)
+        for _ in range(warmup):
+            step()
+        sync_all()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    model = build(args.config, state=sd)[2]
+    B = args.batch
+    clips = O.make_clips(B, T, H, W, seed=2 + rank).cuda()
+    out = out_buffers(model, B)
     for _ in range(warmup):
-        step()
+        model.forward_raw(clips, None, out)
     sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    sync_all()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = timed(model, clips, out, args.steps, B * world)
     clocks = sampler.stop() if rank == 0 else None
     launches_per_step = lib.tuber_last_launches(model.plan())
 
@@ -262,22 +363,25 @@ def main():
         hc.copy_(clips)
     h_out = [model._host_out(B) for _ in range(2)]
 
-    def e2e_run(n):
-        model.forward_host_submit(0, h_clips[0], None, h_out[0])
+    def pipelined(submit, bufs, n):
+        submit(0, bufs[0], None, h_out[0])
         for i in range(1, n):
-            model.forward_host_submit(i & 1, h_clips[i & 1], None, h_out[i & 1])
+            submit(i & 1, bufs[i & 1], None, h_out[i & 1])
             model.forward_host_wait((i - 1) & 1)
         model.forward_host_wait((n - 1) & 1)
 
-    e2e_run(3)
-    sync_all()
-    e2e_steps = max(4, min(args.steps, 50))
-    t0 = time.perf_counter()
-    e2e_run(e2e_steps)                              # returns after the last step's D2H copies have completed
-    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_val = B * world * e2e_steps / float(e2e_s.item())
+    def e2e_rate(submit, bufs, n):
+        pipelined(submit, bufs, 3)
+        sync_all()
+        t0 = time.perf_counter()
+        pipelined(submit, bufs, n)                  # returns after the last step's D2H copies have completed
+        s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(s, op=dist.ReduceOp.MAX)
+        return B * world * n / float(s.item())
+
+    e2e_steps = max(4, min(args.steps, 60))
+    e2e_val = e2e_rate(model.forward_host_submit, h_clips, e2e_steps)
     h2d = h_clips[0].numel() * 4
     d2h = sum(v.numel() for v in h_out[0].values()) * 4
     # the same, one synchronous call per step (no overlap), for reference
@@ -287,54 +391,120 @@ def main():
     for _ in range(e2e_steps):
         model.forward_host(h_clips[0], None, h_out[0])
     e2e_sync_val = B * e2e_steps / (time.perf_counter() - t0)
-    # the same pipeline fed with decoded uint8 frames (B,T,H,W,3): 3 bytes per pixel cross the bus and the reference's ToTensor +
-    # Normalize run on the device (tuber_forward_host_u8_submit) -- reported beside e2e, not instead of it
-    h_frames = [O.make_frames_u8(B, T, H, W, seed=20 + rank + 100 * i).pin_memory() for i in range(2)]
-
-    def e2e_u8_run(n):
-        model.forward_host_u8_submit(0, h_frames[0], None, h_out[0])
-        for i in range(1, n):
-            model.forward_host_u8_submit(i & 1, h_frames[i & 1], None, h_out[i & 1])
-            model.forward_host_wait((i - 1) & 1)
-        model.forward_host_wait((n - 1) & 1)
-
-    e2e_u8_run(3)
+    # host -> device ceiling of this box with every rank copying at once: the pinned clip buffer alone, no kernels
     sync_all()
+    dst = torch.empty_like(clips)
     t0 = time.perf_counter()
-    e2e_u8_run(e2e_steps)
-    e2e_u8_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    for i in range(8):
+        dst.copy_(h_clips[i & 1], non_blocking=True)
+    torch.cuda.synchronize()
+    probe_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(e2e_u8_s, op=dist.ReduceOp.MAX)
-    e2e_u8_val = B * world * e2e_steps / float(e2e_u8_s.item())
+        dist.all_reduce(probe_s, op=dist.ReduceOp.MAX)
+    h2d_probe_gbs = 8 * h2d * world / float(probe_s.item()) / 1e9
+    del dst
+    # the same pipeline fed with decoded uint8 frames (B,T,H,W,3): 3 bytes per pixel cross the bus and the reference's ToTensor +
+    # Normalize run on the device (tuber_forward_host_u8_submit)
+    h_frames = [O.make_frames_u8(B, T, H, W, seed=20 + rank + 100 * i).pin_memory() for i in range(2)]
+    e2e_u8_val = e2e_rate(model.forward_host_u8_submit, h_frames, e2e_steps)
+    e2e_u8 = {"value": e2e_u8_val, "unit": UNIT, "h2d_bytes_per_step": h_frames[0].numel(), "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+              "api": "forward_host_u8_submit/_wait: uint8 (B,T,H,W,3) frames in pinned host memory, ToTensor + Normalize on the device "
+                     "(+1 launch per step)"}
+    del h_frames
 
-    # ---- the metric's other backbone: BASELINE.json quotes "clips/sec (32x256x256, CSN-152)", its configs[2] is
-    # TubeR_CSN152_AVA21.yaml sharded over the GPUs -- same batch per GPU, same timing rules, reported beside the headline workload
+    # ---- per-kernel profile of one forward (CUDA events around every launch) + stage timers, headline model
+    kernels, roof, stage_ms = [], None, {}
+    if rank == 0:
+        _lib.check(lib.tuber_set_kernel_profiling(model.plan(), 1))
+        model.forward_raw(clips, None, out)
+        torch.cuda.synchronize()
+        n = C.c_int32()
+        _lib.check(lib.tuber_get_kernel_profile(model.plan(), None, 0, C.byref(n)))
+        stats = (_lib.TuberKernelStat * n.value)()
+        _lib.check(lib.tuber_get_kernel_profile(model.plan(), stats, n.value, C.byref(n)))
+        _lib.check(lib.tuber_set_kernel_profiling(model.plan(), 0))
+        peaks = _peaks()
+        tot_ms = sum(s.ms for s in stats) or 1.0
+        for s in sorted(stats, key=lambda s: -s.ms):
+            gbs = s.bytes / (s.ms * 1e-3) / 1e9 if s.ms > 0 else 0.0
+            tfs = s.flops / (s.ms * 1e-3) / 1e12 if s.ms > 0 else 0.0
+            kernels.append({"kernel": s.name.decode(), "launches": s.launches, "ms": round(s.ms, 4), "share": round(s.ms / tot_ms, 4),
+                            "GB/s": round(gbs, 1), "TFLOP/s": round(tfs, 2), "hbm_frac": round(gbs / peaks["hbm_gbs"], 4),
+                            "tensor_frac": round(tfs / peaks["bf16_tflops"], 4)})
+        top = max(stats, key=lambda s: s.ms)
+        t_hbm = top.bytes / (peaks["hbm_gbs"] * 1e9)
+        # tensor-core work a kernel ISSUES per algorithmic FLOP, in bf16-rate units: the split kernels run three bf16 passes
+        # (hi*hi + hi*mid + mid*hi); a kind::tf32 kernel runs one pass at half the bf16 rate
+        passes = 2.0 if b"tf32" in top.name else 3.0
+        on_tc = any(t in top.name for t in (b"tcgen05", b"gemm_bf16x3", b"gemm2_bf16x3", b"gemm_tf32", b"attention_tc", b"stem"))
+        t_tc = passes * top.flops / (peaks["bf16_tflops"] * 1e12) if on_tc else 0.0
+        if t_hbm >= t_tc:
+            ach = top.bytes / (top.ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
+        else:
+            ach = passes * top.flops / (top.ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                    "note": f"issued bf16-equivalent FLOPs: {passes:g} tensor-core passes per contraction"}
+        traffic, traffic_src = _ncu_traffic(top.name.decode())
+        roof.update({"kernel": top.name.decode(), "launches_per_step": top.launches, "avg_launch_ms": top.ms / max(1, top.launches),
+                     "algorithmic_bytes_per_launch": top.bytes / max(1, top.launches),
+                     "algorithmic_flops_per_launch": top.flops / max(1, top.launches), "peak_source": peaks["src"], "traffic": traffic,
+                     "traffic_source": traffic_src,
+                     "how": "CUDA events around every launch of one extra forward (same stream, same buffers, after the timed region)"})
+        stage_ms = model.stage_times_ms(clips)
+
+    # ---- the other BASELINE.json configs, same timing rules (every rank takes part: the all-gather is inside the step)
     also = []
-    if not args.no_also and args.config != "TubeR_CSN152_AVA21.yaml":
-        cfg2 = tuber_b200.load_cfg("TubeR_CSN152_AVA21.yaml")
-        model2, _, _ = tuber_b200.build_model(cfg2)
-        model2.load_state_dict(O.make_state_dict(cfg2, seed=0, bn="random"), strict=True)
-        model2 = model2.cuda().eval()
-        model2.use_cuda_graph(not args.no_graph)
-        out2 = {"pred_logits": torch.empty((B, model2.dec_layers, model2.num_queries, model2.num_class_out), device="cuda"),
-                "pred_boxes": torch.empty((B, model2.dec_layers, model2.num_queries, 4), device="cuda"),
-                "pred_logits_b": torch.empty((B, model2.dec_layers, model2.num_queries, 3), device="cuda")}
-        for _ in range(warmup):
-            model2.forward_raw(clips, None, out2)
-        steps2 = max(5, min(args.steps, 30))
-        sync_all()
-        e0.record()
-        for _ in range(steps2):
-            model2.forward_raw(clips, None, out2)
-        e1.record()
-        sync_all()
-        ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        also.append({"workload": f"TubeR_CSN152_AVA21.yaml shapes (BASELINE.json configs[2] backbone), {B} synthetic {T}x{H}x{W} clips per GPU per step",
-                     "value": B * world * steps2 / (float(ms2.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(ms2.item()) / steps2,
-                     "steps": steps2, "launches_per_step": lib.tuber_last_launches(model2.plan())})
-        del model2, out2
+    steps2 = max(5, min(args.steps, 40))
+
+    def also_entry(name, m, x, n_local, **kw):
+        o = out_buffers(m, n_local)
+        ms = timed(m, x, o, steps2, n_local * world, **kw)
+        e = {"workload": name, "value": n_local * world * steps2 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps2, "steps": steps2,
+             "per_gpu_batch": n_local, "global_batch": n_local * world, "launches_per_step": lib.tuber_last_launches(m.plan())}
+        also.append(e)
+        return e
+
+    if not args.no_also:
+        # (1) the headline model on a clip of the size the reference's evaluation transform produces for 4:3 video (256 x 341)
+        xw = O.make_clips(B, T, H, 341, seed=50 + rank).cuda()
+        also_entry(f"{args.config} shapes, {B} synthetic {T}x{H}x341 clips per GPU per step (Resize_Custom output for 4:3 video, "
+                   "datasets/video_transforms.py:213-228)", model, xw, B)
+        del xw
+        # (2) BASELINE configs[2] as written: 16 clips in total, sharded 16/N per GPU (strong scaling)
+        if 16 % world == 0:
+            nloc = 16 // world
+            xs = clips[:nloc].contiguous() if nloc <= B else torch.cat((clips, O.make_clips(nloc - B, T, H, W, seed=70 + rank).cuda()))
+            e = also_entry(f"BASELINE.json configs[2]: {args.config} shapes, 16 synthetic {T}x{H}x{W} clips in total sharded over {world} GPU(s) "
+                           f"({nloc} per GPU)", model, xs, nloc)
+            e["scaling"] = "strong"
+            del xs
+    del model, out, h_clips, h_out
+    torch.cuda.empty_cache()
+    if not args.no_also:
+        # (3) BASELINE configs[1]: CSN-50 backbone, decode pool (round 1's headline workload)
+        m2 = build("TubeR_CSN50_AVA21.yaml")[2]
+        also_entry(f"BASELINE.json configs[1]: TubeR_CSN50_AVA21.yaml shapes, {B} synthetic {T}x{H}x{W} clips per GPU per step", m2, clips, B)
+        del m2
+        torch.cuda.empty_cache()
+        # (4) BASELINE configs[4]: JHMDB head (320 queries, 22-way softmax, centre-slice pool), 16-frame clips
+        m4 = build("Tuber_CSN152_JHMDB.yaml")[2]
+        xj = O.make_clips(B, 16, H, W, seed=60 + rank).cuda()
+        also_entry(f"BASELINE.json configs[4]: Tuber_CSN152_JHMDB.yaml shapes (320 queries), {B} synthetic 16x{H}x{W} clips per GPU per step", m4, xj, B)
+        del m4, xj
+        torch.cuda.empty_cache()
+        # (5) BASELINE configs[3]: CSN-152 / decode pool + long-term context bank, one 64-clip window (16 384 tokens) PER CLIP
+        m3 = build("TubeR_CSN152_AVA22.yaml", ["CONFIG.USE_LFB", True], extra_sd=O.make_ltc_state_dict)[2]
+        entries = torch.empty(m3.bank_entry_shape(B, T, H, W), device="cuda")
+        m3.forward_raw(clips, bank_out=entries)
+        tokens = entries.shape[1]
+        bank = (torch.randn(B, 64 * tokens, 256, device="cuda") * entries.std() + entries.mean()).contiguous()
+        bank[:, :tokens] = entries
+        e = also_entry(f"BASELINE.json configs[3]: TubeR_CSN152_AVA22.yaml shapes + long-term context bank (in-repo definition, parity unpinned: "
+                       f"the reference never released the layer), 64-clip window = {64 * tokens} bank tokens per clip, {B} synthetic {T}x{H}x{W} "
+                       "clips per GPU per step", m3, clips, B, bank=bank)
+        e["bank_tokens_per_clip"] = int(64 * tokens)
+        del m3, bank, entries
         torch.cuda.empty_cache()
 
     if rank != 0:
@@ -342,44 +512,13 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- per-kernel profile of one forward (CUDA events around every launch)
-    _lib.check(lib.tuber_set_kernel_profiling(model.plan(), 1))
-    model.forward_raw(clips, None, out)
-    torch.cuda.synchronize()
-    n = C.c_int32()
-    _lib.check(lib.tuber_get_kernel_profile(model.plan(), None, 0, C.byref(n)))
-    stats = (_lib.TuberKernelStat * n.value)()
-    _lib.check(lib.tuber_get_kernel_profile(model.plan(), stats, n.value, C.byref(n)))
-    _lib.check(lib.tuber_set_kernel_profiling(model.plan(), 0))
-    peaks = _peaks()
-    kernels = []
-    tot_ms = sum(s.ms for s in stats) or 1.0
-    for s in sorted(stats, key=lambda s: -s.ms):
-        gbs = s.bytes / (s.ms * 1e-3) / 1e9 if s.ms > 0 else 0.0
-        tfs = s.flops / (s.ms * 1e-3) / 1e12 if s.ms > 0 else 0.0
-        kernels.append({"kernel": s.name.decode(), "launches": s.launches, "ms": round(s.ms, 4), "share": round(s.ms / tot_ms, 4),
-                        "GB/s": round(gbs, 1), "TFLOP/s": round(tfs, 2), "hbm_frac": round(gbs / peaks["hbm_gbs"], 4),
-                        "tensor_frac": round(tfs / peaks["bf16_tflops"], 4)})
-    top = max(stats, key=lambda s: s.ms)
-    t_hbm = top.bytes / (peaks["hbm_gbs"] * 1e9)
-    t_tc = 3.0 * top.flops / (peaks["bf16_tflops"] * 1e12) if (b"tcgen05" in top.name or b"gemm_bf16x3" in top.name or b"gemm2_bf16x3" in top.name) else 0.0   # bf16x3: 3 MMA passes
-    if t_hbm >= t_tc:
-        ach = top.bytes / (top.ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
-    else:
-        ach = 3.0 * top.flops / (top.ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"]}
-    traffic, traffic_src = _ncu_traffic(top.name.decode())
-    roof.update({"kernel": top.name.decode(), "launches_per_step": top.launches, "avg_launch_ms": top.ms / max(1, top.launches),
-                 "algorithmic_bytes_per_launch": top.bytes / max(1, top.launches), "peak_source": peaks["src"], "traffic": traffic,
-                 "traffic_source": traffic_src,
-                 "how": "CUDA events around every launch of one extra forward (same stream, same buffers, after the timed region)"})
-    stage_ms = model.stage_times_ms(clips)
-
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:                 # rank 0 at N = 1 only
-        v, cores, sample = _cpu_reference(cfg, sd, T, H, W, budget_s=15.0, max_clips=32)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    cpu = same_box = None
+    if world == 1:                                                            # rank 0 at N = 1 only
+        if not args.no_also:
+            same_box = _same_box_baseline(cfg, sd, clips)
+        if not args.no_cpu_baseline:
+            v, cores, kind, sample = _cpu_reference(cfg, sd, T, H, W, budget_s=15.0, max_clips=32)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
 
     value = B * world * args.steps / (ms_total * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -387,12 +526,13 @@ def main():
             "data": "synthetic", "config": workload, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "forward_host_submit/_wait (double-buffered: H2D of step i+1 overlaps step i)",
-                    "synchronous_per_call_rank0": e2e_sync_val, "rank0_cpus_bound": numa},
-            "e2e_u8": {"value": e2e_u8_val, "unit": UNIT, "h2d_bytes_per_step": h_frames[0].numel(), "d2h_bytes_per_step": d2h,
-                       "steps": e2e_steps, "api": "forward_host_u8_submit/_wait: uint8 (B,T,H,W,3) frames in pinned host memory, "
-                                                  "ToTensor + Normalize on the device (+1 launch per step)"},
+                    "synchronous_per_call_rank0": e2e_sync_val, "rank0_cpus_bound": numa,
+                    "h2d_needed_gbs": e2e_val * h2d / B / 1e9, "h2d_probe_gbs": h2d_probe_gbs,
+                    "h2d_probe": "all ranks copying their pinned fp32 clip buffer at once, no kernels: the host -> device ceiling of this box",
+                    "u8": e2e_u8},
+            "e2e_u8": e2e_u8,
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "cuda_graph": not args.no_graph, "roofline": roof, "cpu_baseline": cpu, "also": also, "kernels": kernels,
+            "cuda_graph": use_graph, "roofline": roof, "cpu_baseline": cpu, "same_box_baseline": same_box, "also": also, "kernels": kernels,
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "arithmetic": "fp32 storage; GEMMs = 3-pass bf16 split (hi*hi+hi*lo+lo*hi) on tcgen05 with fp32 TMEM accumulation"}
     emit(line)
