@@ -104,7 +104,7 @@ def test_reference_eval_loop_runs_on_the_b200_model_unchanged(tmp_path, monkeypa
                                                         "CONFIG.MODEL.PRETRAIN_TRANSFORMER_DIR", str(tmp_path / "detr.pth"),
                                                         "CONFIG.MODEL.PRETRAINED_PATH", str(tmp_path / "tuber.pth"), "CONFIG.MODEL.LOAD", True])
     sd = O.make_state_dict(cfg, seed=31, bn="random")
-    sd["class_embed_b.bias"] = torch.tensor([0.0, 2.5, 0.0])             # opens PostProcessAVA's 0.8 actor gate for most queries
+    sd["class_embed_b.bias"] = torch.tensor([0.0, 4.0, 0.0])             # opens PostProcessAVA's 0.8 actor gate for most queries
     # deploy_model unconditionally loads DETR-COCO weights into the wrapped model (model_utils.py:10-36,60): a synthetic detr.pth with
     # the wrapper's key prefix; it carries 100 COCO queries, of which the loader keeps QUERY_NUM
     detr = {"module." + k: v.clone() for k, v in sd.items() if k.split(".")[0] in ("transformer", "bbox_embed")}

@@ -1,7 +1,10 @@
-// Long-sequence attention core on tcgen05 (sm_100a): O = softmax(scale * Q K^T) V for head_dim 32 when a (sequence, head) has
-// at least one full 128-query tile and thousands of keys -- the long-term context layer (tuber_forward_ltc: 1024 class-branch
-// tokens of a clip over a 64-clip bank window = 16 384 keys).  The short attention sites of the forward
-// stay on the warp-level kernels of attn_mma.cu (their tiles are mostly padding at UMMA sizes).
+// Attention core on tcgen05 (sm_100a): O = softmax(scale * Q K^T + key padding mask) V for head_dim 32 wherever a (sequence, head)
+// fills at least half of a 128-query tile and has at least one 128-key chunk: the encoder self-attention (L = S = H'W', 256 at
+// 256 x 256 input, transformer.py:158-164), the class branch's spatial attention (L = S = H'W', batch T'B, transformer_layers.py:79-84),
+// the class cross-attention (L = DEC_LAYERS x Q queries over S = T'H'W' tokens, tuber_ava.py:137-139), JHMDB's decoder self-attention
+// (L = S = 320) and the long-term context layer (tuber_forward_ltc: 1024 tokens over a 64-clip window = 16 384 keys).  Only the
+// 15-query decoder attentions and the per-pixel temporal attention (T' <= 8 keys) stay on the warp-level kernels of attn_mma.cu.
+// A key padding mask (utils/misc.py:385-399, True = padding) travels as one flag byte per key next to the chunk in shared memory.
 //
 // One CTA = one (sequence n, head h, tile of 128 queries); it walks the keys in chunks of 128, flash-attention style, with the
 // library's usual precision (common.cuh): every fp32 operand is split into bf16 hi + mid and a product is evaluated as
@@ -37,7 +40,8 @@ constexpr int VT_PLANE = 2 * 32 * 128;            // [2 key atoms][32 dims][64 k
 constexpr int STAGE_BYTES = K_BYTES + 2 * VT_PLANE;   // 32 KB
 constexpr int OFF_Q = 0, OFF_STAGE = Q_BYTES, OFF_BAR = OFF_STAGE + 2 * STAGE_BYTES;
 constexpr int OFF_XCH = OFF_BAR + 128;              // [2][128] floats
-constexpr int SMEM_BYTES = OFF_XCH + 1024;
+constexpr int OFF_MASK = OFF_XCH + 1024;            // [2 stages][128 keys] bytes: 1 = the key is padding (key_padding_mask)
+constexpr int SMEM_BYTES = OFF_MASK + 256;
 constexpr int THREADS = 416;                      // warp 0 MMA, warps 1-8 softmax (two per query row), warps 9-12 loaders
 constexpr int THREADS_PREP = 320;                 // PREP: warp 9 = one thread issuing bulk copies; softmax group 0 stages Q
 constexpr int TMEM_COLS = 256;
@@ -313,12 +317,21 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
       fence_proxy_async();
       mbar_arrive(q_full);
     }
+    const bool has_mask = !PREP && p.kpm != nullptr;
     for (int c = 0; c < nchunks; ++c) {
       const int nvalid = min(KC, p.S - c * KC) - 64 * g;           // valid keys among this thread's 64 (may be <= 0 in the last chunk)
       mbar_wait(s_full, (uint32_t)(c & 1));
       tcgen05_fence_after();
+      // padding flags of this thread's 64 keys (written by the loaders before the chunk's kv_full arrive)
+      const uint8_t* mflag = smem + OFF_MASK + (c & 1) * 128 + 64 * g;
+      bool plain = nvalid >= 64;
+      if (has_mask) {
+        const uint4* mf = reinterpret_cast<const uint4*>(mflag);
+        const uint4 f0 = mf[0], f1 = mf[1], f2 = mf[2], f3 = mf[3];
+        plain = plain && ((f0.x | f0.y | f0.z | f0.w | f1.x | f1.y | f1.z | f1.w | f2.x | f2.y | f2.z | f2.w | f3.x | f3.y | f3.z | f3.w) == 0u);
+      }
       float cm = -INFINITY;
-      if (nvalid >= 64) {                                        // full half chunk: no key predicates
+      if (plain) {                                               // full half chunk without padding: no key predicates
 #pragma unroll 1
         for (int b = 0; b < 2; ++b) {
           uint32_t v[32];
@@ -336,22 +349,31 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
         for (int b = 0; b < 2; ++b) {
           uint32_t v[32];
           tmem_ld32(t_lane + col_s + 32 * b, v);
+          uint32_t fw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if (has_mask) {
+            const uint4 a = *reinterpret_cast<const uint4*>(mflag + 32 * b), bb = *reinterpret_cast<const uint4*>(mflag + 32 * b + 16);
+            fw[0] = a.x; fw[1] = a.y; fw[2] = a.z; fw[3] = a.w; fw[4] = bb.x; fw[5] = bb.y; fw[6] = bb.z; fw[7] = bb.w;
+          }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) cm = fmaxf(cm, (32 * b + j < nvalid) ? __uint_as_float(v[j]) : -INFINITY);
+          for (int j = 0; j < 32; ++j) {
+            const bool use = (32 * b + j < nvalid) && ((fw[j >> 2] >> (8 * (j & 3))) & 0xffu) == 0u;
+            cm = fmaxf(cm, use ? __uint_as_float(v[j]) : -INFINITY);
+          }
         }
       }
       xch[g * 128 + row] = cm;
       asm volatile("bar.sync 1, 256;" ::: "memory");             // (the slot is rewritten only after every thread has passed p_full of this chunk)
       cm = fmaxf(cm, xch[(g ^ 1) * 128 + row]);
-      const float m_new = fmaxf(m, cm);                          // finite: every chunk holds at least one key
-      const float corr = ex2(m - m_new);                         // first chunk: 2^-inf = 0
+      const float m_new = fmaxf(m, cm);                          // -inf only while every key seen so far was padding
+      const float m_sub = (m_new == -INFINITY) ? 0.f : m_new;
+      const float corr = (m_new == -INFINITY) ? 1.f : ex2(m - m_new);   // first chunk with a key: 2^-inf = 0
       float psum = 0.f;
 #pragma unroll 1
       for (int b = 0; b < 2; ++b) {
         uint32_t v[32];
         tmem_ld32(t_lane + col_s + 32 * b, v);
         uint32_t hi[16], mid[16];
-        if (nvalid >= 64) {
+        if (plain) {
           const u64 negm = pack2(-m_new, -m_new), neg1 = pack2(-1.f, -1.f);
           u64 ps2 = pack2(0.f, 0.f);
 #pragma unroll
@@ -373,10 +395,17 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
           unpack2(ps2, s0, s1);
           psum += s0 + s1;
         } else {
+          uint32_t fw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if (has_mask) {
+            const uint4 a = *reinterpret_cast<const uint4*>(mflag + 32 * b), bb = *reinterpret_cast<const uint4*>(mflag + 32 * b + 16);
+            fw[0] = a.x; fw[1] = a.y; fw[2] = a.z; fw[3] = a.w; fw[4] = bb.x; fw[5] = bb.y; fw[6] = bb.z; fw[7] = bb.w;
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float p0 = (32 * b + 2 * j < nvalid) ? ex2(__uint_as_float(v[2 * j]) - m_new) : 0.f;
-            const float p1 = (32 * b + 2 * j + 1 < nvalid) ? ex2(__uint_as_float(v[2 * j + 1]) - m_new) : 0.f;
+            const bool u0 = (32 * b + 2 * j < nvalid) && ((fw[j >> 1] >> (16 * (j & 1))) & 0xffu) == 0u;
+            const bool u1 = (32 * b + 2 * j + 1 < nvalid) && ((fw[j >> 1] >> (16 * (j & 1) + 8)) & 0xffu) == 0u;
+            const float p0 = u0 ? ex2(__uint_as_float(v[2 * j]) - m_sub) : 0.f;
+            const float p1 = u1 ? ex2(__uint_as_float(v[2 * j + 1]) - m_sub) : 0.f;
             psum += p0 + p1;
             split_bf16x2(p0, p1, hi[j], mid[j]);
           }
@@ -452,6 +481,10 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
         const uint32_t st_base = sb + OFF_STAGE + stage * STAGE_BYTES;
         if (c >= 2) mbar_wait(kv_empty(stage), (uint32_t)(((c >> 1) - 1) & 1));
         stage_chunk(st_base, t, p, h, k0, c);
+        if (p.kpm) {                                             // padding flag of key t of this chunk (read by the softmax warps)
+          const int key = c * KC + t;
+          smem[OFF_MASK + stage * 128 + t] = key < p.S ? p.kpm[(long long)(n / p.kpm_div) * p.S + key] : (uint8_t)0;
+        }
         fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core's reads
         mbar_arrive(kv_full(stage));
       }
@@ -469,8 +502,17 @@ attn_tc_kernel(AttnArgs p, const uint8_t* __restrict__ img) {
 }  // namespace attn_tc
 
 bool attention_tc_supported(const AttnArgs& a) {
-  return a.D == attn_tc::D && a.kpm == nullptr && a.L >= attn_tc::QT && a.S >= 1024 && a.NB > 0 && a.NB <= 65535 && a.H <= 65535 &&
+  return a.D == attn_tc::D && a.L >= attn_tc::QT / 2 && a.S >= attn_tc::KC && a.NB > 0 && a.NB <= 65535 && a.H <= 65535 &&
          a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0 && a.ldo % 4 == 0;
+}
+
+// pre-converted K / V images pay when several query tiles read the same keys: the long-term context layer (8 tiles per clip, or
+// every clip's tiles on a shared window) and JHMDB's class cross-attention (15 tiles); not with a key padding mask (the image has none)
+bool attention_tc_wants_prep(const AttnArgs& a) {
+  if (!attention_tc_supported(a) || a.kpm != nullptr) return false;
+  const bool shared = a.km.outer == 0 && a.km.inner_stride == 0;
+  const long long tiles_per_kv = (long long)ceil_div(a.L, attn_tc::QT) * (shared ? a.NB : 1);
+  return a.S >= 512 && tiles_per_kv >= 4;
 }
 
 size_t attention_tc_scratch_bytes(const AttnArgs& a) {
@@ -495,7 +537,8 @@ cudaError_t launch_attention_tc(const AttnArgs& a0, cudaStream_t st) {
   AttnArgs a = a0;
   a.tc_shared_kv = (a.km.outer == 0 && a.km.inner_stride == 0) ? 1 : 0;
   dim3 grid(ceil_div(a.L, QT), a.H, a.NB);
-  if (a.tc_scratch == nullptr) return launch_pdl(attn_tc_kernel<false>, grid, dim3(THREADS), SMEM_BYTES, st, a, (const uint8_t*)nullptr);
+  if (a.tc_scratch == nullptr || a.kpm != nullptr)
+    return launch_pdl(attn_tc_kernel<false>, grid, dim3(THREADS), SMEM_BYTES, st, a, (const uint8_t*)nullptr);
   dim3 pgrid(ceil_div(a.S, KC), a.H, a.tc_shared_kv ? 1 : a.NB);
   cudaError_t e = launch_pdl(attn_tc_prep_kernel, pgrid, dim3(128), STAGE_BYTES, st, a, (uint8_t*)a.tc_scratch);
   if (e != cudaSuccess) return e;

@@ -113,9 +113,10 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st);
 cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t st);
 // attn_mma.cu; cudaErrorNotSupported when the shape is outside what it covers
 cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);
-// attn_tc.cu: tcgen05 flash attention for long sequences (head dim 32, no key mask, L >= 128, S >= 1024: the long-term context layer);
+// attn_tc.cu: tcgen05 flash attention (head dim 32, L >= 64 queries and S >= 128 keys per sequence, optional key padding mask);
 // TUBER_ATTN_NO_TC=1 in the environment keeps those shapes on the mma.sync kernel (the tests' cross-check)
 bool attention_tc_supported(const AttnArgs& a);
+bool attention_tc_wants_prep(const AttnArgs& a);
 size_t attention_tc_scratch_bytes(const AttnArgs& a);
 cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t st);
 

@@ -682,13 +682,15 @@ struct Ctx {
     // long sequences run on the tcgen05 kernel, which wants K / V pre-converted once into per-chunk tile images (attn_tc.cu)
     static const bool no_tc = [] { const char* e = getenv("TUBER_ATTN_NO_TC"); return e && e[0] == '1'; }();
     static const bool no_prep = [] { const char* e = getenv("TUBER_ATTN_NO_PREP"); return e && e[0] == '1'; }();
-    if (!no_tc && !no_prep && attention_tc_supported(a)) {
+    static const bool attn_simt = [] { const char* e = getenv("TUBER_ATTN_SIMT"); return e && e[0] == '1'; }();
+    const bool on_tc = !no_tc && !attn_simt && attention_tc_supported(a);
+    if (on_tc && !no_prep && attention_tc_wants_prep(a)) {
       a.tc_scratch = ws.alloc(attention_tc_scratch_bytes(a));
       ++launches;                                              // the conversion launch (part of launch_attention_tc)
     }
     if (p->kprof) snprintf(tag, sizeof tag, "NB=%d H=%d L=%d S=%d D=%d", NB, H, L, S, D);
     const double e = (double)H * D;
-    launch("attention", 4.0 * e * ((double)NB * L * 2 + (double)NB * S * 2), 4.0 * (double)NB * H * L * S * D,
+    launch(on_tc ? "attention_tc" : "attention", 4.0 * e * ((double)NB * L * 2 + (double)NB * S * 2), 4.0 * (double)NB * H * L * S * D,
            [&] { return launch_attention(a, st); });
   }
 
