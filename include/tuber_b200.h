@@ -230,6 +230,10 @@ int tuber_op_layernorm(const float* x_dev, const float* res_dev, const float* ga
 int tuber_op_attention(const float* q_dev, const float* k_dev, const float* v_dev, const uint8_t* kpm_dev,
                        float* out_dev, int32_t NB, int32_t H, int32_t L, int32_t S, int32_t D, float scale,
                        void* stream);
+/* Name of the kernel tuber_op_attention / the plan dispatch a contiguous (NB, L|S, H*D) problem to: "attn_tc_kernel" (tcgen05: head
+ * dim 32, L >= 64, S >= 128, with or without a key padding mask), "attn_mma_kernel" / "attn_mma_split_kernel" / "attn_tiny_kernel"
+ * (mma.sync / registers: the 15-query decoder attentions, T' <= 8 temporal attention), "attn_simt_kernel" (other head dims). */
+const char* tuber_op_attention_kernel(int32_t NB, int32_t H, int32_t L, int32_t S, int32_t D, int32_t masked);
 /* uint8 frames (B, pixels_per_clip, 3) -> fp32 (B, 3, pixels_per_clip) = ((u / 255) - mean[c]) / std[c].  Synchronises the stream. */
 int tuber_op_normalize_u8(const uint8_t* frames_dev, const float* mean, const float* std, float* out_dev, int32_t B,
                           int64_t pixels_per_clip, void* stream);

@@ -159,9 +159,22 @@ def test_layernorm(abi, c):
                                                # long sequences, no mask: the tcgen05 flash-attention kernel (attn_tc.cu) -- exact tiles,
                                                # query / key tails, one chunk pair, many chunks
                                                (1, 8, 128, 1024, 32, False), (2, 4, 300, 2500, 32, False), (1, 2, 129, 1025, 32, False),
-                                               (1, 8, 256, 16384, 32, False)])
+                                               (1, 8, 256, 16384, 32, False),
+                                               # the reference path's own attention sites on the tcgen05 kernel: encoder self-attention
+                                               # (L = S = H'W' = 256; 352 at 256 x 341 input) with and without a key padding mask (one
+                                               # sequence loses a whole chunk, one every third key), the class branch's spatial attention
+                                               # (batch T'B), JHMDB's decoder self-attention (320) and class cross-attention (1920 x 512),
+                                               # a ragged feature map (15 x 22 = 330 keys), the smallest supported tile
+                                               (2, 8, 256, 256, 32, True), (2, 8, 256, 256, 32, False), (4, 8, 352, 352, 32, True),
+                                               (32, 8, 256, 256, 32, False), (2, 8, 320, 320, 32, True), (2, 8, 1920, 512, 32, False),
+                                               (2, 8, 200, 330, 32, True), (3, 8, 64, 128, 32, True)])
 def test_attention(abi, nb, h, l, s, d, masked):
     from tuber_b200 import _lib
+    kernel = _lib.load().tuber_op_attention_kernel(nb, h, l, s, d, int(masked)).decode()
+    if d == 32 and l >= 64 and s >= 128:                      # the tcgen05 kernel takes every such shape, masked or not
+        assert kernel == "attn_tc_kernel", kernel
+    else:
+        assert kernel != "attn_tc_kernel", kernel
     e = h * d
     g = torch.Generator(device="cuda").manual_seed(nb * 1000 + l * 7 + s)
     q, k, v = (torch.randn(nb, n, e, device="cuda", generator=g) for n in (l, s, s))

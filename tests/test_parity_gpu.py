@@ -439,3 +439,33 @@ def test_two_devices_in_one_process():
         for key in ("pred_logits", "pred_boxes", "pred_logits_b"):
             emax, el2 = _rel(_layers_first(out, key), torch.from_numpy(g[key]))
             assert emax <= TOL and el2 <= TOL, (dev, key, emax, el2)
+
+
+def test_attention_sites_run_on_tcgen05_with_a_padding_mask():
+    """north_star: "tcgen05 tensor-core MMA for ... the QK^T / PV contractions".  A ragged batch at full spatial size (H'W' = 256 tokens,
+    one clip zero-padded, so the key padding mask is live): the encoder self-attention of every layer and the class branch's spatial
+    attention must be dispatched to the tcgen05 kernel (profile family "attention_tc"), and the outputs must match the CPU oracle."""
+    import ctypes as C
+    import tuber_b200
+    from oracle import tuber_oracle as O
+    from tuber_b200 import _lib
+    cfg = tuber_b200.load_cfg("TubeR_CSN50_AVA21.yaml", ["CONFIG.MODEL.ENC_LAYERS", 2, "CONFIG.MODEL.DEC_LAYERS", 2, "CONFIG.MODEL.TEMP_LEN", 8])
+    sd = O.make_state_dict(cfg, seed=41, bn="random")
+    clips = [O.make_clips(1, 8, 256, 256, seed=42)[0], O.make_clips(1, 8, 256, 176, seed=43)[0]]
+    batch, mask = O.pad_clips(clips)
+    ref = O.forward(cfg, sd, batch, mask)
+    model = _model(cfg, sd)
+    lib = _lib.load()
+    _lib.check(lib.tuber_set_kernel_profiling(model.plan(), 1))
+    got = model.forward_raw(batch.cuda(), mask.cuda())
+    torch.cuda.synchronize()
+    n = C.c_int32()
+    _lib.check(lib.tuber_get_kernel_profile(model.plan(), None, 0, C.byref(n)))
+    stats = (_lib.TuberKernelStat * n.value)()
+    _lib.check(lib.tuber_get_kernel_profile(model.plan(), stats, n.value, C.byref(n)))
+    _lib.check(lib.tuber_set_kernel_profiling(model.plan(), 0))
+    fam = {s.name.decode(): s.launches for s in stats}
+    assert fam.get("attention_tc", 0) >= 3, fam               # 2 encoder layers + the class branch's spatial attention
+    for k in ("pred_logits", "pred_boxes", "pred_logits_b"):
+        emax, el2 = _rel(_layers_first(got, k), ref[k])
+        assert emax <= TOL and el2 <= TOL, (k, emax, el2)

@@ -85,6 +85,7 @@ PROTOTYPES = {
     "tuber_op_stem": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "tuber_op_layernorm": (_I, [_P, _P, _P, _P, _P, _L, _I, _P]),
     "tuber_op_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "tuber_op_attention_kernel": (C.c_char_p, [_I, _I, _I, _I, _I, _I]),
     "tuber_op_normalize_u8": (_I, [_P, C.POINTER(_F), C.POINTER(_F), _P, _I, _L, _P]),
     "tuber_op_posenc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
 }

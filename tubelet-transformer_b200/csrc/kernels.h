@@ -111,6 +111,7 @@ struct AttnArgs {
 // CUDA-core kernels, the cross-check of the tests); other head dims -> the CUDA-core warp kernel
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st);
 cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t st);
+const char* attention_kernel_name(const AttnArgs& a);     // the kernel launch_attention dispatches this shape to
 // attn_mma.cu; cudaErrorNotSupported when the shape is outside what it covers
 cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);
 // attn_tc.cu: tcgen05 flash attention (head dim 32, L >= 64 queries and S >= 128 keys per sequence, optional key padding mask);

@@ -1308,6 +1308,19 @@ attn_tile_kernel(AttnArgs p) {
   }
 }
 
+// which kernel launch_attention picks for a shape (unit tests assert the dispatch through tuber_op_attention_kernel)
+const char* attention_kernel_name(const AttnArgs& a) {
+  const char* fs = getenv("TUBER_ATTN_SIMT");
+  const char* nt = getenv("TUBER_ATTN_NO_TC");
+  const bool force_simt = fs && fs[0] == '1', no_tc = nt && nt[0] == '1';
+  if (!force_simt && !no_tc && attention_tc_supported(a)) return "attn_tc_kernel";
+  if (!force_simt && a.D == 32 && a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0 && a.ldo % 4 == 0) {
+    if (a.L <= 8 && a.S <= 8 && a.H % 8 == 0) return "attn_tiny_kernel";
+    if (a.NB <= 65535 && a.H <= 65535) return (a.L <= 16 && a.S > 64) ? "attn_mma_split_kernel" : "attn_mma_kernel";
+  }
+  return "attn_simt_kernel";
+}
+
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st) {
   static const bool force_simt = [] { const char* e = getenv("TUBER_ATTN_SIMT"); return e && e[0] == '1'; }();
   static const bool no_tc = [] { const char* e = getenv("TUBER_ATTN_NO_TC"); return e && e[0] == '1'; }();

@@ -1746,6 +1746,15 @@ int tuber_op_attention(const float* q, const float* k, const float* v, const uin
   CK(launch_attention(a, (cudaStream_t)stream));
   return TUBER_OK;
 }
+const char* tuber_op_attention_kernel(int32_t NB, int32_t H, int32_t L, int32_t S, int32_t D, int32_t masked) {
+  AttnArgs a{};
+  const int E = H * D;
+  a.ldq = a.ldk = a.ldv = a.ldo = E;
+  a.qm = seqmap(1, L, 0, 1); a.km = seqmap(1, S, 0, 1); a.om = seqmap(1, L, 0, 1);
+  a.kpm = masked ? reinterpret_cast<const uint8_t*>(uintptr_t(16)) : nullptr;       // only tested for null-ness
+  a.kpm_div = 1; a.NB = NB; a.H = H; a.L = L; a.S = S; a.D = D;
+  return attention_kernel_name(a);
+}
 int tuber_op_normalize_u8(const uint8_t* frames, const float* mean, const float* stdv, float* out, int32_t B, int64_t pixels_per_clip,
                           void* stream) {
   if (!frames || !mean || !stdv || !out || B <= 0 || pixels_per_clip <= 0) return fail(TUBER_ERR_INVALID, "bad argument");
