@@ -119,7 +119,10 @@ def test_dwconv(abi, c, st_t, st_s, dims):
     assert _rel(got, ref) < 3e-5
 
 
-@pytest.mark.parametrize("dims", [(1, 4, 32, 32), (2, 3, 45, 70), (1, 2, 64, 300), (1, 3, 130, 256)])
+@pytest.mark.parametrize("dims", [(1, 4, 32, 32), (2, 3, 45, 70), (1, 2, 64, 300), (1, 3, 130, 256),
+                                  # conv rows wider than 128 outputs: column tiles of the pair kernel with a one-column pool halo --
+                                  # the evaluation widths 341 / 455 (W1 = 171 / 228), one column past a tile (257, 258), three tiles (520)
+                                  (1, 2, 40, 341), (1, 2, 34, 455), (1, 1, 20, 257), (1, 1, 20, 258), (1, 1, 18, 520), (1, 1, 12, 506)])
 def test_stem(abi, dims):
     from tuber_b200 import _lib
     b, t, h, w = dims

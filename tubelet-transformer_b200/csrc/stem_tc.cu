@@ -64,6 +64,7 @@ struct Params {
   void* pooled;                             // split [B*T*H2*W2, 64] (fused pool) or null
   int B, T, H, W, H1, W1, H2, W2;
   int fuse_pool;
+  int ct_n;                                 // stem_tc2_kernel: column tiles per conv row (1 when W1 <= 128, see there)
 };
 
 TB_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -596,7 +597,12 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                         // = which 32 output channels this CTA's filter half holds
   const int rb_n = (p.H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
-  const int units = p.B * p.T * rb_n;
+  // Conv rows wider than the 128 TMEM lanes (W1 = 171 / 228 at the 256 x 341 / 256 x 455 clips the reference's evaluation transform
+  // produces) are cut into column tiles: tile ct computes the 128 conv columns from c0 = 126 ct - 1 and emits the 63 pooled columns
+  // 63 ct .. 63 ct + 62, whose 3-wide windows (conv columns 2 pw - 1 .. 2 pw + 1) lie inside it -- a one-column halo on the left
+  // instead of a second pass over the conv rows.  A single tile (W1 <= 128) keeps c0 = 0 and 64 pooled columns.
+  const int ct_n = p.ct_n > 1 ? p.ct_n : 1;
+  const int units = p.B * p.T * rb_n * ct_n;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int steps = (units + 1) / 2;                               // pair steps; step i = units 2i (rank 0) and 2i+1 (rank 1)
 
@@ -692,8 +698,12 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
     int it = 0;
     for (int i = pair; i < steps; i += npairs) {
       const int u = min(2 * i + (int)rank, units - 1);             // odd unit count: the last step's rank 1 repeats the last unit
-      const int rb = u % rb_n, bt = u / rb_n;
+      const int ct = u % ct_n, ur = u / ct_n;
+      const int rb = ur % rb_n, bt = ur / rb_n;
       const int r0 = rb * ROWS_PER_UNIT;
+      const int c0 = ct_n > 1 ? 126 * ct - 1 : 0;                  // first conv column of this tile (TMEM lane 0)
+      const int pwg = (ct_n > 1 ? 63 * ct : 0) + pw;               // this thread's pooled column in the image
+      const bool pw_ok = pw < (ct_n > 1 ? 63 : 64) && pwg < p.W2;
       float4 run[8];                                               // running maximum over the rows seen so far (post-ReLU: >= 0)
 #pragma unroll
       for (int e = 0; e < 8; ++e) run[e] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -730,14 +740,14 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
         float4 hm[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) hm[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pw < p.W2) {
+        if (pw_ok) {
 #pragma unroll
           for (int dc = -1; dc <= 1; ++dc) {
-            const int cc = 2 * pw + dc;
+            const int cc = 2 * pwg + dc;
             if (cc < 0 || cc >= p.W1) continue;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const uint4 v = lds128(rswz(cc, 2 * e + hq));
+              const uint4 v = lds128(rswz(cc - c0, 2 * e + hq));
               hm[e].x = fmaxf(hm[e].x, __uint_as_float(v.x)); hm[e].y = fmaxf(hm[e].y, __uint_as_float(v.y));
               hm[e].z = fmaxf(hm[e].z, __uint_as_float(v.z)); hm[e].w = fmaxf(hm[e].w, __uint_as_float(v.w));
             }
@@ -753,9 +763,9 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
             run[e].z = fmaxf(run[e].z, hm[e].z); run[e].w = fmaxf(run[e].w, hm[e].w);
           }
         }
-        if (emit && pw < p.W2) {
+        if (emit && pw_ok) {
           const int ph = oh >> 1;
-          const long long vox = ((long long)bt * p.H2 + ph) * p.W2 + pw;
+          const long long vox = ((long long)bt * p.H2 + ph) * p.W2 + pwg;
           __nv_bfloat16* hi = split_hi(p.pooled, vox, 64) + hq * 4;
 #pragma unroll
           for (int e = 0; e < 8; ++e) store_split4(hi + 8 * e, hi + 64 + 8 * e, run[e]);
@@ -784,10 +794,11 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
     uint32_t phase = 0;
     for (int i = pair; i < steps; i += npairs) {
       const int u = min(2 * i + (int)rank, units - 1);
-      const int rb = u % rb_n, bt = u / rb_n;
+      const int ct = u % ct_n, ur = u / ct_n;
+      const int rb = ur % rb_n, bt = ur / rb_n;
       const int b = bt / p.T, t = bt % p.T;
       const int first = rb * ROWS_PER_UNIT - 1, r1 = first + UNIT_ROWS;
-      const int iw0 = -3;
+      const int iw0 = 2 * (ct_n > 1 ? 126 * ct - 1 : 0) - 3;        // input column of tap 0 of the tile's first conv column
       const int spr = bt_ & 127, srr = bt_ >> 7;
       const int xpr = 128 + (bt_ & 3), xrow = bt_ >> 2;
       auto col_ok = [&](int j) { return iw0 + j >= 0 && iw0 + j < p.W; };
@@ -931,7 +942,12 @@ cudaError_t launch_stem_pack_weight(const float* w_oc441, void* out, cudaStream_
   return cudaGetLastError();
 }
 
-bool stem_pool_is_fused(int W1) { return W1 <= 128; }
+// conv rows of any width run on the pair kernel with the pool fused (column tiles, see stem_tc2_kernel); TUBER_STEM_SINGLE=1 in the
+// environment keeps rows wider than 128 outputs on the single-CTA kernel + separate pool (the cross-check of the tests)
+bool stem_pool_is_fused(int W1) {
+  static const bool single = [] { const char* e = getenv("TUBER_STEM_SINGLE"); return e && e[0] == '1'; }();
+  return W1 <= 128 || !single;
+}
 
 // y: fp32 conv rows [B,T,H1,W1,64] (only written when the pool is not fused; may be null otherwise);
 // pooled: split [B,T,H2,W2,64] (only written when stem_pool_is_fused(W1))
@@ -951,8 +967,10 @@ cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale
   }
   const bool fuse = stem_pool_is_fused(W1) && pooled != nullptr;
   if (fuse) {                                                      // CTA pairs (cta_group::2), pool fused
-    Params p{x, scale, shift, pooled, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, (W1 - 1) / 2 + 1, 1};
-    const int units = B * T * ((H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT);
+    const int W2 = (W1 - 1) / 2 + 1;
+    const int ct_n = W1 <= 128 ? 1 : (W2 + 62) / 63;
+    Params p{x, scale, shift, pooled, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, W2, 1, ct_n};
+    const int units = B * T * ((H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT) * ct_n;
     int pairs = device_num_sms() / 2;
     if (pairs > (units + 1) / 2) pairs = (units + 1) / 2;
     if (pairs < 1) pairs = 1;
@@ -969,7 +987,7 @@ cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
   }
-  Params p{x, scale, shift, fuse ? pooled : nullptr, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, (W1 - 1) / 2 + 1, fuse ? 1 : 0};
+  Params p{x, scale, shift, fuse ? pooled : nullptr, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, (W1 - 1) / 2 + 1, fuse ? 1 : 0, 1};
   const int units = B * T * ((W1 + 127) / 128) * ((H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT);
   int pairs = device_num_sms() / 2;
   if (pairs > units) pairs = units;
