@@ -36,20 +36,30 @@ namespace tc {
 constexpr int BM = 128, BK = 64;            // BK bf16 = 128 bytes = one swizzle-128B row
 constexpr int NUM_THREADS = 224;            // 7 warps
 constexpr int EPI_WARP0 = 3;                // warps 3..6 (warp % 4 = 3,0,1,2: all four TMEM lane groups)
+constexpr int FUSED2_EPI_GROUPS = 2;        // gemm_fused2_kernel: epilogue warp quartets
+constexpr int FUSED2_THREADS = 96 + 128 * FUSED2_EPI_GROUPS;
 constexpr int A_PLANE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int PANEL_BYTES = 32768, SUB_BYTES = 16384;
 
 enum ResMode { RES_NONE = 0, RES_TMA = 1, RES_DIRECT = 2 };
 
-template <int BN_, int STAGES_, int PANELS_> struct Cfg {
-  static constexpr int BN = BN_, STAGES = STAGES_, PANELS = PANELS_;
+// EPI_GROUPS: independent epilogue warp quartets (each reaches all four TMEM lane groups) that take the tile's 64-column panels in
+// turn.  With short K the epilogue -- one dependent chain tcgen05.ld -> scale/shift -> residual (shared memory) -> split -> st.shared
+// per thread -- is the kernel: four warps (one per scheduler) cannot hide its latencies, eight can.
+template <int BN_, int STAGES_, int PANELS_, int EPI_GROUPS_ = 1> struct Cfg {
+  static constexpr int BN = BN_, STAGES = STAGES_, PANELS = PANELS_, EPI_GROUPS = EPI_GROUPS_;
+  static constexpr int THREADS = 96 + 128 * EPI_GROUPS;
   static constexpr int W_PLANE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * W_PLANE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;                      // power of two >= 32
   static constexpr int PANELS_PER_TILE = BN / 64;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SS_STAGES = BN > 128 ? 1 : 2;            // BN = 256: one copy (the epilogue's panel barrier orders reuse), to fit 227 KB
-  static constexpr int SS_BYTES = SS_STAGES * 2 * BN * 4;       // scale, shift per accumulator stage
+  // scale / shift copies: per accumulator stage with one epilogue group (BN = 256: one copy, the panel barrier orders reuse, to
+  // fit 227 KB); with several groups each group keeps its own single copy (it restages at the top of every tile it works on)
+  static constexpr int SS_STAGES = EPI_GROUPS > 1 ? EPI_GROUPS : (BN > 128 ? 1 : 2);
+  static constexpr int SS_BYTES = SS_STAGES * 2 * BN * 4;
+  static constexpr int TEMPTY_COUNT = 4 * (EPI_GROUPS < PANELS_PER_TILE ? EPI_GROUPS : PANELS_PER_TILE);
+  static_assert(EPI_GROUPS == 1 || PANELS >= EPI_GROUPS, "one panel buffer per epilogue group at least");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PANELS * PANEL_BYTES + BAR_BYTES + SS_BYTES;
   static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared-memory limit");
   static_assert(2 * STAGES + 4 + 2 * PANELS + 1 <= BAR_BYTES / 8, "barrier area too small");
@@ -188,7 +198,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 TB_DEVINL uint32_t swz(uint32_t sub_base, int r, int j) { return sub_base + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4); }
 
 template <class C>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(C::THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
                    const __grid_constant__ CUtensorMap tmR, Params p) {
@@ -228,7 +238,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), C::TEMPTY_COUNT);
     }
     for (int s = 0; s < C::PANELS; ++s) {
       mbar_init(pfull_bar(s), 1);
@@ -327,18 +337,21 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    // ================= epilogue (warps 3..6) =================
+    // ================= epilogue (warps 3..6 [, 7..10]): group eg takes the panels with (running panel index) % groups == eg ====
+    constexpr int G = C::EPI_GROUPS, PPT = C::PANELS_PER_TILE;
     const int lg = warp & 3;                              // TMEM lane group this warp may access
-    const int et = threadIdx.x - EPI_WARP0 * 32;          // 0..127
+    const int eg = (warp - EPI_WARP0) >> 2;               // epilogue group
+    const int et = (threadIdx.x - EPI_WARP0 * 32) & 127;  // 0..127 inside the group
     const int r = lg * 32 + lane;                         // accumulator row = panel row of this thread
-    int it = 0, slot = 0, prev_slot = -1;
-    uint32_t pphase = 0;
+    const int gbar = 1 + eg;                              // named barrier of this group
+    int it = 0, prev_slot = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (G > 1 && PPT < G && (it * PPT) % G != eg) continue;   // one panel per tile: the groups alternate over tiles
       const int part = tile % ksplit, ot = tile / ksplit;
       const int m_blk = ot / n_tiles, n_blk = ot % n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      float* s_scale = s_ss + (C::SS_STAGES == 2 ? as : 0) * 2 * BN;
+      float* s_scale = s_ss + (G > 1 ? eg : (C::SS_STAGES == 2 ? as : 0)) * 2 * BN;
       float* s_shift = s_scale + BN;
       const int grp = p.group_rows > 0 ? m_blk * BM / p.group_rows : 0;
       const int gcol = grp * p.N;                           // grouped: column / parameter offset of this row block's group
@@ -347,14 +360,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         s_scale[cidx] = p.scale ? __ldg(p.scale + gcol + n_blk * BN + cidx) : 1.f;
         s_shift[cidx] = (p.shift && part == 0) ? __ldg(p.shift + gcol + n_blk * BN + cidx) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
+      asm volatile("bar.sync %0, 128;" ::"r"(gbar) : "memory");      // this epilogue group only
       mbar_wait(tfull_bar(as), aphase);
       tcgen05_fence_after();
       const long long row = (long long)m_blk * BM + r;
       const bool row_ok = row < p.M;
       const long long rrow = p.res_mod > 0 ? row % p.res_mod : row;
 #pragma unroll 1
-      for (int j = 0; j < C::PANELS_PER_TILE; ++j) {
+      for (int j = 0; j < PPT; ++j) {
+        const int gp = it * PPT + j;                      // running panel index: the producer fills the buffers in this order
+        if (G > 1 && gp % G != eg) continue;
+        const int slot = gp % C::PANELS;
+        const uint32_t pphase = (uint32_t)((gp / C::PANELS) & 1);
         mbar_wait(pfull_bar(slot), pphase);
         const uint32_t pb = panel_base + slot * PANEL_BYTES;
 #pragma unroll 1
@@ -435,13 +452,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           }
         }
-        if (j == C::PANELS_PER_TILE - 1) {                // accumulator fully read: hand it back to the MMA warp
+        if (j + G >= PPT) {                               // this group's last panel of the tile: its part of the accumulator is read
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
         fence_proxy_async();                              // generic-proxy writes -> visible to the TMA store
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(gbar) : "memory");
         if (et == 0) {
           const int col = gcol + n_blk * BN + j * 64;
           const int orow = m_blk * BM - grp * p.group_rows + part * p.part_rows;
@@ -449,7 +466,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           else tma_store_3d(&tmC, pb, col, orow, 0);
           bulk_commit();
           // keep at most PANELS-2 stores in flight, then recycle the buffer(s) whose store has drained
-          if constexpr (C::PANELS == 1) {
+          if constexpr (C::PANELS == 1 || G > 1) {          // several groups: each drains its own store (the other group computes meanwhile)
             bulk_wait_read<0>();
             mbar_arrive(pfree_bar(slot));
           } else {
@@ -462,7 +479,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           }
         }
-        if (++slot == C::PANELS) { slot = 0; pphase ^= 1; }
       }
     }
     if (et == 0) bulk_wait_all();                         // shared memory must outlive the last stores
@@ -500,7 +516,7 @@ struct Params2 {
 };
 
 template <int N1, int N2>   // N1 = channels of x' (256: layer1, 512: layer2), N2 = planes of the next bottleneck's conv1
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(FUSED2_THREADS, 1)
 gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmW2,
@@ -546,12 +562,12 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC2) : "memory");
     if (p.res_mode == RES_TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * FUSED2_EPI_GROUPS); }
     for (int s = 0; s < PANELS; ++s) {
       mbar_init(pfull_bar(s), 1); mbar_init(pfree_bar(s), 1); mbar_init(pready_bar(s), 1); mbar_init(pcons_bar(s), 1);
     }
     mbar_init(d2full_bar, 1);
-    mbar_init(d2empty_bar, 4);
+    mbar_init(d2empty_bar, 4 * (P2 < FUSED2_EPI_GROUPS ? P2 : FUSED2_EPI_GROUPS));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -710,38 +726,39 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    // ================= epilogue (warps 3..6) =================
+    // ================= epilogue: two warp quartets (warps 3..6 and 7..10); group eg takes panel jj == eg of every 128-column
+    // sub-tile of x' and panel jp % 2 == eg of t1'.  One quartet (one warp per scheduler) cannot hide the latencies of its
+    // dependent chain tcgen05.ld -> scale/shift -> residual (shared memory) -> split -> st.shared; with two, one group computes
+    // while the other drains its store.  Panels travel through the ring in the running order gp (slot = gp % PANELS), which both
+    // groups count; the group that owns a panel publishes it (pready), stores it, and recycles its buffer as soon as the store has
+    // read it and -- for an x' panel -- the second GEMM has consumed it (a lazy recycle would make the two groups take turns).
+    constexpr int G = FUSED2_EPI_GROUPS;
     const int lg = warp & 3;
-    const int et = threadIdx.x - EPI_WARP0 * 32;
+    const int eg = (warp - EPI_WARP0) >> 2;
+    const int et = (threadIdx.x - EPI_WARP0 * 32) & 127;
     const int r = lg * 32 + lane;
-    int tl = 0, slot = 0, prev_slot = -1;
+    const int gbar = 1 + eg;
+    int tl = 0;
     int acc_seen[2] = {0, 0};
-    bool prev_is_x = false;
-    uint32_t pphase = 0, cons_ph = 0;                        // cons_ph bit s: parity of the next pcons[s] completion
-    // et == 0: issue the store of panel `slot`, then recycle the previous panel once its store has drained (and, if it
-    // was an x' panel, the second GEMM has consumed it)
-    auto store_and_recycle = [&](bool is_x) {
-      bulk_commit();
-      bulk_wait_read<PANELS - 2>();
-      if (prev_slot >= 0) {
-        if (prev_is_x) {
-          mbar_wait(pcons_bar(prev_slot), (cons_ph >> prev_slot) & 1u);
-          cons_ph ^= 1u << prev_slot;
-        }
-        mbar_arrive(pfree_bar(prev_slot));
-      }
-      prev_slot = slot;
-      prev_is_x = is_x;
-    };
+    int xuse[PANELS];                                        // x' panels each ring slot has carried so far (parity of its pcons barrier)
+#pragma unroll
+    for (int i = 0; i < PANELS; ++i) xuse[i] = 0;
     for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x, ++tl) {
+      const int gp0 = tl * (P1 + P2);
       for (int sub = 0; sub < NSUB; ++sub) {
         const int as = sub & 1;
         mbar_wait(tfull_bar(as), (uint32_t)(acc_seen[as] & 1));
         ++acc_seen[as];
         tcgen05_fence_after();
-#pragma unroll 1
+#pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
-          mbar_wait(pfull_bar(slot), pphase);
+          const int gp = gp0 + 2 * sub + jj, slot = gp % PANELS;
+          uint32_t cons_parity = 0;
+#pragma unroll
+          for (int i = 0; i < PANELS; ++i)
+            if (i == slot) { cons_parity = (uint32_t)(xuse[i] & 1); ++xuse[i]; }
+          if (jj % G != eg) continue;
+          mbar_wait(pfull_bar(slot), (uint32_t)((gp / PANELS) & 1));
           const uint32_t pb = panel_base + slot * PANEL_BYTES;
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {
@@ -784,27 +801,34 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               sts128(swz(pb + SUB_BYTES, r, 4 * h + c8), mid);
             }
           }
-          if (jj == 1) {
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
-          }
+          // this group's only panel of the sub-tile: its columns of the accumulator have been read
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
           fence_proxy_async();                               // visible to the TMA store AND to the second GEMM's MMAs
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(gbar) : "memory");
           if (et == 0) {
             mbar_arrive(pready_bar(slot));
             tma_store_3d(&tmC, pb, sub * BN + jj * 64, m_blk * BM, 0);
-            store_and_recycle(true);
+            bulk_commit();
+            bulk_wait_read<0>();                             // the store has read the panel ...
+            mbar_wait(pcons_bar(slot), cons_parity);         // ... and so has the second GEMM
+            mbar_arrive(pfree_bar(slot));
           }
-          if (++slot == PANELS) { slot = 0; pphase ^= 1; }
         }
       }
       // ---- second accumulator: t1' = relu(scale2 * D2 + shift2), fp32 panels ----
-      mbar_wait(d2full_bar, (uint32_t)(tl & 1));
-      tcgen05_fence_after();
+      bool d2_waited = false;
 #pragma unroll 1
       for (int jp = 0; jp < P2; ++jp) {
-        mbar_wait(pfull_bar(slot), pphase);
+        const int gp = gp0 + P1 + jp, slot = gp % PANELS;
+        if (jp % G != eg) continue;
+        if (!d2_waited) {
+          mbar_wait(d2full_bar, (uint32_t)(tl & 1));
+          tcgen05_fence_after();
+          d2_waited = true;
+        }
+        mbar_wait(pfull_bar(slot), (uint32_t)((gp / PANELS) & 1));
         const uint32_t pb = panel_base + slot * PANEL_BYTES;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -823,18 +847,19 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             sts128(swz(pb + h * SUB_BYTES, r, c4), o);
           }
         }
-        if (jp == P2 - 1) {
+        if (jp + G >= P2) {                                  // this group's last panel of t1'
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(d2empty_bar);
         }
         fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(gbar) : "memory");
         if (et == 0) {
           tma_store_3d(&tmC2, pb, 0, m_blk * BM, (jp * 64) >> 5);
-          store_and_recycle(false);
+          bulk_commit();
+          bulk_wait_read<0>();
+          mbar_arrive(pfree_bar(slot));
         }
-        if (++slot == PANELS) { slot = 0; pphase ^= 1; }
       }
     }
     if (et == 0) bulk_wait_all();
@@ -887,22 +912,28 @@ TB_DEVINL void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint3
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+// STAGES x 64 KB operand ring + PANELS x 32 KB epilogue panels: <3, 1> for the deep-K shapes (the next tile's main loop hides the
+// one-panel epilogue), <2, 3> for short K with a residual (conv4 of the 1024-channel stage: K = 256, so the epilogue IS the kernel --
+// panels pipelined load | compute | store as in gemm_bf16x3_kernel)
+template <int STAGES, int PANELS, int G>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(96 + 128 * G, 1)
 gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
                     const __grid_constant__ CUtensorMap tmR, Params p) {
-  constexpr int BN2 = 256, BNH = 128, STAGES = 3, STAGE_BYTES = 65536, PPT = BN2 / 64;
+  constexpr int BN2 = 256, BNH = 128, STAGE_BYTES = 65536, PPT = BN2 / 64;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t panel_base = smem_base + STAGES * STAGE_BYTES;
-  const uint32_t bar_base = panel_base + PANEL_BYTES;
+  const uint32_t bar_base = panel_base + PANELS * PANEL_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (3 + s); };
-  auto xfull_bar = [&](int s) { return bar_base + 8u * (6 + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (9 + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (11 + s); };
-  const uint32_t pfull_bar = bar_base + 8u * 13, pfree_bar = bar_base + 8u * 14;
-  const uint32_t tmem_slot = bar_base + 8u * 15;
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto xfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * STAGES + 2 + s); };
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (3 * STAGES + 4 + s); };
+  auto pfree_bar = [&](int s) { return bar_base + 8u * (3 * STAGES + 4 + PANELS + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4 + 2 * PANELS);
+  static_assert(8 * (3 * STAGES + 4 + 2 * PANELS + 1) <= 256, "barrier block");
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_base));
   float* s_ss = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_base));   // scale[256] | shift[256]
 
@@ -921,9 +952,8 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     if (p.res_mode == RES_TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(xfull_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
-    mbar_init(pfull_bar, 1);
-    mbar_init(pfree_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8 * G); }
+    for (int s = 0; s < PANELS; ++s) { mbar_init(pfull_bar(s), 1); mbar_init(pfree_bar(s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -1008,44 +1038,49 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 2) {
     // ================= panel producer =================
     if (lane == 0) {
+      int slot = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += npairs) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int row0 = m_blk * 2 * BM + (int)rank * BM;
         for (int j = 0; j < PPT; ++j) {
-          mbar_wait(pfree_bar, phase ^ 1);
+          mbar_wait(pfree_bar(slot), phase ^ 1);
           if (p.res_mode == RES_TMA) {
             const int col = n_blk * BN2 + j * 64;
-            mbar_expect_tx(pfull_bar, PANEL_BYTES);
-            if (p.out_fmt == FMT_F32) tma_load_3d(panel_base, &tmR, pfull_bar, 0, row0, col >> 5);
-            else tma_load_3d(panel_base, &tmR, pfull_bar, col, row0, 0);
+            mbar_expect_tx(pfull_bar(slot), PANEL_BYTES);
+            if (p.out_fmt == FMT_F32) tma_load_3d(panel_base + slot * PANEL_BYTES, &tmR, pfull_bar(slot), 0, row0, col >> 5);
+            else tma_load_3d(panel_base + slot * PANEL_BYTES, &tmR, pfull_bar(slot), col, row0, 0);
           } else {
-            mbar_arrive(pfull_bar);
+            mbar_arrive(pfull_bar(slot));
           }
-          phase ^= 1;
+          if (++slot == PANELS) { slot = 0; phase ^= 1; }
         }
       }
     }
   } else {
     // ================= epilogue (warps 3..6): this CTA's 128 rows x 256 columns =================
     const int lg = warp & 3;
-    const int et = threadIdx.x - EPI_WARP0 * 32;
+    const int et = (threadIdx.x - EPI_WARP0 * 32) & 127;
     const int r = lg * 32 + lane;
     const uint32_t tempty_remote0 = mapa_rank(tempty_bar(0), 0), tempty_remote1 = mapa_rank(tempty_bar(1), 0);
     float* s_scale = s_ss;
     float* s_shift = s_ss + BN2;
-    int it = 0;
-    uint32_t pphase = 0;
+    const int eg = (warp - EPI_WARP0) >> 2;               // epilogue group: takes the panels j with j % G == eg (PPT = 4)
+    const int gbar = 1 + eg;
+    int it = 0, prev_slot = -1;
     for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = it & 1;
       const int grp = p.group_rows > 0 ? m_blk * 2 * BM / p.group_rows : 0;
       const int gcol = grp * p.N;
-      for (int c = et; c < BN2; c += 128) {
+      // one scale / shift copy for all groups: nobody restages it while a group still reads the previous tile's values
+      if (G > 1) asm volatile("bar.sync 3, %0;" ::"r"(128 * G) : "memory");
+      for (int c = threadIdx.x - EPI_WARP0 * 32; c < BN2; c += 128 * G) {
         s_scale[c] = p.scale ? __ldg(p.scale + gcol + n_blk * BN2 + c) : 1.f;
         s_shift[c] = p.shift ? __ldg(p.shift + gcol + n_blk * BN2 + c) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (G > 1) asm volatile("bar.sync 3, %0;" ::"r"(128 * G) : "memory");
+      else asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(tfull_bar(as), (it >> 1) & 1);
       tcgen05_fence_after();
       const int row0 = m_blk * 2 * BM + (int)rank * BM;
@@ -1054,8 +1089,12 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const long long rrow = p.res_mod > 0 ? row % p.res_mod : row;
 #pragma unroll 1
       for (int j = 0; j < PPT; ++j) {
-        mbar_wait(pfull_bar, pphase);
-        const uint32_t pb = panel_base;
+        if (G > 1 && j % G != eg) continue;
+        const int gp = it * PPT + j;                      // running panel index (the producer's order)
+        const int slot = gp % PANELS;
+        const uint32_t pphase = (uint32_t)((gp / PANELS) & 1);
+        mbar_wait(pfull_bar(slot), pphase);
+        const uint32_t pb = panel_base + slot * PANEL_BYTES;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           uint32_t acc[32];
@@ -1130,23 +1169,33 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
-        if (j == PPT - 1) {                                  // accumulator fully read: hand it back to the leader's MMA warp
+        if (j + G >= PPT) {                                  // this group's last panel: its part of the accumulator is read
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(as ? tempty_remote1 : tempty_remote0);
         }
         fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(gbar) : "memory");
         if (et == 0) {
           const int col = gcol + n_blk * BN2 + j * 64;
           const int orow = row0 - grp * p.group_rows;
           if (p.out_fmt == FMT_F32) tma_store_3d(&tmC, pb, 0, orow, col >> 5);
           else tma_store_3d(&tmC, pb, col, orow, 0);
           bulk_commit();
-          bulk_wait_read<0>();
-          mbar_arrive(pfree_bar);
+          // keep at most PANELS-2 stores in flight, then recycle the buffer(s) whose store has drained
+          if constexpr (PANELS == 1 || G > 1) {
+            bulk_wait_read<0>();
+            mbar_arrive(pfree_bar(slot));
+          } else {
+            bulk_wait_read<PANELS - 2>();
+            if constexpr (PANELS == 2) {
+              mbar_arrive(pfree_bar(slot));
+            } else {
+              if (prev_slot >= 0) mbar_arrive(pfree_bar(prev_slot));
+              prev_slot = slot;
+            }
+          }
         }
-        pphase ^= 1;
       }
     }
     if (et == 0) bulk_wait_all();
@@ -1166,13 +1215,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-using CfgWide = Cfg<128, 2, 3>;   // memory-bound shapes: panels pipelined (load residual | compute | store)
+using CfgWide = Cfg<128, 2, 3, 2>;   // memory-bound shapes: panels pipelined (load residual | compute | store), two epilogue groups
 using CfgDeep = Cfg<128, 3, 1>;   // K >= 512: deeper operand ring, one panel buffer
-using CfgN64 = Cfg<64, 3, 2>;     // N == 64 (or N % 128 != 0)
+using CfgN64 = Cfg<64, 3, 2, 2>;     // N == 64 (or N % 128 != 0): one panel per tile, the two epilogue groups alternate over tiles
 using CfgBig = Cfg<256, 2, 1>;    // K >= 512, N % 256 == 0 and enough row blocks: 128 x 256 tiles (A tile reused over 256 columns,
                                   // 25 % less L2 -> shared-memory traffic per FLOP; these shapes are L2-bandwidth / tensor bound)
 
-constexpr int PAIR_SMEM_BYTES = 3 * 65536 + PANEL_BYTES + 256 + 2 * 256 * 4;   // gemm2_bf16x3_kernel
+constexpr int PAIR_SMEM_BYTES = 3 * 65536 + PANEL_BYTES + 256 + 2 * 256 * 4;   // gemm2_bf16x3_kernel<3, 1> and <2, 3> (2 x 64 KB + 3 panels: same size)
+static_assert(2 * 65536 + 3 * PANEL_BYTES == 3 * 65536 + PANEL_BYTES, "pair kernel configurations share one shared-memory size");
 static_assert(PAIR_SMEM_BYTES <= 232448, "over the 227 KB shared-memory limit");
 
 static char g_err[256] = "";
@@ -1192,7 +1242,8 @@ static cudaError_t init_once() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDeep::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgN64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgN64::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgBig::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel<3, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel<2, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
@@ -1274,7 +1325,7 @@ static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmA2, c
                               const Params& p, cudaStream_t st) {
   const int tiles = ceil_div(p.M, BM) * (p.N / C::BN) * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = tiles < device_num_sms() ? tiles : device_num_sms();
-  return launch_pdl(gemm_bf16x3_kernel<C>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
+  return launch_pdl(gemm_bf16x3_kernel<C>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
 }
 
 }  // namespace tc
@@ -1344,7 +1395,9 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   if (pair_tiles) {
     const int tiles = ceil_div(p.M, 2 * BM) * (p.N / 256);
     const int pairs = tiles < device_num_sms() / 2 ? tiles : device_num_sms() / 2;
-    return launch_pdl(gemm2_bf16x3_kernel, dim3(2 * pairs), dim3(NUM_THREADS), PAIR_SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
+    if (KT < 512)                                             // short K: the epilogue dominates, pipeline its panels
+      return launch_pdl(gemm2_bf16x3_kernel<2, 3, 2>, dim3(2 * pairs), dim3(96 + 128 * 2), PAIR_SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
+    return launch_pdl(gemm2_bf16x3_kernel<3, 1, 1>, dim3(2 * pairs), dim3(NUM_THREADS), PAIR_SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
   }
   if (bn == 256) return launch_cfg<CfgBig>(tmA, tmA2, tmW, tmC, tmR, p, st);
   if (bn == 64) return launch_cfg<CfgN64>(tmA, tmA2, tmW, tmC, tmR, p, st);
@@ -1413,9 +1466,9 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
   if (!encode_f32_panel_map(&tmC2, C2, N2, a.M, ldc2)) return cudaErrorInvalidValue;
   const int m_tiles = ceil_div(a.M, BM);
   const int grid = m_tiles < device_num_sms() ? m_tiles : device_num_sms();
-  if (a.N == 512) return launch_pdl(gemm_fused2_kernel<512, 128>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
-  if (N2 == 64) return launch_pdl(gemm_fused2_kernel<256, 64>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
-  return launch_pdl(gemm_fused2_kernel<256, 128>, dim3(grid), dim3(NUM_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
+  if (a.N == 512) return launch_pdl(gemm_fused2_kernel<512, 128>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
+  if (N2 == 64) return launch_pdl(gemm_fused2_kernel<256, 64>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
+  return launch_pdl(gemm_fused2_kernel<256, 128>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
 }
 
 // fp32 [N,K] -> bf16 [2][N][K] (hi plane, mid plane)
