@@ -1,14 +1,15 @@
 """Summarise an ncu launch list (--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv) of
 tools/run_forward.py --n 2 into per-kernel-family totals of the SECOND forward (warm library state):
     python tools/ncu_launches_summary.py gpurun_out/launches.csv profiles/r1_launches_vNN_summary.json
-bench.py reads the newest profiles/*_summary.json for roofline.traffic (DRAM bytes per launch of the dominant kernel)."""
+bench.py reads the newest round's profiles/r<N>_*_summary.json for roofline.traffic (DRAM bytes per launch of the dominant kernel)."""
 import collections
 import csv
 import json
 import sys
 
-FAMILY = [("gemm_fused2", "gemm_fused2_tcgen05"), ("gemm2_bf16x3", "gemm2_bf16x3_pair"), ("Cfg<128, 2, 3>", "gemm_bf16x3_wide"), ("Cfg<128, 3, 1>", "gemm_bf16x3_deep"),
-          ("Cfg<64, 3, 2>", "gemm_bf16x3_n64"), ("Cfg<256, 2, 1>", "gemm_bf16x3_big"), ("stem_tc", "stem_conv"), ("dwconv", "dwconv3x3x3"), ("attn", "attention"),
+FAMILY = [("gemm_fused2", "gemm_fused2_tcgen05"), ("gemm2_bf16x3", "gemm2_bf16x3_pair"), ("Cfg<128, 2, 3", "gemm_bf16x3_wide"), ("Cfg<128, 3, 1", "gemm_bf16x3_deep"),
+          ("Cfg<64, 3, 2", "gemm_bf16x3_n64"), ("Cfg<256, 2, 1", "gemm_bf16x3_big"), ("stem_tc", "stem_conv"), ("dwconv", "dwconv3x3x3"), ("attn_tc", "attention_tc"),
+          ("attn", "attention"),
           ("layernorm", "layernorm"), ("gather_rows", "gather_rows"), ("sgemm", "sgemm_fp32"), ("head_gemm", "sgemm_fp32"), ("pool_mix", "pool_mix"), ("maxpool", "maxpool"),
           ("tpool", "tpool"), ("posenc", "posenc"), ("mask_resize", "mask_resize"), ("to_split", "to_split")]
 

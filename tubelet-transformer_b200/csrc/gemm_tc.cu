@@ -1395,7 +1395,11 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   if (pair_tiles) {
     const int tiles = ceil_div(p.M, 2 * BM) * (p.N / 256);
     const int pairs = tiles < device_num_sms() / 2 ? tiles : device_num_sms() / 2;
-    if (KT < 512)                                             // short K: the epilogue dominates, pipeline its panels
+    // short K: the epilogue dominates, pipeline its panels.  Also when every pair gets at most one tile (conv1 of the 1024-channel
+    // stage at 8 clips: 64 tiles for 74 pairs): nothing follows the tile, so its epilogue is fully exposed
+    static const int force23 = [] { const char* e = getenv("TUBER_PAIR_CFG23"); return e ? atoi(e) : -1; }();
+    const bool single_round = tiles <= device_num_sms() / 2;
+    if (force23 == 1 || (force23 != 0 && KT < 512) || (force23 == 2 && single_round))
       return launch_pdl(gemm2_bf16x3_kernel<2, 3, 2>, dim3(2 * pairs), dim3(96 + 128 * 2), PAIR_SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
     return launch_pdl(gemm2_bf16x3_kernel<3, 1, 1>, dim3(2 * pairs), dim3(NUM_THREADS), PAIR_SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
   }
