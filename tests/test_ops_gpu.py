@@ -65,7 +65,9 @@ def test_gemm_tc(abi, m, n, k, variant):
                                                     (5000, 64, 0, 256, 128, True), (33333, 64, 64, 256, 128, False),
                                                     (300, 128, 0, 256, 64, True), (50000, 64, 64, 256, 64, False),
                                                     (70001, 128, 0, 256, 128, True), (700, 128, 0, 512, 128, True),
-                                                    (45000, 128, 0, 512, 128, True), (30001, 128, 256, 512, 128, False)])
+                                                    (45000, 128, 0, 512, 128, True), (30001, 128, 256, 512, 128, False),
+                                                    (16384, 256, 0, 1024, 256, True), (900, 256, 512, 1024, 256, False),
+                                                    (40001, 256, 0, 1024, 256, True)])
 def test_gemm_tc_fused2(abi, m, k, kb, n1, n2, with_res):
     """conv4 (+ residual / K-concatenated shortcut) chained with the next block's conv1 through the shared-memory panels"""
     g = torch.Generator(device="cuda").manual_seed(m + k + kb + n2)

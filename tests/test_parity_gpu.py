@@ -308,6 +308,36 @@ def test_fused_and_folded_paths_match_the_plain_launch_sequence(monkeypatch):
         assert emax < 1e-4 and el2 < 1e-4, (k, emax, el2)
 
 
+@pytest.mark.parametrize("yaml,batch,masked", [("TubeR_CSN152_AVA21.yaml", 3, False), ("TubeR_CSN50_AVA21.yaml", 9, True)])
+def test_decoder_megakernel_matches_the_per_operation_sequence(monkeypatch, yaml, batch, masked):
+    """decoder_mega.cu (the decoder stack as one persistent cooperative kernel, fp32 state) against the launch-per-operation
+    sequence it replaces (TUBER_NO_DEC_MEGA is read at plan creation), with and without a key padding mask; 9 clips = 135 rows,
+    more than one staged row chunk."""
+    import tuber_b200
+    from oracle import tuber_oracle as O
+    cfg = tuber_b200.load_cfg(yaml)
+    sd = O.make_state_dict(cfg, seed=3, bn="random")
+    clips = O.make_clips(batch, 32, 128, 160, seed=4).cuda()
+    mask = None
+    if masked:
+        mask = torch.zeros(batch, 128, 160, dtype=torch.bool, device="cuda")
+        mask[1, :, 120:] = True
+        mask[batch - 1, 96:, :] = True
+        clips = clips * (~mask)[:, None, None].float()
+    lib = tuber_b200._lib.load()
+    m = _model(cfg, sd)
+    fast = {k: v.clone() for k, v in m.forward_raw(clips, mask).items()}
+    n_fast = lib.tuber_last_launches(m.plan())
+    monkeypatch.setenv("TUBER_NO_DEC_MEGA", "1")
+    m2 = _model(cfg, sd)
+    plain = m2.forward_raw(clips, mask)
+    n_plain = lib.tuber_last_launches(m2.plan())
+    assert n_fast <= n_plain - 50, (n_fast, n_plain)                 # ~60 decoder launches became one
+    for k in fast:
+        emax, el2 = _rel(fast[k], plain[k])
+        assert emax < 1e-4 and el2 < 1e-4, (k, emax, el2)
+
+
 def test_detection_rows_match_reference_postprocessors():
     """tuber_postprocess (fused post-processing + row packing) against the reference's PostProcessAVA / PostProcess outputs
     (tests/golden/postprocess.npz) and through the PostProcess* modules of build_model."""

@@ -526,7 +526,8 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   constexpr int W2_CHUNK = N2 * 256;                        // bytes of one k-block of W1' (hi + mid planes)
   constexpr int KBW = STAGE_BYTES / W2_CHUNK;               // k-blocks of the second GEMM per ring stage (4 or 2)
   constexpr int D2_COL = 2 * BN;                            // TMEM: [0,256) two conv4 accumulators, [256, 256+N2) the second GEMM
-  static_assert(KBW == 2 || KBW == 4, "W1' chunking");
+  static_assert(KBW == 1 || KBW == 2 || KBW == 4, "W1' chunking");
+  static_assert(D2_COL + N2 <= 512, "tensor memory: two conv4 accumulators + the second GEMM's accumulator");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t panel_base = smem_base + STAGES * STAGE_BYTES;
@@ -618,6 +619,7 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         };
         for (int sub = 0; sub < NSUB; ++sub) {
           if ((2 * sub) % KBW == 0) load_w2(2 * sub / KBW);
+          if (KBW == 1) load_w2(2 * sub + 1);                // one k-block of W1' per stage (N2 = 256): a chunk per panel
           if (!delay) load_g(sub + 2);
         }
         if (delay)
@@ -1247,6 +1249,7 @@ static cudaError_t init_once() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     return e;
   });
 }
@@ -1432,8 +1435,8 @@ const char* gemm_tc_config_name(const GemmArgs& a) {
   return KT >= 512 ? "gemm_bf16x3_deep" : "gemm_bf16x3_wide";
 }
 
-// conv4 (a: N must be 256, split output, TMA or no residual) fused with the next bottleneck's conv1 (W2p packed
-// [2][N2][256], N2 in {64, 128}; fp32 result C2 [M, ldc2])
+// conv4 (a: split output, TMA or no residual) fused with the next bottleneck's conv1 (W2p packed [2][N2][N]; fp32 result
+// C2 [M, ldc2]); (N, N2) in {(256, 64), (256, 128), (512, 128), (1024, 256)} = the 256-, 512- and 1024-channel stages
 cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const float* scale2, const float* shift2, float* C2, int N2,
                                   int ldc2, cudaStream_t st) {
   using namespace tc;
@@ -1442,10 +1445,10 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const int KT = a.K + (a.Ab ? a.Kb : 0);
   const bool res_ok = !a.res || (a.res_mod <= 0 && a.res_fmt == FMT_SPLIT && aligned16(a.res) && a.ldr % 8 == 0 && a.N <= a.ldr);
-  if (a.M <= 0 || !(a.N == 256 || (a.N == 512 && N2 == 128)) || a.K % 64 != 0 || a.lda % 8 != 0 || a.K > a.lda || a.a_fmt != FMT_SPLIT || a.Wp == nullptr ||
+  if (a.M <= 0 || !((a.N == 256 && (N2 == 64 || N2 == 128)) || (a.N == 512 && N2 == 128) || (a.N == 1024 && N2 == 256)) || a.K % 64 != 0 || a.lda % 8 != 0 || a.K > a.lda || a.a_fmt != FMT_SPLIT || a.Wp == nullptr ||
       a.c_fmt != FMT_SPLIT || a.act == ACT_SIGMOID || !aligned16(a.A) || !aligned16(a.Wp) || !aligned16(a.C) || a.ldc % 8 != 0 ||
       a.N > a.ldc || (a.Ab && (a.Kb % 64 != 0 || a.Kb <= 0 || a.ldb % 8 != 0 || a.Kb > a.ldb || !aligned16(a.Ab))) || !res_ok ||
-      (N2 != 64 && N2 != 128) || W2p == nullptr || !aligned16(W2p) || C2 == nullptr || !aligned16(C2) || ldc2 % 8 != 0 || N2 > ldc2) {
+      W2p == nullptr || !aligned16(W2p) || C2 == nullptr || !aligned16(C2) || ldc2 % 8 != 0 || N2 > ldc2) {
     snprintf(g_err, sizeof g_err, "gemm_tc_fused2: unsupported problem M=%d N=%d K=%d N2=%d", a.M, a.N, KT, N2);
     return cudaErrorInvalidValue;
   }
@@ -1470,6 +1473,7 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
   if (!encode_f32_panel_map(&tmC2, C2, N2, a.M, ldc2)) return cudaErrorInvalidValue;
   const int m_tiles = ceil_div(a.M, BM);
   const int grid = m_tiles < device_num_sms() ? m_tiles : device_num_sms();
+  if (a.N == 1024) return launch_pdl(gemm_fused2_kernel<1024, 256>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   if (a.N == 512) return launch_pdl(gemm_fused2_kernel<512, 128>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   if (N2 == 64) return launch_pdl(gemm_fused2_kernel<256, 64>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   return launch_pdl(gemm_fused2_kernel<256, 128>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);

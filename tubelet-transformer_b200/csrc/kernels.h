@@ -121,6 +121,35 @@ bool attention_tc_wants_prep(const AttnArgs& a);
 size_t attention_tc_scratch_bytes(const AttnArgs& a);
 cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t st);
 
+// ---- the DETR decoder stack as one persistent cooperative kernel (decoder_mega.cu; transformer.py:98-127,218-249) ----------
+// fp32 weights: *_w row-major [N, K] (the GEMM's Lin::wf), *_t K-major copies [K, N]; biases [N]; LayerNorm gamma / beta [256]
+constexpr int DEC_MEGA_MAX_LAYERS = 8;
+struct DecMegaLayer {
+  const float* sa_in_w; const float* sa_in_b; const float* pq_sa;     // [3d, d], [3d], [Q, 3d] query_pos terms of q and k
+  const float* sa_out_t; const float* sa_out_b; const float* n1_g; const float* n1_b;
+  const float* ca_q_t; const float* ca_q_b; const float* pq_ca;       // [d, d] K-major, [d], [Q, d]
+  const float* ca_out_t; const float* ca_out_b; const float* n2_g; const float* n2_b;
+  const float* lin1_w; const float* lin1_b; const float* lin2_w; const float* lin2_b;   // [ff, d], [ff], [d, ff], [d]
+  const float* n3_g; const float* n3_b;
+};
+struct DecMegaArgs {
+  DecMegaLayer L[DEC_MEGA_MAX_LAYERS];
+  int Ld, B, Q, Ntok, dim_ff, kv_ld, ntok_pad;
+  float eps;
+  const float* memkv;                        // [B*Ntok, kv_ld]: per layer [K | V] of the cross attention (kv_ld = Ld * 2d)
+  const uint8_t* kpm;                        // key padding mask [B, Ntok] or null
+  const float* dec0_c1; const float* dec0_qc;   // layer 0 folded at finalize ([d], [Q, d]); both set
+  const float* nf_g; const float* nf_b;      // the decoder's shared final norm
+  float* tgt;                                // [B*Q, d] fp32 state (scratch)
+  float* qkv;                                // [B*Q, 3d] scratch
+  float* part;                               // [dim_ff / 16][B*Q][d] feed-forward partial sums (scratch)
+  void* hs;                                  // split [B, Ld, Q, d]: every layer's output after the final norm
+  unsigned* barrier;                         // 4 bytes of device memory for the grid barrier
+  unsigned long long* trace;                 // optional [1 + 4 * Ld]: %globaltimer of CTA 0 at the start and after every phase
+};
+bool decoder_mega_supported(int d_model, int nhead, int dim_ff, int Q, int Ntok);
+cudaError_t launch_decoder_mega(DecMegaArgs a, cudaStream_t st);
+
 // ---- post-processing + detection rows (criterion.py:413-482; video_action_recognition.py:411-415) -------------
 // logits [B, Q, C] (clip stride l_sb floats), boxes [B, Q, 4] (b_sb), logits_b [B, Q, 3] (AVA) or [B, 2] (lb_sb), sizes [B, 2] = (H, W);
 // out [B*Q, 4 + C + 1] = xyxy scaled | scores | foreground probability

@@ -86,6 +86,7 @@ struct DecLayer {
   LnP n1, n2, n3;
   float* pq_sa = nullptr;   // [Q, 3d]: query_embed x [Wq;Wk;0]^T   (q = k = tgt + query_pos, transformer.py:225)
   float* pq_ca = nullptr;   // [Q, d] : query_embed x Wq^T           (query = tgt + query_pos, :232)
+  float* sa_out_t = nullptr; float* ca_q_t = nullptr; float* ca_out_t = nullptr;   // K-major fp32 copies [d, d] (decoder_mega.cu)
 };
 
 struct KernelRec { const char* name; double bytes, flops; cudaEvent_t e0, e1; char tag[64]; };
@@ -154,7 +155,9 @@ struct TuberPlan {
   // uint8 input path (tuber_forward_u8*): value table of the reference's ToTensor + Normalize and the fp32 clip it expands into
   float* in_lut = nullptr;           // [3][256] on the device
   float* u8_clip = nullptr; size_t u8_clip_cap = 0;
-  bool force_simt = false, no_fuse2 = false, pool_unfolded = false, no_strided_tma = false;
+  bool no_dec_mega = false;
+  unsigned long long* dec_trace = nullptr; int dec_trace_n = 0;   // per-phase timestamps of the decoder kernel (kernel profiling only)
+  bool force_simt = false, no_fuse2 = false, fuse2_deep = false, pool_unfolded = false, no_strided_tma = false;
   bool profiling = false, debug_keep = false, use_graph = false;
   cudaEvent_t ev[TUBER_NUM_STAGES + 1] = {};
   bool ev_valid = false;
@@ -502,6 +505,19 @@ int do_finalize(TuberPlan* p) {
       host_embed_proj(*qe, Q, d, *cw, 0, d, pc.data(), d);
       l.pq_sa = pk.upload(pq);
       l.pq_ca = pk.upload(pc);
+      const HostTensor* so = pk.get(P + ".self_attn.out_proj.weight", {d, d});
+      const HostTensor* co = pk.get(P + ".multihead_attn.out_proj.weight", {d, d});
+      if (so && co) {
+        auto transposed = [&](const float* w) {              // rows [0, d) of w [*, d] -> K-major [d][d]
+          std::vector<float> t((size_t)d * d);
+          for (int n = 0; n < d; ++n)
+            for (int k = 0; k < d; ++k) t[(size_t)k * d + n] = w[(size_t)n * d + k];
+          return t;
+        };
+        l.sa_out_t = pk.upload(transposed(so->data.data()));
+        l.ca_q_t = pk.upload(transposed(cw->data.data()));
+        l.ca_out_t = pk.upload(transposed(co->data.data()));
+      }
       memcpy(memw.data() + (size_t)i * 2 * d * d, cw->data.data() + (size_t)d * d, (size_t)2 * d * d * sizeof(float));
       memcpy(memb.data() + (size_t)i * 2 * d, cb->data.data() + d, (size_t)2 * d * sizeof(float));
       // position term of the cross-attention keys: k = (memory + pos) Wk^T
@@ -829,7 +845,8 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
       // 256-channel stage: conv4 of this block and conv1 of the next one run as one kernel (the next block's input tile is
       // multiplied while it still sits in shared memory), see gemm_fused2_kernel
       const bool fuse = !p->force_simt && !p->no_fuse2 && nb && nb->cin == b.cout && b.planes % 64 == 0 && b.cin % 64 == 0 &&
-                        ((b.cout == 256 && (nb->planes == 64 || nb->planes == 128)) || (b.cout == 512 && nb->planes == 128));
+                        ((b.cout == 256 && (nb->planes == 64 || nb->planes == 128)) || (b.cout == 512 && nb->planes == 128) ||
+                         (b.cout == 1024 && nb->planes == 256 && p->fuse2_deep));
       const void* xa = nullptr;                              // the shortcut's input rows (strided voxel gather when the block strides)
       const int geo[7] = {wo, ho, w, h, B * t, b.st_t, b.st_s};
       const int* ab_geo = nullptr;                           // set: the GEMM reads the strided rows itself (5-D TMA with element strides)
@@ -1004,6 +1021,34 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     float* memkv = cx.f32(Mtok, Ld * 2 * d);                // per layer [K | V] of the cross attention
     cx.gemm(src_s, FMT_SPLIT, d, Mtok, p->mem_kv, posp + (size_t)Le * 3 * d, FMT_F32, NP, pos_mod, memkv, FMT_F32, Ld * 2 * d,
             ACT_NONE);
+    const bool mega = !p->force_simt && !p->no_dec_mega && p->dec0_c1 && p->dec0_qc && Ld <= DEC_MEGA_MAX_LAYERS &&
+                      decoder_mega_supported(d, nh, c.dim_ff, Q, Ntok) && p->dec[0].sa_out_t != nullptr;
+    if (mega) {
+      // the whole stack as one persistent cooperative kernel (decoder_mega.cu): fp32 state, grid barriers between the phases
+      DecMegaArgs m{};
+      for (int i = 0; i < Ld; ++i) {
+        const DecLayer& l = p->dec[i];
+        DecMegaLayer& o = m.L[i];
+        o.sa_in_w = l.sa_in.wf; o.sa_in_b = l.sa_in.shift; o.pq_sa = l.pq_sa;
+        o.sa_out_t = l.sa_out_t; o.sa_out_b = l.sa_out.shift; o.n1_g = l.n1.g; o.n1_b = l.n1.b;
+        o.ca_q_t = l.ca_q_t; o.ca_q_b = l.ca_q.shift; o.pq_ca = l.pq_ca;
+        o.ca_out_t = l.ca_out_t; o.ca_out_b = l.ca_out.shift; o.n2_g = l.n2.g; o.n2_b = l.n2.b;
+        o.lin1_w = l.lin1.wf; o.lin1_b = l.lin1.shift; o.lin2_w = l.lin2.wf; o.lin2_b = l.lin2.shift;
+        o.n3_g = l.n3.g; o.n3_b = l.n3.b;
+      }
+      m.Ld = Ld; m.B = B; m.Q = Q; m.Ntok = Ntok; m.dim_ff = c.dim_ff; m.kv_ld = Ld * 2 * d; m.eps = LN_EPS;
+      m.memkv = memkv; m.kpm = kpm; m.dec0_c1 = p->dec0_c1; m.dec0_qc = p->dec0_qc; m.nf_g = p->dec_norm.g; m.nf_b = p->dec_norm.b;
+      m.tgt = cx.f32(Mq, d); m.qkv = cx.f32(Mq, 3 * d); m.part = cx.f32((long long)(c.dim_ff / 16) * Mq, d);
+      m.hs = hs_s; m.barrier = reinterpret_cast<unsigned*>(cx.ws.alloc(256));
+      m.trace = reinterpret_cast<unsigned long long*>(cx.ws.alloc(8 * 256));
+      if (!dry) { p->dec_trace = p->kprof ? m.trace : nullptr; p->dec_trace_n = 1 + 4 * Ld; }
+      if (!p->kprof) m.trace = nullptr;
+      const double wbytes = 4.0 * Ld * (6.0 * d * d + 2.0 * d * c.dim_ff);
+      if (p->kprof) snprintf(cx.tag, sizeof cx.tag, "B=%d Q=%d Ntok=%d layers=%d", B, Q, Ntok, Ld);
+      cx.launch("decoder_mega", wbytes + 4.0 * Mtok * Ld * 2 * d + 4.0 * Mh * d,
+                2.0 * Ld * ((double)Mq * (6.0 * d * d + 2.0 * d * c.dim_ff) + 4.0 * Mq * (Q + Ntok) * d),
+                [&] { return launch_decoder_mega(m, st); });
+    }
     void* tgt_s = cx.split(Mq, d);
     // tgt = zeros_like(query_embed), transformer.py:60 (all-zero bits are zero in split format too); with layer 0 folded at
     // finalize the zero state is never read
@@ -1017,7 +1062,7 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     const int ksd = p->force_simt ? 1 : choose_ksplit(Mq, d, c.dim_ff);
     const long long prd = (Mq + 127) / 128 * 128;
     float* od = ksd > 1 ? cx.f32((long long)ksd * prd, d) : nullptr;
-    for (int i = 0; i < Ld; ++i) {
+    for (int i = 0; i < Ld && !mega; ++i) {
       const DecLayer& l = p->dec[i];
       const bool folded0 = i == 0 && p->dec0_c1 != nullptr;
       if (!folded0) {
@@ -1189,6 +1234,12 @@ int tuber_plan_create(const TuberConfig* cfg, TuberPlan** out_plan) {
   p->force_simt = fs && fs[0] == '1';
   const char* nf = getenv("TUBER_NO_FUSE2");
   p->no_fuse2 = nf && nf[0] == '1';
+  // 1024-channel stage: gemm_fused2_kernel<1024, 256> is correct but not faster than the separate launches (70 vs 30 + 37 us per
+  // block at 8 clips: one CTA per 128-row block pulls 4.1 MB through L2 -> shared memory, the pair GEMM shares W across two SMs), so off
+  const char* nfd = getenv("TUBER_FUSE2_L3");
+  p->fuse2_deep = nfd && nfd[0] == '1';
+  const char* ndm = getenv("TUBER_NO_DEC_MEGA");             // decoder as one launch per operation (cross-check of decoder_mega.cu)
+  p->no_dec_mega = ndm && ndm[0] == '1';
   const char* pu = getenv("TUBER_POOL_UNFOLDED");
   p->pool_unfolded = pu && pu[0] == '1';
   const char* ns = getenv("TUBER_NO_STRIDED_TMA");
@@ -1605,6 +1656,20 @@ int tuber_get_kernel_profile(TuberPlan* p, TuberKernelStat* out, int32_t capacit
       s = &agg.back();
     }
     s->launches += 1; s->ms += ms; s->bytes += r.bytes; s->flops += r.flops;
+  }
+  if (dump && dump[0] == '1' && p->dec_trace && p->dec_trace_n > 1) {
+    std::vector<unsigned long long> t(p->dec_trace_n);
+    if (cudaMemcpy(t.data(), p->dec_trace, t.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "decoder_mega phases (us, A | BC | D | E per layer, barriers included):");
+      for (int i = 1; i < p->dec_trace_n; ++i) fprintf(stderr, "%s%.1f", (i - 1) % 4 == 0 ? "  | " : " ", (double)(t[i] - t[i - 1]) * 1e-3);
+      fprintf(stderr, "\n");
+    }
+    std::vector<unsigned long long> t2(192);
+    if (cudaMemcpy(t2.data(), p->dec_trace + 64, t2.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "decoder_mega CTA 0 sub-stamps (us):");
+      for (int i = 1; i < 60; ++i) fprintf(stderr, " %.1f", (double)((long long)(t2[i] - t2[i - 1])) * 1e-3);
+      fprintf(stderr, "\n");
+    }
   }
   *n_out = (int32_t)agg.size();
   if (out) for (int i = 0; i < (int)agg.size() && i < capacity; ++i) out[i] = agg[i];
