@@ -901,6 +901,11 @@ TB_DEVINL uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
 TB_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// release at cluster scope: the arriving thread's (and, through the preceding CTA barrier, its group's) shared-memory writes are
+// visible to whoever acquires the barrier in the other CTA (compiles to a MEMBAR: only where data is published, not for counters)
+TB_DEVINL void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 TB_DEVINL void umma2_commit_mc(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -1212,6 +1217,366 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// =============================================================================================================
+// CTA-pair form of the fused conv4 -> conv1 kernel for the 1024-channel stage (layer3 of ir-CSN-152: 36 bottlenecks, N1 = 1024,
+// N2 = 256, K = 256).  gemm_fused2_kernel<1024, 256> is correct but one CTA per 128-row block pulls 4.1 MB through L2 -> shared
+// memory (A re-read for each of its 8 sub-tiles, all of W4 and W1'), which is what bounds it (70 us per block at 8 clips against
+// 30 + 37 us for the separate pair / single-CTA launches).  Here a cluster of two CTAs owns 256 rows and issues
+// tcgen05.mma.cta_group::2 (M = 256): each CTA loads its own 128 rows of A and HALF of every weight tile, and the conv4 sub-tiles
+// are 256 columns wide (A is read 4 times instead of 8): 2.6 MB per CTA.
+//   tensor memory (per CTA): [0, 256) the conv4 accumulator of the current sub-tile (single: the second GEMM over its four
+//   panels keeps the tensor pipe busy while the epilogue drains it), [256, 512) the second GEMM's accumulator.
+//   barriers as in gemm_fused2_kernel; `tempty`, `pready`, `d2empty` live in the leader and count arrivals from both CTAs
+//   (remote mbarrier.arrive), `xfull[s]` is the peer's relay of its TMA completions, every tcgen05.commit is multicast to both.
+// =============================================================================================================
+template <int N1, int N2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSED2_THREADS, 1)
+gemm_fused2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
+                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmW2,
+                    const __grid_constant__ CUtensorMap tmC2, Params p, Params2 q) {
+  constexpr int BNS = 256, BNH = 128, STAGES = 2, PANELS = 3, STAGE_BYTES = 65536;
+  constexpr int NSUB = N1 / BNS, PPS = BNS / 64, P1 = N1 / 64, P2 = N2 / 64;
+  constexpr int W2_CHUNK = (N2 / 2) * 256;                  // bytes of one k-block of this CTA's half of W1' (hi + mid planes)
+  constexpr int KBW = STAGE_BYTES / W2_CHUNK;               // k-blocks of the second GEMM per ring stage
+  constexpr int D2_COL = BNS;
+  constexpr int G = FUSED2_EPI_GROUPS;
+  static_assert(N1 % BNS == 0 && N2 == 256 && KBW == 2 && PPS % KBW == 0 && D2_COL + N2 <= 512, "built for the 1024 -> 256 shapes");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t panel_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = panel_base + PANELS * PANEL_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto xfull_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  const uint32_t tfull_bar = bar_base + 8u * 6, tempty_bar = bar_base + 8u * 7;
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto pfree_bar = [&](int s) { return bar_base + 8u * (11 + s); };
+  auto pready_bar = [&](int s) { return bar_base + 8u * (14 + s); };
+  auto pcons_bar = [&](int s) { return bar_base + 8u * (17 + s); };
+  const uint32_t d2full_bar = bar_base + 8u * 20, d2empty_bar = bar_base + 8u * 21;
+  const uint32_t tmem_slot = bar_base + 8u * 22;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
+  const int kblocks = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_base & 1023u) __trap();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    if (p.kb1 < kblocks) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC2) : "memory");
+    if (p.res_mode == RES_TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(xfull_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 2 * 4 * G);
+    for (int s = 0; s < PANELS; ++s) {
+      mbar_init(pfull_bar(s), 1); mbar_init(pfree_bar(s), 1); mbar_init(pready_bar(s), 2); mbar_init(pcons_bar(s), 1);
+    }
+    mbar_init(d2full_bar, 1);
+    mbar_init(d2empty_bar, 2 * 4 * (P2 < G ? P2 : G));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // Ring order = the MMA warp's consumption order, per row-block pair and sub-tile: the K stages [A rows | W4 half] of the
+  // sub-tile, then the PPS / KBW chunks of W1' that its four panels multiply
+  if (warp == 0) {
+    // ================= operand producer (both CTAs): own 128 rows of A, own half of the weight rows =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pair; pb < m_pairs; pb += npairs) {
+        const int row0 = pb * 2 * BM + (int)rank * BM;
+        for (int sub = 0; sub < NSUB; ++sub) {
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            if (kb < p.kb1) tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, row0, 0);
+            else load_a2(sa, &tmA2, full_bar(stage), (kb - p.kb1) * BK, row0, p.a2_wo, p.a2_ho, p.a2_st, p.a2_ss);
+            tma_load_3d(sa + 2 * A_PLANE_BYTES, &tmW, full_bar(stage), kb * BK, sub * BNS + (int)rank * BNH, 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          for (int c = 0; c < PPS / KBW; ++c) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            mbar_expect_tx(full_bar(stage), KBW * W2_CHUNK);
+            for (int e = 0; e < KBW; ++e)
+              tma_load_3d(sa + e * W2_CHUNK, &tmW2, full_bar(stage), ((sub * (PPS / KBW) + c) * KBW + e) * BK, (int)rank * (N2 / 2), 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank != 0) {
+      // ================= relay (peer CTA): report each locally completed stage to the leader =================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t remote[STAGES];
+        for (int s = 0; s < STAGES; ++s) remote[s] = mapa_rank(xfull_bar(s), 0);
+        for (int pb = pair; pb < m_pairs; pb += npairs)
+          for (int i = 0; i < NSUB * (kblocks + PPS / KBW); ++i) {
+            mbar_wait(full_bar(stage), phase);
+            mbar_arrive_cluster(remote[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+      }
+    } else {
+      // ================= MMA issuer (leader CTA) =================
+      constexpr uint32_t idesc1 = make_idesc(2 * BM, BNS), idesc2 = make_idesc(2 * BM, N2);
+      const uint64_t desc0 = make_smem_desc(smem_base);
+      const uint64_t pdesc0 = make_smem_desc(panel_base);
+      int stage = 0, pslot = 0, tl = 0, nsub = 0;
+      uint32_t phase = 0, ready_ph = 0;                      // ready_ph bit s: parity of the next pready[s] completion
+      for (int pb = pair; pb < m_pairs; pb += npairs, ++tl) {
+        for (int sub = 0; sub < NSUB; ++sub, ++nsub) {
+          // ---- conv4 sub-tile -> D1 (both epilogues have drained the previous one) ----
+          mbar_wait(tempty_bar, (uint32_t)((nsub & 1) ^ 1));
+          tcgen05_fence_after();
+#pragma unroll 1
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            mbar_wait(xfull_bar(stage), phase);
+            tcgen05_fence_after();
+            if (elect_one()) {
+              const uint64_t a_hi = desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4)), a_mid = a_hi + (A_PLANE_BYTES >> 4);
+              const uint64_t w_hi = a_hi + ((2 * A_PLANE_BYTES) >> 4), w_mid = w_hi + ((BNH * BK * 2) >> 4);
+              const uint32_t first = kb == 0 ? 0u : 1u;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_base, a_mid + 2 * k, w_hi + 2 * k, idesc1, k == 0 ? first : 1u);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_base, a_hi + 2 * k, w_mid + 2 * k, idesc1, 1);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_base, a_hi + 2 * k, w_hi + 2 * k, idesc1, 1);
+              umma2_commit_mc(empty_bar(stage));
+              if (kb == kblocks - 1) umma2_commit_mc(tfull_bar);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          // ---- second GEMM over the sub-tile's four panels (k-block j = output panel j of x', read from both CTAs' buffers) ----
+          int w2_stage = 0;
+          for (int jj = 0; jj < PPS; ++jj) {
+            const int j = sub * PPS + jj;
+            if (j == 0) {
+              mbar_wait(d2empty_bar, (uint32_t)((tl & 1) ^ 1));   // both epilogues have drained the previous pair-block's t1'
+              tcgen05_fence_after();
+            }
+            if (jj % KBW == 0) {
+              mbar_wait(full_bar(stage), phase);
+              mbar_wait(xfull_bar(stage), phase);
+              w2_stage = stage;
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            mbar_wait(pready_bar(pslot), (ready_ph >> pslot) & 1u);
+            ready_ph ^= 1u << pslot;
+            tcgen05_fence_after();
+            if (elect_one()) {
+              const uint32_t tmem_d2 = tmem_base + (uint32_t)D2_COL;
+              const uint64_t a_hi = pdesc0 + (uint64_t)(pslot * (PANEL_BYTES >> 4)), a_mid = a_hi + (SUB_BYTES >> 4);
+              const uint64_t w_hi = desc0 + (uint64_t)(w2_stage * (STAGE_BYTES >> 4)) + (uint64_t)((jj % KBW) * (W2_CHUNK >> 4));
+              const uint64_t w_mid = w_hi + (((N2 / 2) * BK * 2) >> 4);
+              const uint32_t first = j == 0 ? 0u : 1u;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_d2, a_mid + 2 * k, w_hi + 2 * k, idesc2, k == 0 ? first : 1u);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_d2, a_hi + 2 * k, w_mid + 2 * k, idesc2, 1);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma2_bf16(tmem_d2, a_hi + 2 * k, w_hi + 2 * k, idesc2, 1);
+              umma2_commit_mc(pcons_bar(pslot));
+              if (jj % KBW == KBW - 1) umma2_commit_mc(empty_bar(w2_stage));
+              if (j == P1 - 1) umma2_commit_mc(d2full_bar);
+            }
+            __syncwarp();
+            if (++pslot == PANELS) pslot = 0;
+          }
+        }
+        for (int jp = 0; jp < P2; ++jp)                        // the t1' panels use ring slots too (not operands)
+          if (++pslot == PANELS) pslot = 0;
+      }
+    }
+  } else if (warp == 2) {
+    // ================= panel producer (both CTAs) =================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int pb = pair; pb < m_pairs; pb += npairs) {
+        const int row0 = pb * 2 * BM + (int)rank * BM;
+        for (int j = 0; j < P1 + P2; ++j) {
+          mbar_wait(pfree_bar(slot), phase ^ 1);
+          if (j < P1 && p.res_mode == RES_TMA) {
+            mbar_expect_tx(pfull_bar(slot), PANEL_BYTES);
+            tma_load_3d(panel_base + slot * PANEL_BYTES, &tmR, pfull_bar(slot), j * 64, row0, 0);
+          } else {
+            mbar_arrive(pfull_bar(slot));
+          }
+          if (++slot == PANELS) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue (both CTAs): two warp quartets; group eg takes the panels jj with jj % 2 == eg =================
+    const int lg = warp & 3;
+    const int eg = (warp - EPI_WARP0) >> 2;
+    const int et = (threadIdx.x - EPI_WARP0 * 32) & 127;
+    const int r = lg * 32 + lane;
+    const int gbar = 1 + eg;
+    const uint32_t tempty_remote = mapa_rank(tempty_bar, 0), d2empty_remote = mapa_rank(d2empty_bar, 0);
+    uint32_t pready_remote[PANELS];
+#pragma unroll
+    for (int i = 0; i < PANELS; ++i) pready_remote[i] = mapa_rank(pready_bar(i), 0);
+    int tl = 0, nsub = 0;
+    int xuse[PANELS];                                        // x' panels each ring slot has carried so far (parity of its pcons barrier)
+#pragma unroll
+    for (int i = 0; i < PANELS; ++i) xuse[i] = 0;
+    for (int pb = pair; pb < m_pairs; pb += npairs, ++tl) {
+      const int row0 = pb * 2 * BM + (int)rank * BM;
+      const int gp0 = tl * (P1 + P2);
+      for (int sub = 0; sub < NSUB; ++sub, ++nsub) {
+        mbar_wait(tfull_bar, (uint32_t)(nsub & 1));
+        tcgen05_fence_after();
+#pragma unroll
+        for (int jj = 0; jj < PPS; ++jj) {
+          const int gp = gp0 + PPS * sub + jj, slot = gp % PANELS;
+          uint32_t cons_parity = 0, pr_remote = 0;
+#pragma unroll
+          for (int i = 0; i < PANELS; ++i)
+            if (i == slot) { cons_parity = (uint32_t)(xuse[i] & 1); ++xuse[i]; pr_remote = pready_remote[i]; }
+          if (jj % G != eg) continue;
+          mbar_wait(pfull_bar(slot), (uint32_t)((gp / PANELS) & 1));
+          const uint32_t pb_addr = panel_base + slot * PANEL_BYTES;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(jj * 64 + h * 32), acc);
+            const int c0 = sub * BNS + jj * 64 + h * 32;     // column of x'
+            float v[32];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              const float4 sc = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + c0) + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
+              const float4 sh = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift + c0) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[4 * c4] = fmaf(__uint_as_float(acc[4 * c4]), sc.x, sh.x);
+              v[4 * c4 + 1] = fmaf(__uint_as_float(acc[4 * c4 + 1]), sc.y, sh.y);
+              v[4 * c4 + 2] = fmaf(__uint_as_float(acc[4 * c4 + 2]), sc.z, sh.z);
+              v[4 * c4 + 3] = fmaf(__uint_as_float(acc[4 * c4 + 3]), sc.w, sh.w);
+            }
+            if (p.res_mode == RES_TMA) {
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) {
+                const uint4 a = lds128(swz(pb_addr, r, 4 * h + c8));
+                const uint4 b = lds128(swz(pb_addr + SUB_BYTES, r, 4 * h + c8));
+                v[8 * c8] += bf16_lo_to_f32(a.x) + bf16_lo_to_f32(b.x); v[8 * c8 + 1] += bf16_hi_to_f32(a.x) + bf16_hi_to_f32(b.x);
+                v[8 * c8 + 2] += bf16_lo_to_f32(a.y) + bf16_lo_to_f32(b.y); v[8 * c8 + 3] += bf16_hi_to_f32(a.y) + bf16_hi_to_f32(b.y);
+                v[8 * c8 + 4] += bf16_lo_to_f32(a.z) + bf16_lo_to_f32(b.z); v[8 * c8 + 5] += bf16_hi_to_f32(a.z) + bf16_hi_to_f32(b.z);
+                v[8 * c8 + 6] += bf16_lo_to_f32(a.w) + bf16_lo_to_f32(b.w); v[8 * c8 + 7] += bf16_hi_to_f32(a.w) + bf16_hi_to_f32(b.w);
+              }
+            }
+            if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+            }
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              uint4 hi, mid;
+              split_bf16x2(v[8 * c8], v[8 * c8 + 1], hi.x, mid.x);
+              split_bf16x2(v[8 * c8 + 2], v[8 * c8 + 3], hi.y, mid.y);
+              split_bf16x2(v[8 * c8 + 4], v[8 * c8 + 5], hi.z, mid.z);
+              split_bf16x2(v[8 * c8 + 6], v[8 * c8 + 7], hi.w, mid.w);
+              sts128(swz(pb_addr, r, 4 * h + c8), hi);
+              sts128(swz(pb_addr + SUB_BYTES, r, 4 * h + c8), mid);
+            }
+          }
+          if (jj + G >= PPS) {                                 // this group's last panel of the sub-tile: its columns of D1 are read
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_remote);
+          }
+          fence_proxy_async();                               // visible to the TMA store AND to the second GEMM's MMAs
+          asm volatile("bar.sync %0, 128;" ::"r"(gbar) : "memory");
+          if (et == 0) {
+            mbar_arrive_cluster_release(pr_remote);          // leader: this CTA's half of the panel is final
+            tma_store_3d(&tmC, pb_addr, sub * BNS + jj * 64, row0, 0);
+            bulk_commit();
+            bulk_wait_read<0>();                             // the store has read the panel ...
+            mbar_wait(pcons_bar(slot), cons_parity);         // ... and so has the second GEMM
+            mbar_arrive(pfree_bar(slot));
+          }
+        }
+      }
+      // ---- second accumulator: t1' = relu(scale2 * D2 + shift2), fp32 panels ----
+      bool d2_waited = false;
+#pragma unroll 1
+      for (int jp = 0; jp < P2; ++jp) {
+        const int gp = gp0 + P1 + jp, slot = gp % PANELS;
+        if (jp % G != eg) continue;
+        if (!d2_waited) {
+          mbar_wait(d2full_bar, (uint32_t)(tl & 1));
+          tcgen05_fence_after();
+          d2_waited = true;
+        }
+        mbar_wait(pfull_bar(slot), (uint32_t)((gp / PANELS) & 1));
+        const uint32_t pb_addr = panel_base + slot * PANEL_BYTES;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(D2_COL + jp * 64 + h * 32), acc);
+          const int c0 = jp * 64 + h * 32;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(q.scale2 + c0) + c4);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(q.shift2 + c0) + c4);
+            uint4 o;
+            o.x = __float_as_uint(fmaxf(fmaf(__uint_as_float(acc[4 * c4]), sc.x, sh.x), 0.f));
+            o.y = __float_as_uint(fmaxf(fmaf(__uint_as_float(acc[4 * c4 + 1]), sc.y, sh.y), 0.f));
+            o.z = __float_as_uint(fmaxf(fmaf(__uint_as_float(acc[4 * c4 + 2]), sc.z, sh.z), 0.f));
+            o.w = __float_as_uint(fmaxf(fmaf(__uint_as_float(acc[4 * c4 + 3]), sc.w, sh.w), 0.f));
+            sts128(swz(pb_addr + h * SUB_BYTES, r, c4), o);
+          }
+        }
+        if (jp + G >= P2) {                                  // this group's last panel of t1'
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(d2empty_remote);
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync %0, 128;" ::"r"(gbar) : "memory");
+        if (et == 0) {
+          tma_store_3d(&tmC2, pb_addr, 0, row0, (jp * 64) >> 5);
+          bulk_commit();
+          bulk_wait_read<0>();
+          mbar_arrive(pfree_bar(slot));
+        }
+      }
+    }
+    if (et == 0) bulk_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                        // the leader's MMAs read this CTA's shared memory until its last commit
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1250,6 +1615,7 @@ static cudaError_t init_once() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2p_kernel<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     return e;
   });
 }
@@ -1468,11 +1834,18 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
   if (!encode_split_map(&tmC, a.C, a.N, a.M, a.ldc, BM)) return cudaErrorInvalidValue;
   tmR = tmC;
   if (a.res && !encode_split_map(&tmR, a.res, a.N, a.M, a.ldr, BM)) return cudaErrorInvalidValue;
-  if (!encode3(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, W2p, a.N, N2, 2, (uint64_t)a.N * 2, (uint64_t)N2 * a.N * 2, 64, N2, 2))
+  static const bool single1024 = [] { const char* e = getenv("TUBER_FUSE2_SINGLE"); return e && e[0] == '1'; }();
+  const bool pair_form = a.N == 1024 && !single1024;       // gemm_fused2p_kernel: each CTA of the pair loads half of the W1' rows
+  if (!encode3(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, W2p, a.N, N2, 2, (uint64_t)a.N * 2, (uint64_t)N2 * a.N * 2, 64, pair_form ? N2 / 2 : N2, 2))
     return cudaErrorInvalidValue;
   if (!encode_f32_panel_map(&tmC2, C2, N2, a.M, ldc2)) return cudaErrorInvalidValue;
   const int m_tiles = ceil_div(a.M, BM);
   const int grid = m_tiles < device_num_sms() ? m_tiles : device_num_sms();
+  if (pair_form) {
+    const int m_pairs = ceil_div(a.M, 2 * BM), max_pairs = device_num_sms() / 2;
+    const int pairs = m_pairs < max_pairs ? m_pairs : max_pairs;
+    return launch_pdl(gemm_fused2p_kernel<1024, 256>, dim3(2 * pairs), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
+  }
   if (a.N == 1024) return launch_pdl(gemm_fused2_kernel<1024, 256>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   if (a.N == 512) return launch_pdl(gemm_fused2_kernel<512, 128>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   if (N2 == 64) return launch_pdl(gemm_fused2_kernel<256, 64>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);

@@ -254,13 +254,19 @@ constexpr int W_F4 = 27 * (CC / 4);
 constexpr int OFF_W = NSLOT * PLANE_BYTES;                // two weight buffers (item parity)
 constexpr int OFF_BAR = OFF_W + 2 * W_F4 * 16;
 constexpr int SMEM_BYTES = OFF_BAR + NSLOT * 8;
-constexpr int THREADS = TH * (TW / 8) * (CC / 4);         // 256
+constexpr int THREADS = TH * (TW / 8) * (CC / 4);         // 256 (CPT = 4); the CPT = 2 variant runs 512
 }  // namespace dwr
 
-__global__ void __launch_bounds__(dwr::THREADS, 1)
+// CPT = channels per thread.  4: 8 warps, a thread owns 8 voxels x 4 channels (two packed pairs per voxel).  2: 16 warps, 8 voxels x
+// one packed pair -- the same shared-memory wavefronts and FFMA2 count per CTA, but four warps per scheduler instead of two to hide
+// the LDS -> FFMA2 latencies (the kernel is issue / latency bound, not FLOP or HBM bound: profiles/r1_ncu_dwroll_v9.txt).
+template <int CPT>
+__global__ void __launch_bounds__(dwr::TH * (dwr::TW / 8) * (dwr::CC / CPT), 1)
 dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __restrict__ wpk, const float* __restrict__ scale,
                       const float* __restrict__ shift, void* __restrict__ out, int B, int T, int H, int W, int C, int TC, int nitems) {
   using namespace dwr;
+  constexpr int NP = CPT / 2;                               // packed fp32 pairs per voxel and thread
+  constexpr int CG = CC / CPT;                              // threads along the channel slice
   extern __shared__ __align__(128) float4 dwr_smem[];
   const int tid = threadIdx.x;
   const int wt = (W + TW - 1) / TW, ht = (H + TH - 1) / TH, tcn = (T + TC - 1) / TC, nch = C / CC;
@@ -298,24 +304,27 @@ dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __r
   if (tid == 0)
     for (int q = 0; q < NSLOT - 1 && q < total; ++q) issue(q);
 
-  const int c4 = tid & 7, wh = (tid >> 3) & 1, lh = tid >> 4;
+  const int cg = tid % CG, wh = (tid / CG) & 1, lh = tid / (2 * CG);
   // accumulators as packed fp32 pairs (FFMA2: one issue slot per two FMAs -- the kernel is issue bound, not FLOP bound)
   typedef unsigned long long u64;
-  u64 accA[8][2], accB[8][2], accC[8][2];
-  auto zero = [](u64 (&a)[8][2]) {
+  u64 accA[8][NP], accB[8][NP], accC[8][NP];
+  auto zero = [](u64 (&a)[8][NP]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j][0] = a[j][1] = 0ull;
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < NP; ++e) a[j][e] = 0ull;
   };
-  // acc += the 3 taps (kw) of filter row (kt, kh) applied to the input row x
-  auto add_row = [&](u64 (&acc)[8][2], const ulonglong2 (&x)[10], const ulonglong2* wsm, int kt, int kh) {
+  // acc += the 3 taps (kw) of filter row (kt, kh) applied to the input row x; a thread's CPT channels are NP consecutive u64
+  auto add_row = [&](u64 (&acc)[8][NP], const u64 (&x)[10][NP], const u64* wsm, int kt, int kh) {
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
-      const ulonglong2 wv = wsm[((kt * 3 + kh) * 3 + kw) * (CC / 4) + c4];
+      u64 wv[NP];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j][0]) : "l"(x[j + kw].x), "l"(wv.x));
-        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j][1]) : "l"(x[j + kw].y), "l"(wv.y));
-      }
+      for (int e = 0; e < NP; ++e) wv[e] = wsm[(((kt * 3 + kh) * 3 + kw) * CG + cg) * NP + e];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < NP; ++e) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j][e]) : "l"(x[j + kw][e]), "l"(wv[e]));
     }
   };
 
@@ -325,15 +334,16 @@ dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __r
     decode(blockIdx.x + k * gridDim.x, b, t0, h0, w0, cb);
     float4* wsm4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(dwr_smem) + OFF_W) + (k & 1) * W_F4;
     if (tid < W_F4) wsm4[tid] = __ldg(reinterpret_cast<const float4*>(wpk + (tid >> 3) * C + cb) + (tid & 7));
-    const ulonglong2* wsm = reinterpret_cast<const ulonglong2*>(wsm4);
-    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cb) + c4);
-    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cb) + c4);
+    const u64* wsm = reinterpret_cast<const u64*>(wsm4);
+    float sc[CPT], sh[CPT];
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) { sc[e] = __ldg(scale + cb + cg * CPT + e); sh[e] = __ldg(shift + cb + cg * CPT + e); }
     __syncthreads();
     const int oh = h0 + lh, ow0 = w0 + wh * 8;
     const int tend = min(t0 + TC, T);                       // output frames of this item: [t0, tend)
     zero(accA); zero(accB); zero(accC);
     // roles rotate every step: frame it updates P (output it-1, kt=2), Cc (output it, kt=1), N (output it+1, kt=0)
-    auto step = [&](int s, u64 (&P)[8][2], u64 (&Cc)[8][2], u64 (&N)[8][2]) {
+    auto step = [&](int s, u64 (&P)[8][NP], u64 (&Cc)[8][NP], u64 (&N)[8][NP]) {
       if (tid == 0 && q + NSLOT - 1 < total) issue(q + NSLOT - 1);   // its slot was released by the barrier ending step q-1
       {
         const uint32_t bar = bar0 + 8 * (q % NSLOT), par = (uint32_t)((q / NSLOT) & 1);
@@ -342,14 +352,22 @@ dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __r
             ::"r"(bar), "r"(par) : "memory");
       }
       const int it = t0 - 1 + s;
-      const ulonglong2* tsm = reinterpret_cast<const ulonglong2*>(dwr_smem) + (q % NSLOT) * PLANE_F4;
+      const u64* tsm = reinterpret_cast<const u64*>(dwr_smem) + (size_t)(q % NSLOT) * PLANE_F4 * 2;
       if (it >= 0 && it < T) {                               // (frames outside the clip are all zero: nothing to add)
         const bool do_p = it - 1 >= t0, do_c = it >= t0 && it < tend, do_n = it + 1 < tend;
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
-          ulonglong2 x[10];
+          u64 x[10][NP];
 #pragma unroll
-          for (int j = 0; j < 10; ++j) x[j] = tsm[((lh + kh) * IW + wh * 8 + j) * (CC / 4) + c4];
+          for (int j = 0; j < 10; ++j) {
+            const u64* xp = tsm + (((lh + kh) * IW + wh * 8 + j) * CG + cg) * NP;
+            if constexpr (NP == 2) {
+              const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xp);
+              x[j][0] = v.x; x[j][1] = v.y;
+            } else {
+              x[j][0] = xp[0];
+            }
+          }
           if (do_p) add_row(P, x, wsm, 2, kh);
           if (do_c) add_row(Cc, x, wsm, 1, kh);
           if (do_n) add_row(N, x, wsm, 0, kh);
@@ -361,13 +379,21 @@ dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __r
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (ow0 + j < W) {
-            float4 o;
-            o.x = fmaxf(fmaf(__uint_as_float((uint32_t)P[j][0]), sc.x, sh.x), 0.f);
-            o.y = fmaxf(fmaf(__uint_as_float((uint32_t)(P[j][0] >> 32)), sc.y, sh.y), 0.f);
-            o.z = fmaxf(fmaf(__uint_as_float((uint32_t)P[j][1]), sc.z, sh.z), 0.f);
-            o.w = fmaxf(fmaf(__uint_as_float((uint32_t)(P[j][1] >> 32)), sc.w, sh.w), 0.f);
-            __nv_bfloat16* hi = split_hi(out, orow0 + j, C) + cb + c4 * 4;
-            store_split4(hi, hi + C, o);
+            float o[CPT];
+#pragma unroll
+            for (int e = 0; e < NP; ++e) {
+              o[2 * e] = fmaxf(fmaf(__uint_as_float((uint32_t)P[j][e]), sc[2 * e], sh[2 * e]), 0.f);
+              o[2 * e + 1] = fmaxf(fmaf(__uint_as_float((uint32_t)(P[j][e] >> 32)), sc[2 * e + 1], sh[2 * e + 1]), 0.f);
+            }
+            __nv_bfloat16* hi = split_hi(out, orow0 + j, C) + cb + cg * CPT;
+            if constexpr (CPT == 4) {
+              store_split4(hi, hi + C, make_float4(o[0], o[1], o[2], o[3]));
+            } else {
+              uint32_t h2, m2;
+              split_bf16x2(o[0], o[1], h2, m2);
+              *reinterpret_cast<uint32_t*>(hi) = h2;
+              *reinterpret_cast<uint32_t*>(hi + C) = m2;
+            }
           }
         }
       }
@@ -552,7 +578,8 @@ static cudaError_t init_once() {
     }
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_s1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_s1_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dwr::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_s1_roll_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dwr::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_s1_roll_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dwr::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_s2_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dws::SMEM_BYTES);
     return e;
   });
@@ -605,7 +632,11 @@ cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale,
       }
       const long long items = cols * ceil_div(Ti, TC);
       const int grid = (int)(items < device_num_sms() ? items : device_num_sms());
-      return launch_pdl(dwconv_s1_roll_kernel, dim3(grid), dim3(dwr::THREADS), dwr::SMEM_BYTES, st, tmR, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, TC, (int)items);
+      // 16 warps (a packed channel pair per thread) unless TUBER_DW_WARPS8=1 (the 8-warp variant: the tests' cross-check)
+      static const bool warps8 = [] { const char* e = getenv("TUBER_DW_WARPS8"); return e && e[0] == '1'; }();
+      if (warps8)
+        return launch_pdl(dwconv_s1_roll_kernel<4>, dim3(grid), dim3(dwr::THREADS), dwr::SMEM_BYTES, st, tmR, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, TC, (int)items);
+      return launch_pdl(dwconv_s1_roll_kernel<2>, dim3(grid), dim3(2 * dwr::THREADS), dwr::SMEM_BYTES, st, tmR, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, TC, (int)items);
     }
     const long long tiles = (long long)B * ceil_div(Ti, TT) * ceil_div(Hi, TH) * ceil_div(Wi, TW) * (C / CC);
     const long long slots = (long long)device_num_sms() * (NSTAGE == 1 ? 2 : 1);

@@ -1234,8 +1234,10 @@ int tuber_plan_create(const TuberConfig* cfg, TuberPlan** out_plan) {
   p->force_simt = fs && fs[0] == '1';
   const char* nf = getenv("TUBER_NO_FUSE2");
   p->no_fuse2 = nf && nf[0] == '1';
-  // 1024-channel stage: gemm_fused2_kernel<1024, 256> is correct but not faster than the separate launches (70 vs 30 + 37 us per
-  // block at 8 clips: one CTA per 128-row block pulls 4.1 MB through L2 -> shared memory, the pair GEMM shares W across two SMs), so off
+  // 1024-channel stage: the fused conv4 -> conv1 kernels exist (gemm_fused2p_kernel on CTA pairs; gemm_fused2_kernel<1024, 256> with
+  // TUBER_FUSE2_SINGLE=1) and are correct, but at 8 clips a CTA owns ONE 128-row block of the stage and its chain load -> conv4 ->
+  // epilogue -> second GEMM has nothing to overlap with: 74 / 70 us per bottleneck against 30 + 37 us for the two separate launches
+  // (profiles/r2_fused2_layer3_experiment.json).  Off unless TUBER_FUSE2_L3=1.
   const char* nfd = getenv("TUBER_FUSE2_L3");
   p->fuse2_deep = nfd && nfd[0] == '1';
   const char* ndm = getenv("TUBER_NO_DEC_MEGA");             // decoder as one launch per operation (cross-check of decoder_mega.cu)
