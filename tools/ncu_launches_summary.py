@@ -7,7 +7,7 @@ import csv
 import json
 import sys
 
-FAMILY = [("gemm_fused2", "gemm_fused2_tcgen05"), ("gemm2_bf16x3", "gemm2_bf16x3_pair"), ("Cfg<128, 2, 3", "gemm_bf16x3_wide"), ("Cfg<128, 3, 1", "gemm_bf16x3_deep"),
+FAMILY = [("decoder_mega", "decoder_mega"), ("gemm_fused2", "gemm_fused2_tcgen05"), ("gemm2_bf16x3", "gemm2_bf16x3_pair"), ("Cfg<128, 2, 3", "gemm_bf16x3_wide"), ("Cfg<128, 3, 1", "gemm_bf16x3_deep"),
           ("Cfg<64, 3, 2", "gemm_bf16x3_n64"), ("Cfg<256, 2, 1", "gemm_bf16x3_big"), ("stem_tc", "stem_conv"), ("dwconv", "dwconv3x3x3"), ("attn_tc", "attention_tc"),
           ("attn", "attention"),
           ("layernorm", "layernorm"), ("gather_rows", "gather_rows"), ("sgemm", "sgemm_fp32"), ("head_gemm", "sgemm_fp32"), ("pool_mix", "pool_mix"), ("maxpool", "maxpool"),

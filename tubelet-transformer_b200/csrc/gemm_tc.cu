@@ -1511,7 +1511,7 @@ gemm_fused2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_proxy_async();                               // visible to the TMA store AND to the second GEMM's MMAs
           asm volatile("bar.sync %0, 128;" ::"r"(gbar) : "memory");
           if (et == 0) {
-            mbar_arrive_cluster_release(pr_remote);          // leader: this CTA's half of the panel is final
+            mbar_arrive_cluster_release(pr_remote);          // leader: this CTA's half of the panel is final (default-scope arrive: 70 vs 74 us)
             tma_store_3d(&tmC, pb_addr, sub * BNS + jj * 64, row0, 0);
             bulk_commit();
             bulk_wait_read<0>();                             // the store has read the panel ...
