@@ -247,7 +247,7 @@ dwconv_s1_tiled_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_co
 // LDS.128 for the input + 3.4 for the broadcast weights, against 108 FMAs), which moves the kernel from shared-memory bound
 // to HBM / FMA bound; items, steps and ring slots run as one flat software pipeline (prefetch distance 3) across items.
 namespace dwr {
-constexpr int TH = 16, TW = 16, CC = 32, IH = TH + 2, IW = TW + 2, NSLOT = 4, TCMAX = 16;
+constexpr int TH = 16, TW = 16, CC = 32, IH = TH + 2, IW = TW + 2, NSLOT = 5, TCMAX = 16;
 constexpr int PLANE_F4 = IH * IW * (CC / 4);              // float4 slots of one input frame of the halo tile
 constexpr int PLANE_BYTES = PLANE_F4 * 16;                // 41472
 constexpr int W_F4 = 27 * (CC / 4);
