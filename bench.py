@@ -55,14 +55,14 @@ def _peaks():
 
 def _ncu_traffic(kernel: str):
     """DRAM bytes per launch of `kernel` from the committed ncu launch-list summary of the current round's build
-    (profiles/r<round>_*_summary.json, newest round first; written by tools/ncu_launches_summary.py from
+    (profiles/r<round>_*_summary.json, newest round first, the round's `*final*` file before its earlier ones; written by tools/ncu_launches_summary.py from
     `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over this very command)."""
     import glob
     import re
 
     def round_of(path):
         m = re.match(r"r(\d+)_", os.path.basename(path))
-        return (int(m.group(1)) if m else 0, os.path.basename(path))
+        return (int(m.group(1)) if m else 0, "final" in os.path.basename(path), os.path.basename(path))
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_summary.json")), key=round_of)
     for f in reversed(files):
         try:
