@@ -247,13 +247,16 @@ dwconv_s1_tiled_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_co
 // LDS.128 for the input + 3.4 for the broadcast weights, against 108 FMAs), which moves the kernel from shared-memory bound
 // to HBM / FMA bound; items, steps and ring slots run as one flat software pipeline (prefetch distance 3) across items.
 namespace dwr {
-constexpr int TH = 16, TW = 16, CC = 32, IH = TH + 2, IW = TW + 2, NSLOT = 5, TCMAX = 16;
+constexpr int TH = 16, TW = 16, CC = 32, IH = TH + 2, IW = TW + 2, NSLOT = 4, TCMAX = 16;
 constexpr int PLANE_F4 = IH * IW * (CC / 4);              // float4 slots of one input frame of the halo tile
 constexpr int PLANE_BYTES = PLANE_F4 * 16;                // 41472
 constexpr int W_F4 = 27 * (CC / 4);
 constexpr int OFF_W = NSLOT * PLANE_BYTES;                // two weight buffers (item parity)
-constexpr int OFF_BAR = OFF_W + 2 * W_F4 * 16;
+constexpr int OFF_OUT = OFF_W + 2 * W_F4 * 16;            // one output frame of the tile in split format: [h][w][hi 64 B | mid 64 B]
+constexpr int OUT_BYTES = TH * TW * CC * 4;               // 32 KB
+constexpr int OFF_BAR = OFF_OUT + OUT_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + NSLOT * 8;
+static_assert(OFF_OUT % 128 == 0 && SMEM_BYTES <= 232448, "shared-memory layout");
 constexpr int THREADS = TH * (TW / 8) * (CC / 4);         // 256 (CPT = 4); the CPT = 2 variant runs 512
 }  // namespace dwr
 
@@ -262,8 +265,8 @@ constexpr int THREADS = TH * (TW / 8) * (CC / 4);         // 256 (CPT = 4); the 
 // the LDS -> FFMA2 latencies (the kernel is issue / latency bound, not FLOP or HBM bound: profiles/r1_ncu_dwroll_v9.txt).
 template <int CPT>
 __global__ void __launch_bounds__(dwr::TH * (dwr::TW / 8) * (dwr::CC / CPT), 1)
-dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __restrict__ wpk, const float* __restrict__ scale,
-                      const float* __restrict__ shift, void* __restrict__ out, int B, int T, int H, int W, int C, int TC, int nitems) {
+dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ wpk,
+                      const float* __restrict__ scale, const float* __restrict__ shift, int B, int T, int H, int W, int C, int TC, int nitems) {
   using namespace dwr;
   constexpr int NP = CPT / 2;                               // packed fp32 pairs per voxel and thread
   constexpr int CG = CC / CPT;                              // threads along the channel slice
@@ -373,32 +376,48 @@ dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __r
           if (do_n) add_row(N, x, wsm, 0, kh);
         }
       }
+      // emit output frame it-1 through a shared-memory staging tile and ONE asynchronous TMA store (per-thread 4 / 8-byte global
+      // stores kept the warps in the LSU: the store phase did not overlap the next step's FMAs).  The tensor map clips the tile
+      // at the volume's edges.
       const int ot = it - 1;
-      if (ot >= t0 && ot < tend && oh < H) {
-        const long long orow0 = (((long long)b * T + ot) * H + oh) * W + ow0;
+      const bool emit = ot >= t0 && ot < tend;               // uniform over the CTA
+      if (emit && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the staging tile
+      __syncthreads();                                       // every reader is done with this input slot; the staging tile is free
+      if (emit) {
+        char* stg = reinterpret_cast<char*>(dwr_smem) + OFF_OUT + (lh * TW + wh * 8) * (CC * 4) + cg * CPT * 2;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (ow0 + j < W) {
-            float o[CPT];
+          float o[CPT];
 #pragma unroll
-            for (int e = 0; e < NP; ++e) {
-              o[2 * e] = fmaxf(fmaf(__uint_as_float((uint32_t)P[j][e]), sc[2 * e], sh[2 * e]), 0.f);
-              o[2 * e + 1] = fmaxf(fmaf(__uint_as_float((uint32_t)(P[j][e] >> 32)), sc[2 * e + 1], sh[2 * e + 1]), 0.f);
-            }
-            __nv_bfloat16* hi = split_hi(out, orow0 + j, C) + cb + cg * CPT;
-            if constexpr (CPT == 4) {
-              store_split4(hi, hi + C, make_float4(o[0], o[1], o[2], o[3]));
-            } else {
-              uint32_t h2, m2;
-              split_bf16x2(o[0], o[1], h2, m2);
-              *reinterpret_cast<uint32_t*>(hi) = h2;
-              *reinterpret_cast<uint32_t*>(hi + C) = m2;
-            }
+          for (int e = 0; e < NP; ++e) {
+            o[2 * e] = fmaxf(fmaf(__uint_as_float((uint32_t)P[j][e]), sc[2 * e], sh[2 * e]), 0.f);
+            o[2 * e + 1] = fmaxf(fmaf(__uint_as_float((uint32_t)(P[j][e] >> 32)), sc[2 * e + 1], sh[2 * e + 1]), 0.f);
+          }
+          char* vp = stg + j * (CC * 4);
+          if constexpr (CPT == 4) {
+            uint2 h2, m2;
+            split_bf16x2(o[0], o[1], h2.x, m2.x);
+            split_bf16x2(o[2], o[3], h2.y, m2.y);
+            *reinterpret_cast<uint2*>(vp) = h2;
+            *reinterpret_cast<uint2*>(vp + CC * 2) = m2;
+          } else {
+            uint32_t h2, m2;
+            split_bf16x2(o[0], o[1], h2, m2);
+            *reinterpret_cast<uint32_t*>(vp) = h2;
+            *reinterpret_cast<uint32_t*>(vp + CC * 2) = m2;
           }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
       zero(P);                                               // becomes the N set of the next step
-      __syncthreads();                                       // every reader is done with this slot
+      if (emit) {
+        __syncthreads();                                     // staging tile complete
+        if (tid == 0) {
+          asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                       ::"l"(&tmOut), "r"(sbase + OFF_OUT), "r"(cb), "r"(0), "r"(w0), "r"(h0), "r"(b * T + ot) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
       ++q;
     };
     int s = 0;
@@ -410,6 +429,7 @@ dwconv_s1_roll_kernel(const __grid_constant__ CUtensorMap tmIn, const float* __r
     if (s < S) { step(s, accA, accB, accC); ++s; }
     if (s < S) { step(s, accB, accC, accA); ++s; }
   }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the last store
 }
 
 // Stride-(2,2,2) variant of the rolling-t kernel (first block of layer2 / layer3, ir_CSN_152.py:48-51 with stride 2): a work
@@ -632,11 +652,20 @@ cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale,
       }
       const long long items = cols * ceil_div(Ti, TC);
       const int grid = (int)(items < device_num_sms() ? items : device_num_sms());
+      CUtensorMap tmO;                                       // split output [B*T, H, W, 2 planes, C] bf16, box = one 16 x 16 x 32-channel frame tile
+      {
+        cuuint64_t od[5] = {(cuuint64_t)C, 2, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)B * Ti};
+        cuuint64_t os[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 4, (cuuint64_t)Wi * C * 4, (cuuint64_t)Hi * Wi * C * 4};
+        cuuint32_t ob[5] = {dwr::CC, 2, dwr::TW, dwr::TH, 1}, oe[5] = {1, 1, 1, 1, 1};
+        if (g_encode(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, out_split, od, os, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return cudaErrorInvalidValue;
+      }
       // 16 warps (a packed channel pair per thread) unless TUBER_DW_WARPS8=1 (the 8-warp variant: the tests' cross-check)
       static const bool warps8 = [] { const char* e = getenv("TUBER_DW_WARPS8"); return e && e[0] == '1'; }();
       if (warps8)
-        return launch_pdl(dwconv_s1_roll_kernel<4>, dim3(grid), dim3(dwr::THREADS), dwr::SMEM_BYTES, st, tmR, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, TC, (int)items);
-      return launch_pdl(dwconv_s1_roll_kernel<2>, dim3(grid), dim3(2 * dwr::THREADS), dwr::SMEM_BYTES, st, tmR, wpk, scale, shift, out_split, B, Ti, Hi, Wi, C, TC, (int)items);
+        return launch_pdl(dwconv_s1_roll_kernel<4>, dim3(grid), dim3(dwr::THREADS), dwr::SMEM_BYTES, st, tmR, tmO, wpk, scale, shift, B, Ti, Hi, Wi, C, TC, (int)items);
+      return launch_pdl(dwconv_s1_roll_kernel<2>, dim3(grid), dim3(2 * dwr::THREADS), dwr::SMEM_BYTES, st, tmR, tmO, wpk, scale, shift, B, Ti, Hi, Wi, C, TC, (int)items);
     }
     const long long tiles = (long long)B * ceil_div(Ti, TT) * ceil_div(Hi, TH) * ceil_div(Wi, TW) * (C / CC);
     const long long slots = (long long)device_num_sms() * (NSTAGE == 1 ? 2 : 1);
