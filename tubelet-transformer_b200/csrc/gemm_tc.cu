@@ -515,7 +515,10 @@ struct Params2 {
   int N2;
 };
 
-template <int N1, int N2>   // N1 = channels of x' (256: layer1, 512: layer2), N2 = planes of the next bottleneck's conv1
+// KBW_MAX caps the k-blocks of W1' per ring stage: with N2 = 64 a full stage holds the W1' rows of all four panels of a 256-column
+// block, which pins one of the two ring slots for the whole block and forces the serial `delay` order whenever conv4 has more than one
+// k-block (the first bottleneck of layer1, K = 64 + 64); half-filled stages (KBW = 2) are released per sub-tile instead.
+template <int N1, int N2, int KBW_MAX = 4>   // N1 = channels of x' (256: layer1, 512: layer2), N2 = planes of the next bottleneck's conv1
 __global__ void __launch_bounds__(FUSED2_THREADS, 1)
 gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
@@ -524,7 +527,7 @@ gemm_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   constexpr int BN = 128, STAGES = 2, PANELS = 3, STAGE_BYTES = 65536;
   constexpr int NSUB = N1 / BN, P1 = N1 / 64, P2 = N2 / 64;  // x' = NSUB sub-tiles of 128 columns = P1 panels; t1' = P2 panels
   constexpr int W2_CHUNK = N2 * 256;                        // bytes of one k-block of W1' (hi + mid planes)
-  constexpr int KBW = STAGE_BYTES / W2_CHUNK;               // k-blocks of the second GEMM per ring stage (4 or 2)
+  constexpr int KBW = STAGE_BYTES / W2_CHUNK < KBW_MAX ? STAGE_BYTES / W2_CHUNK : KBW_MAX;   // k-blocks of the second GEMM per ring stage
   constexpr int D2_COL = 2 * BN;                            // TMEM: [0,256) two conv4 accumulators, [256, 256+N2) the second GEMM
   static_assert(KBW == 1 || KBW == 2 || KBW == 4, "W1' chunking");
   static_assert(D2_COL + N2 <= 512, "tensor memory: two conv4 accumulators + the second GEMM's accumulator");
@@ -1612,6 +1615,7 @@ static cudaError_t init_once() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel<3, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel<2, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
@@ -1848,6 +1852,10 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
   }
   if (a.N == 1024) return launch_pdl(gemm_fused2_kernel<1024, 256>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   if (a.N == 512) return launch_pdl(gemm_fused2_kernel<512, 128>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
+  static const bool kbw2 = [] { const char* e = getenv("TUBER_FUSE2_KBW4"); return !(e && e[0] == '1'); }();
+  static const bool kbw2_all = [] { const char* e = getenv("TUBER_FUSE2_KBW2_ALL"); return e && e[0] == '1'; }();
+  if (N2 == 64 && (KT > BK || kbw2_all) && kbw2)                          // more than one conv4 k-block: half-filled W1' stages instead of the serial order
+    return launch_pdl(gemm_fused2_kernel<256, 64, 2>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   if (N2 == 64) return launch_pdl(gemm_fused2_kernel<256, 64>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   return launch_pdl(gemm_fused2_kernel<256, 128>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
 }
