@@ -76,6 +76,7 @@ struct Params {
   int ksplit, part_rows;                                // split-K: work item = (tile, part); part s -> rows + s*part_rows of C
   int a2_wo;                                            // > 0: A2 is a strided 5-D map; output rows per (b,t) frame = a2_wo * a2_ho
   int a2_ho, a2_st, a2_ss;
+  int tail_panels;                                      // gemm2 kernel, one tile per pair, no residual: the finished operand stages serve as panel buffers
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -1047,7 +1048,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 2) {
     // ================= panel producer =================
-    if (lane == 0) {
+    if (lane == 0 && !p.tail_panels) {
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += npairs) {
@@ -1103,8 +1104,11 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int gp = it * PPT + j;                      // running panel index (the producer's order)
         const int slot = gp % PANELS;
         const uint32_t pphase = (uint32_t)((gp / PANELS) & 1);
-        mbar_wait(pfull_bar(slot), pphase);
-        const uint32_t pb = panel_base + slot * PANEL_BYTES;
+        // tail mode (one tile per pair, no residual): after tfull every MMA has read its operands and no load is outstanding, so
+        // panel j > 0 is built in the first half of operand stage j - 1: four buffers, the stores of all panels in flight at once
+        const bool tail = p.tail_panels != 0;
+        if (!tail) mbar_wait(pfull_bar(slot), pphase);
+        const uint32_t pb = tail ? (j == 0 ? panel_base : smem_base + (uint32_t)(j - 1) * STAGE_BYTES) : panel_base + slot * PANEL_BYTES;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           uint32_t acc[32];
@@ -1193,7 +1197,9 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else tma_store_3d(&tmC, pb, col, orow, 0);
           bulk_commit();
           // keep at most PANELS-2 stores in flight, then recycle the buffer(s) whose store has drained
-          if constexpr (PANELS == 1 || G > 1) {
+          if (tail) {
+            // nothing to recycle: every panel has its own buffer (bulk_wait_all below keeps shared memory alive)
+          } else if constexpr (PANELS == 1 || G > 1) {
             bulk_wait_read<0>();
             mbar_arrive(pfree_bar(slot));
           } else {
@@ -1614,6 +1620,7 @@ static cudaError_t init_once() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16x3_kernel<CfgBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgBig::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel<3, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel<2, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel<3, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
@@ -1774,6 +1781,13 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
     const bool single_round = tiles <= device_num_sms() / 2;
     if (force23 == 1 || (force23 != 0 && KT < 512) || (force23 == 2 && single_round))
       return launch_pdl(gemm2_bf16x3_kernel<2, 3, 2>, dim3(2 * pairs), dim3(96 + 128 * 2), PAIR_SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
+    // one tile per pair and no residual (conv1 of the 1024-channel stage at 8 clips): nothing follows the tile, its four panels go
+    // through the freed operand stages with two epilogue groups instead of one buffer and one group
+    static const bool no_tail = [] { const char* e = getenv("TUBER_PAIR_NO_TAIL"); return e && e[0] == '1'; }();
+    if (single_round && p.res_mode == RES_NONE && !no_tail) {
+      p.tail_panels = 1;
+      return launch_pdl(gemm2_bf16x3_kernel<3, 1, 2>, dim3(2 * pairs), dim3(96 + 128 * 2), PAIR_SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
+    }
     return launch_pdl(gemm2_bf16x3_kernel<3, 1, 1>, dim3(2 * pairs), dim3(NUM_THREADS), PAIR_SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
   }
   if (bn == 256) return launch_cfg<CfgBig>(tmA, tmA2, tmW, tmC, tmR, p, st);
