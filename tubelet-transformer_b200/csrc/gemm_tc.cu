@@ -1779,7 +1779,11 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
     // stage at 8 clips: 64 tiles for 74 pairs): nothing follows the tile, so its epilogue is fully exposed
     static const int force23 = [] { const char* e = getenv("TUBER_PAIR_CFG23"); return e ? atoi(e) : -1; }();
     const bool single_round = tiles <= device_num_sms() / 2;
-    if (force23 == 1 || (force23 != 0 && KT < 512) || (force23 == 2 && single_round))
+    // K = 512 with a residual (conv4 of the 2048-channel stage): 8 k-blocks do not hide a one-buffer, one-group epilogue of four
+    // residual panels either
+    static const bool res512 = [] { const char* e = getenv("TUBER_PAIR_RES512"); return !(e && e[0] == '0'); }();
+    if (force23 == 1 || (force23 != 0 && KT < 512) || (force23 == 2 && single_round) ||
+        (force23 != 0 && res512 && KT <= 512 && p.res_mode != RES_NONE))
       return launch_pdl(gemm2_bf16x3_kernel<2, 3, 2>, dim3(2 * pairs), dim3(96 + 128 * 2), PAIR_SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
     // one tile per pair and no residual (conv1 of the 1024-channel stage at 8 clips): nothing follows the tile, its four panels go
     // through the freed operand stages with two epilogue groups instead of one buffer and one group
