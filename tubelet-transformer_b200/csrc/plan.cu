@@ -1321,6 +1321,7 @@ int tuber_forward(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev,
     CK(cudaDeviceSynchronize());
     if (p->ws) cudaFree(p->ws);
     p->ws = nullptr; p->ws_cap = 0;
+    p->dec_trace = nullptr;                                  // (pointed into the old workspace)
     for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);     // captured pointers are stale now
     p->graphs.clear();
     void* w = nullptr;
