@@ -207,7 +207,7 @@ int tuber_op_gemm_tc(const void* a_split_dev, const void* w_packed_dev, const fl
 /* Two chained pointwise convolutions in one kernel (reference ir_CSN_152.py:84-90 of block i then :73-75 of block i+1):
  * C[M,N1] = relu(scale*([A | Ab] W^T) + shift + res) (split),  C2[M,N2] = relu(scale2*(C W2^T) + shift2) (fp32).
  * A split [M,K], Ab split [M,Kb] or NULL, W packed [2][N1][K+Kb], res split [M,N1] or NULL, W2 packed [2][N2][N1];
- * (N1, N2) in {(256, 64), (256, 128), (512, 128), (1024, 256)}. */
+ * (N1, N2) in {(256, 64), (256, 128), (512, 128), (512, 256), (1024, 256)}. */
 int tuber_op_gemm_tc_fused2(const void* a_split_dev, const void* ab_split_dev, const void* w_packed_dev, const float* scale_dev,
                             const float* shift_dev, const void* res_split_dev, void* c_split_dev, int32_t M, int32_t K, int32_t Kb,
                             const void* w2_packed_dev, const float* scale2_dev, const float* shift2_dev, float* c2_dev, int32_t N1,

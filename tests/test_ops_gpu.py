@@ -66,6 +66,7 @@ def test_gemm_tc(abi, m, n, k, variant):
                                                     (300, 128, 0, 256, 64, True), (50000, 64, 64, 256, 64, False),
                                                     (70001, 128, 0, 256, 128, True), (700, 128, 0, 512, 128, True),
                                                     (45000, 128, 0, 512, 128, True), (30001, 128, 256, 512, 128, False),
+                                                    (20000, 128, 0, 512, 256, True), (5001, 128, 256, 512, 256, False),
                                                     (16384, 256, 0, 1024, 256, True), (900, 256, 512, 1024, 256, False),
                                                     (40001, 256, 0, 1024, 256, True)])
 def test_gemm_tc_fused2(abi, m, k, kb, n1, n2, with_res):

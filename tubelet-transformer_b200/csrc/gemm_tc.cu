@@ -1626,6 +1626,7 @@ static cudaError_t init_once() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<512, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2p_kernel<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     return e;
   });
@@ -1824,7 +1825,7 @@ const char* gemm_tc_config_name(const GemmArgs& a) {
 }
 
 // conv4 (a: split output, TMA or no residual) fused with the next bottleneck's conv1 (W2p packed [2][N2][N]; fp32 result
-// C2 [M, ldc2]); (N, N2) in {(256, 64), (256, 128), (512, 128), (1024, 256)} = the 256-, 512- and 1024-channel stages
+// C2 [M, ldc2]); (N, N2) in {(256, 64), (256, 128), (512, 128), (512, 256), (1024, 256)} = the 256-, 512- and 1024-channel stages
 cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const float* scale2, const float* shift2, float* C2, int N2,
                                   int ldc2, cudaStream_t st) {
   using namespace tc;
@@ -1833,7 +1834,7 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const int KT = a.K + (a.Ab ? a.Kb : 0);
   const bool res_ok = !a.res || (a.res_mod <= 0 && a.res_fmt == FMT_SPLIT && aligned16(a.res) && a.ldr % 8 == 0 && a.N <= a.ldr);
-  if (a.M <= 0 || !((a.N == 256 && (N2 == 64 || N2 == 128)) || (a.N == 512 && N2 == 128) || (a.N == 1024 && N2 == 256)) || a.K % 64 != 0 || a.lda % 8 != 0 || a.K > a.lda || a.a_fmt != FMT_SPLIT || a.Wp == nullptr ||
+  if (a.M <= 0 || !((a.N == 256 && (N2 == 64 || N2 == 128)) || (a.N == 512 && (N2 == 128 || N2 == 256)) || (a.N == 1024 && N2 == 256)) || a.K % 64 != 0 || a.lda % 8 != 0 || a.K > a.lda || a.a_fmt != FMT_SPLIT || a.Wp == nullptr ||
       a.c_fmt != FMT_SPLIT || a.act == ACT_SIGMOID || !aligned16(a.A) || !aligned16(a.Wp) || !aligned16(a.C) || a.ldc % 8 != 0 ||
       a.N > a.ldc || (a.Ab && (a.Kb % 64 != 0 || a.Kb <= 0 || a.ldb % 8 != 0 || a.Kb > a.ldb || !aligned16(a.Ab))) || !res_ok ||
       W2p == nullptr || !aligned16(W2p) || C2 == nullptr || !aligned16(C2) || ldc2 % 8 != 0 || N2 > ldc2) {
@@ -1869,6 +1870,8 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
     return launch_pdl(gemm_fused2p_kernel<1024, 256>, dim3(2 * pairs), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   }
   if (a.N == 1024) return launch_pdl(gemm_fused2_kernel<1024, 256>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
+  if (a.N == 512 && N2 == 256)                              // last bottleneck of the 512-channel stage -> first conv1 of the 1024-channel stage
+    return launch_pdl(gemm_fused2_kernel<512, 256>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   if (a.N == 512) return launch_pdl(gemm_fused2_kernel<512, 128>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   static const bool kbw2 = [] { const char* e = getenv("TUBER_FUSE2_KBW4"); return !(e && e[0] == '1'); }();
   static const bool kbw2_all = [] { const char* e = getenv("TUBER_FUSE2_KBW2_ALL"); return e && e[0] == '1'; }();

@@ -155,7 +155,7 @@ struct TuberPlan {
   // uint8 input path (tuber_forward_u8*): value table of the reference's ToTensor + Normalize and the fp32 clip it expands into
   float* in_lut = nullptr;           // [3][256] on the device
   float* u8_clip = nullptr; size_t u8_clip_cap = 0;
-  bool no_dec_mega = false;
+  bool no_dec_mega = false, no_fuse2_s23 = false;
   unsigned long long* dec_trace = nullptr; int dec_trace_n = 0;   // per-phase timestamps of the decoder kernel (kernel profiling only)
   bool force_simt = false, no_fuse2 = false, fuse2_deep = false, pool_unfolded = false, no_strided_tma = false;
   bool profiling = false, debug_keep = false, use_graph = false;
@@ -846,6 +846,7 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
       // multiplied while it still sits in shared memory), see gemm_fused2_kernel
       const bool fuse = !p->force_simt && !p->no_fuse2 && nb && nb->cin == b.cout && b.planes % 64 == 0 && b.cin % 64 == 0 &&
                         ((b.cout == 256 && (nb->planes == 64 || nb->planes == 128)) || (b.cout == 512 && nb->planes == 128) ||
+                         (b.cout == 512 && nb->planes == 256 && !p->no_fuse2_s23) ||
                          (b.cout == 1024 && nb->planes == 256 && p->fuse2_deep));
       const void* xa = nullptr;                              // the shortcut's input rows (strided voxel gather when the block strides)
       const int geo[7] = {wo, ho, w, h, B * t, b.st_t, b.st_s};
@@ -1240,6 +1241,10 @@ int tuber_plan_create(const TuberConfig* cfg, TuberPlan** out_plan) {
   // (profiles/r2_fused2_layer3_experiment.json).  Off unless TUBER_FUSE2_L3=1.
   const char* nfd = getenv("TUBER_FUSE2_L3");
   p->fuse2_deep = nfd && nfd[0] == '1';
+  // last conv4 of the 512-channel stage + first conv1 of the 1024-channel stage (gemm_fused2_kernel<512, 256>): measured 193 us against
+  // 109 + 80 us for the separate launches (the fused kernel is tensor bound on one CTA per row block) -> only with TUBER_FUSE2_S23=1
+  const char* n23 = getenv("TUBER_FUSE2_S23");
+  p->no_fuse2_s23 = !(n23 && n23[0] == '1');
   const char* ndm = getenv("TUBER_NO_DEC_MEGA");             // decoder as one launch per operation (cross-check of decoder_mega.cu)
   p->no_dec_mega = ndm && ndm[0] == '1';
   const char* pu = getenv("TUBER_POOL_UNFOLDED");
