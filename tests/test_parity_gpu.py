@@ -289,19 +289,25 @@ def test_full_size_properties(yaml, batch):
     assert (info.Tf, info.Hf, info.Wf, info.Tp) == (4, 16, 16, 1)
 
 
-def test_fused_and_folded_paths_match_the_plain_launch_sequence(monkeypatch):
+@pytest.mark.parametrize("nclips", [3, 8])
+def test_fused_and_folded_paths_match_the_plain_launch_sequence(monkeypatch, nclips):
     """BASELINE.json configs[1] at full clip size: the fused conv4 -> conv1 kernel of the 256-channel stage and the folded
     decode pool (key projection folded into the pooled query, frames mixed before the value projection, grouped GEMM)
-    against the plain one-kernel-per-layer sequence (TUBER_NO_FUSE2 / TUBER_POOL_UNFOLDED are read at plan creation)."""
+    against the plain one-kernel-per-layer sequence (TUBER_NO_FUSE2 / TUBER_POOL_UNFOLDED are read at plan creation).
+    3 clips: row blocks that straddle clips (M % 128 == 0 only per clip); 8 clips: the bench batch, where the grouped GEMM and
+    the deep-K convolutions run on CTA pairs (one tile per pair: tail-panel mode) and the decoder kernel sees 120 rows."""
     import tuber_b200
     from oracle import tuber_oracle as O
     cfg = tuber_b200.load_cfg("TubeR_CSN50_AVA21.yaml")
     sd = O.make_state_dict(cfg, seed=0, bn="random")
-    clips = O.make_clips(3, 32, 256, 256, seed=2).cuda()           # 3 clips: row blocks that straddle clips, M % 128 == 0 only per clip
+    clips = O.make_clips(nclips, 32, 256, 256, seed=2).cuda()
     fast = {k: v.clone() for k, v in _model(cfg, sd).forward_raw(clips).items()}
     monkeypatch.setenv("TUBER_NO_FUSE2", "1")
     monkeypatch.setenv("TUBER_POOL_UNFOLDED", "1")
     monkeypatch.setenv("TUBER_NO_STRIDED_TMA", "1")              # shortcut rows through gather_rows instead of the strided tensor map
+    monkeypatch.setenv("TUBER_NO_PAIR_GEMM", "1")                # single-CTA deep-K GEMMs
+    monkeypatch.setenv("TUBER_NO_DEC_MEGA", "1")                 # decoder as one launch per operation
+    monkeypatch.setenv("TUBER_DW_WARPS8", "1")                   # 8-warp depthwise kernel
     plain = _model(cfg, sd).forward_raw(clips)
     for k in fast:
         emax, el2 = _rel(fast[k], plain[k])

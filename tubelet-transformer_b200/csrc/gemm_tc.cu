@@ -1670,7 +1670,8 @@ static bool use_big_tiles(const GemmArgs& a, int KT) {
 
 // CTA pairs (cta_group::2, 256 x 256 tiles) for the deep-K shapes
 static bool use_pair_tiles(const GemmArgs& a, int KT) {
-  static const bool off = [] { const char* e = getenv("TUBER_NO_PAIR_GEMM"); return e && e[0] == '1'; }();
+  const char* npe = getenv("TUBER_NO_PAIR_GEMM");           // read per call: the tests switch it between two plans of one process
+  const bool off = npe && npe[0] == '1';
   static const int min_k = [] { const char* e = getenv("TUBER_PAIR_MINK"); return e ? atoi(e) : 512; }();
   if (off || KT < min_k || a.N % 256 != 0 || a.ksplit > 1) return false;
   if (a.group_rows > 0 && a.group_rows % (2 * BM) != 0) return false;

@@ -662,7 +662,8 @@ cudaError_t launch_dwconv(const float* in, const float* wpk, const float* scale,
           return cudaErrorInvalidValue;
       }
       // 16 warps (a packed channel pair per thread) unless TUBER_DW_WARPS8=1 (the 8-warp variant: the tests' cross-check)
-      static const bool warps8 = [] { const char* e = getenv("TUBER_DW_WARPS8"); return e && e[0] == '1'; }();
+      const char* w8e = getenv("TUBER_DW_WARPS8");            // read per call: the tests switch it between two plans of one process
+      const bool warps8 = w8e && w8e[0] == '1';
       if (warps8)
         return launch_pdl(dwconv_s1_roll_kernel<4>, dim3(grid), dim3(dwr::THREADS), dwr::SMEM_BYTES, st, tmR, tmO, wpk, scale, shift, B, Ti, Hi, Wi, C, TC, (int)items);
       return launch_pdl(dwconv_s1_roll_kernel<2>, dim3(grid), dim3(2 * dwr::THREADS), dwr::SMEM_BYTES, st, tmR, tmO, wpk, scale, shift, B, Ti, Hi, Wi, C, TC, (int)items);
