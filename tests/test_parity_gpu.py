@@ -160,11 +160,15 @@ def test_host_entry_points_match_device_path():
         model.forward_host_wait(0)                            # nothing in flight
 
 
-def test_uint8_frames_path_is_bit_identical_to_the_float_path():
+@pytest.mark.parametrize("stem_reads_frames", [False, True])
+def test_uint8_frames_path_is_bit_identical_to_the_float_path(monkeypatch, stem_reads_frames):
     """tuber_forward_u8 / tuber_forward_host_u8 / ..._u8_submit on decoded uint8 frames give, bit for bit, what the fp32 entry
     points give on the clip the reference's host transform (oracle.frames_to_clips, pinned by tests/golden/input_u8.npz) makes of
-    those frames -- and therefore the reference's outputs within the same tolerance."""
+    those frames -- and therefore the reference's outputs within the same tolerance.  Both forms: normalize_u8_kernel in front of
+    the forward (default) and the stem reading the frames through the value table itself (TUBER_STEM_U8=1, stem_tc2_kernel<true>)."""
     from oracle import tuber_oracle as O
+    if stem_reads_frames:
+        monkeypatch.setenv("TUBER_STEM_U8", "1")
     cfg, sd, clips, _ = build_case("A_csn50_avg_bnrand")
     B, _, T, H, W = clips.shape
     model = _model(cfg, sd)

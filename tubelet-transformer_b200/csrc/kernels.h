@@ -15,8 +15,11 @@ cudaError_t launch_stem_pack_weight(const float* w_oc441, void* out, cudaStream_
 // max-pooled result (split [B,T,H2,W2,64]) itself and y is not touched; otherwise it writes the conv rows
 // y = relu(conv*scale+shift) (fp32 NDHWC [B,T,H1,W1,64]) and launch_maxpool_hw must follow.
 bool stem_pool_is_fused(int W1);
+// frames_u8 / lut (optional, fused-pool pair kernel only): decoded uint8 frames (B,T,H,W,3) + the value table [3][256] of the reference's
+// ToTensor + Normalize instead of x -- the stem's staging threads normalise while they fill the input ring
 cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale, const float* shift, float* y, void* pooled,
-                             int B, int T, int H, int W, int H1, int W1, cudaStream_t st);
+                             int B, int T, int H, int W, int H1, int W1, cudaStream_t st, const uint8_t* frames_u8 = nullptr,
+                             const float* lut = nullptr);
 // (1,3,3)/s(1,2,2)/p(0,1,1) max pool, fp32 [BT,H1,W1,C] -> split [BT,H2,W2,C]
 cudaError_t launch_maxpool_hw(const float* in, void* out_split, int BT, int H1, int W1, int H2, int W2,
                               int C, cudaStream_t st);

@@ -154,6 +154,7 @@ struct TuberPlan {
   bool slot_busy[2] = {false, false};
   // uint8 input path (tuber_forward_u8*): value table of the reference's ToTensor + Normalize and the fp32 clip it expands into
   float* in_lut = nullptr;           // [3][256] on the device
+  const uint8_t* in_frames = nullptr; // argument of the uint8 call in progress: the stem reads the frames itself (read by run_forward and the graph key)
   float* u8_clip = nullptr; size_t u8_clip_cap = 0;
   bool no_dec_mega = false, no_fuse2_s23 = false;
   unsigned long long* dec_trace = nullptr; int dec_trace_n = 0;   // per-phase timestamps of the decoder kernel (kernel profiling only)
@@ -818,7 +819,8 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     const double vin = (double)B * 3 * T * H * W, v1 = (double)B * T * g.H1 * g.W1 * 64, v2 = (double)B * T * g.H2 * g.W2 * 64;
     const bool fused = stem_pool_is_fused(g.W1);
     cx.launch("stem_conv", 4.0 * (vin + (fused ? v2 : v1)), 2.0 * 441 * v1, [&] {
-      return launch_stem_conv(clips, p->stem_w, p->stem_scale, p->stem_shift, (float*)bufA, bufB, B, T, H, W, g.H1, g.W1, st);
+      return launch_stem_conv(p->in_frames ? nullptr : clips, p->stem_w, p->stem_scale, p->stem_shift, (float*)bufA, bufB, B, T, H, W, g.H1, g.W1, st,
+                              p->in_frames, p->in_frames ? p->in_lut : nullptr);
     });
     if (!fused)
       cx.launch("maxpool", 4.0 * (v1 + v2), 9.0 * v2,
@@ -1351,7 +1353,7 @@ int tuber_forward(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev,
   }
   std::vector<uintptr_t> key = {(uintptr_t)clips_dev, (uintptr_t)mask_dev, (uintptr_t)B, (uintptr_t)T, (uintptr_t)H, (uintptr_t)W,
                                 (uintptr_t)logits_dev, (uintptr_t)boxes_dev, (uintptr_t)logits_b_dev, (uintptr_t)p->ltc_bank,
-                                (uintptr_t)p->ltc_bank_clips, (uintptr_t)p->ltc_bank_tokens, (uintptr_t)p->ltc_new};
+                                (uintptr_t)p->ltc_bank_clips, (uintptr_t)p->ltc_bank_tokens, (uintptr_t)p->ltc_new, (uintptr_t)p->in_frames};
   for (auto& g : p->graphs)
     if (g.key == key) { CK(cudaGraphLaunch(g.exec, st)); return TUBER_OK; }
   // first call for this (shape, buffers): run eagerly (this call's result; also performs the one-time
@@ -1416,6 +1418,12 @@ int upload_input_lut(TuberPlan* p, const float mean[3], const float stdv[3]) {
 
 const float kImageNetMean[3] = {0.485f, 0.456f, 0.406f}, kImageNetStd[3] = {0.229f, 0.224f, 0.225f};   // ava_frame.py:159-162
 
+// uint8 frames straight into the stem (stem_tc2_kernel<true>) instead of through normalize_u8_kernel; read per call (the tests switch it)
+bool stem_u8_enabled() {
+  const char* e = getenv("TUBER_STEM_U8");
+  return e && e[0] == '1';
+}
+
 int ensure_input_lut(TuberPlan* p) { return p->in_lut ? TUBER_OK : upload_input_lut(p, kImageNetMean, kImageNetStd); }
 
 // H2D (+mask) -> forward -> D2H of one batch through staging slot `slot`.  `in_st` carries the input copies,
@@ -1463,8 +1471,16 @@ int host_step(TuberPlan* p, int slot, const float* clips_host, const uint8_t* fr
     CK(cudaEventRecord(p->h2d_done[slot], in_st));
     CK(cudaStreamWaitEvent(st, p->h2d_done[slot], 0));
   }
-  if (frames_host) CK(launch_normalize_u8(d_frames, p->in_lut, d_clips, B, (long long)T * H * W, st));
-  TRY(tuber_forward(p, d_clips, d_mask, B, T, H, W, d_logits, d_boxes, d_lb, st));
+  // uint8 path: normalize_u8_kernel expands the frames into the slot's fp32 clip (40 us, one extra launch).  With TUBER_STEM_U8=1 the
+  // pair stem reads the frames itself and normalises while it stages its input rows (stem_tc2_kernel<true>: bit-identical, no fp32
+  // clip, no extra launch) -- measured SLOWER: the staging threads are the stem's bottleneck and a byte load + table lookup per
+  // staged pixel costs them 0.15 ms per 8-clip step (e2e 912 against 929 clips/s), so it is not the default
+  const bool stem_reads_u8 = frames_host && stem_u8_enabled() && stem_pool_is_fused((W + 6 - 7) / 2 + 1);
+  if (frames_host && !stem_reads_u8) CK(launch_normalize_u8(d_frames, p->in_lut, d_clips, B, (long long)T * H * W, st));
+  p->in_frames = stem_reads_u8 ? d_frames : nullptr;
+  const int fwd_status = tuber_forward(p, d_clips, d_mask, B, T, H, W, d_logits, d_boxes, d_lb, st);
+  p->in_frames = nullptr;
+  TRY(fwd_status);
   // pipelined form: the result copies run on their own stream so that the next slot's kernels are not held up by them
   cudaStream_t ost = st;
   if (out_st && out_st != st) {
@@ -1551,6 +1567,13 @@ int tuber_forward_u8(TuberPlan* p, const uint8_t* frames_dev, const uint8_t* mas
   TRY(check_forward_args(p, B, T, H, W));
   if (!frames_dev || !logits_dev || !boxes_dev || !logits_b_dev) return fail(TUBER_ERR_INVALID, "null device pointer");
   TRY(ensure_input_lut(p));
+  if (stem_u8_enabled() && stem_pool_is_fused((W + 6 - 7) / 2 + 1)) {
+    // TUBER_STEM_U8=1: the pair stem normalises while it stages its input rows: no fp32 clip is written, no extra launch (see host_step)
+    p->in_frames = frames_dev;
+    const int s = tuber_forward(p, reinterpret_cast<const float*>(frames_dev), mask_dev, B, T, H, W, logits_dev, boxes_dev, logits_b_dev, stream);
+    p->in_frames = nullptr;
+    return s;
+  }
   const size_t need = (size_t)B * 3 * T * H * W * 4;
   if (need > p->u8_clip_cap) {
     CK(cudaDeviceSynchronize());

@@ -59,6 +59,7 @@ constexpr int TMEM_COLS = 512;              // 128 + 2 x 192
 constexpr int ROWS_PER_UNIT = 32;
 
 struct Params {
+  const uint8_t* xu8; const float* lut;     // stem_tc2_kernel only: decoded frames (B,T,H,W,3) uint8 + value table [3][256] instead of x
   const float* x;                           // (B,3,T,H,W) fp32
   const float* scale; const float* shift;   // [64]
   void* pooled;                             // split [B*T*H2*W2, 64] (fused pool) or null
@@ -580,6 +581,9 @@ TB_DEVINL void umma2_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, u
       "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 
+// U8: the staging threads read decoded uint8 frames through the value table instead of the fp32 clip (a separate instantiation:
+// the fp32 kernel keeps its register allocation)
+template <bool U8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
   using namespace p2;
@@ -805,10 +809,18 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
       const bool ok0 = col_ok(2 * spr), ok1 = col_ok(2 * spr + 1), xok0 = col_ok(2 * xpr), xok1 = col_ok(2 * xpr + 1);
       const float* xb = p.x + (long long)b * 3 * p.T * p.H * p.W + iw0;
       const long long plane_stride = (long long)p.H * p.W;
-      auto row_ptr = [&](int plane, int ih) -> const float* {
+      // input value at (plane, row ih, column iw0 + j): the fp32 clip, or -- uint8 path -- the decoded frame's byte through the value
+      // table of the reference's ToTensor + Normalize (video_transforms.py:294-296,308-314; the table holds exactly the floats
+      // normalize_u8_kernel would have written, so both paths feed the tensor core identical bits).  Zero outside the volume.
+      auto in_val = [&](int plane, int ih, int j, bool ok) -> float {
         const int c = plane / 3, f = t + plane % 3 - 1;
-        if (f < 0 || f >= p.T || ih < 0 || ih >= p.H) return nullptr;
-        return xb + ((long long)c * p.T + f) * plane_stride + (long long)ih * p.W;
+        if (!ok || f < 0 || f >= p.T || ih < 0 || ih >= p.H) return 0.f;
+        if constexpr (U8) {
+          const uint8_t v = __ldg(p.xu8 + ((((long long)b * p.T + f) * p.H + ih) * p.W + (iw0 + j)) * 3 + c);
+          return __ldg(p.lut + c * 256 + v);
+        } else {
+          return __ldg(xb + ((long long)c * p.T + f) * plane_stride + (long long)ih * p.W + j);
+        }
       };
       auto store_pair = [&](int plane, int ih, int pr, float v0, float v1) {
         __nv_bfloat16 h0, m0, h1, m1;
@@ -824,9 +836,8 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
 #pragma unroll
         for (int g2 = 0; g2 < 4; ++g2) {
           const int rr = 2 * g2 + srr;
-          const float* rp = rr < 7 ? row_ptr(plane, 2 * first - 3 + rr) : nullptr;
-          v0[g2] = (rp && ok0) ? __ldg(rp + 2 * spr) : 0.f;
-          v1[g2] = (rp && ok1) ? __ldg(rp + 2 * spr + 1) : 0.f;
+          v0[g2] = in_val(plane, 2 * first - 3 + rr, 2 * spr, rr < 7 && ok0);
+          v1[g2] = in_val(plane, 2 * first - 3 + rr, 2 * spr + 1, rr < 7 && ok1);
         }
 #pragma unroll
         for (int g2 = 0; g2 < 4; ++g2)
@@ -834,8 +845,7 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
       }
       if (xrow < 63) {
         const int plane = xrow / 7, ih = 2 * first - 3 + xrow % 7;
-        const float* rp = row_ptr(plane, ih);
-        store_pair(plane, ih, xpr, (rp && xok0) ? __ldg(rp + 2 * xpr) : 0.f, (rp && xok1) ? __ldg(rp + 2 * xpr + 1) : 0.f);
+        store_pair(plane, ih, xpr, in_val(plane, ih, 2 * xpr, xok0), in_val(plane, ih, 2 * xpr + 1, xok1));
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");
       for (int oh = first; oh < r1; ++oh) {
@@ -844,14 +854,12 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
         if (more) {
 #pragma unroll
           for (int plane = 0; plane < 9; ++plane) {
-            const float* rp = row_ptr(plane, 2 * oh + 4 + srr);
-            pf0[plane] = (rp && ok0) ? __ldg(rp + 2 * spr) : 0.f;
-            pf1[plane] = (rp && ok1) ? __ldg(rp + 2 * spr + 1) : 0.f;
+            pf0[plane] = in_val(plane, 2 * oh + 4 + srr, 2 * spr, ok0);
+            pf1[plane] = in_val(plane, 2 * oh + 4 + srr, 2 * spr + 1, ok1);
           }
           if (xrow < 18) {
-            const float* rp = row_ptr(xrow >> 1, 2 * oh + 4 + (xrow & 1));
-            px0 = (rp && xok0) ? __ldg(rp + 2 * xpr) : 0.f;
-            px1 = (rp && xok1) ? __ldg(rp + 2 * xpr + 1) : 0.f;
+            px0 = in_val(xrow >> 1, 2 * oh + 4 + (xrow & 1), 2 * xpr, xok0);
+            px1 = in_val(xrow >> 1, 2 * oh + 4 + (xrow & 1), 2 * xpr + 1, xok1);
           }
         }
         uint32_t slot_off[4];
@@ -930,7 +938,8 @@ static cudaError_t init_once() {
     }
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p2::SMEM2_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2::SMEM2_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2::SMEM2_BYTES);
     return e;
   });
 }
@@ -952,8 +961,9 @@ bool stem_pool_is_fused(int W1) {
 // y: fp32 conv rows [B,T,H1,W1,64] (only written when the pool is not fused; may be null otherwise);
 // pooled: split [B,T,H2,W2,64] (only written when stem_pool_is_fused(W1))
 cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale, const float* shift, float* y, void* pooled, int B,
-                             int T, int H, int W, int H1, int W1, cudaStream_t st) {
+                             int T, int H, int W, int H1, int W1, cudaStream_t st, const uint8_t* frames_u8, const float* lut) {
   using namespace stemtc;
+  if (frames_u8 && !(stem_pool_is_fused(W1) && pooled != nullptr && lut != nullptr)) return cudaErrorInvalidValue;   // uint8 input: pair kernel only
   cudaError_t e = init_once();
   if (e != cudaSuccess) return e;
   CUtensorMap tmW, tmOut;
@@ -969,12 +979,13 @@ cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale
   if (fuse) {                                                      // CTA pairs (cta_group::2), pool fused
     const int W2 = (W1 - 1) / 2 + 1;
     const int ct_n = W1 <= 128 ? 1 : (W2 + 62) / 63;
-    Params p{x, scale, shift, pooled, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, W2, 1, ct_n};
+    Params p{frames_u8, lut, x, scale, shift, pooled, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, W2, 1, ct_n};
     const int units = B * T * ((H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT) * ct_n;
     int pairs = device_num_sms() / 2;
     if (pairs > (units + 1) / 2) pairs = (units + 1) / 2;
     if (pairs < 1) pairs = 1;
-    stem_tc2_kernel<<<2 * pairs, NUM_THREADS, p2::SMEM2_BYTES, st>>>(tmW, p);
+    if (frames_u8) stem_tc2_kernel<true><<<2 * pairs, NUM_THREADS, p2::SMEM2_BYTES, st>>>(tmW, p);
+    else stem_tc2_kernel<false><<<2 * pairs, NUM_THREADS, p2::SMEM2_BYTES, st>>>(tmW, p);
     return cudaGetLastError();
   }
   tmOut = tmW;
@@ -987,7 +998,7 @@ cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
   }
-  Params p{x, scale, shift, fuse ? pooled : nullptr, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, (W1 - 1) / 2 + 1, fuse ? 1 : 0, 1};
+  Params p{nullptr, nullptr, x, scale, shift, fuse ? pooled : nullptr, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, (W1 - 1) / 2 + 1, fuse ? 1 : 0, 1};
   const int units = B * T * ((W1 + 127) / 128) * ((H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT);
   int pairs = device_num_sms() / 2;
   if (pairs > units) pairs = units;
