@@ -1,0 +1,57 @@
+"""CPU: the frame-loading oracle (oracle/frame_oracle.py: baseline JPEG decode as libjpeg does it + Pillow's bicubic resize) against
+pixels produced by Pillow itself (tests/golden/frames.npz, oracle/make_golden_frames.py) -- bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import frame_oracle as F
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frames.npz"))
+JPEG_CASES = sorted({k.split("/")[0] for k in GOLD.files if k.endswith("/jpeg")})
+RESIZE_CASES = sorted({k.split("/")[0] for k in GOLD.files if k.endswith("/src")})
+
+
+@pytest.mark.parametrize("name", JPEG_CASES)
+def test_decode_matches_pillow(name):
+    px = F.decode_jpeg(GOLD[name + "/jpeg"].tobytes())
+    assert px.dtype == np.uint8 and np.array_equal(px, GOLD[name + "/pixels"])
+
+
+@pytest.mark.parametrize("name", JPEG_CASES)
+def test_decode_then_resize_matches_pillow(name):
+    want = GOLD[name + "/resized"]
+    got = F.load_frame(GOLD[name + "/jpeg"].tobytes(), want.shape[0], want.shape[1])
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", RESIZE_CASES)
+def test_resize_matches_pillow(name):
+    want = GOLD[name + "/dst"]
+    assert np.array_equal(F.resize_bicubic(GOLD[name + "/src"], want.shape[0], want.shape[1]), want)
+
+
+def test_live_pillow_if_present():
+    """the same comparison against the Pillow of the machine the tests run on (skipped without Pillow)"""
+    PIL = pytest.importorskip("PIL")
+    import io
+    from PIL import Image
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, size=(45, 61, 3), dtype=np.uint8)
+    buf = io.BytesIO()
+    Image.fromarray(img).save(buf, format="JPEG", quality=88)
+    ref = Image.open(io.BytesIO(buf.getvalue()))
+    assert np.array_equal(F.decode_jpeg(buf.getvalue()), np.asarray(ref))
+    assert np.array_equal(F.load_frame(buf.getvalue(), 30, 50), np.asarray(ref.resize((50, 30))))
+
+
+def test_rejects_what_it_does_not_restate():
+    with pytest.raises(AssertionError):
+        F.parse_jpeg(b"not a jpeg")
+    PIL = pytest.importorskip("PIL")
+    import io
+    from PIL import Image
+    buf = io.BytesIO()
+    Image.fromarray(np.zeros((16, 16, 3), dtype=np.uint8)).save(buf, format="JPEG", progressive=True)
+    with pytest.raises(ValueError):
+        F.decode_jpeg(buf.getvalue())
