@@ -241,6 +241,23 @@ int tuber_op_normalize_u8(const uint8_t* frames_dev, const float* mean, const fl
 int tuber_op_posenc(const uint8_t* fmask_dev, float* pos_dev, int32_t B, int32_t T, int32_t H, int32_t W,
                     int32_t d_model, void* stream);
 
+/* ---- frame loading (widened row f4 of the scope contract) --------------------------------------------------------------------
+ * Replaces, per frame, the reference loader's  Image.open(path)  +  .resize((w, h))  (datasets/ava_frame.py:146-150; Pillow's
+ * default filter for RGB images: BICUBIC) -- bit-identical to Pillow on libjpeg(-turbo): Huffman decoding on host threads,
+ * dequantisation + "islow" inverse DCT, "fancy" chroma upsampling, YCbCr -> RGB and Pillow's two-pass 8-bit resample on the GPU.
+ * Baseline sequential YCbCr JPEGs (4:4:4 / 4:2:2 / 4:2:0, restart intervals); anything else is refused (TUBER_ERR_INVALID). */
+typedef struct TuberFrameDecoder TuberFrameDecoder;
+int tuber_frames_create(TuberFrameDecoder** out_decoder, int32_t max_host_threads /* <= 0: all */);
+void tuber_frames_destroy(TuberFrameDecoder* decoder);
+/* n JPEG byte ranges in host memory -> RGB uint8 [n, out_h, out_w, 3] on the device (the input layout of tuber_forward_u8).
+ * Entropy decoding runs before the call returns; the copies and kernels are ordered on `stream`.  One call at a time per decoder. */
+int tuber_frames_decode(TuberFrameDecoder* decoder, const uint8_t* const* jpeg_ptrs_host, const int64_t* jpeg_sizes, int32_t n,
+                        int32_t out_h, int32_t out_w, uint8_t* frames_dev, void* stream);
+const char* tuber_frames_last_error(void);
+/* host only, no device needed: the entropy decoder by itself.  info_out[10] = {W, H, luma h, luma v, blocks_x / blocks_y of Y, Cb, Cr};
+ * coef_out (may be NULL to query the sizes) receives the quantised coefficients, int16, natural order, [Y | Cb | Cr] blocks of 64. */
+int tuber_op_jpeg_coefficients(const uint8_t* jpeg_host, int64_t size, int16_t* coef_out, int64_t capacity, int32_t* info_out);
+
 const char* tuber_last_error(void);
 int tuber_abi_version(void);
 

@@ -55,3 +55,27 @@ def test_rejects_what_it_does_not_restate():
     Image.fromarray(np.zeros((16, 16, 3), dtype=np.uint8)).save(buf, format="JPEG", progressive=True)
     with pytest.raises(ValueError):
         F.decode_jpeg(buf.getvalue())
+
+
+@pytest.mark.parametrize("name", JPEG_CASES)
+def test_host_entropy_decoder_matches_the_oracle(name):
+    """the product's host-side half (marker parsing + Huffman decoding in csrc/frames.cu, tuber_op_jpeg_coefficients: no device needed)
+    against the oracle's coefficient arrays; truncated files are refused, a missing EOI marker is tolerated"""
+    import ctypes as C
+    import tuber_b200  # noqa: F401
+    from tuber_b200 import _lib
+    lib = _lib.load()
+    data = GOLD[name + "/jpeg"].tobytes()
+    info = (C.c_int32 * 10)()
+    assert lib.tuber_op_jpeg_coefficients(data, len(data), None, 0, info) == 0
+    _, coefs = F.decode_coefficients(data)
+    assert [info[4 + 2 * c] * info[5 + 2 * c] for c in range(3)] == [c.shape[0] * c.shape[1] for c in coefs]
+    total = sum(c.size for c in coefs)
+    buf = np.zeros(total, dtype=np.int16)
+    assert lib.tuber_op_jpeg_coefficients(data, len(data), buf.ctypes.data_as(C.c_void_p), total, info) == 0
+    assert np.array_equal(buf, np.concatenate([c.reshape(-1) for c in coefs]).astype(np.int16))
+    assert lib.tuber_op_jpeg_coefficients(data, len(data), buf.ctypes.data_as(C.c_void_p), total - 1, info) != 0      # buffer too small
+    assert lib.tuber_op_jpeg_coefficients(data[:-2], len(data) - 2, buf.ctypes.data_as(C.c_void_p), total, info) == 0  # no EOI
+    half = data[: len(data) // 2]
+    assert lib.tuber_op_jpeg_coefficients(half, len(half), buf.ctypes.data_as(C.c_void_p), total, info) != 0
+    assert b"truncated" in lib.tuber_frames_last_error()

@@ -15,7 +15,8 @@ from .utils.misc import NestedTensor, nested_tensor_from_tensor_list  # noqa: F4
 from .utils.context_bank import ContextBank  # noqa: F401
 from .distributed import gather_detections, pack_detections, shard_range, unpack_detections  # noqa: F401
 from .launch import spawn_workers  # noqa: F401
+from .frames import FrameDecoder, clip_size  # noqa: F401
 
 __all__ = ["CfgNode", "get_cfg_defaults", "load_cfg", "DETR", "build_model", "PostProcess", "PostProcessAVA",
            "NestedTensor", "nested_tensor_from_tensor_list", "shard_range", "pack_detections",
-           "unpack_detections", "gather_detections", "format_detection_lines", "ContextBank", "spawn_workers"]
+           "unpack_detections", "gather_detections", "format_detection_lines", "ContextBank", "spawn_workers", "FrameDecoder", "clip_size"]

@@ -88,6 +88,11 @@ PROTOTYPES = {
     "tuber_op_attention_kernel": (C.c_char_p, [_I, _I, _I, _I, _I, _I]),
     "tuber_op_normalize_u8": (_I, [_P, C.POINTER(_F), C.POINTER(_F), _P, _I, _L, _P]),
     "tuber_op_posenc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "tuber_frames_create": (_I, [C.POINTER(_P), _I]),
+    "tuber_frames_destroy": (None, [_P]),
+    "tuber_frames_decode": (_I, [_P, C.POINTER(_P), C.POINTER(_L), _I, _I, _I, _P, _P]),
+    "tuber_frames_last_error": (C.c_char_p, []),
+    "tuber_op_jpeg_coefficients": (_I, [_P, _L, _P, _L, C.POINTER(_I)]),
 }
 
 _lib = None

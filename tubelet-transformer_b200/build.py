@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtuber_b200.so")
-SOURCES = ["plan.cu", "gemm_tc.cu", "stem_tc.cu", "kernels_simt.cu", "attn_mma.cu", "attn_tc.cu", "decoder_mega.cu"]
+SOURCES = ["plan.cu", "gemm_tc.cu", "stem_tc.cu", "kernels_simt.cu", "attn_mma.cu", "attn_tc.cu", "decoder_mega.cu", "frames.cu"]
 HEADERS = ["kernels.h", "common.cuh", os.path.join("..", "..", "include", "tuber_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
