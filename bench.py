@@ -220,6 +220,70 @@ def _same_box_baseline(cfg, sd, clips, steps=5):
     return res
 
 
+def _frame_loading_leg(B, T, H, W, model, seconds=2.0):
+    """the reference loader's per-frame Image.open + resize (datasets/ava_frame.py:146-150) through
+    tuber_b200.FrameDecoder (host Huffman decoding + CUDA kernels, bit-identical to Pillow) against Pillow itself on the host
+    cores, on synthetic 360x480 JPEG frames resized to the clip size; then the whole chain JPEG bytes -> detections."""
+    import io
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
+    import tuber_b200
+    try:
+        from PIL import Image
+    except ImportError:
+        return None
+    from oracle.make_golden_frames import synth
+    jpegs = []
+    for i in range(T):
+        buf = io.BytesIO()
+        Image.fromarray(synth(360, 480, 500 + i)).save(buf, format="JPEG", quality=75)
+        jpegs.append(buf.getvalue())
+    jpegs = jpegs * B                                                        # one 8-clip step: B * T frames
+    n = len(jpegs)
+    dec = tuber_b200.FrameDecoder()
+    frames = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        dec.decode(jpegs, H, W, out=frames)
+    torch.cuda.synchronize()
+    reps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        dec.decode(jpegs, H, W, out=frames)
+        reps += 1
+    torch.cuda.synchronize()
+    gpu_fps = n * reps / (time.perf_counter() - t0)
+    # the chain: JPEG bytes -> frames -> detections (decode of step i+1 on the host overlaps the forward of step i on the device)
+    out = None
+    for _ in range(2):
+        out = model.forward_raw_u8(dec.decode(jpegs, H, W, out=frames).view(B, T, H, W, 3), None, out)
+    torch.cuda.synchronize()
+    reps2, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        out = model.forward_raw_u8(dec.decode(jpegs, H, W, out=frames).view(B, T, H, W, 3), None, out)
+        reps2 += 1
+    torch.cuda.synchronize()
+    chain = B * reps2 / (time.perf_counter() - t0)
+    dec.close()
+    # Pillow, all host cores (decode and resize release the GIL)
+    cores = len(os.sched_getaffinity(0))
+
+    def one(b):
+        return np.asarray(Image.open(io.BytesIO(b)).resize((W, H)))
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(one, jpegs[:cores]))
+        done, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            list(ex.map(one, jpegs))
+            done += n
+        pil_fps = done / (time.perf_counter() - t0)
+    return {"workload": f"{n} baseline 4:2:0 JPEG frames 360x480 (quality 75, {sum(map(len, jpegs)) // n} bytes on average) -> RGB uint8 "
+                        f"{H}x{W} as the reference loader makes them (Image.open + resize, bicubic), one {B}-clip step per call",
+            "value": gpu_fps, "unit": "frames/s", "clips_per_s_equivalent": gpu_fps / T,
+            "jpeg_to_detections": {"value": chain, "unit": UNIT, "what": "FrameDecoder.decode + forward_raw_u8 per step, same stream"},
+            "cpu_baseline": {"value": pil_fps, "unit": "frames/s", "cores": cores, "kind": "reference",
+                             "sample": f"Pillow {__import__('PIL').__version__} Image.open + resize on {cores} threads, {done} frames"}}
+
+
 def main():
     # stdout carries exactly one line, the JSON result: libraries that print to fd 1 (NCCL's version banner, ...) go to stderr
     sys.stdout.flush()
@@ -479,6 +543,9 @@ def main():
                            f"({nloc} per GPU)", model, xs, nloc)
             e["scaling"] = "strong"
             del xs
+    frame_leg = None
+    if world == 1 and not args.no_also:                                      # rank 0 at N = 1 only: host threads are not shared with other ranks
+        frame_leg = _frame_loading_leg(B, T, H, W, model)
     del model, out, h_clips, h_out
     torch.cuda.empty_cache()
     if not args.no_also:
@@ -532,7 +599,7 @@ def main():
                     "u8": e2e_u8},
             "e2e_u8": e2e_u8,
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "cuda_graph": use_graph, "roofline": roof, "cpu_baseline": cpu, "same_box_baseline": same_box, "also": also, "kernels": kernels,
+            "cuda_graph": use_graph, "roofline": roof, "cpu_baseline": cpu, "same_box_baseline": same_box, "frame_loading": frame_leg, "also": also, "kernels": kernels,
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "arithmetic": "fp32 storage; GEMMs = 3-pass bf16 split (hi*hi+hi*lo+lo*hi) on tcgen05 with fp32 TMEM accumulation"}
     emit(line)

@@ -650,11 +650,16 @@ int tuber_frames_decode(TuberFrameDecoder* d, const uint8_t* const* jpeg_ptrs, c
     return ffail(TUBER_ERR_CUDA, "frame decoder: out of memory");
   // ---- entropy decoding: host threads, frame i on thread i % T, straight into pinned memory ----
   int16_t* hc = reinterpret_cast<int16_t*>(d->h_coef);
-  memset(hc, 0, (size_t)coef_total * 2);
   std::vector<const char*> errs(n, nullptr);
   const int T = d->threads < n ? d->threads : n;
   auto work = [&](int t) {
-    for (int i = t; i < n; i += T) errs[i] = decode_scan(hdr[i], hc + metas[i].coef_off[0]);
+    for (int i = t; i < n; i += T) {
+      int16_t* dst = hc + metas[i].coef_off[0];
+      long long cnt = 0;
+      for (int c = 0; c < 3; ++c) cnt += (long long)metas[i].bx[c] * metas[i].by[c] * 64;
+      memset(dst, 0, (size_t)cnt * 2);                              // (zeroed by the thread that fills it)
+      errs[i] = decode_scan(hdr[i], dst);
+    }
   };
   if (T <= 1) {
     work(0);
