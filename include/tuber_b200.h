@@ -250,7 +250,9 @@ typedef struct TuberFrameDecoder TuberFrameDecoder;
 int tuber_frames_create(TuberFrameDecoder** out_decoder, int32_t max_host_threads /* <= 0: all */);
 void tuber_frames_destroy(TuberFrameDecoder* decoder);
 /* n JPEG byte ranges in host memory -> RGB uint8 [n, out_h, out_w, 3] on the device (the input layout of tuber_forward_u8).
- * Entropy decoding runs before the call returns; the copies and kernels are ordered on `stream`.  One call at a time per decoder. */
+ * Entropy decoding runs before the call returns; the copies and kernels are ordered on `stream` (use ONE stream per decoder: the
+ * device buffers are reused from call to call; the pinned staging is double-buffered, so the host work of call i+1 overlaps the
+ * device work of call i).  One call at a time per decoder. */
 int tuber_frames_decode(TuberFrameDecoder* decoder, const uint8_t* const* jpeg_ptrs_host, const int64_t* jpeg_sizes, int32_t n,
                         int32_t out_h, int32_t out_w, uint8_t* frames_dev, void* stream);
 const char* tuber_frames_last_error(void);

@@ -504,17 +504,19 @@ static Coeffs precompute(int in_size, int out_size) {
 struct TuberFrameDecoder {
   int threads = 1;
   // pinned host staging + device buffers, grown on demand
-  void* h_coef = nullptr; size_t h_coef_cap = 0;
-  void* h_meta = nullptr; size_t h_meta_cap = 0;
-  void* h_tab = nullptr; size_t h_tab_cap = 0;
+  // (the pinned staging exists twice: call i+1 decodes into one set while the copies of call i still read the other)
+  void* h_coef_s[2] = {nullptr, nullptr}; size_t h_coef_cap_s[2] = {0, 0};
+  void* h_meta_s[2] = {nullptr, nullptr}; size_t h_meta_cap_s[2] = {0, 0};
+  void* h_tab_s[2] = {nullptr, nullptr}; size_t h_tab_cap_s[2] = {0, 0};
+  int slot = 0;
   void* d_coef = nullptr; size_t d_coef_cap = 0;
   void* d_meta = nullptr; size_t d_meta_cap = 0;
   void* d_tab = nullptr; size_t d_tab_cap = 0;
   void* d_planes = nullptr; size_t d_planes_cap = 0;
   void* d_rgb = nullptr; size_t d_rgb_cap = 0;
   void* d_tmp = nullptr; size_t d_tmp_cap = 0;
-  cudaEvent_t done = nullptr;                 // the previous call's copies out of the pinned buffers have finished
-  bool pending = false;
+  cudaEvent_t done_s[2] = {nullptr, nullptr}; // the copies out of a slot's pinned buffers have finished
+  bool pending_s[2] = {false, false};
   std::map<std::pair<int, int>, frames::Coeffs> cache;
   char err[256] = "";
 };
@@ -545,20 +547,23 @@ int tuber_frames_create(TuberFrameDecoder** out, int32_t max_threads) {
   int hw = (int)std::thread::hardware_concurrency();
   if (hw < 1) hw = 1;
   d->threads = max_threads > 0 ? (max_threads < hw ? max_threads : hw) : hw;
-  if (cudaEventCreateWithFlags(&d->done, cudaEventDisableTiming) != cudaSuccess) { delete d; return ffail(TUBER_ERR_CUDA, "cudaEventCreate failed"); }
+  for (int i = 0; i < 2; ++i)
+    if (cudaEventCreateWithFlags(&d->done_s[i], cudaEventDisableTiming) != cudaSuccess) { delete d; return ffail(TUBER_ERR_CUDA, "cudaEventCreate failed"); }
   *out = d;
   return TUBER_OK;
 }
 
 void tuber_frames_destroy(TuberFrameDecoder* d) {
   if (!d) return;
-  if (d->pending) cudaEventSynchronize(d->done);
-  if (d->h_coef) cudaFreeHost(d->h_coef);
-  if (d->h_meta) cudaFreeHost(d->h_meta);
-  if (d->h_tab) cudaFreeHost(d->h_tab);
+  for (int i = 0; i < 2; ++i) {
+    if (d->pending_s[i]) cudaEventSynchronize(d->done_s[i]);
+    if (d->h_coef_s[i]) cudaFreeHost(d->h_coef_s[i]);
+    if (d->h_meta_s[i]) cudaFreeHost(d->h_meta_s[i]);
+    if (d->h_tab_s[i]) cudaFreeHost(d->h_tab_s[i]);
+    if (d->done_s[i]) cudaEventDestroy(d->done_s[i]);
+  }
   for (void* p : {d->d_coef, d->d_meta, d->d_tab, d->d_planes, d->d_rgb, d->d_tmp})
     if (p) cudaFree(p);
-  if (d->done) cudaEventDestroy(d->done);
   delete d;
 }
 
@@ -612,10 +617,22 @@ int tuber_frames_decode(TuberFrameDecoder* d, const uint8_t* const* jpeg_ptrs, c
     }
     k_off = pos->second.first; b_off = pos->second.second; ksize = it->second.ksize;
   };
+  // headers (markers, Huffman table construction) on the host threads too: ~14 us per frame adds up over a 256-frame call
+  std::vector<const char*> errs(n, nullptr);
+  const int T = d->threads < n ? d->threads : n;
+  auto run_threads = [&](auto&& fn) {
+    if (T <= 1) { fn(0); return; }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(fn, t);
+    fn(0);
+    for (auto& th : pool) th.join();
+  };
+  run_threads([&](int t) {
+    for (int i = t; i < n; i += T) errs[i] = parse_header(jpeg_ptrs[i], jpeg_sizes[i], hdr[i]);
+  });
   for (int i = 0; i < n; ++i) {
-    const char* msg = parse_header(jpeg_ptrs[i], jpeg_sizes[i], hdr[i]);
-    if (msg) {
-      snprintf(g_frames_error, sizeof g_frames_error, "frame %d: %s", i, msg);
+    if (errs[i]) {
+      snprintf(g_frames_error, sizeof g_frames_error, "frame %d: %s", i, errs[i]);
       return TUBER_ERR_INVALID;
     }
     const Header& h = hdr[i];
@@ -641,18 +658,24 @@ int tuber_frames_decode(TuberFrameDecoder* d, const uint8_t* const* jpeg_ptrs, c
   }
   if (tab.empty()) tab.push_back(0);
   // ---- buffers (the pinned ones may still be read by the previous call's copies) ----
-  if (d->pending) { if (cudaEventSynchronize(d->done) != cudaSuccess) return ffail(TUBER_ERR_CUDA, "previous decode failed"); d->pending = false; }
-  if (!grow(&d->h_coef, &d->h_coef_cap, (size_t)coef_total * 2, true) || !grow(&d->h_meta, &d->h_meta_cap, metas.size() * sizeof(FrameMeta), true) ||
-      !grow(&d->h_tab, &d->h_tab_cap, tab.size() * 4, true) || !grow(&d->d_coef, &d->d_coef_cap, (size_t)coef_total * 2, false) ||
+  const int sl = d->slot;
+  d->slot ^= 1;
+  if (d->pending_s[sl]) {
+    if (cudaEventSynchronize(d->done_s[sl]) != cudaSuccess) return ffail(TUBER_ERR_CUDA, "a previous decode failed");
+    d->pending_s[sl] = false;
+  }
+  void*& h_coef = d->h_coef_s[sl];
+  void*& h_meta = d->h_meta_s[sl];
+  void*& h_tab = d->h_tab_s[sl];
+  if (!grow(&h_coef, &d->h_coef_cap_s[sl], (size_t)coef_total * 2, true) || !grow(&h_meta, &d->h_meta_cap_s[sl], metas.size() * sizeof(FrameMeta), true) ||
+      !grow(&h_tab, &d->h_tab_cap_s[sl], tab.size() * 4, true) || !grow(&d->d_coef, &d->d_coef_cap, (size_t)coef_total * 2, false) ||
       !grow(&d->d_meta, &d->d_meta_cap, metas.size() * sizeof(FrameMeta), false) || !grow(&d->d_tab, &d->d_tab_cap, tab.size() * 4, false) ||
       !grow(&d->d_planes, &d->d_planes_cap, (size_t)plane_total, false) || !grow(&d->d_rgb, &d->d_rgb_cap, (size_t)rgb_total, false) ||
       !grow(&d->d_tmp, &d->d_tmp_cap, (size_t)tmp_total, false))
     return ffail(TUBER_ERR_CUDA, "frame decoder: out of memory");
   // ---- entropy decoding: host threads, frame i on thread i % T, straight into pinned memory ----
-  int16_t* hc = reinterpret_cast<int16_t*>(d->h_coef);
-  std::vector<const char*> errs(n, nullptr);
-  const int T = d->threads < n ? d->threads : n;
-  auto work = [&](int t) {
+  int16_t* hc = reinterpret_cast<int16_t*>(h_coef);
+  run_threads([&](int t) {
     for (int i = t; i < n; i += T) {
       int16_t* dst = hc + metas[i].coef_off[0];
       long long cnt = 0;
@@ -660,22 +683,14 @@ int tuber_frames_decode(TuberFrameDecoder* d, const uint8_t* const* jpeg_ptrs, c
       memset(dst, 0, (size_t)cnt * 2);                              // (zeroed by the thread that fills it)
       errs[i] = decode_scan(hdr[i], dst);
     }
-  };
-  if (T <= 1) {
-    work(0);
-  } else {
-    std::vector<std::thread> pool;
-    for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
-    work(0);
-    for (auto& th : pool) th.join();
-  }
+  });
   for (int i = 0; i < n; ++i)
     if (errs[i]) {
       snprintf(g_frames_error, sizeof g_frames_error, "frame %d: %s", i, errs[i]);
       return TUBER_ERR_INVALID;
     }
-  memcpy(d->h_meta, metas.data(), metas.size() * sizeof(FrameMeta));
-  memcpy(d->h_tab, tab.data(), tab.size() * 4);
+  memcpy(h_meta, metas.data(), metas.size() * sizeof(FrameMeta));
+  memcpy(h_tab, tab.data(), tab.size() * 4);
   // ---- device: copies, inverse DCT, upsampling + colour, resize ----
 #define FCK(expr)                                                                                         \
   do {                                                                                                    \
@@ -685,11 +700,11 @@ int tuber_frames_decode(TuberFrameDecoder* d, const uint8_t* const* jpeg_ptrs, c
       return TUBER_ERR_CUDA;                                                                              \
     }                                                                                                     \
   } while (0)
-  FCK(cudaMemcpyAsync(d->d_coef, d->h_coef, (size_t)coef_total * 2, cudaMemcpyHostToDevice, st));
-  FCK(cudaMemcpyAsync(d->d_meta, d->h_meta, metas.size() * sizeof(FrameMeta), cudaMemcpyHostToDevice, st));
-  FCK(cudaMemcpyAsync(d->d_tab, d->h_tab, tab.size() * 4, cudaMemcpyHostToDevice, st));
-  FCK(cudaEventRecord(d->done, st));
-  d->pending = true;
+  FCK(cudaMemcpyAsync(d->d_coef, h_coef, (size_t)coef_total * 2, cudaMemcpyHostToDevice, st));
+  FCK(cudaMemcpyAsync(d->d_meta, h_meta, metas.size() * sizeof(FrameMeta), cudaMemcpyHostToDevice, st));
+  FCK(cudaMemcpyAsync(d->d_tab, h_tab, tab.size() * 4, cudaMemcpyHostToDevice, st));
+  FCK(cudaEventRecord(d->done_s[sl], st));
+  d->pending_s[sl] = true;
   const FrameMeta* dm = reinterpret_cast<const FrameMeta*>(d->d_meta);
   const int* dt = reinterpret_cast<const int*>(d->d_tab);
   unsigned char* planes = reinterpret_cast<unsigned char*>(d->d_planes);
