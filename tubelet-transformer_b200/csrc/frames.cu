@@ -226,7 +226,7 @@ static inline int decode_symbol(BitReader& br, const HuffTable& t) {
 }
 static inline int extend(int v, int t) { return v < (1 << (t - 1)) ? v - (1 << t) + 1 : v; }
 
-// coefficients of one frame -> out (int16, natural order, zero-initialised by the caller): [Y blocks | Cb blocks | Cr blocks], each
+// coefficients of one frame -> out (int16, natural order; every block is zeroed before it is filled): [Y blocks | Cb blocks | Cr blocks], each
 // component as [blocks_y][blocks_x][64] over whole MCUs
 static const char* decode_scan(const Header& h, int16_t* out) {
   int bx[3], by[3];
@@ -250,9 +250,10 @@ static const char* decode_scan(const Header& h, int16_t* out) {
       for (int v = 0; v < h.comp[c].v; ++v)
         for (int u = 0; u < h.comp[c].h; ++u) {
           int16_t* blk = out + off[c] + ((int64_t)(my * h.comp[c].v + v) * bx[c] + (mx * h.comp[c].h + u)) * 64;
+          memset(blk, 0, 128);                                   // (zeroed right before it is filled: the block stays in L1)
           int t = decode_symbol(br, dct);
           if (t < 0 || t > 15) return "bad DC code";
-          if (t) { br.fill(); pred[c] += extend((int)br.get(t), t); }
+          if (t) pred[c] += extend((int)br.get(t), t);           // (>= 17 bits are left after a symbol: no refill needed)
           blk[0] = (int16_t)pred[c];
           for (int k = 1; k < 64;) {
             br.fill();
@@ -273,7 +274,6 @@ static const char* decode_scan(const Header& h, int16_t* out) {
             }
             k += r;
             if (k > 63) return "coefficient index out of range";
-            br.fill();
             blk[kZigzag[k]] = (int16_t)extend((int)br.get(s), s);
             ++k;
           }
@@ -582,7 +582,6 @@ int tuber_op_jpeg_coefficients(const uint8_t* jpeg, int64_t size, int16_t* coef_
   }
   if (!coef_out) return TUBER_OK;
   if (capacity < total) return ffail(TUBER_ERR_SHAPE, "coefficient buffer too small");
-  memset(coef_out, 0, (size_t)total * 2);
   msg = decode_scan(h, coef_out);
   if (msg) return ffail(TUBER_ERR_INVALID, msg);
   return TUBER_OK;
@@ -680,8 +679,8 @@ int tuber_frames_decode(TuberFrameDecoder* d, const uint8_t* const* jpeg_ptrs, c
       int16_t* dst = hc + metas[i].coef_off[0];
       long long cnt = 0;
       for (int c = 0; c < 3; ++c) cnt += (long long)metas[i].bx[c] * metas[i].by[c] * 64;
-      memset(dst, 0, (size_t)cnt * 2);                              // (zeroed by the thread that fills it)
-      errs[i] = decode_scan(hdr[i], dst);
+      (void)cnt;
+      errs[i] = decode_scan(hdr[i], dst);                           // (zeroes every block it fills)
     }
   });
   for (int i = 0; i < n; ++i)
