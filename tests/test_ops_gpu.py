@@ -61,6 +61,14 @@ def test_gemm_tc(abi, m, n, k, variant):
     assert _rel(out, ref) < 3e-5, (m, n, k, variant)
 
 
+@pytest.mark.parametrize("m,n,k", [(16384, 1024, 256), (9500, 1024, 128), (20000, 512, 256)])
+@pytest.mark.parametrize("variant", ["plain", "bn_relu_res", "split_out_split_res", "res_mod", "mixed_res_f32_out_split", "split_out"])
+def test_gemm_tc_pair128(abi, monkeypatch, m, n, k, variant):
+    """the same problems through gemm2_bf16x3_kernel<3, 2, 2, 128> (CTA pairs, 256 x 128 tiles; TUBER_PAIR128 is read per call)"""
+    monkeypatch.setenv("TUBER_PAIR128", "1")
+    test_gemm_tc(abi, m, n, k, variant)
+
+
 @pytest.mark.parametrize("m,k,kb,n1,n2,with_res", [(1000, 64, 0, 256, 64, True), (128, 64, 64, 256, 64, False), (40000, 64, 0, 256, 64, True),
                                                     (5000, 64, 0, 256, 128, True), (33333, 64, 64, 256, 128, False),
                                                     (300, 128, 0, 256, 64, True), (50000, 64, 64, 256, 64, False),

@@ -926,12 +926,17 @@ TB_DEVINL void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint3
 // STAGES x 64 KB operand ring + PANELS x 32 KB epilogue panels: <3, 1> for the deep-K shapes (the next tile's main loop hides the
 // one-panel epilogue), <2, 3> for short K with a residual (conv4 of the 1024-channel stage: K = 256, so the epilogue IS the kernel --
 // panels pipelined load | compute | store as in gemm_bf16x3_kernel)
-template <int STAGES, int PANELS, int G>
+// BN2 = 128 (256 x 128 pair tiles, each CTA loads its 128 rows of A and 64 of the tile's 128 W rows: 48 KB per k-block instead of the
+// 64 KB of a single-CTA 128 x 128 tile) keeps the tile count of the single-CTA kernel -- for the short-K, wide-N shapes that are bound
+// by L2 -> shared-memory throughput and whose 256-column pair tiles quantise badly (conv4 of the 1024-channel stage: 512 tiles on 74 pairs).
+template <int STAGES, int PANELS, int G, int BN2 = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(96 + 128 * G, 1)
 gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
                     const __grid_constant__ CUtensorMap tmR, Params p) {
-  constexpr int BN2 = 256, BNH = 128, STAGE_BYTES = 65536, PPT = BN2 / 64;
+  constexpr int BNH = BN2 / 2, STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * BNH * BK * 2, PPT = BN2 / 64;
+  static_assert(BN2 == 256 || BN2 == 128, "pair tile width");
+  static_assert(STAGE_BYTES % 1024 == 0, "operand stages must keep the 1024-byte alignment of the swizzled tiles");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t panel_base = smem_base + STAGES * STAGE_BYTES;
@@ -1600,6 +1605,10 @@ using CfgBig = Cfg<256, 2, 1>;    // K >= 512, N % 256 == 0 and enough row block
 constexpr int PAIR_SMEM_BYTES = 3 * 65536 + PANEL_BYTES + 256 + 2 * 256 * 4;   // gemm2_bf16x3_kernel<3, 1> and <2, 3> (2 x 64 KB + 3 panels: same size)
 static_assert(2 * 65536 + 3 * PANEL_BYTES == 3 * 65536 + PANEL_BYTES, "pair kernel configurations share one shared-memory size");
 static_assert(PAIR_SMEM_BYTES <= 232448, "over the 227 KB shared-memory limit");
+// gemm2_bf16x3_kernel<2, 3, 2, 128>: 2 x 48 KB operand stages + 3 panels
+constexpr int PAIR128_STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * 64 * BK * 2;
+constexpr int PAIR128_SMEM_BYTES = 2 * PAIR128_STAGE_BYTES + 3 * PANEL_BYTES + 256 + 2 * 256 * 4;
+static_assert(PAIR128_SMEM_BYTES <= 232448, "over the 227 KB shared-memory limit");
 
 static char g_err[256] = "";
 static EncodeTiledFn g_encode = nullptr;
@@ -1621,6 +1630,7 @@ static cudaError_t init_once() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel<3, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel<2, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel<3, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_bf16x3_kernel<2, 3, 2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR128_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
@@ -1679,6 +1689,18 @@ static bool use_pair_tiles(const GemmArgs& a, int KT) {
   return tiles >= 48;                                       // at least ~2/3 of the 74 pairs busy
 }
 
+// CTA pairs with 256 x 128 tiles for the short-K, wide-N shapes with several rounds of tiles (conv4 of the 1024-channel stage).
+// Measured (profiles/r2_pair128_experiment.json): 17 % less operand traffic through L2 -> shared memory and NOT faster than the
+// single-CTA 128 x 128 kernel (43.4 us at 1912 MHz against 41-43 us at 1815-1830 MHz per launch; 49.5 us with three stages and two
+// panels) -- the shape is not bound by the L2 throughput cap alone.  Correct (tests/test_ops_gpu.py::test_gemm_tc_pair128), kept off.
+static bool use_pair128_tiles(const GemmArgs& a, int KT) {
+  const char* e = getenv("TUBER_PAIR128");                  // read per call (tests / experiments): 1 = on, 0 = off
+  const bool on = e ? e[0] == '1' : false;
+  if (!on || KT > 256 || KT < 128 || a.N % 128 != 0 || a.N < 512 || a.ksplit > 1 || a.group_rows > 0) return false;
+  const long long tiles = (long long)ceil_div(a.M, 2 * BM) * (a.N / 128);
+  return tiles >= 4 * (device_num_sms() / 2);               // at least four rounds over the pairs
+}
+
 // A2 as a strided gather: dims {K, Wi, Hi, BTi, 2 planes}, element strides {1, ss, ss, st, 1}, box = 128 output voxels
 static bool encode_a2(CUtensorMap* map, const GemmArgs& a, Params& p) {
   p.a2_wo = 0;
@@ -1733,6 +1755,8 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   if (use_big_tiles(a, KT)) bn = 256;
   const bool pair_tiles = use_pair_tiles(a, KT);
   if (pair_tiles) bn = 128;                                 // W box: each CTA of the pair loads 128 of the tile's 256 rows
+  const bool pair128 = !pair_tiles && use_pair128_tiles(a, KT);
+  if (pair128) bn = 64;                                     // W box: 64 of the tile's 128 rows
   Params p{};
   p.scale = a.scale; p.shift = a.shift;
   p.out_fmt = a.c_fmt;
@@ -1773,6 +1797,11 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   if (p.res_mode == RES_TMA) {
     ok = a.c_fmt == FMT_F32 ? encode_f32_panel_map(&tmR, a.res, a.N, a.M, a.ldr) : encode_split_map(&tmR, a.res, a.N, a.M, a.ldr, BM);
     if (!ok) return cudaErrorInvalidValue;
+  }
+  if (pair128) {
+    const int tiles = ceil_div(p.M, 2 * BM) * (p.N / 128);
+    const int pairs = tiles < device_num_sms() / 2 ? tiles : device_num_sms() / 2;
+    return launch_pdl(gemm2_bf16x3_kernel<2, 3, 2, 128>, dim3(2 * pairs), dim3(96 + 128 * 2), PAIR128_SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, p);
   }
   if (pair_tiles) {
     const int tiles = ceil_div(p.M, 2 * BM) * (p.N / 256);
@@ -1820,6 +1849,7 @@ const char* gemm_tc_config_name(const GemmArgs& a) {
   int bn = (a.N % 128 == 0) ? 128 : 64;
   if (bn == 128 && (long long)ceil_div(a.M, tc::BM) * (a.N / 128) * 2 * (a.ksplit > 1 ? a.ksplit : 1) <= device_num_sms()) bn = 64;
   if (tc::use_pair_tiles(a, KT)) return "gemm2_bf16x3_pair";
+  if (tc::use_pair128_tiles(a, KT)) return "gemm2_bf16x3_pair128";
   if (tc::use_big_tiles(a, KT)) return "gemm_bf16x3_big";
   if (bn == 64) return "gemm_bf16x3_n64";
   return KT >= 512 ? "gemm_bf16x3_deep" : "gemm_bf16x3_wide";
