@@ -98,6 +98,13 @@ def test_gemm_tc_fused2(abi, m, k, kb, n1, n2, with_res):
     assert _rel(t1, ref_t) < 3e-5
 
 
+@pytest.mark.parametrize("m,k,kb,with_res", [(700, 128, 0, True), (45000, 128, 0, True), (30001, 128, 256, False), (131072, 128, 0, True)])
+def test_gemm_tc_fused2_pair_512(abi, monkeypatch, m, k, kb, with_res):
+    """the 512 -> 128 shapes through the CTA-pair form gemm_fused2p_kernel<512, 128> (TUBER_FUSE2P_L2 is read per call)"""
+    monkeypatch.setenv("TUBER_FUSE2P_L2", "1")
+    test_gemm_tc_fused2(abi, m, k, kb, 512, 128, with_res)
+
+
 @pytest.mark.parametrize("m,n,k,act", [(90, 3, 256, 0), (90, 4, 256, 2), (720, 80, 256, 0), (8, 2, 2048, 0), (333, 256, 64, 1)])
 def test_sgemm(abi, m, n, k, act):
     a = torch.randn(m, k, device="cuda")

@@ -1255,7 +1255,7 @@ gemm_fused2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int KBW = STAGE_BYTES / W2_CHUNK;               // k-blocks of the second GEMM per ring stage
   constexpr int D2_COL = BNS;
   constexpr int G = FUSED2_EPI_GROUPS;
-  static_assert(N1 % BNS == 0 && N2 == 256 && KBW == 2 && PPS % KBW == 0 && D2_COL + N2 <= 512, "built for the 1024 -> 256 shapes");
+  static_assert(N1 % BNS == 0 && (N2 == 256 || N2 == 128) && PPS % KBW == 0 && D2_COL + N2 <= 512, "built for the 1024 -> 256 and 512 -> 128 shapes");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t panel_base = smem_base + STAGES * STAGE_BYTES;
@@ -1638,6 +1638,7 @@ static cudaError_t init_once() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2_kernel<512, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2p_kernel<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_fused2p_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgWide::SMEM_BYTES);
     return e;
   });
 }
@@ -1889,7 +1890,14 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
   tmR = tmC;
   if (a.res && !encode_split_map(&tmR, a.res, a.N, a.M, a.ldr, BM)) return cudaErrorInvalidValue;
   static const bool single1024 = [] { const char* e = getenv("TUBER_FUSE2_SINGLE"); return e && e[0] == '1'; }();
-  const bool pair_form = a.N == 1024 && !single1024;       // gemm_fused2p_kernel: each CTA of the pair loads half of the W1' rows
+  // 512 -> 128 (the 512-channel stage): per 128-row block the single-CTA kernel pulls 1.34 MB through L2 -> shared memory (t2 re-read for each
+  // of its four sub-tiles, all of W4 and W1') for 0.64 MB of HBM traffic, the pair form 0.96 MB.  Measured (profiles/r2_fused2p_layer2_experiment.json):
+  // the first bottleneck of the stage (K = 128 + 256 with the shortcut: six k-blocks per sub-tile) 240 -> 219 us; the K = 128 ones 145 -> 170 us (two
+  // k-blocks do not hide the single conv4 accumulator's epilogue -> MMA hand-over), so the pair form takes K >= 256 only.
+  // TUBER_FUSE2P_L2 (read per call): 1 = every 512 -> 128 launch, 0 = none.
+  const char* p2e = getenv("TUBER_FUSE2P_L2");
+  const bool pair512 = a.N == 512 && N2 == 128 && (p2e && (p2e[0] == '0' || p2e[0] == '1') ? p2e[0] == '1' : KT >= 256);
+  const bool pair_form = (a.N == 1024 && !single1024) || pair512;   // gemm_fused2p_kernel: each CTA of the pair loads half of the weight rows
   if (!encode3(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, W2p, a.N, N2, 2, (uint64_t)a.N * 2, (uint64_t)N2 * a.N * 2, 64, pair_form ? N2 / 2 : N2, 2))
     return cudaErrorInvalidValue;
   if (!encode_f32_panel_map(&tmC2, C2, N2, a.M, ldc2)) return cudaErrorInvalidValue;
@@ -1898,6 +1906,8 @@ cudaError_t launch_gemm_tc_fused2(const GemmArgs& a, const void* W2p, const floa
   if (pair_form) {
     const int m_pairs = ceil_div(a.M, 2 * BM), max_pairs = device_num_sms() / 2;
     const int pairs = m_pairs < max_pairs ? m_pairs : max_pairs;
+    if (pair512)
+      return launch_pdl(gemm_fused2p_kernel<512, 128>, dim3(2 * pairs), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
     return launch_pdl(gemm_fused2p_kernel<1024, 256>, dim3(2 * pairs), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
   }
   if (a.N == 1024) return launch_pdl(gemm_fused2_kernel<1024, 256>, dim3(grid), dim3(FUSED2_THREADS), CfgWide::SMEM_BYTES, st, tmA, tmA2, tmW, tmC, tmR, tmW2, tmC2, p, q);
