@@ -348,6 +348,40 @@ def test_decoder_megakernel_matches_the_per_operation_sequence(monkeypatch, yaml
         assert emax < 1e-4 and el2 < 1e-4, (k, emax, el2)
 
 
+@pytest.mark.parametrize("yaml,batch,masked", [("TubeR_CSN152_AVA21.yaml", 2, False), ("TubeR_CSN50_AVA21.yaml", 3, True)])
+def test_side_branches_on_their_own_streams_are_bit_identical(monkeypatch, yaml, batch, masked):
+    """TUBER_OVERLAP=1 (read at plan creation): the position-code chain and the class-branch encoder run on side streams beside the
+    stem / the DETR encoder + decoder (plan.cu, Ctx::side_begin / side_end / side_join), eagerly and as parallel branches of the
+    recorded graph; same kernels on the same data, so the outputs must be bit-identical to the one-stream order."""
+    import tuber_b200
+    from oracle import tuber_oracle as O
+    cfg = tuber_b200.load_cfg(yaml)
+    sd = O.make_state_dict(cfg, seed=5, bn="random")
+    clips = O.make_clips(batch, 32, 128, 160, seed=6).cuda()
+    mask = None
+    if masked:
+        mask = torch.zeros(batch, 128, 160, dtype=torch.bool, device="cuda")
+        mask[0, :, 100:] = True
+        clips = clips * (~mask)[:, None, None].float()
+    plain = {k: v.clone() for k, v in _model(cfg, sd).forward_raw(clips, mask).items()}
+    monkeypatch.setenv("TUBER_OVERLAP", "1")
+    m = _model(cfg, sd)
+    for step in range(2):
+        out = m.forward_raw(clips, mask)
+        torch.cuda.synchronize()
+        for k in plain:
+            assert torch.equal(out[k], plain[k]), (k, "eager", step)
+    m.use_cuda_graph(True)
+    out = {k: torch.empty_like(v) for k, v in plain.items()}
+    for step in range(4):
+        for v in out.values():
+            v.zero_()
+        m.forward_raw(clips, mask, out)
+        torch.cuda.synchronize()
+        for k in plain:
+            assert torch.equal(out[k], plain[k]), (k, "graph", step)
+
+
 def test_detection_rows_match_reference_postprocessors():
     """tuber_postprocess (fused post-processing + row packing) against the reference's PostProcessAVA / PostProcess outputs
     (tests/golden/postprocess.npz) and through the PostProcess* modules of build_model."""

@@ -109,8 +109,20 @@ struct DeviceOnce {
     return e;
   }
 };
-// SM count of the CURRENT device (cached per device)
+// Optional cap on the SMs a persistent launch may take (0 = none), per host thread: set around the launches of a side branch
+// (plan.cu, Ctx::side_begin) so that a kernel of the branch cannot fill the machine in front of the main chain's next launch.
+// Every launcher sizes its grid from device_num_sms(), so the kernels see a consistently smaller machine.
+inline int& sm_cap_ref() {
+  static thread_local int cap = 0;
+  return cap;
+}
+// SM count of the CURRENT device (cached per device), limited by the calling thread's cap
+static inline int device_num_sms_uncapped();
 static inline int device_num_sms() {
+  const int n = device_num_sms_uncapped(), cap = sm_cap_ref();
+  return cap > 0 && cap < n ? cap : n;
+}
+static inline int device_num_sms_uncapped() {
   static int cache[DeviceOnce::MAX_DEVICES] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= DeviceOnce::MAX_DEVICES) return 1;

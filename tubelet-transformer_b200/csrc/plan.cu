@@ -89,6 +89,7 @@ struct DecLayer {
   float* sa_out_t = nullptr; float* ca_q_t = nullptr; float* ca_out_t = nullptr;   // K-major fp32 copies [d, d] (decoder_mega.cu)
 };
 
+constexpr int SIDE_CTAS_DEFAULT = 0;   // SM cap of the class-branch side stream (0 = none); TUBER_SIDE_CTAS overrides
 struct KernelRec { const char* name; double bytes, flops; cudaEvent_t e0, e1; char tag[64]; };
 struct Tap { const void* ptr; int fmt; long long rows; int cols; void* keep; };
 
@@ -166,6 +167,13 @@ struct TuberPlan {
   int launches = 0;
   bool kprof = false;
   cudaStream_t cap_stream = nullptr;
+  // side branches of a forward (Ctx::side_begin / side_end / side_join): the position-code chain (needs only the mask) and the
+  // class-branch encoder (needs only class_proj's output) run on their own streams beside the backbone / the DETR encoder + decoder,
+  // whose token-sized launches leave most SMs idle; recorded into the CUDA graph as parallel branches
+  static constexpr int NUM_SIDE = 2;
+  cudaStream_t side[NUM_SIDE] = {}; cudaEvent_t ev_fork[NUM_SIDE] = {}, ev_join[NUM_SIDE] = {};
+  bool side_valid = false, no_overlap = false;
+  int side_ctas = 0;                 // > 0: CTAs (SMs) a persistent kernel of the class-branch side stream may occupy
   std::vector<KernelRec> kp; int kp_used = 0;
   struct GraphEntry { std::vector<uintptr_t> key; cudaGraphExec_t exec; };
   std::vector<GraphEntry> graphs;
@@ -617,6 +625,35 @@ struct Ctx {
   char tag[64] = "";     // optional shape note for the next launch (per-kernel profile dump)
 
   bool ok() const { return status == TUBER_OK; }
+  // ---- side branches: work that does not depend on the main chain runs on p->side[k] between side_begin(k) and side_end(k);
+  // side_join(k) makes the main stream wait for it.  With `overlap` off (the default; always in the profiling modes) the
+  // three calls do nothing and the branch simply runs in program order on the main stream.
+  bool overlap = false;
+  cudaStream_t main_st = nullptr;
+  int side_open = -1;
+  void side_begin(int k) {
+    if (!overlap || dry || !ok()) return;
+    main_st = st;
+    cudaError_t e = cudaEventRecord(p->ev_fork[k], st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(p->side[k], p->ev_fork[k], 0);
+    if (e != cudaSuccess) { status = fail(TUBER_ERR_CUDA, "side branch %d: %s", k, cudaGetErrorString(e)); return; }
+    st = p->side[k];
+    side_open = k;
+    if (k == 1) sm_cap_ref() = p->side_ctas;                 // launchers called from this thread size their grids for that many SMs
+  }
+  void side_end(int k) {
+    if (!overlap || dry || side_open != k) return;
+    cudaError_t e = cudaEventRecord(p->ev_join[k], st);
+    st = main_st;
+    side_open = -1;
+    sm_cap_ref() = 0;
+    if (e != cudaSuccess && ok()) status = fail(TUBER_ERR_CUDA, "side branch %d: %s", k, cudaGetErrorString(e));
+  }
+  void side_join(int k) {
+    if (!overlap || dry) return;                            // (also after an error: a capture in progress needs every branch joined)
+    cudaError_t e = cudaStreamWaitEvent(st, p->ev_join[k], 0);
+    if (e != cudaSuccess && ok()) status = fail(TUBER_ERR_CUDA, "side branch %d join: %s", k, cudaGetErrorString(e));
+  }
   // every device operation of a forward goes through here: counted, optionally bracketed by CUDA events
   // (per-kernel profiling), skipped in the dry (sizing) pass
   template <class F>
@@ -783,10 +820,38 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
   TuberPlan* p = cx.p;
   const TuberConfig& c = p->cfg;
   const bool dry = cx.dry;
-  cudaStream_t st = cx.st;
+  cudaStream_t& st = cx.st;                                 // the CURRENT stream: a side branch switches it (Ctx::side_begin)
+  const bool ov = cx.overlap;
   Geometry g;
   TRY(compute_geometry(c, T, H, W, g));
   const int d = c.d_model, nh = c.nhead, hd = d / nh, Q = c.num_queries, Le = c.enc_layers, Ld = c.dec_layers;
+  const int Tf = g.Tf, HW = g.Hf * g.Wf, Tp = g.Tp, CB = POOL_DIM;
+  const int Ntok = Tp * HW;
+  const long long Mc = (long long)B * Tf * HW;             // class-branch tokens
+  const long long Mtok = (long long)B * Ntok;              // DETR encoder tokens
+
+  // ---- padding mask at feature resolution, 3-D sine position code and its projections: needs only the mask, so with overlap on
+  // it runs as side branch 0 beside the stem (joined in front of the encoder) ----
+  const int Bp = mask ? B : 1;                              // without padding every clip has the same code
+  const int NP = Le * 3 * d + Ld * 2 * d;
+  uint8_t* fmask = nullptr; float* pos = nullptr; float* posp = nullptr;
+  auto position_codes = [&] {
+    fmask = (uint8_t*)cx.ws.alloc((size_t)Bp * Ntok);
+    pos = cx.f32((long long)Bp * Ntok, d);
+    void* pos_s = cx.split((long long)Bp * Ntok, d);
+    posp = cx.f32((long long)Bp * Ntok, NP);
+    const double n = (double)Bp * Ntok * d;
+    cx.launch("mask_resize", (double)Bp * Ntok, 0.0, [&] { return launch_mask_resize(mask, fmask, Bp, H, W, Tp, g.Hf, g.Wf, st); });
+    cx.launch("posenc", 4.0 * n, 8.0 * n,
+              [&] { return launch_posenc(fmask, p->dim_t, p->dim_s, pos, Bp, Tp, g.Hf, g.Wf, d / 8 * 2, d / 8 * 3, st); });
+    cx.launch("to_split", 8.0 * n, 0.0, [&] { return launch_to_split(pos, d, pos_s, d, (long long)Bp * Ntok, d, st); });
+    cx.gemm(pos_s, FMT_SPLIT, d, (long long)Bp * Ntok, p->pos_proj, nullptr, 0, 0, 0, posp, FMT_F32, NP, ACT_NONE);
+  };
+  if (ov) {
+    cx.side_begin(0);
+    position_codes();
+    cx.side_end(0);
+  }
 
   // ---- backbone buffers (ping-pong block outputs, conv1 / depthwise / shortcut scratch) ----
   size_t max_out = (size_t)B * T * g.H1 * g.W1 * 64, max_t1 = 0, max_t2 = 0, max_xg = 0;
@@ -895,11 +960,7 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     cx.tap(names[li], cur, FMT_SPLIT, (long long)B * t * h * w, p->blocks[li].back().cout);
   }
   if (!cx.ok()) return cx.status;
-  const int Tf = g.Tf, HW = g.Hf * g.Wf, Tp = g.Tp, CB = POOL_DIM;
   const void* xt = cur;                                    // S [B*Tf*HW, 2048]
-  const long long Mc = (long long)B * Tf * HW;             // class-branch tokens
-  const int Ntok = Tp * HW;
-  const long long Mtok = (long long)B * Ntok;              // DETR encoder tokens
   cx.tap("xt", xt, FMT_SPLIT, Mc, CB);
 
   // ---- temporal pooling (backbone_builder.py:70-80) ----
@@ -955,20 +1016,8 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
 
   // ---- padding mask at feature resolution, 3-D sine position code and its projections ----
   cx.stage_mark(6);
-  const int Bp = mask ? B : 1;                              // without padding every clip has the same code
-  uint8_t* fmask = (uint8_t*)cx.ws.alloc((size_t)Bp * Ntok);
-  float* pos = cx.f32((long long)Bp * Ntok, d);
-  void* pos_s = cx.split((long long)Bp * Ntok, d);
-  const int NP = Le * 3 * d + Ld * 2 * d;
-  float* posp = cx.f32((long long)Bp * Ntok, NP);
-  {
-    const double n = (double)Bp * Ntok * d;
-    cx.launch("mask_resize", (double)Bp * Ntok, 0.0, [&] { return launch_mask_resize(mask, fmask, Bp, H, W, Tp, g.Hf, g.Wf, st); });
-    cx.launch("posenc", 4.0 * n, 8.0 * n,
-              [&] { return launch_posenc(fmask, p->dim_t, p->dim_s, pos, Bp, Tp, g.Hf, g.Wf, d / 8 * 2, d / 8 * 3, st); });
-    cx.launch("to_split", 8.0 * n, 0.0, [&] { return launch_to_split(pos, d, pos_s, d, (long long)Bp * Ntok, d, st); });
-  }
-  cx.gemm(pos_s, FMT_SPLIT, d, (long long)Bp * Ntok, p->pos_proj, nullptr, 0, 0, 0, posp, FMT_F32, NP, ACT_NONE);
+  if (ov) cx.side_join(0);
+  else position_codes();
   const uint8_t* kpm = mask ? fmask : nullptr;
   const int pos_mod = mask ? 0 : Ntok;
   cx.tap("pos", pos, FMT_F32, (long long)Bp * Ntok, d);
@@ -985,6 +1034,69 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     cx.launch("tpool", 4.0 * ((double)Mc + (double)B * HW) * d, (double)Mc * d,
               [&] { return launch_tpool(srcc_s, e_s, B, Tf, HW, d, Tf, 1, 0, st); });
     cx.launch("from_split", 8.0 * B * HW * d, 0.0, [&] { return launch_from_split(e_s, d, p->ltc_new, d, (long long)B * HW, d, st); });
+  }
+
+  // The class branch up to the keys / values of its cross attention depends only on class_proj's output: with overlap on it is side
+  // branch 1, running beside the DETR encoder and decoder (token-sized launches that leave most SMs idle) and joined in front
+  // of the class cross-attention; otherwise it runs here in program order.
+  void* memc_s = nullptr;
+  float* kvx = nullptr;
+  auto class_memory = [&] {
+    // class-branch encoder layer (transformer_layers.py:71-97), evaluated once per clip: the reference runs
+    // DEC_LAYERS identical replicas of it (tuber_ava.py:133-135)
+    memc_s = cx.split(Mc, d);
+    {
+      float* qkv = cx.f32(Mc, 3 * d);
+      void* att = cx.split(Mc, d);
+      void* o = cx.split(Mc, d);
+      void* cat = cx.split(Mc, 2 * d);
+      void* hdn = cx.split(Mc, CLS_FF);
+      const int ch = d / CLS_HEADS;
+      // "_t": attention inside a frame over its HW positions
+      cx.gemm(srcc_s, FMT_SPLIT, d, Mc, p->ct_in, nullptr, 0, 0, 0, qkv, FMT_F32, 3 * d, ACT_NONE);
+      cx.attention(qkv, 3 * d, seqmap(1, HW, 0, 1), qkv + d, qkv + 2 * d, 3 * d, seqmap(1, HW, 0, 1), att, d, seqmap(1, HW, 0, 1),
+                   nullptr, B * Tf, CLS_HEADS, HW, HW, ch);
+      cx.gemm(att, FMT_SPLIT, d, Mc, p->ct_out, srcc_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->c_n1t, Mc, nullptr, 0, cat, 2 * d, 0);
+      // "_s": attention inside a pixel over its Tf frames
+      cx.gemm(srcc_s, FMT_SPLIT, d, Mc, p->cs_in, nullptr, 0, 0, 0, qkv, FMT_F32, 3 * d, ACT_NONE);
+      const SeqMap pix = seqmap(HW, (long long)Tf * HW, 1, HW);
+      cx.attention(qkv, 3 * d, pix, qkv + d, qkv + 2 * d, 3 * d, pix, att, d, pix, nullptr, B * HW, CLS_HEADS, Tf, Tf, ch);
+      cx.gemm(att, FMT_SPLIT, d, Mc, p->cs_out, srcc_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->c_n1s, Mc, nullptr, 0, cat, 2 * d, d);
+      cx.gemm(cat, FMT_SPLIT, 2 * d, Mc, p->c_lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, CLS_FF, ACT_RELU);
+      cx.gemm(hdn, FMT_SPLIT, CLS_FF, Mc, p->c_lin2, srcc_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->c_n2, Mc, nullptr, 0, memc_s, d);
+    }
+    cx.tap("mem_c", memc_s, FMT_SPLIT, Mc, d);
+    // long-term context layer: every class-branch token of a clip attends over the bank window (bank_clips = 1: one window shared
+    // by the batch; = B: one per clip), post-norm like every other layer of the model:  mem_c <- LN(mem_c + MHA(mem_c, bank, bank))
+    if (p->ltc_bank && p->ltc_bank_tokens > 0) {
+      const int Nb = p->ltc_bank_tokens, Bb = p->ltc_bank_clips, Nc = Tf * HW;
+      const long long Mb = (long long)Bb * Nb;
+      void* bank_s = cx.split(Mb, d);
+      float* kvb = cx.f32(Mb, 2 * d);
+      float* ql = cx.f32(Mc, d);
+      void* att = cx.split(Mc, d);
+      void* o = cx.split(Mc, d);
+      void* memc2 = cx.split(Mc, d);
+      cx.launch("to_split", 8.0 * Mb * d, 0.0, [&] { return launch_to_split(p->ltc_bank, d, bank_s, d, Mb, d, st); });
+      cx.gemm(bank_s, FMT_SPLIT, d, Mb, p->ltc_kv, nullptr, 0, 0, 0, kvb, FMT_F32, 2 * d, ACT_NONE);
+      cx.gemm(memc_s, FMT_SPLIT, d, Mc, p->ltc_q, nullptr, 0, 0, 0, ql, FMT_F32, d, ACT_NONE);
+      cx.attention(ql, d, seqmap(1, Nc, 0, 1), kvb, kvb + d, 2 * d, seqmap(1, Bb == 1 ? 0 : Nb, 0, 1), att, d, seqmap(1, Nc, 0, 1), nullptr,
+                   B, CLS_HEADS, Nc, Nb, d / CLS_HEADS);
+      cx.gemm(att, FMT_SPLIT, d, Mc, p->ltc_out, memc_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
+      cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->ltc_n, Mc, nullptr, 0, memc2, d);
+      memc_s = memc2;
+      cx.tap("mem_ltc", memc_s, FMT_SPLIT, Mc, d);
+    }
+    kvx = cx.f32(Mc, 2 * d);
+    cx.gemm(memc_s, FMT_SPLIT, d, Mc, p->x_kv, nullptr, 0, 0, 0, kvx, FMT_F32, 2 * d, ACT_NONE);
+  };
+  if (ov) {
+    cx.side_begin(1);
+    class_memory();
+    cx.side_end(1);
   }
 
   // ---- DETR encoder (transformer.py:153-168): post-norm, q = k = src + pos, v = src ----
@@ -1115,63 +1227,15 @@ int run_forward(Ctx& cx, const float* clips, const uint8_t* mask, int B, int T, 
     cx.gemm(h1, FMT_SPLIT, d, Mh, p->bbox1, nullptr, 0, 0, 0, h2, FMT_SPLIT, d, ACT_RELU);
     cx.gemm(h2, FMT_SPLIT, d, Mh, p->bbox2, nullptr, 0, 0, 0, boxes, FMT_F32, 4, ACT_SIGMOID);
   }
-  // class-branch encoder layer (transformer_layers.py:71-97), evaluated once per clip: the reference runs
-  // DEC_LAYERS identical replicas of it (tuber_ava.py:133-135)
-  void* memc_s = cx.split(Mc, d);
-  {
-    float* qkv = cx.f32(Mc, 3 * d);
-    void* att = cx.split(Mc, d);
-    void* o = cx.split(Mc, d);
-    void* cat = cx.split(Mc, 2 * d);
-    void* hdn = cx.split(Mc, CLS_FF);
-    const int ch = d / CLS_HEADS;
-    // "_t": attention inside a frame over its HW positions
-    cx.gemm(srcc_s, FMT_SPLIT, d, Mc, p->ct_in, nullptr, 0, 0, 0, qkv, FMT_F32, 3 * d, ACT_NONE);
-    cx.attention(qkv, 3 * d, seqmap(1, HW, 0, 1), qkv + d, qkv + 2 * d, 3 * d, seqmap(1, HW, 0, 1), att, d, seqmap(1, HW, 0, 1),
-                 nullptr, B * Tf, CLS_HEADS, HW, HW, ch);
-    cx.gemm(att, FMT_SPLIT, d, Mc, p->ct_out, srcc_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
-    cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->c_n1t, Mc, nullptr, 0, cat, 2 * d, 0);
-    // "_s": attention inside a pixel over its Tf frames
-    cx.gemm(srcc_s, FMT_SPLIT, d, Mc, p->cs_in, nullptr, 0, 0, 0, qkv, FMT_F32, 3 * d, ACT_NONE);
-    const SeqMap pix = seqmap(HW, (long long)Tf * HW, 1, HW);
-    cx.attention(qkv, 3 * d, pix, qkv + d, qkv + 2 * d, 3 * d, pix, att, d, pix, nullptr, B * HW, CLS_HEADS, Tf, Tf, ch);
-    cx.gemm(att, FMT_SPLIT, d, Mc, p->cs_out, srcc_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
-    cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->c_n1s, Mc, nullptr, 0, cat, 2 * d, d);
-    cx.gemm(cat, FMT_SPLIT, 2 * d, Mc, p->c_lin1, nullptr, 0, 0, 0, hdn, FMT_SPLIT, CLS_FF, ACT_RELU);
-    cx.gemm(hdn, FMT_SPLIT, CLS_FF, Mc, p->c_lin2, srcc_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
-    cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->c_n2, Mc, nullptr, 0, memc_s, d);
-  }
-  cx.tap("mem_c", memc_s, FMT_SPLIT, Mc, d);
-  // long-term context layer: every class-branch token of a clip attends over the bank window (bank_clips = 1: one window shared
-  // by the batch; = B: one per clip), post-norm like every other layer of the model:  mem_c <- LN(mem_c + MHA(mem_c, bank, bank))
-  if (p->ltc_bank && p->ltc_bank_tokens > 0) {
-    const int Nb = p->ltc_bank_tokens, Bb = p->ltc_bank_clips, Nc = Tf * HW;
-    const long long Mb = (long long)Bb * Nb;
-    void* bank_s = cx.split(Mb, d);
-    float* kvb = cx.f32(Mb, 2 * d);
-    float* ql = cx.f32(Mc, d);
-    void* att = cx.split(Mc, d);
-    void* o = cx.split(Mc, d);
-    void* memc2 = cx.split(Mc, d);
-    cx.launch("to_split", 8.0 * Mb * d, 0.0, [&] { return launch_to_split(p->ltc_bank, d, bank_s, d, Mb, d, st); });
-    cx.gemm(bank_s, FMT_SPLIT, d, Mb, p->ltc_kv, nullptr, 0, 0, 0, kvb, FMT_F32, 2 * d, ACT_NONE);
-    cx.gemm(memc_s, FMT_SPLIT, d, Mc, p->ltc_q, nullptr, 0, 0, 0, ql, FMT_F32, d, ACT_NONE);
-    cx.attention(ql, d, seqmap(1, Nc, 0, 1), kvb, kvb + d, 2 * d, seqmap(1, Bb == 1 ? 0 : Nb, 0, 1), att, d, seqmap(1, Nc, 0, 1), nullptr,
-                 B, CLS_HEADS, Nc, Nb, d / CLS_HEADS);
-    cx.gemm(att, FMT_SPLIT, d, Mc, p->ltc_out, memc_s, FMT_SPLIT, d, 0, o, FMT_SPLIT, d, ACT_NONE);
-    cx.layernorm(o, FMT_SPLIT, d, nullptr, 0, 0, p->ltc_n, Mc, nullptr, 0, memc2, d);
-    memc_s = memc2;
-    cx.tap("mem_ltc", memc_s, FMT_SPLIT, Mc, d);
-  }
+  if (!ov) class_memory();
   // class cross-attention (tuber_ava.py:137-139) + class_fc (:141; Dropout(0.5) is the identity in eval)
   {
     const int Nc = Tf * HW, LQ = Ld * Q;
     float* qx = cx.f32(Mh, d);
-    float* kvx = cx.f32(Mc, 2 * d);
     void* att = cx.split(Mh, d);
     void* oc = cx.split(Mh, d);
     cx.gemm(hs_s, FMT_SPLIT, d, Mh, p->x_q, nullptr, 0, 0, 0, qx, FMT_F32, d, ACT_NONE);
-    cx.gemm(memc_s, FMT_SPLIT, d, Mc, p->x_kv, nullptr, 0, 0, 0, kvx, FMT_F32, 2 * d, ACT_NONE);
+    if (ov) cx.side_join(1);
     cx.attention(qx, d, seqmap(1, LQ, 0, 1), kvx, kvx + d, 2 * d, seqmap(1, Nc, 0, 1), att, d, seqmap(1, LQ, 0, 1), nullptr, B,
                  CLS_HEADS, LQ, Nc, d / CLS_HEADS);
     cx.gemm(att, FMT_SPLIT, d, Mh, p->x_out, nullptr, 0, 0, 0, oc, FMT_SPLIT, d, ACT_NONE);
@@ -1186,6 +1250,7 @@ int ensure_workspace(TuberPlan* p, int B, int T, int H, int W, bool has_mask, si
   cx.dry = true;
   cx.ws.dry = true;
   cx.st = 0;
+  cx.overlap = !p->no_overlap && !p->profiling && !p->debug_keep && !p->kprof;   // same program order as the forward (same sizes either way)
   // the sizing pass must see the same mask / no-mask choice as the real one (per-clip position codes)
   const uint8_t* mask_tag = has_mask ? reinterpret_cast<const uint8_t*>((uintptr_t)0x1000) : nullptr;
   TRY(run_forward(cx, nullptr, mask_tag, B, T, H, W, nullptr, nullptr, nullptr));
@@ -1253,6 +1318,13 @@ int tuber_plan_create(const TuberConfig* cfg, TuberPlan** out_plan) {
   p->pool_unfolded = pu && pu[0] == '1';
   const char* ns = getenv("TUBER_NO_STRIDED_TMA");
   p->no_strided_tma = ns && ns[0] == '1';
+  // Side branches on their own streams: correct (tests/test_parity_gpu.py), but measured without gain at 8 clips -- 8.96 ms per step
+  // against 8.88 ms in program order (profiles/r2_overlap_experiment.json): the encoder's launches are short but 64..148 CTAs wide
+  // with one CTA per SM (shared memory), so a side kernel finds no idle SM, only a turn in the same queue.  On with TUBER_OVERLAP=1.
+  const char* no = getenv("TUBER_OVERLAP");
+  p->no_overlap = !(no && no[0] == '1');
+  const char* sc = getenv("TUBER_SIDE_CTAS");
+  p->side_ctas = sc ? (atoi(sc) & ~1) : SIDE_CTAS_DEFAULT;   // even: CTA-pair kernels
   *out_plan = p;
   return TUBER_OK;
 }
@@ -1263,6 +1335,11 @@ void tuber_plan_destroy(TuberPlan* p) {
   for (auto& kv : p->taps) if (kv.second.keep) cudaFree(kv.second.keep);
   for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+  for (int k = 0; k < TuberPlan::NUM_SIDE; ++k) {
+    if (p->side[k]) cudaStreamDestroy(p->side[k]);
+    if (p->ev_fork[k]) cudaEventDestroy(p->ev_fork[k]);
+    if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]);
+  }
   if (p->ws) cudaFree(p->ws);
   if (p->in_lut) cudaFree(p->in_lut);
   if (p->u8_clip) cudaFree(p->u8_clip);
@@ -1340,10 +1417,23 @@ int tuber_forward(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev,
     for (auto& e : p->ev) CK(cudaEventCreate(&e));
     p->ev_valid = true;
   }
+  // side branches (position codes, class-branch encoder) on their own streams, except in the modes that time or copy per launch
+  const bool overlap = !p->no_overlap && !p->profiling && !p->debug_keep && !p->kprof;
+  if (overlap && !p->side_valid) {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // lo = least urgent (numerically largest), hi = most urgent
+    for (int k = 0; k < TuberPlan::NUM_SIDE; ++k) {
+      CK(cudaStreamCreateWithPriority(&p->side[k], cudaStreamNonBlocking, lo));
+      CK(cudaEventCreateWithFlags(&p->ev_fork[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&p->ev_join[k], cudaEventDisableTiming));
+    }
+    p->side_valid = true;
+  }
   Ctx cx{p};
   cx.dry = false;
   cx.ws.base = p->ws; cx.ws.cap = p->ws_cap;
   cx.st = st;
+  cx.overlap = overlap;
   p->kp_used = 0;
   const bool graph = p->use_graph && !p->profiling && !p->debug_keep && !p->kprof;
   if (!graph) {
@@ -1367,9 +1457,15 @@ int tuber_forward(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev,
   cap.dry = false;
   cap.ws.base = p->ws; cap.ws.cap = p->ws_cap;
   cap.st = st;
+  cap.overlap = overlap;
   // record on a private stream (the caller's may be the legacy default stream, which cannot capture);
-  // the instantiated graph is launched on the caller's stream
-  if (!p->cap_stream) CK(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+  // the instantiated graph is launched on the caller's stream.  Most urgent priority: the main chain's kernel nodes go in front of
+  // the side branches' (least urgent streams) whenever both have CTAs to place.
+  if (!p->cap_stream) {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&p->cap_stream, cudaStreamNonBlocking, hi));
+  }
   cap.st = p->cap_stream;
   cudaGraph_t graph_obj = nullptr;
   CK(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
