@@ -105,7 +105,8 @@ def test_gemm_tc_fused2_pair_512(abi, monkeypatch, m, k, kb, with_res):
     test_gemm_tc_fused2(abi, m, k, kb, 512, 128, with_res)
 
 
-@pytest.mark.parametrize("m,n,k,act", [(90, 3, 256, 0), (90, 4, 256, 2), (720, 80, 256, 0), (8, 2, 2048, 0), (333, 256, 64, 1)])
+@pytest.mark.parametrize("m,n,k,act", [(90, 3, 256, 0), (90, 4, 256, 2), (720, 80, 256, 0), (8, 2, 2048, 0), (333, 256, 64, 1),
+                                       (15360, 22, 256, 0), (15361, 4, 256, 2), (2049, 3, 256, 1), (3, 5, 1024, 0)])
 def test_sgemm(abi, m, n, k, act):
     a = torch.randn(m, k, device="cuda")
     w = torch.randn(n, k, device="cuda") / math.sqrt(k)

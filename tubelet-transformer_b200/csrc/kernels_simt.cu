@@ -876,22 +876,39 @@ cudaError_t launch_pool_mix(const void* xt_split, const float* U, void* y_split,
   return launch_pdl(pool_mix_kernel<8>, dim3(B * HW), dim3(256), 0, st, xt_split, U, y_split, B, Tf, HW, group_stride);
 }
 
-// AdaptiveAvgPool3d(1) over all positions (tuber_ava.py:48,124): split [B,N,C] -> fp32 [B,C]
-__global__ void global_avgpool_kernel(const void* __restrict__ in, float* __restrict__ out, int N, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  int b = blockIdx.y;
-  if (c >= C) return;
-  float acc = 0.f;
-  for (int i = 0; i < N; ++i) {
-    const __nv_bfloat16* hi = split_hi(in, (long long)b * N + i, C);
-    acc += __bfloat162float(hi[c]) + __bfloat162float(hi[C + c]);
+// AdaptiveAvgPool3d(1) over all positions (tuber_ava.py:48,124): split [B,N,C] -> fp32 [B,C].  A CTA = (clip, 64 channels):
+// 16 lanes x 4 channels (8-byte loads of each plane) x 16 row groups, every row group summing its rows i = g, g+16, ... in order,
+// then the 16 partial sums are added in order -- 16 independent load chains per channel instead of one thread walking all N rows
+// (53 us for the JHMDB head's 512 rows x 2048 channels per clip).
+__global__ void __launch_bounds__(256)
+global_avgpool_kernel(const void* __restrict__ in, float* __restrict__ out, int N, int C) {
+  __shared__ float4 part[16][16];
+  const int cq = threadIdx.x & 15, g = threadIdx.x >> 4;
+  const int c = blockIdx.x * 64 + cq * 4, b = blockIdx.y;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+#pragma unroll 4
+    for (int i = g; i < N; i += 16) {
+      const __nv_bfloat16* hi = split_hi(in, (long long)b * N + i, C) + c;
+      const float4 v = load_split4(hi, hi + C);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
   }
-  out[(long long)b * C + c] = acc / (float)N;
+  part[g][cq] = acc;
+  __syncthreads();
+  if (g == 0 && c < C) {
+    float4 t = part[0][cq];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) { const float4 u = part[j][cq]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    const float inv = 1.f / (float)N;
+    *reinterpret_cast<float4*>(out + (long long)b * C + c) = make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv);
+  }
 }
 
 cudaError_t launch_global_avgpool(const void* in_split, float* out, int B, int N, int C, cudaStream_t st) {
-  dim3 grid(ceil_div(C, 128), B);
-  global_avgpool_kernel<<<grid, 128, 0, st>>>(in_split, out, N, C);
+  if (C % 4 != 0) return cudaErrorInvalidValue;
+  dim3 grid(ceil_div(C, 64), B);
+  global_avgpool_kernel<<<grid, 256, 0, st>>>(in_split, out, N, C);
   return cudaGetLastError();
 }
 
@@ -1007,13 +1024,18 @@ sgemm_kernel(GemmArgs p) {
   }
 }
 
-__global__ void head_gemm_kernel(GemmArgs p);
+template <int LANES> __global__ void head_gemm_kernel(GemmArgs p);
+__global__ void head_gemm_rows_kernel(GemmArgs p);
 
 cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st) {
   if (a.K % 16 != 0 || a.Kb % 16 != 0 || a.M <= 0 || a.N <= 0 || a.Wf == nullptr) return cudaErrorInvalidValue;
   if (a.N <= 96 && !a.Ab && !a.res && !a.C2 && a.c_fmt == FMT_F32 && a.K <= 2048 && a.lda % 4 == 0) {
+    if (a.K == 256 && a.M >= 2048)                        // many rows: two rows of A in registers per 8 lanes, all N outputs each
+      return launch_pdl(head_gemm_rows_kernel, dim3(ceil_div((long long)ceil_div(a.M, 2) * 8, 256)), dim3(256), 0, st, a);
+    if ((long long)a.M * a.N <= 1024 && a.K >= 1024)      // few outputs, long K: a warp per output
+      return launch_pdl(head_gemm_kernel<32>, dim3(ceil_div((long long)a.M * a.N * 32, 256)), dim3(256), 0, st, a);
     const long long total = (long long)a.M * a.N * 8;
-    return launch_pdl(head_gemm_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, st, a);
+    return launch_pdl(head_gemm_kernel<8>, dim3(ceil_div(total, 256)), dim3(256), 0, st, a);
   }
   dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64));
   sgemm_kernel<<<grid, 256, 0, st>>>(a);
@@ -1123,14 +1145,16 @@ layernorm_kernel(LnArgs p) {
 // tuber_ava.py:64-73,121-125,141-142): one thread per output element, K <= 2048, A fp32 or split.  The tiled SIMT GEMM
 // above needs 64 x 64 tiles to be efficient and took ~20 us for these 0.1 - 30 MFLOP products.
 // =============================================================================================
+template <int LANES>   // lanes per output element: 8, or 32 for the products with few outputs and a long K (JHMDB clip head: 8 x 2, K = 2048)
 __global__ void __launch_bounds__(256)
 head_gemm_kernel(GemmArgs p) {
   pdl_trigger();
   pdl_wait();
-  // 8 lanes per output element: lane s takes the float4 chunks s, s+8, s+16, ... of the K axis, so the 8 lanes read 128
-  // contiguous bytes of the weight row and of the activation row per step; xor-shuffle reduction at the end
-  const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  const int s = threadIdx.x & 7;
+  // LANES lanes per output element: lane s takes the float4 chunks s, s+LANES, ... of the K axis, so the lanes read contiguous
+  // runs of the weight row and of the activation row per step; xor-shuffle reduction at the end
+  constexpr int SH = LANES == 32 ? 5 : 3;
+  const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> SH;
+  const int s = threadIdx.x & (LANES - 1);
   const bool live = idx < (long long)p.M * p.N;
   const int n = live ? (int)(idx % p.N) : 0;
   const long long m = live ? idx / p.N : 0;
@@ -1138,27 +1162,83 @@ head_gemm_kernel(GemmArgs p) {
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
   if (p.a_fmt == FMT_F32) {
     const float4* a = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.A) + m * p.lda);
-    for (int k = s; k < p.K / 4; k += 8) {
+#pragma unroll 4
+    for (int k = s; k < p.K / 4; k += LANES) {
       const float4 x = __ldg(a + k), y = __ldg(w + k);
       acc0 = fmaf(x.x, y.x, acc0); acc1 = fmaf(x.y, y.y, acc1); acc2 = fmaf(x.z, y.z, acc2); acc3 = fmaf(x.w, y.w, acc3);
     }
   } else {
     const __nv_bfloat16* h = split_hi(p.A, m, p.lda);
-    for (int k = s; k < p.K / 4; k += 8) {
+#pragma unroll 4
+    for (int k = s; k < p.K / 4; k += LANES) {
       const float4 x = load_split4(h + 4 * k, h + p.lda + 4 * k), y = __ldg(w + k);
       acc0 = fmaf(x.x, y.x, acc0); acc1 = fmaf(x.y, y.y, acc1); acc2 = fmaf(x.z, y.z, acc2); acc3 = fmaf(x.w, y.w, acc3);
     }
   }
   float v = (acc0 + acc1) + (acc2 + acc3);
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
+#pragma unroll
+  for (int o = 1; o < LANES; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if (!live || s != 0) return;
   if (p.scale) v *= __ldg(p.scale + n);
   if (p.shift) v += __ldg(p.shift + n);
   if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
   else if (p.act == ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
   reinterpret_cast<float*>(p.C)[m * p.ldc + n] = v;
+}
+
+// Many rows, K = 256 (the JHMDB heads over B x 6 x 320 = 15 360 query rows: class_fc N = 22, bbox_embed.layers.2 N = 4): 8 lanes own
+// TWO rows of A, held in registers (lane s: float4 chunks s, s+8, ..., of both rows), and walk all N weight rows -- A is read once
+// instead of N times and every weight chunk serves two rows (the one-output-per-8-lanes form moved 2 KB through L1 per output: 47 us
+// for N = 22).  Same summation order per output as head_gemm_kernel<8>.
+__global__ void __launch_bounds__(256)
+head_gemm_rows_kernel(GemmArgs p) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int CH = 8;                                     // float4 chunks per lane and row: K = 256
+  const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int s = threadIdx.x & 7;
+  const long long m0 = grp * 2;
+  const bool live0 = m0 < p.M, live1 = m0 + 1 < p.M;
+  const long long r0 = live0 ? m0 : 0, r1 = live1 ? m0 + 1 : r0;
+  float4 a0[CH], a1[CH];
+  if (p.a_fmt == FMT_F32) {
+    const float4* q0 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.A) + r0 * p.lda);
+    const float4* q1 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.A) + r1 * p.lda);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) { a0[j] = __ldg(q0 + s + 8 * j); a1[j] = __ldg(q1 + s + 8 * j); }
+  } else {
+    const __nv_bfloat16* h0 = split_hi(p.A, r0, p.lda);
+    const __nv_bfloat16* h1 = split_hi(p.A, r1, p.lda);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      a0[j] = load_split4(h0 + 4 * (s + 8 * j), h0 + p.lda + 4 * (s + 8 * j));
+      a1[j] = load_split4(h1 + 4 * (s + 8 * j), h1 + p.lda + 4 * (s + 8 * j));
+    }
+  }
+  float* c0 = reinterpret_cast<float*>(p.C) + r0 * p.ldc;
+  float* c1 = reinterpret_cast<float*>(p.C) + r1 * p.ldc;
+#pragma unroll 2
+  for (int n = 0; n < p.N; ++n) {
+    const float4* w = reinterpret_cast<const float4*>(p.Wf + (long long)n * p.K);
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f, y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const float4 wv = __ldg(w + s + 8 * j);
+      x0 = fmaf(a0[j].x, wv.x, x0); x1 = fmaf(a0[j].y, wv.y, x1); x2 = fmaf(a0[j].z, wv.z, x2); x3 = fmaf(a0[j].w, wv.w, x3);
+      y0 = fmaf(a1[j].x, wv.x, y0); y1 = fmaf(a1[j].y, wv.y, y1); y2 = fmaf(a1[j].z, wv.z, y2); y3 = fmaf(a1[j].w, wv.w, y3);
+    }
+    float u = (x0 + x1) + (x2 + x3), v = (y0 + y1) + (y2 + y3);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) { u += __shfl_xor_sync(0xffffffffu, u, o); v += __shfl_xor_sync(0xffffffffu, v, o); }
+    if (s == (n & 7)) {                                     // spread the stores over the 8 lanes
+      if (p.scale) { const float sc = __ldg(p.scale + n); u *= sc; v *= sc; }
+      if (p.shift) { const float sh = __ldg(p.shift + n); u += sh; v += sh; }
+      if (p.act == ACT_RELU) { u = fmaxf(u, 0.f); v = fmaxf(v, 0.f); }
+      else if (p.act == ACT_SIGMOID) { u = 1.f / (1.f + expf(-u)); v = 1.f / (1.f + expf(-v)); }
+      if (live0) c0[n] = u;
+      if (live1) c1[n] = v;
+    }
+  }
 }
 
 cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t st) {
