@@ -162,6 +162,14 @@ def test_stem(abi, dims):
     assert _rel(got, refp) < 3e-5
 
 
+@pytest.mark.parametrize("dims", [(1, 4, 32, 32), (2, 3, 45, 70), (1, 3, 130, 256), (2, 2, 256, 256), (1, 2, 40, 341), (1, 1, 20, 258),
+                                  (1, 1, 18, 520), (3, 5, 70, 64)])
+def test_stem_two_rows_per_batch(abi, monkeypatch, dims):
+    """stem_tc3_kernel (TUBER_STEM3 is read per call): two conv rows per accumulator batch sharing their A K-steps"""
+    monkeypatch.setenv("TUBER_STEM3", "1")
+    test_stem(abi, dims)
+
+
 @pytest.mark.parametrize("c", [256, 2048])
 def test_layernorm(abi, c):
     from tuber_b200 import _lib

@@ -910,6 +910,383 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
   }
 }
 
+// =============================================================================================================
+// stem_tc3_kernel: the pair kernel above with TWO conv rows per accumulator batch, sharing their A K-steps.
+//
+// A K-step (16 elements = 8 TMEM columns) of plane (c, kt) holds two filter-row groups = 8 pixels of each of TWO consecutive input
+// rows (y, y + 1), y = 2 oh - 3 + 2 k for K-step k of conv row oh.  Conv row oh + 1 reads input rows two further down, so ITS K-step
+// k is conv row oh's K-step k + 1: the rows (oh, oh + 1) together need 5 distinct K-steps per plane, not 8.  The builders therefore
+// write ONE plane per stage -- 5 K-steps, [hi 40 columns | mid 40 columns] -- and the MMA warp multiplies K-steps r .. r + 3 of it with
+// the plane's four weight K-steps into the accumulator of row r (two independent accumulators, issued alternately).  The stem is
+// bound by the A build (shared-memory reads + tcgen05.st; tensor pipe 42 % busy in stem_tc2_kernel): this cuts the build work per
+// conv row to 5/8 with the same MMAs.  Tensor memory: 2 accumulator sets x 2 rows x 64 columns + 3 stages x 80 columns = 496.
+// The input ring keeps 12 row slots per plane (a batch reads rows 2 oh - 3 .. 2 oh + 6 and stages 2 oh + 6 .. 2 oh + 9 for the next).
+// MEASURED (profiles/r2_stem3_experiment.json): correct, and NOT faster than stem_tc2_kernel (0.99 - 1.02 ms against 0.95 - 0.99 ms
+// at 8 clips 32 x 256 x 256): knocking out one role at a time shows the A build is only 0.17 ms of the kernel; the skeleton of
+// cluster-wide stage handshakes alone (every role's work removed) takes 0.37 ms.  Kept behind TUBER_STEM3=1 with its tests.
+// =============================================================================================================
+namespace p3 {
+constexpr int RB = 2;                        // conv rows per batch
+constexpr int KSTEPS = RB + 3;               // distinct A K-steps of a plane per batch
+constexpr int HALF_COLS = KSTEPS * 8;        // 40 TMEM columns per precision part
+constexpr int STAGE3_COLS = 2 * HALF_COLS;   // 80: [hi | mid] of one plane
+constexpr int A3_STAGES = 3;
+constexpr int ACC3_COLS = RB * 64;           // one accumulator set
+constexpr int A_COL0_3 = 2 * ACC3_COLS;      // 256
+static_assert(A_COL0_3 + A3_STAGES * STAGE3_COLS <= TMEM_COLS, "tensor memory budget");
+constexpr int RING3_SLOTS = 12;
+constexpr int RING3_PLANE_BYTES = 9 * RING3_SLOTS * RING_PAIRS * 4;   // 57024 per precision part
+constexpr int OFF_W3 = 0;
+constexpr int OFF_ROW3 = OFF_W3 + W_BYTES;
+constexpr int OFF_RING_HI3 = OFF_ROW3 + p2::ROW2_BYTES;
+constexpr int OFF_RING_MID3 = OFF_RING_HI3 + RING3_PLANE_BYTES;
+constexpr int OFF_BAR3 = OFF_RING_MID3 + ((RING3_PLANE_BYTES + 127) / 128) * 128;
+constexpr int OFF_SS3 = OFF_BAR3 + 128;
+constexpr int SMEM3_BYTES = OFF_SS3 + 512;
+static_assert(SMEM3_BYTES <= 232448, "shared memory budget");
+static_assert(OFF_RING_HI3 % 128 == 0, "alignment");
+constexpr int NBATCH = (p2::UNIT_ROWS + RB - 1) / RB;   // 17 batches walk 34 rows: the last one is a dummy
+}  // namespace p3
+
+TB_DEVINL void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+TB_DEVINL void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+stem_tc3_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
+  using namespace p2;
+  using namespace p3;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bar = sb + OFF_BAR3;
+  auto full_bar = [&](int s) { return bar + 8u * s; };                       // leader: A stage written by both CTAs' builders
+  auto empty_bar = [&](int s) { return bar + 8u * (A3_STAGES + s); };        // each CTA: A stage consumed by the MMAs
+  auto tfull_bar = [&](int s) { return bar + 8u * (2 * A3_STAGES + s); };    // each CTA: accumulator set complete
+  auto tempty_bar = [&](int s) { return bar + 8u * (2 * A3_STAGES + 2 + s); };  // leader: accumulator set drained by both epilogues
+  const uint32_t w_bar = bar + 8u * (2 * A3_STAGES + 4);
+  const uint32_t tmem_slot = bar + 8u * (2 * A3_STAGES + 5);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR3 + 8 * (2 * A3_STAGES + 5));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int rb_n = (p.H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+  const int ct_n = p.ct_n > 1 ? p.ct_n : 1;                        // column tiles of a conv row, as in stem_tc2_kernel
+  const int units = p.B * p.T * rb_n * ct_n;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int steps = (units + 1) / 2;
+
+  if (threadIdx.x == 0) {
+    if (sb & 1023u) __trap();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    for (int s = 0; s < A3_STAGES; ++s) {
+      mbar_init(full_bar(s), 2 * NBUILD / 32);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);
+    }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= filter half load (both CTAs) + MMA issuer (leader CTA only) =================
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, W_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_3d(sb + OFF_W3 + kb * W_KB_BYTES, &tmW, w_bar, kb * 64, (int)rank * NCH, 0);
+    }
+    __syncwarp();
+    if (rank == 0) {
+      mbar_wait(w_bar, 0);
+      constexpr uint32_t idesc = make_idesc(256, NCH2);
+      const uint64_t w_desc0 = make_smem_desc(sb + OFF_W3);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int i = pair; i < steps; i += npairs) {
+        for (int bch = 0; bch < NBATCH; ++bch, ++it) {
+          const int as = it & 1;
+          mbar_wait_cluster(tempty_bar(as), ((it >> 1) & 1) ^ 1);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACC3_COLS);
+#pragma unroll 1
+          for (int plane = 0; plane < KB; ++plane) {
+            mbar_wait_cluster(full_bar(stage), phase);
+            tcgen05_fence_after();
+            if (elect_one()) {
+              const uint32_t a0 = tmem_base + (uint32_t)(A_COL0_3 + stage * STAGE3_COLS);
+              const uint64_t w_hi = w_desc0 + (uint64_t)(plane * (W_KB_BYTES >> 4)), w_mid = w_hi + ((NCH * 128) >> 4);
+              const uint32_t first_k = plane == 0 ? 0u : 1u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {                     // row r reads K-steps r .. r + 3 of the plane
+                  const uint32_t a_hi = a0 + (uint32_t)(8 * (k + r)), a_mid = a_hi + HALF_COLS, d = tmem_d + (uint32_t)(r * NCH2);
+                  umma2_bf16_ts(d, a_mid, w_hi + 2 * k, idesc, k == 0 ? first_k : 1u);
+                  umma2_bf16_ts(d, a_hi, w_mid + 2 * k, idesc, 1u);
+                  umma2_bf16_ts(d, a_hi, w_hi + 2 * k, idesc, 1u);
+                }
+              }
+              umma2_commit_mc(empty_bar(stage));
+              if (plane == KB - 1) umma2_commit_mc(tfull_bar(as));
+            }
+            __syncwarp();
+            if (++stage == A3_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp <= 4) {
+    // ================= epilogue: BN + ReLU + 3x3/s2 max pool, the batch's two rows one after the other =================
+    const int lg = warp & 3;
+    const int m = lg * 32 + lane;
+    const int et = threadIdx.x - 32;
+    float* s_sc = reinterpret_cast<float*>(smem + OFF_SS3);
+    float* s_sh = s_sc + NCH2;
+    if (et < NCH2) {
+      s_sc[et] = __ldg(p.scale + et);
+      s_sh[et] = __ldg(p.shift + et);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int pw = et >> 1, hq = et & 1;
+    const uint32_t rowb = sb + OFF_ROW3;
+    auto rswz = [&](int pos, int chunk) { return rowb + (uint32_t)pos * 256u + (uint32_t)((((chunk ^ pos) & 7) | (chunk & 8)) << 4); };
+    const uint32_t tempty_remote0 = mapa_rank(tempty_bar(0), 0), tempty_remote1 = mapa_rank(tempty_bar(1), 0);
+    int it = 0;
+    for (int i = pair; i < steps; i += npairs) {
+      const int u = min(2 * i + (int)rank, units - 1);
+      const int ct = u % ct_n, ur = u / ct_n;
+      const int rb = ur % rb_n, bt = ur / rb_n;
+      const int r0 = rb * ROWS_PER_UNIT;
+      const int c0 = ct_n > 1 ? 126 * ct - 1 : 0;
+      const int pwg = (ct_n > 1 ? 63 * ct : 0) + pw;
+      const bool pw_ok = pw < (ct_n > 1 ? 63 : 64) && pwg < p.W2;
+      float4 run[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) run[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int bch = 0; bch < NBATCH; ++bch, ++it) {
+        const int as = it & 1;
+        mbar_wait(tfull_bar(as), (it >> 1) & 1);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int rr = 0; rr < RB; ++rr) {
+          const int r = RB * bch + rr;
+          const int oh = r0 - 1 + r;
+          const bool valid = r < UNIT_ROWS && oh >= 0 && oh < p.H1;  // uniform over the CTA
+          if (valid) {
+            const uint32_t t0 = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * ACC3_COLS + rr * NCH2);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t part[32];
+              tmem_ld32(t0 + 32 * hh, part);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 sc = *reinterpret_cast<const float4*>(s_sc + 32 * hh + 4 * q), sh = *reinterpret_cast<const float4*>(s_sh + 32 * hh + 4 * q);
+                uint4 o;
+                o.x = __float_as_uint(fmaxf(fmaf(__uint_as_float(part[4 * q]), sc.x, sh.x), 0.f));
+                o.y = __float_as_uint(fmaxf(fmaf(__uint_as_float(part[4 * q + 1]), sc.y, sh.y), 0.f));
+                o.z = __float_as_uint(fmaxf(fmaf(__uint_as_float(part[4 * q + 2]), sc.z, sh.z), 0.f));
+                o.w = __float_as_uint(fmaxf(fmaf(__uint_as_float(part[4 * q + 3]), sc.w, sh.w), 0.f));
+                sts128(rswz(m, 8 * hh + q), o);
+              }
+            }
+          }
+          if (rr == RB - 1) {                                      // both rows of the set have left tensor memory
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(as ? tempty_remote1 : tempty_remote0);
+          }
+          if (!valid) continue;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float4 hm[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) hm[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pw_ok) {
+#pragma unroll
+            for (int dc = -1; dc <= 1; ++dc) {
+              const int cc = 2 * pwg + dc;
+              if (cc < 0 || cc >= p.W1) continue;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const uint4 v = lds128(rswz(cc - c0, 2 * e + hq));
+                hm[e].x = fmaxf(hm[e].x, __uint_as_float(v.x)); hm[e].y = fmaxf(hm[e].y, __uint_as_float(v.y));
+                hm[e].z = fmaxf(hm[e].z, __uint_as_float(v.z)); hm[e].w = fmaxf(hm[e].w, __uint_as_float(v.w));
+              }
+            }
+          }
+          const bool odd = oh & 1;
+          const bool emit = r > 0 && (odd || oh == p.H1 - 1);
+          if (!odd || r > 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              run[e].x = fmaxf(run[e].x, hm[e].x); run[e].y = fmaxf(run[e].y, hm[e].y);
+              run[e].z = fmaxf(run[e].z, hm[e].z); run[e].w = fmaxf(run[e].w, hm[e].w);
+            }
+          }
+          if (emit && pw_ok) {
+            const int ph = oh >> 1;
+            const long long vox = ((long long)bt * p.H2 + ph) * p.W2 + pwg;
+            __nv_bfloat16* hi = split_hi(p.pooled, vox, 64) + hq * 4;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) store_split4(hi + 8 * e, hi + 64 + 8 * e, run[e]);
+          }
+          if (odd) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) run[e] = hm[e];
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+      }
+    }
+  } else {
+    // ================= ring staging + A builders: warps 5-8 write the hi part of a stage, warps 9-12 the mid part =================
+    const int bt_ = threadIdx.x - 160;                             // 0..255
+    const int m = (warp & 3) * 32 + lane;
+    const int gh = (warp - 5) >> 2;                                // 0: hi, 1: mid
+    const uint32_t ring_hi = sb + OFF_RING_HI3, ring_mid = sb + OFF_RING_MID3;
+    for (int i = bt_; i < RING3_PLANE_BYTES / 4; i += NBUILD) {
+      sts32(ring_hi + 4u * i, 0u);
+      sts32(ring_mid + 4u * i, 0u);
+    }
+    const uint32_t ring_mine = gh ? ring_mid : ring_hi;
+    const uint32_t a_dst = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(A_COL0_3 + gh * HALF_COLS);
+    uint32_t full_remote[A3_STAGES];
+#pragma unroll
+    for (int s = 0; s < A3_STAGES; ++s) full_remote[s] = mapa_rank(full_bar(s), 0);
+    mbar_wait(w_bar, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = pair; i < steps; i += npairs) {
+      const int u = min(2 * i + (int)rank, units - 1);
+      const int ct = u % ct_n, ur = u / ct_n;
+      const int rb = ur % rb_n, bt = ur / rb_n;
+      const int b = bt / p.T, t = bt % p.T;
+      const int first = rb * ROWS_PER_UNIT - 1;
+      const int iw0 = 2 * (ct_n > 1 ? 126 * ct - 1 : 0) - 3;
+      const int spr = bt_ & 127, srr = bt_ >> 7;
+      const int xpr = 128 + (bt_ & 3), xrow = bt_ >> 2;
+      auto col_ok = [&](int j) { return iw0 + j >= 0 && iw0 + j < p.W; };
+      const bool ok0 = col_ok(2 * spr), ok1 = col_ok(2 * spr + 1), xok0 = col_ok(2 * xpr), xok1 = col_ok(2 * xpr + 1);
+      const float* xb = p.x + (long long)b * 3 * p.T * p.H * p.W + iw0;
+      const long long plane_stride = (long long)p.H * p.W;
+      auto in_val = [&](int plane, int ih, int j, bool ok) -> float {
+        const int c = plane / 3, f = t + plane % 3 - 1;
+        if (!ok || f < 0 || f >= p.T || ih < 0 || ih >= p.H) return 0.f;
+        return __ldg(xb + ((long long)c * p.T + f) * plane_stride + (long long)ih * p.W + j);
+      };
+      auto slot_of = [&](int ih) { return (ih + 2 * RING3_SLOTS) % RING3_SLOTS; };   // ih >= -5
+      auto store_pair = [&](int plane, int ih, int pr, float v0, float v1) {
+        __nv_bfloat16 h0, m0, h1, m1;
+        split_bf16(v0, h0, m0);
+        split_bf16(v1, h1, m1);
+        const uint32_t off = (uint32_t)(((plane * RING3_SLOTS + slot_of(ih)) * RING_PAIRS + pr) * 4);
+        sts32(ring_hi + off, pack_bf16x2(h0, h1));
+        sts32(ring_mid + off, pack_bf16x2(m0, m1));
+      };
+      asm volatile("bar.sync 2, 256;" ::: "memory");               // previous unit's readers are done
+      const int y0 = 2 * first - 3;                                // rows y0 .. y0 + 8 feed the first batch (y0 + 9 only meets zero weights)
+      for (int plane = 0; plane < 9; ++plane) {
+        float v0[5], v1[5];
+#pragma unroll
+        for (int g2 = 0; g2 < 5; ++g2) {
+          const int rr = 2 * g2 + srr;
+          v0[g2] = in_val(plane, y0 + rr, 2 * spr, rr < 9 && ok0);
+          v1[g2] = in_val(plane, y0 + rr, 2 * spr + 1, rr < 9 && ok1);
+        }
+#pragma unroll
+        for (int g2 = 0; g2 < 5; ++g2)
+          if (2 * g2 + srr < 9) store_pair(plane, y0 + 2 * g2 + srr, spr, v0[g2], v1[g2]);
+      }
+      for (int idx = xrow; idx < 81; idx += 64) {
+        const int plane = idx / 9, ih = y0 + idx % 9;
+        store_pair(plane, ih, xpr, in_val(plane, ih, 2 * xpr, xok0), in_val(plane, ih, 2 * xpr + 1, xok1));
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      for (int bch = 0; bch < NBATCH; ++bch) {
+        const int oh = first + RB * bch;                            // the batch's first conv row
+        // rows 2 oh + 6 .. 2 oh + 9 for the next batch, fetched while this one is built
+        float pf0[18], pf1[18], px0 = 0.f, px1 = 0.f;
+        const bool more = bch + 1 < NBATCH;
+        if (more) {
+#pragma unroll
+          for (int plane = 0; plane < 9; ++plane) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              pf0[2 * plane + h2] = in_val(plane, 2 * oh + 6 + 2 * h2 + srr, 2 * spr, ok0);
+              pf1[2 * plane + h2] = in_val(plane, 2 * oh + 6 + 2 * h2 + srr, 2 * spr + 1, ok1);
+            }
+          }
+          if (xrow < 36) {
+            px0 = in_val(xrow >> 2, 2 * oh + 6 + (xrow & 3), 2 * xpr, xok0);
+            px1 = in_val(xrow >> 2, 2 * oh + 6 + (xrow & 3), 2 * xpr + 1, xok1);
+          }
+        }
+        uint32_t slot_off[2 * KSTEPS];                              // group g = input row 2 oh - 3 + g
+#pragma unroll
+        for (int g = 0; g < 2 * KSTEPS; ++g) slot_off[g] = (uint32_t)((slot_of(2 * oh - 3 + g) * RING_PAIRS + m) * 4);
+#pragma unroll 1
+        for (int plane = 0; plane < 9; ++plane) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t pl = ring_mine + (uint32_t)(plane * RING3_SLOTS * RING_PAIRS * 4);
+          uint32_t v[8 * KSTEPS];
+#pragma unroll
+          for (int g = 0; g < 2 * KSTEPS; ++g) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[4 * g + e] = lds32(pl + slot_off[g] + 4u * e);
+          }
+          tmem_st32(a_dst + (uint32_t)(stage * STAGE3_COLS), v);
+          tmem_st8(a_dst + (uint32_t)(stage * STAGE3_COLS + 32), v + 32);
+          tmem_st_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(full_remote[stage]);
+          if (++stage == A3_STAGES) { stage = 0; phase ^= 1; }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (more) {
+#pragma unroll
+          for (int plane = 0; plane < 9; ++plane) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) store_pair(plane, 2 * oh + 6 + 2 * h2 + srr, spr, pf0[2 * plane + h2], pf1[2 * plane + h2]);
+          }
+          if (xrow < 36) store_pair(xrow >> 2, 2 * oh + 6 + (xrow & 3), xpr, px0, px1);
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
 // reference filter (64,3,3,7,7) = [oc][441] fp32 -> packed split [2][64][576] bf16 in the kernel's K order
 __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -940,6 +1317,7 @@ static cudaError_t init_once() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2::SMEM2_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2::SMEM2_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p3::SMEM3_BYTES);
     return e;
   });
 }
@@ -984,7 +1362,10 @@ cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale
     int pairs = device_num_sms() / 2;
     if (pairs > (units + 1) / 2) pairs = (units + 1) / 2;
     if (pairs < 1) pairs = 1;
+    const char* s3 = getenv("TUBER_STEM3");                          // read per call: the tests compare both forms in one process
+    const bool stem3 = s3 && s3[0] == '1';
     if (frames_u8) stem_tc2_kernel<true><<<2 * pairs, NUM_THREADS, p2::SMEM2_BYTES, st>>>(tmW, p);
+    else if (stem3) stem_tc3_kernel<<<2 * pairs, NUM_THREADS, p3::SMEM3_BYTES, st>>>(tmW, p);
     else stem_tc2_kernel<false><<<2 * pairs, NUM_THREADS, p2::SMEM2_BYTES, st>>>(tmW, p);
     return cudaGetLastError();
   }
