@@ -7,8 +7,8 @@
 // GEMM view per tile: M = 128 consecutive output columns of one conv row (b, t, oh), N = 32 output channels (a CTA
 // owns one half of the 64 channels so that its packed filter bank, 72 KB, stays resident in shared memory),
 // K = 576 = 9 k-blocks x 8 groups x 8: k-block = input plane (c, kt), group = filter row kh (group 7 is all zero),
-// and a group holds the 7 taps kw = 0..6 of that filter row plus one zero tap.  The patch row of a group is simply 8
-// consecutive pixels in[c, t+kt-1, 2*oh+kh-3, 2*ow-3 .. 2*ow+4], so the A operand is built by threads from a ring of
+// and a group holds one zero tap followed by the 7 taps kw = 0..6 of that filter row.  The patch row of a group is simply 8
+// consecutive pixels in[c, t+kt-1, 2*oh+kh-3, 2*ow-4 .. 2*ow+3], so the A operand is built by threads from a ring of
 // input rows kept in shared memory:
 //
 //   ring      two planar arrays (bf16 hi, bf16 mid) of [9 (c,kt) planes][8 row slots][132 pixel pairs]; a new conv row
@@ -66,6 +66,7 @@ struct Params {
   int B, T, H, W, H1, W1, H2, W2;
   int fuse_pool;
   int ct_n;                                 // stem_tc2_kernel: column tiles per conv row (1 when W1 <= 128, see there)
+  int vec4;                                 // stem_tc2_kernel: fp32 rows staged with 16-byte loads (W % 4 == 0, one column tile, x 16-byte aligned)
 };
 
 TB_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -158,6 +159,7 @@ TB_DEVINL uint2 lds64(uint32_t addr) {
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
   return v;
 }
+TB_DEVINL void sts64(uint32_t addr, uint2 v) { asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory"); }
 TB_DEVINL void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 // K-major, 128B-swizzle shared-memory matrix descriptor (same encoding as gemm_tc.cu)
@@ -398,7 +400,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       const int b = bt / p.T, t = bt % p.T;
       int first, r0, r1;
       unit_rows(rb, first, r0, r1);
-      const int iw0 = 2 * owb * 128 - 3;
+      const int iw0 = 2 * owb * 128 - 4;                            // tap 0 is the zero tap (see stem_pack_weight_kernel): pairs start at even columns
       // ring pixel (plane, ih, j) <- x[b, c, t+kt-1, ih, iw0+j], 0 outside the clip (the conv's zero padding).
       // Staging map: thread = (pixel pair spr in [0,128), row parity srr); the 4 pairs 128..131 of each row are a
       // second, mostly idle step.  Row pointers are warp-uniform, column validity is a per-thread constant.
@@ -802,7 +804,7 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
       const int rb = ur % rb_n, bt = ur / rb_n;
       const int b = bt / p.T, t = bt % p.T;
       const int first = rb * ROWS_PER_UNIT - 1, r1 = first + UNIT_ROWS;
-      const int iw0 = 2 * (ct_n > 1 ? 126 * ct - 1 : 0) - 3;        // input column of tap 0 of the tile's first conv column
+      const int iw0 = 2 * (ct_n > 1 ? 126 * ct - 1 : 0) - 4;        // input column of tap 0 (the zero tap) of the tile's first conv column: even
       const int spr = bt_ & 127, srr = bt_ >> 7;
       const int xpr = 128 + (bt_ & 3), xrow = bt_ >> 2;
       auto col_ok = [&](int j) { return iw0 + j >= 0 && iw0 + j < p.W; };
@@ -830,7 +832,41 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
         sts32(ring_hi + off, pack_bf16x2(h0, h1));
         sts32(ring_mid + off, pack_bf16x2(m0, m1));
       };
+      // Vector form of the staging (fp32 clip, W % 4 == 0, one column tile): a thread moves QUADS -- four pixels = two ring pairs =
+      // one aligned 16-byte global load, two packed hi / mid splits, one 8-byte store into each ring -- instead of single pixels:
+      // quad q = columns 4q - 4 .. 4q - 1 of a row, 64 quads + 2 border quads per row; thread = (quad bt_ & 63, row selector bt_ >> 6).
+      const bool vec = !U8 && p.vec4 != 0;
+      const int vq = bt_ & 63, vsel = bt_ >> 6;
+      const bool vq_ok = vq >= 1 && 4 * vq <= p.W;                  // columns 4 vq - 4 .. 4 vq - 1 inside the row
+      const int xq = 64 + (bt_ & 1);
+      const bool xq_ok = 4 * xq <= p.W;
+      auto in_quad = [&](int plane, int ih, int q, bool ok) -> float4 {
+        const int c = plane / 3, f = t + plane % 3 - 1;
+        if (!ok || f < 0 || f >= p.T || ih < 0 || ih >= p.H) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return __ldg(reinterpret_cast<const float4*>(xb + ((long long)c * p.T + f) * plane_stride + (long long)ih * p.W + 4 * q));
+      };
+      auto store_quad = [&](int plane, int ih, int q, const float4& v) {
+        uint2 h, md;
+        split_bf16x2(v.x, v.y, h.x, md.x);
+        split_bf16x2(v.z, v.w, h.y, md.y);
+        const uint32_t off = (uint32_t)(((plane * 8 + (ih & 7)) * RING_PAIRS + 2 * q) * 4);
+        sts64(ring_hi + off, h);
+        sts64(ring_mid + off, md);
+      };
       asm volatile("bar.sync 2, 256;" ::: "memory");               // previous unit's readers are done
+      if (vec) {                                                     // rows 2*first-3 .. 2*first+3 of every plane: 63 (plane, row) combinations
+        for (int k = 0; k < 16; ++k) {
+          const int combo = 4 * k + vsel;
+          if (combo < 63) {
+            const int plane = combo / 7, ih = 2 * first - 3 + combo % 7;
+            store_quad(plane, ih, vq, in_quad(plane, ih, vq, vq_ok));
+          }
+        }
+        if (bt_ < 126) {
+          const int combo = bt_ >> 1, plane = combo / 7, ih = 2 * first - 3 + combo % 7;
+          store_quad(plane, ih, xq, in_quad(plane, ih, xq, xq_ok));
+        }
+      } else {
       for (int plane = 0; plane < 9; ++plane) {                     // rows 2*first-3 .. 2*first+3 of every plane
         float v0[4], v1[4];
 #pragma unroll
@@ -847,11 +883,20 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
         const int plane = xrow / 7, ih = 2 * first - 3 + xrow % 7;
         store_pair(plane, ih, xpr, in_val(plane, ih, 2 * xpr, xok0), in_val(plane, ih, 2 * xpr + 1, xok1));
       }
+      }
       asm volatile("bar.sync 2, 256;" ::: "memory");
       for (int oh = first; oh < r1; ++oh) {
         float pf0[9], pf1[9], px0 = 0.f, px1 = 0.f;
+        float4 pv[5], pxv = make_float4(0.f, 0.f, 0.f, 0.f);       // vector form: the 18 (plane, row) combinations of rows 2 oh + 4, 2 oh + 5
         const bool more = oh + 1 < r1;
-        if (more) {
+        if (more && vec) {
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int combo = 4 * k + vsel;
+            pv[k] = in_quad(combo >> 1, 2 * oh + 4 + (combo & 1), vq, vq_ok && combo < 18);
+          }
+          if (bt_ < 36) pxv = in_quad(bt_ >> 2, 2 * oh + 4 + ((bt_ >> 1) & 1), xq, xq_ok);
+        } else if (more) {
 #pragma unroll
           for (int plane = 0; plane < 9; ++plane) {
             pf0[plane] = in_val(plane, 2 * oh + 4 + srr, 2 * spr, ok0);
@@ -891,7 +936,14 @@ stem_tc2_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (more) {
+        if (more && vec) {
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int combo = 4 * k + vsel;
+            if (combo < 18) store_quad(combo >> 1, 2 * oh + 4 + (combo & 1), vq, pv[k]);
+          }
+          if (bt_ < 36) store_quad(bt_ >> 2, 2 * oh + 4 + ((bt_ >> 1) & 1), xq, pxv);
+        } else if (more) {
 #pragma unroll
           for (int plane = 0; plane < 9; ++plane) store_pair(plane, 2 * oh + 4 + srr, spr, pf0[plane], pf1[plane]);
           if (xrow < 18) store_pair(xrow >> 1, 2 * oh + 4 + (xrow & 1), xpr, px0, px1);
@@ -1183,7 +1235,7 @@ stem_tc3_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
       const int rb = ur % rb_n, bt = ur / rb_n;
       const int b = bt / p.T, t = bt % p.T;
       const int first = rb * ROWS_PER_UNIT - 1;
-      const int iw0 = 2 * (ct_n > 1 ? 126 * ct - 1 : 0) - 3;
+      const int iw0 = 2 * (ct_n > 1 ? 126 * ct - 1 : 0) - 4;
       const int spr = bt_ & 127, srr = bt_ >> 7;
       const int xpr = 128 + (bt_ & 3), xrow = bt_ >> 2;
       auto col_ok = [&](int j) { return iw0 + j >= 0 && iw0 + j < p.W; };
@@ -1292,7 +1344,9 @@ __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * KTOT) return;
   const int oc = i / KTOT, k = i % KTOT, plane = k / 64, kh = (k % 64) / 8, kw = k % 8;
-  const float v = (kh < 7 && kw < 7) ? w[oc * 441 + (plane * 7 + kh) * 7 + kw] : 0.f;
+  // tap slot 0 of a group is the zero tap, slots 1..7 are kw = 0..6: a group's 8 pixels then start at the EVEN input column
+  // 2 ow - 4, so the ring's pixel pairs are aligned pairs of the input row (8- / 16-byte global loads in the staging threads)
+  const float v = (kh < 7 && kw >= 1) ? w[oc * 441 + (plane * 7 + kh) * 7 + kw - 1] : 0.f;
   __nv_bfloat16 hi, mid;
   split_bf16(v, hi, mid);
   out[i] = hi;
@@ -1357,7 +1411,9 @@ cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale
   if (fuse) {                                                      // CTA pairs (cta_group::2), pool fused
     const int W2 = (W1 - 1) / 2 + 1;
     const int ct_n = W1 <= 128 ? 1 : (W2 + 62) / 63;
-    Params p{frames_u8, lut, x, scale, shift, pooled, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, W2, 1, ct_n};
+    const char* nv = getenv("TUBER_STEM_NO_VEC");                    // read per call: scalar staging (the tests' cross-check)
+    const int vec4 = (!frames_u8 && ct_n == 1 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && !(nv && nv[0] == '1')) ? 1 : 0;
+    Params p{frames_u8, lut, x, scale, shift, pooled, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, W2, 1, ct_n, vec4};
     const int units = B * T * ((H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT) * ct_n;
     int pairs = device_num_sms() / 2;
     if (pairs > (units + 1) / 2) pairs = (units + 1) / 2;
@@ -1379,7 +1435,7 @@ cudaError_t launch_stem_conv(const float* x, const void* wpk, const float* scale
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
   }
-  Params p{nullptr, nullptr, x, scale, shift, fuse ? pooled : nullptr, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, (W1 - 1) / 2 + 1, fuse ? 1 : 0, 1};
+  Params p{nullptr, nullptr, x, scale, shift, fuse ? pooled : nullptr, B, T, H, W, H1, W1, (H1 - 1) / 2 + 1, (W1 - 1) / 2 + 1, fuse ? 1 : 0, 1, 0};
   const int units = B * T * ((W1 + 127) / 128) * ((H1 + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT);
   int pairs = device_num_sms() / 2;
   if (pairs > units) pairs = units;
