@@ -760,6 +760,7 @@ __global__ void tpool_kernel(const void* __restrict__ in, void* __restrict__ out
   int to = (int)(r % Tout);
   long long b = r / Tout;
   float4 a = is_max ? make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
   for (int i = 0; i < k; ++i) {
     long long row = (b * Tin + (long long)to * k + i) * HW + p;
     const __nv_bfloat16* hi = split_hi(in, row, C) + c4 * 4;
@@ -1025,13 +1026,10 @@ sgemm_kernel(GemmArgs p) {
 }
 
 template <int LANES> __global__ void head_gemm_kernel(GemmArgs p);
-__global__ void head_gemm_rows_kernel(GemmArgs p);
 
 cudaError_t launch_sgemm(const GemmArgs& a, cudaStream_t st) {
   if (a.K % 16 != 0 || a.Kb % 16 != 0 || a.M <= 0 || a.N <= 0 || a.Wf == nullptr) return cudaErrorInvalidValue;
   if (a.N <= 96 && !a.Ab && !a.res && !a.C2 && a.c_fmt == FMT_F32 && a.K <= 2048 && a.lda % 4 == 0) {
-    if (a.K == 256 && a.M >= 2048)                        // many rows: two rows of A in registers per 8 lanes, all N outputs each
-      return launch_pdl(head_gemm_rows_kernel, dim3(ceil_div((long long)ceil_div(a.M, 2) * 8, 256)), dim3(256), 0, st, a);
     if ((long long)a.M * a.N <= 1024 && a.K >= 1024)      // few outputs, long K: a warp per output
       return launch_pdl(head_gemm_kernel<32>, dim3(ceil_div((long long)a.M * a.N * 32, 256)), dim3(256), 0, st, a);
     const long long total = (long long)a.M * a.N * 8;
@@ -1184,61 +1182,6 @@ head_gemm_kernel(GemmArgs p) {
   if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
   else if (p.act == ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
   reinterpret_cast<float*>(p.C)[m * p.ldc + n] = v;
-}
-
-// Many rows, K = 256 (the JHMDB heads over B x 6 x 320 = 15 360 query rows: class_fc N = 22, bbox_embed.layers.2 N = 4): 8 lanes own
-// TWO rows of A, held in registers (lane s: float4 chunks s, s+8, ..., of both rows), and walk all N weight rows -- A is read once
-// instead of N times and every weight chunk serves two rows (the one-output-per-8-lanes form moved 2 KB through L1 per output: 47 us
-// for N = 22).  Same summation order per output as head_gemm_kernel<8>.
-__global__ void __launch_bounds__(256)
-head_gemm_rows_kernel(GemmArgs p) {
-  pdl_trigger();
-  pdl_wait();
-  constexpr int CH = 8;                                     // float4 chunks per lane and row: K = 256
-  const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  const int s = threadIdx.x & 7;
-  const long long m0 = grp * 2;
-  const bool live0 = m0 < p.M, live1 = m0 + 1 < p.M;
-  const long long r0 = live0 ? m0 : 0, r1 = live1 ? m0 + 1 : r0;
-  float4 a0[CH], a1[CH];
-  if (p.a_fmt == FMT_F32) {
-    const float4* q0 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.A) + r0 * p.lda);
-    const float4* q1 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.A) + r1 * p.lda);
-#pragma unroll
-    for (int j = 0; j < CH; ++j) { a0[j] = __ldg(q0 + s + 8 * j); a1[j] = __ldg(q1 + s + 8 * j); }
-  } else {
-    const __nv_bfloat16* h0 = split_hi(p.A, r0, p.lda);
-    const __nv_bfloat16* h1 = split_hi(p.A, r1, p.lda);
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      a0[j] = load_split4(h0 + 4 * (s + 8 * j), h0 + p.lda + 4 * (s + 8 * j));
-      a1[j] = load_split4(h1 + 4 * (s + 8 * j), h1 + p.lda + 4 * (s + 8 * j));
-    }
-  }
-  float* c0 = reinterpret_cast<float*>(p.C) + r0 * p.ldc;
-  float* c1 = reinterpret_cast<float*>(p.C) + r1 * p.ldc;
-#pragma unroll 2
-  for (int n = 0; n < p.N; ++n) {
-    const float4* w = reinterpret_cast<const float4*>(p.Wf + (long long)n * p.K);
-    float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f, y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const float4 wv = __ldg(w + s + 8 * j);
-      x0 = fmaf(a0[j].x, wv.x, x0); x1 = fmaf(a0[j].y, wv.y, x1); x2 = fmaf(a0[j].z, wv.z, x2); x3 = fmaf(a0[j].w, wv.w, x3);
-      y0 = fmaf(a1[j].x, wv.x, y0); y1 = fmaf(a1[j].y, wv.y, y1); y2 = fmaf(a1[j].z, wv.z, y2); y3 = fmaf(a1[j].w, wv.w, y3);
-    }
-    float u = (x0 + x1) + (x2 + x3), v = (y0 + y1) + (y2 + y3);
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) { u += __shfl_xor_sync(0xffffffffu, u, o); v += __shfl_xor_sync(0xffffffffu, v, o); }
-    if (s == (n & 7)) {                                     // spread the stores over the 8 lanes
-      if (p.scale) { const float sc = __ldg(p.scale + n); u *= sc; v *= sc; }
-      if (p.shift) { const float sh = __ldg(p.shift + n); u += sh; v += sh; }
-      if (p.act == ACT_RELU) { u = fmaxf(u, 0.f); v = fmaxf(v, 0.f); }
-      else if (p.act == ACT_SIGMOID) { u = 1.f / (1.f + expf(-u)); v = 1.f / (1.f + expf(-v)); }
-      if (live0) c0[n] = u;
-      if (live1) c1[n] = v;
-    }
-  }
 }
 
 cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t st) {
