@@ -477,7 +477,7 @@ def main():
     del h_frames
 
     # ---- per-kernel profile of one forward (CUDA events around every launch) + stage timers, headline model
-    kernels, roof, stage_ms = [], None, {}
+    kernels, roof, stage_ms, stages = [], None, {}, []
     if rank == 0:
         _lib.check(lib.tuber_set_kernel_profiling(model.plan(), 1))
         model.forward_raw(clips, None, out)
@@ -516,6 +516,17 @@ def main():
                      "traffic_source": traffic_src,
                      "how": "CUDA events around every launch of one extra forward (same stream, same buffers, after the timed region)"})
         stage_ms = model.stage_times_ms(clips)
+        # each stage against the roofline that bounds it (BASELINE north_star): algorithmic bytes / flops of the stage's launches
+        # (tuber_get_stage_work: operands read once, results written once, flops = 2 x MACs) over the stage's device time;
+        # "tensor_frac_issued" counts the three bf16 passes the split GEMMs issue per contraction
+        for name, w in model.stage_work().items():
+            ms = stage_ms.get(name, 0.0)
+            if ms <= 0:
+                continue
+            gbs, tfs = w["bytes"] / (ms * 1e-3) / 1e9, w["flops"] / (ms * 1e-3) / 1e12
+            hf, tf = gbs / peaks["hbm_gbs"], tfs / peaks["bf16_tflops"]
+            stages.append({"stage": name, "ms": round(ms, 4), "GB/s": round(gbs, 1), "TFLOP/s": round(tfs, 2), "hbm_frac": round(hf, 4),
+                           "tensor_frac": round(tf, 4), "tensor_frac_issued": round(3 * tf, 4), "bound": "hbm" if hf >= 3 * tf else "tensor"})
 
     # ---- the other BASELINE.json configs, same timing rules (every rank takes part: the all-gather is inside the step)
     also = []
@@ -600,7 +611,7 @@ def main():
             "e2e_u8": e2e_u8,
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "cuda_graph": use_graph, "roofline": roof, "cpu_baseline": cpu, "same_box_baseline": same_box, "frame_loading": frame_leg, "also": also, "kernels": kernels,
-            "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+            "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "stages": stages,
             "arithmetic": "fp32 storage; GEMMs = 3-pass bf16 split (hi*hi+hi*lo+lo*hi) on tcgen05 with fp32 TMEM accumulation"}
     emit(line)
     if world > 1:

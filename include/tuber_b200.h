@@ -167,6 +167,11 @@ int tuber_set_profiling(TuberPlan* plan, int32_t enabled);
 /* ms of the last profiled forward per stage: stem, layer1..4, pool, proj, encoder, decoder,
  * class-branch+heads.  Synchronises on the last event. */
 int tuber_get_stage_ms(TuberPlan* plan, float* ms_out /* [TUBER_NUM_STAGES] */);
+/* ALGORITHMIC bytes / flops of the last forward per stage (same stages, same accounting as tuber_get_kernel_profile: each operand
+ * read once, each result written once, flops = 2 x MACs; SURVEY 8d's per-clip figures x the clips of the call) -- with
+ * tuber_get_stage_ms the per-stage roofline fractions bench.py reports (BASELINE north_star: "each stage reported as achieved
+ * fraction of its HBM-or-tensor-core roofline").  No reference counterpart (the reference has no instrumentation). */
+int tuber_get_stage_work(TuberPlan* plan, double* bytes_out /* [TUBER_NUM_STAGES] */, double* flops_out /* [TUBER_NUM_STAGES] */);
 const char* tuber_stage_name(int32_t i);
 /* Per-kernel profile: when enabled, every launch of a forward is bracketed by its own pair of CUDA
  * events on the launching stream (disables graph replay).  tuber_get_kernel_profile aggregates the last

@@ -382,6 +382,32 @@ def test_side_branches_on_their_own_streams_are_bit_identical(monkeypatch, yaml,
             assert torch.equal(out[k], plain[k]), (k, "graph", step)
 
 
+def test_stage_work_adds_up_to_the_kernel_profile():
+    """tuber_get_stage_work (algorithmic bytes / flops per stage, the numerators of bench.py's per-stage roofline fractions) covers
+    every launch of a forward exactly once: its totals equal those of the per-kernel profile of the same forward."""
+    import ctypes as C
+    import tuber_b200
+    from tuber_b200 import _lib
+    cfg, sd, clips, _ = build_case("A_csn50")
+    model = _model(cfg, sd)
+    lib = _lib.load()
+    x = clips.cuda()
+    _lib.check(lib.tuber_set_kernel_profiling(model.plan(), 1))
+    model.forward_raw(x)
+    torch.cuda.synchronize()
+    n = C.c_int32()
+    _lib.check(lib.tuber_get_kernel_profile(model.plan(), None, 0, C.byref(n)))
+    stats = (_lib.TuberKernelStat * n.value)()
+    _lib.check(lib.tuber_get_kernel_profile(model.plan(), stats, n.value, C.byref(n)))
+    _lib.check(lib.tuber_set_kernel_profiling(model.plan(), 0))
+    work = model.stage_work()
+    assert len(work) == _lib.NUM_STAGES and all(w["bytes"] > 0 for w in work.values())
+    kb, kf = sum(s.bytes for s in stats), sum(s.flops for s in stats)
+    sb, sf = sum(w["bytes"] for w in work.values()), sum(w["flops"] for w in work.values())
+    assert abs(sb - kb) <= 1e-9 * kb and abs(sf - kf) <= 1e-9 * kf, (sb, kb, sf, kf)
+    assert work["stem"]["flops"] > 0 and work["layer1"]["flops"] > work["encoder"]["flops"]
+
+
 def test_detection_rows_match_reference_postprocessors():
     """tuber_postprocess (fused post-processing + row packing) against the reference's PostProcessAVA / PostProcess outputs
     (tests/golden/postprocess.npz) and through the PostProcess* modules of build_model."""

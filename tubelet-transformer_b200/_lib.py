@@ -70,6 +70,7 @@ PROTOTYPES = {
     "tuber_graph_count": (_I, [_P]),
     "tuber_set_profiling": (_I, [_P, _I]),
     "tuber_get_stage_ms": (_I, [_P, C.POINTER(_F)]),
+    "tuber_get_stage_work": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "tuber_stage_name": (C.c_char_p, [_I]),
     "tuber_set_kernel_profiling": (_I, [_P, _I]),
     "tuber_get_kernel_profile": (_I, [_P, C.POINTER(TuberKernelStat), _I, C.POINTER(_I)]),

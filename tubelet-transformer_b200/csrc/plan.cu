@@ -163,6 +163,7 @@ struct TuberPlan {
   bool profiling = false, debug_keep = false, use_graph = false;
   cudaEvent_t ev[TUBER_NUM_STAGES + 1] = {};
   bool ev_valid = false;
+  double stage_bytes[TUBER_NUM_STAGES] = {}, stage_flops[TUBER_NUM_STAGES] = {};   // algorithmic work of the last forward, per stage
   std::map<std::string, Tap> taps;
   int launches = 0;
   bool kprof = false;
@@ -656,10 +657,14 @@ struct Ctx {
   }
   // every device operation of a forward goes through here: counted, optionally bracketed by CUDA events
   // (per-kernel profiling), skipped in the dry (sizing) pass
+  // algorithmic bytes / flops of the launches since each stage mark (also counted in the sizing pass)
+  int cur_stage = -1;
+  double st_bytes[TUBER_NUM_STAGES] = {}, st_flops[TUBER_NUM_STAGES] = {};
   template <class F>
   void launch(const char* name, double bytes, double flops, F&& f) {
     if (!ok()) return;
     ++launches;
+    if (cur_stage >= 0) { st_bytes[cur_stage] += bytes; st_flops[cur_stage] += flops; }
     if (dry) return;
     if (ws.overflow) { status = fail(TUBER_ERR_STATE, "workspace overflow before %s (sizing pass disagrees with the forward)", name); return; }
     const int idx = p->kprof ? kp_begin(name, bytes, flops) : -1;
@@ -766,6 +771,7 @@ struct Ctx {
   }
 
   void stage_mark(int i) {
+    cur_stage = i < TUBER_NUM_STAGES ? i : -1;
     if (dry || !p->profiling || !ok()) return;
     cudaEventRecord(p->ev[i], st);
   }
@@ -1439,6 +1445,7 @@ int tuber_forward(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev,
   if (!graph) {
     int s = run_forward(cx, clips_dev, mask_dev, B, T, H, W, logits_dev, boxes_dev, logits_b_dev);
     p->launches = cx.launches;
+    for (int i = 0; i < TUBER_NUM_STAGES; ++i) { p->stage_bytes[i] = cx.st_bytes[i]; p->stage_flops[i] = cx.st_flops[i]; }
     return s;
   }
   std::vector<uintptr_t> key = {(uintptr_t)clips_dev, (uintptr_t)mask_dev, (uintptr_t)B, (uintptr_t)T, (uintptr_t)H, (uintptr_t)W,
@@ -1451,6 +1458,7 @@ int tuber_forward(TuberPlan* p, const float* clips_dev, const uint8_t* mask_dev,
   {
     int s0 = run_forward(cx, clips_dev, mask_dev, B, T, H, W, logits_dev, boxes_dev, logits_b_dev);
     p->launches = cx.launches;
+    for (int i = 0; i < TUBER_NUM_STAGES; ++i) { p->stage_bytes[i] = cx.st_bytes[i]; p->stage_flops[i] = cx.st_flops[i]; }
     if (s0 != TUBER_OK) return s0;
   }
   Ctx cap{p};
@@ -1811,6 +1819,12 @@ int tuber_get_stage_ms(TuberPlan* p, float* ms_out) {
   if (!p->ev_valid) return fail(TUBER_ERR_STATE, "no profiled forward yet");
   CK(cudaEventSynchronize(p->ev[TUBER_NUM_STAGES]));
   for (int i = 0; i < TUBER_NUM_STAGES; ++i) CK(cudaEventElapsedTime(ms_out + i, p->ev[i], p->ev[i + 1]));
+  return TUBER_OK;
+}
+
+int tuber_get_stage_work(TuberPlan* p, double* bytes_out, double* flops_out) {
+  if (!p || !bytes_out || !flops_out) return fail(TUBER_ERR_INVALID, "null argument");
+  for (int i = 0; i < TUBER_NUM_STAGES; ++i) { bytes_out[i] = p->stage_bytes[i]; flops_out[i] = p->stage_flops[i]; }
   return TUBER_OK;
 }
 

@@ -514,6 +514,13 @@ class DETR(nn.Module):
             _lib.check(lib.tuber_set_profiling(plan, 0))
         return {lib.tuber_stage_name(i).decode(): float(ms[i]) for i in range(_lib.NUM_STAGES)}
 
+    def stage_work(self) -> Dict[str, Dict[str, float]]:
+        """algorithmic bytes / flops of the last forward per stage (tuber_get_stage_work)"""
+        lib = _lib.load()
+        by, fl = (C.c_double * _lib.NUM_STAGES)(), (C.c_double * _lib.NUM_STAGES)()
+        _lib.check(lib.tuber_get_stage_work(self.plan(), by, fl))
+        return {lib.tuber_stage_name(i).decode(): {"bytes": float(by[i]), "flops": float(fl[i])} for i in range(_lib.NUM_STAGES)}
+
     def debug_fetch(self, what: str) -> Tensor:
         lib = _lib.load()
         n = C.c_int64()
